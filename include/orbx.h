@@ -1,0 +1,170 @@
+/* orbx -- B200-native ORB front end for SEND-SLAM: C ABI (drop-in boundary b2 of SURVEY.md §8b).
+ *
+ * One core library (liborbx.so, hand-written CUDA for sm_100a) serves the three seams of the reference:
+ *   b1  C++ class seam   ORB_SLAM3::ORBextractor / ORBmatcher::DescriptorDistance, compiled by the reference
+ *                        from src/ORBextractor.cc, src/ORBmatcher.cc (slam_backends/orb_slam_3/CMakeLists.txt:52-53,
+ *                        headers :80-81) and reached from orbslam3_mono_networked.cc:594 (TrackMonocular);
+ *                        shim/ORBextractor.{h,cc} forwards to this header.
+ *   b3  BEAM seam        nif/orbx_nif.c (erl_nif) -- the Elixir side receives frames as
+ *                        {:camera_frame,{:ok,opts}} (send_slam/lib/send_slam/camera_producer.ex:190-208) and today
+ *                        ships them as PPM over TCP (send_slam/lib/send_slam/slam_handler.ex:59-88).
+ * All entry points: plain pointers and sizes, caller-allocated outputs with explicit capacity, int status
+ * (0 = ok, < 0 = ORBX_E_*), never throw / abort.  A handle is single-flight; distinct handles are independent
+ * (own CUDA stream + workspace, bound to one device).  There is NO CPU fallback: without a usable CUDA device
+ * orbx_create fails with ORBX_E_CUDA.
+ */
+#ifndef ORBX_H
+#define ORBX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORBX_OK 0
+#define ORBX_E_INVALID (-1)   /* bad argument (null pointer, size out of range, unsupported parameter)          */
+#define ORBX_E_CUDA (-2)      /* CUDA runtime error or no device; text in orbx_last_error                       */
+#define ORBX_E_CAPACITY (-3)  /* caller buffer / configured maximum too small                                   */
+#define ORBX_E_EMPTY (-4)     /* empty image: the reference returns -1 from operator() (UPSTREAM assert/empty)  */
+#define ORBX_E_OVERFLOW (-5)  /* internal candidate buffer overflow (cannot happen with the default sizing)     */
+
+#define ORBX_MAX_LEVELS 16
+#define ORBX_DESC_BYTES 32
+
+typedef struct orbx_handle orbx_handle;   /* extractor (+ windowed matcher workspace)  */
+typedef struct orbx_db orbx_db;           /* row shard of a descriptor database (kNN)  */
+
+/* Replaces the five ORBextractor ctor arguments (UPSTREAM include/ORBextractor.h; values the reference passes:
+ * orbslam3_mono_networked.cc:193-206) plus what a GPU workspace needs to be sized once. */
+typedef struct orbx_config {
+    int nfeatures;       /* ORBextractor.nFeatures  (reference: 1250; 5x for the initialisation extractor)   */
+    float scale_factor;  /* ORBextractor.scaleFactor (1.2); supported range (1, 2)                            */
+    int nlevels;         /* ORBextractor.nLevels (8); 1..ORBX_MAX_LEVELS                                      */
+    int ini_th_fast;     /* ORBextractor.iniThFAST (20)                                                       */
+    int min_th_fast;     /* ORBextractor.minThFAST (7)                                                        */
+    int device;          /* CUDA device ordinal                                                               */
+    int max_width;       /* largest frame the handle will see (<= 4095)                                       */
+    int max_height;
+    int max_batch;       /* frames per orbx_extract_batch call (1 for the per-frame seam)                     */
+} orbx_config;
+
+/* Binary-compatible with cv::KeyPoint (7 x 4 bytes) so the shim can memcpy into std::vector<cv::KeyPoint>. */
+typedef struct orbx_keypoint {
+    float x, y;        /* pt, image coordinates (level coordinates * mvScaleFactor[octave])   */
+    float size;        /* (int)(31 * mvScaleFactor[octave])                                    */
+    float angle;       /* IC_Angle, degrees [0,360)                                            */
+    float response;    /* FAST score                                                           */
+    int32_t octave;
+    int32_t class_id;  /* -1                                                                   */
+} orbx_keypoint;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------------- */
+int orbx_create(const orbx_config *cfg, orbx_handle **out);
+void orbx_destroy(orbx_handle *h);
+/* Last error text of this handle (h == NULL: last error of a failed orbx_create / orbx_knn2_create_db on this thread). */
+const char *orbx_last_error(const orbx_handle *h);
+/* Upper bound of keypoints one frame can return (nfeatures + 3 per level + slack); size kp/desc buffers with it. */
+int orbx_keypoint_capacity(const orbx_handle *h);
+
+/* Replaces GetLevels/GetScaleFactor(s)/GetInverseScaleFactors/GetScaleSigmaSquares/GetInverseScaleSigmaSquares
+ * (UPSTREAM include/ORBextractor.h getters, read by the Frame ctor).  Each array (may be NULL) gets nlevels entries.
+ * Returns nlevels. */
+int orbx_get_tables(const orbx_handle *h, float *scale, float *inv_scale, float *sigma2, float *inv_sigma2,
+                    int *features_per_level);
+/* Level geometry for a w x h frame: widths/heights of the nlevels pyramid planes. Returns nlevels. */
+int orbx_get_level_sizes(const orbx_handle *h, int width, int height, int *widths, int *heights);
+
+/* ---- extraction ------------------------------------------------------------------------------------------ */
+/* Replaces ORBextractor::operator()(image, mask, keypoints, descriptors, vLappingArea) for one CV_8UC1 frame in HOST
+ * memory (mask ignored as upstream).  kp_out / desc_out: cap records / cap*32 bytes.  *n_out = keypoints written,
+ * *mono_index_out = the value operator() returns.  Output order is the reference's (stereo slots filled from the
+ * back for lap0 <= x <= lap1, mono slots from the front). */
+int orbx_extract(orbx_handle *h, const uint8_t *gray, int width, int height, int stride, int lap0, int lap1,
+                 orbx_keypoint *kp_out, uint8_t *desc_out, int cap, int *n_out, int *mono_index_out);
+
+/* Same for `batch` equally sized HOST frames (frames[i] = first pixel of frame i).  Outputs are batch blocks of
+ * cap records.  Host<->device copies are pipelined with the kernels on the handle's streams. */
+int orbx_extract_batch(orbx_handle *h, const uint8_t *const *frames, int batch, int width, int height, int stride,
+                       int lap0, int lap1, orbx_keypoint *kp_out, uint8_t *desc_out, int cap, int *n_out,
+                       int *mono_index_out);
+
+/* Device-resident variant: frames already in HBM at d_frames + i*frame_stride_bytes (row pitch `stride`), results
+ * left in HBM (d_kp_out: batch*cap records, d_desc_out: batch*cap*32 B, d_n_out / d_mono_out: batch ints).
+ * Asynchronous on the handle's stream; call orbx_sync before reading results from another stream. */
+int orbx_extract_batch_device(orbx_handle *h, const uint8_t *d_frames, size_t frame_stride_bytes, int batch, int width,
+                              int height, int stride, int lap0, int lap1, orbx_keypoint *d_kp_out,
+                              uint8_t *d_desc_out, int cap, int *d_n_out, int *d_mono_out);
+int orbx_sync(orbx_handle *h);
+/* Number of kernel launches issued by this handle since creation (bench.py's gpu_launches). */
+long long orbx_launch_count(const orbx_handle *h);
+
+/* ---- stage inspection (parity tests; valid after an extract call on the same handle) ------------------------- */
+/* Copies pyramid level `level` of batch frame `frame` (blurred != 0: the Gaussian-blurred plane) to host. */
+int orbx_debug_get_level(orbx_handle *h, int frame, int level, int blurred, uint8_t *out, int out_stride,
+                         int *width_out, int *height_out);
+/* FAST candidates of (frame, level) before the quadtree: triples (x, y, response) relative to (16,16), unordered. */
+int orbx_debug_get_candidates(orbx_handle *h, int frame, int level, float *xyr_out, int cap, int *n_out);
+/* Keypoints selected by the quadtree for (frame, level) in list order: (x, y, response, angle) in level coordinates. */
+int orbx_debug_get_level_keypoints(orbx_handle *h, int frame, int level, float *xyra_out, int cap, int *n_out);
+/* Stand-alone stages on caller data (HOST buffers), for per-kernel parity tests. */
+int orbx_debug_resize(orbx_handle *h, const uint8_t *src, int sw, int sh, int sstride, uint8_t *dst, int dw, int dh,
+                      int dstride);
+int orbx_debug_blur(orbx_handle *h, const uint8_t *src, int w, int ht, int sstride, uint8_t *dst, int dstride);
+/* DistributeOctTree on caller candidates: keys = n x (x, y, response) relative to (minX,minY); out_idx = indices into
+ * keys in final list order. */
+int orbx_debug_octree(orbx_handle *h, const float *keys, int n, int minX, int maxX, int minY, int maxY, int N,
+                      int *out_idx, int cap, int *n_out);
+/* IC_Angle + steered BRIEF for caller keypoints (x, y integer-valued level coordinates) on a caller image / blurred
+ * image; angle_in == NULL: compute angles from `img`, else use the given angles for the descriptors. */
+int orbx_debug_describe(orbx_handle *h, const uint8_t *img, const uint8_t *blurred, int w, int ht, int stride,
+                        const float *xy, int n, const float *angle_in, float *angle_out, uint8_t *desc_out);
+
+/* ---- matching ----------------------------------------------------------------------------------------------- */
+/* Replaces loops of ORBmatcher::DescriptorDistance (UPSTREAM src/ORBmatcher.cc): dist[i] = Hamming(a[i], b[i]),
+ * HOST buffers of n x 32 bytes. */
+int orbx_distance_batch(orbx_handle *h, const uint8_t *a, const uint8_t *b, int n, int32_t *dist_out);
+
+/* Replaces the candidate loop of ORBmatcher::SearchByProjection / SearchForInitialization
+ * (Frame::GetFeaturesInArea + arg-min DescriptorDistance): per query q (descriptor, window centre u,v, radius r,
+ * minLevel, maxLevel) over the train keypoints of one frame (cv::KeyPoint records + descriptors, HOST buffers),
+ * grid = 64 x 48 cells over bounds {minX, minY, maxX, maxY}.  Outputs per query: best / second-best train index
+ * (-1 if none) and distance (256 if none); ties resolved in the reference's visiting order. */
+int orbx_match_windowed(orbx_handle *h, const uint8_t *q_desc, const float *q_uvr, const int32_t *q_levels, int nq,
+                        const orbx_keypoint *t_kp, const uint8_t *t_desc, int nt, const float *bounds4,
+                        int32_t *best_idx, int32_t *best_dist, int32_t *second_idx, int32_t *second_dist);
+
+/* Brute-force Hamming kNN, k = 2 (cv::BFMatcher(NORM_HAMMING).knnMatch): one orbx_db = one row shard resident in HBM.
+ * row_offset = global index of the shard's first row (results carry global indices). */
+int orbx_knn2_create_db(int device, const uint8_t *rows, long long nrows, long long row_offset, orbx_db **out);
+/* Same, rows already in HBM on `device` (not copied; must outlive the db). */
+int orbx_knn2_create_db_device(int device, const uint8_t *d_rows, long long nrows, long long row_offset, orbx_db **out);
+void orbx_knn2_destroy_db(orbx_db *db);
+const char *orbx_knn2_last_error(const orbx_db *db);
+/* HOST queries (nq x 32 B) -> idx[nq*2] (global row, -1 if missing), dist[nq*2] (-1 if missing); ties -> lowest row. */
+int orbx_knn2_query(orbx_db *db, const uint8_t *queries, int nq, int32_t *idx_out, int32_t *dist_out);
+/* Device-resident: d_queries (nq x 32 B) -> d_packed_out[nq*2] = (dist << 32 | global row), 0xFFFF...F if missing.
+ * Asynchronous on the db's stream; orbx_knn2_sync to wait. */
+int orbx_knn2_query_device(orbx_db *db, const uint8_t *d_queries, int nq, unsigned long long *d_packed_out);
+/* Top-2 merge of `nparts` partial results (layout [part][query][2], e.g. the NCCL all-gather of every rank's
+ * orbx_knn2_query_device output) into d_packed_out[nq*2]; all pointers in HBM on the db's device. */
+int orbx_knn2_merge_device(orbx_db *db, const unsigned long long *d_partials, int nparts, int nq,
+                           unsigned long long *d_packed_out);
+int orbx_knn2_sync(orbx_db *db);
+long long orbx_knn2_launch_count(const orbx_db *db);
+
+/* Geometry plan probe, needs NO GPU (used by the CPU-only tests): level sizes, FAST cells per level, per-level
+ * quotas, quadtree roots / tabulated depth and the algorithmic bytes per frame of SURVEY.md §8(d).  Arrays may be NULL.
+ * Returns nlevels or ORBX_E_INVALID. */
+int orbx_plan_probe(int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th, int width, int height,
+                    int *widths, int *heights, int *ncells, int *quota, int *n_ini, int *depth0,
+                    long long *algorithmic_bytes);
+
+/* Library build identification: "orbx <version> sm_100a". */
+const char *orbx_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORBX_H */

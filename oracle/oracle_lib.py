@@ -1,0 +1,241 @@
+"""ctypes binding of oracle/_build/liborb_oracle.so (ORACLE = test infrastructure; see orb_oracle.c header).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "liborb_oracle.so")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "orb_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        L = C.CDLL(_SO)
+        u8p, f32p, i32p = C.POINTER(C.c_uint8), C.POINTER(C.c_float), C.POINTER(C.c_int32)
+        L.orb_oracle_create.restype = C.c_void_p
+        L.orb_oracle_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.orb_oracle_destroy.argtypes = [C.c_void_p]
+        L.orb_oracle_tables.argtypes = [C.c_void_p, f32p, f32p, f32p, f32p, i32p, i32p]
+        L.orb_oracle_level_size.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, i32p, i32p]
+        L.orb_oracle_resize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.orb_oracle_blur7.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.orb_oracle_fast.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.orb_oracle_fast_cells.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.orb_oracle_octree.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.orb_oracle_fast_atan2.restype = C.c_float
+        L.orb_oracle_fast_atan2.argtypes = [C.c_float, C.c_float]
+        L.orb_oracle_ic_moments.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, i32p, i32p, i32p]
+        L.orb_oracle_ic_angle.restype = C.c_float
+        L.orb_oracle_ic_angle.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float]
+        L.orb_oracle_brief.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p]
+        L.orb_oracle_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_int, i32p, i32p]
+        L.orb_oracle_stage_level.argtypes = [C.c_void_p, C.c_int, i32p, i32p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.orb_oracle_stage_keys.argtypes = [C.c_void_p, C.c_int, i32p, C.POINTER(C.c_void_p), i32p, C.POINTER(C.c_void_p),
+                                            C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.orb_oracle_extract_batch.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                               C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                               C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.orb_oracle_distance.argtypes = [C.c_void_p, C.c_void_p]
+        L.orb_oracle_knn2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_int]
+        L.orb_oracle_match_windowed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                                C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Oracle:
+    """One ORBextractor restatement instance."""
+
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+        self.L = lib()
+        self.h = self.L.orb_oracle_create(nfeatures, scale_factor, nlevels, ini_th, min_th)
+        if not self.h:
+            raise ValueError("orb_oracle_create rejected the parameters")
+        self.nfeatures, self.nlevels, self.ini_th, self.min_th = nfeatures, nlevels, ini_th, min_th
+        self.scale_factor = scale_factor
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orb_oracle_destroy(self.h)
+            self.h = None
+
+    def tables(self):
+        n = self.nlevels
+        sc, inv, s2, is2 = (np.zeros(n, np.float32) for _ in range(4))
+        quota, umax = np.zeros(n, np.int32), np.zeros(16, np.int32)
+        f32p, i32p = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+        self.L.orb_oracle_tables(self.h, sc.ctypes.data_as(f32p), inv.ctypes.data_as(f32p), s2.ctypes.data_as(f32p),
+                                 is2.ctypes.data_as(f32p), quota.ctypes.data_as(i32p), umax.ctypes.data_as(i32p))
+        return dict(scale=sc, inv_scale=inv, sigma2=s2, inv_sigma2=is2, quota=quota, umax=umax)
+
+    def level_size(self, w, h, l):
+        a, b = C.c_int32(), C.c_int32()
+        self.L.orb_oracle_level_size(self.h, w, h, l, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def extract(self, img: np.ndarray, lap=(0, 1000), cap=None):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        h, w = img.shape
+        cap = cap or (self.nfeatures + 4 * self.nlevels + 64)
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n, mono = C.c_int32(), C.c_int32()
+        rc = self.L.orb_oracle_extract(self.h, _p(img), w, h, w, lap[0], lap[1], _p(kps), _p(desc), cap,
+                                       C.byref(n), C.byref(mono))
+        if rc != 0:
+            raise RuntimeError(f"orb_oracle_extract rc={rc}")
+        assert n.value <= cap
+        return kps[:n.value].copy(), desc[:n.value].copy(), mono.value
+
+    def stage_level(self, l):
+        w, h = C.c_int32(), C.c_int32()
+        pix, bl = C.c_void_p(), C.c_void_p()
+        self.L.orb_oracle_stage_level(self.h, l, C.byref(w), C.byref(h), C.byref(pix), C.byref(bl))
+        shape = (h.value, w.value)
+        a = np.ctypeslib.as_array(C.cast(pix, C.POINTER(C.c_uint8)), shape=shape).copy()
+        b = np.ctypeslib.as_array(C.cast(bl, C.POINTER(C.c_uint8)), shape=shape).copy() if bl.value else None
+        return a, b
+
+    def stage_keys(self, l):
+        nc, ns = C.c_int32(), C.c_int32()
+        cand, sel, ang, desc = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self.L.orb_oracle_stage_keys(self.h, l, C.byref(nc), C.byref(cand), C.byref(ns), C.byref(sel), C.byref(ang), C.byref(desc))
+        c = np.ctypeslib.as_array(C.cast(cand, C.POINTER(C.c_float)), shape=(nc.value, 3)).copy() if nc.value else np.zeros((0, 3), np.float32)
+        if ns.value:
+            s = np.ctypeslib.as_array(C.cast(sel, C.POINTER(C.c_int32)), shape=(ns.value,)).copy()
+            a = np.ctypeslib.as_array(C.cast(ang, C.POINTER(C.c_float)), shape=(ns.value,)).copy()
+            d = np.ctypeslib.as_array(C.cast(desc, C.POINTER(C.c_uint8)), shape=(ns.value, 32)).copy()
+        else:
+            s, a, d = np.zeros(0, np.int32), np.zeros(0, np.float32), np.zeros((0, 32), np.uint8)
+        return c, s, a, d
+
+
+def resize(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.zeros((dh, dw), np.uint8)
+    lib().orb_oracle_resize(_p(src), src.shape[1], src.shape[0], src.shape[1], _p(dst), dw, dh, dw)
+    return dst
+
+
+def blur7(src: np.ndarray) -> np.ndarray:
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.zeros_like(src)
+    lib().orb_oracle_blur7(_p(src), src.shape[1], src.shape[0], src.shape[1], _p(dst), src.shape[1])
+    return dst
+
+
+def fast(img: np.ndarray, t: int) -> np.ndarray:
+    img = np.ascontiguousarray(img, np.uint8)
+    cap = img.size
+    out = np.zeros((cap, 3), np.float32)
+    n = lib().orb_oracle_fast(_p(img), img.shape[1], img.shape[0], img.shape[1], t, _p(out), cap)
+    return out[:n].copy()
+
+
+def fast_cells(img: np.ndarray, ini_th=20, min_th=7) -> np.ndarray:
+    img = np.ascontiguousarray(img, np.uint8)
+    cap = img.size
+    out = np.zeros((cap, 3), np.float32)
+    n = lib().orb_oracle_fast_cells(_p(img), img.shape[1], img.shape[0], img.shape[1], ini_th, min_th, _p(out), cap)
+    return out[:n].copy()
+
+
+def octree(keys: np.ndarray, minX, maxX, minY, maxY, N) -> np.ndarray:
+    keys = np.ascontiguousarray(keys, np.float32).reshape(-1, 3)
+    out = np.zeros(max(len(keys), 1), np.int32)
+    m = lib().orb_oracle_octree(_p(keys), len(keys), minX, maxX, minY, maxY, N, _p(out), len(out))
+    if m < 0:
+        raise ValueError("octree: bad aspect ratio")
+    return out[:m].copy()
+
+
+def fast_atan2(y: float, x: float) -> float:
+    return float(lib().orb_oracle_fast_atan2(float(y), float(x)))
+
+
+def ic_moments(img: np.ndarray, cx: int, cy: int, umax: np.ndarray):
+    img = np.ascontiguousarray(img, np.uint8)
+    a, b = C.c_int32(), C.c_int32()
+    um = np.ascontiguousarray(umax, np.int32)
+    lib().orb_oracle_ic_moments(_p(img), img.shape[1], int(cx), int(cy), um.ctypes.data_as(C.POINTER(C.c_int32)),
+                                C.byref(a), C.byref(b))
+    return a.value, b.value  # m01, m10
+
+
+def brief(blurred: np.ndarray, x: float, y: float, angle: float) -> np.ndarray:
+    blurred = np.ascontiguousarray(blurred, np.uint8)
+    d = np.zeros(32, np.uint8)
+    lib().orb_oracle_brief(_p(blurred), blurred.shape[1], float(x), float(y), float(angle), _p(d))
+    return d
+
+
+def extract_batch(frames: np.ndarray, nfeatures, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, lap=(0, 1000),
+                  nthreads=1):
+    """frames: [B,H,W] uint8. Returns (kps [B,cap], desc [B,cap,32], n [B], mono [B])."""
+    frames = np.ascontiguousarray(frames, np.uint8)
+    B, H, W = frames.shape
+    cap = nfeatures + 4 * nlevels + 64
+    kps = np.zeros((B, cap), KP_DTYPE)
+    desc = np.zeros((B, cap, 32), np.uint8)
+    n = np.zeros(B, np.int32)
+    mono = np.zeros(B, np.int32)
+    lib().orb_oracle_extract_batch(nfeatures, scale_factor, nlevels, ini_th, min_th, _p(frames), W, H, W, H * W, B,
+                                   lap[0], lap[1], _p(kps), _p(desc), cap, _p(n), _p(mono), nthreads)
+    return kps, desc, n, mono
+
+
+def distance(a: np.ndarray, b: np.ndarray) -> int:
+    a = np.ascontiguousarray(a, np.uint8)
+    b = np.ascontiguousarray(b, np.uint8)
+    return int(lib().orb_oracle_distance(_p(a), _p(b)))
+
+
+def knn2(q: np.ndarray, db: np.ndarray, nthreads=1):
+    q = np.ascontiguousarray(q, np.uint8)
+    db = np.ascontiguousarray(db, np.uint8)
+    idx = np.zeros((len(q), 2), np.int32)
+    dist = np.zeros((len(q), 2), np.int32)
+    lib().orb_oracle_knn2(_p(q), len(q), _p(db), len(db), _p(idx), _p(dist), nthreads)
+    return idx, dist
+
+
+def match_windowed(qdesc, quvr, qlevels, tkp, tdesc, bounds):
+    qdesc = np.ascontiguousarray(qdesc, np.uint8)
+    quvr = np.ascontiguousarray(quvr, np.float32)
+    qlevels = np.ascontiguousarray(qlevels, np.int32)
+    tkp = np.ascontiguousarray(tkp, KP_DTYPE)
+    tdesc = np.ascontiguousarray(tdesc, np.uint8)
+    bounds = np.ascontiguousarray(bounds, np.float32)
+    nq = len(qdesc)
+    out = [np.zeros(nq, np.int32) for _ in range(4)]
+    lib().orb_oracle_match_windowed(_p(qdesc), _p(quvr), _p(qlevels), nq, _p(tkp), _p(tdesc), len(tkp), _p(bounds),
+                                    _p(out[0]), _p(out[1]), _p(out[2]), _p(out[3]))
+    return tuple(out)  # best_idx, best_dist, second_idx, second_dist

@@ -1,0 +1,606 @@
+// C ABI of the extractor (include/orbx.h): host runtime around the kernels of orbx_kernels.cu.
+// One handle = one device, one stream, one workspace sized for (frame size, batch).  No CPU fallback: every entry
+// point that computes anything launches the CUDA kernels or fails with ORBX_E_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/orbx.h"
+#include "orbx_dev.h"
+#include "orbx_plan.h"
+
+using namespace orbx;
+
+static_assert(sizeof(orbx_keypoint) == 28 && sizeof(KeypointRec) == 28, "keypoint record must match cv::KeyPoint");
+
+static thread_local std::string g_create_error;
+
+struct orbx_handle {
+    orbx_config cfg{};
+    ExtractorParams P{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    mutable std::string err;
+    long long launches = 0;
+
+    // plan-dependent state
+    Plan plan;
+    bool planned = false;
+    int batch_cap = 0;
+    int kp_cap = 0;                 // keypoints per frame the internal result buffers hold
+    std::vector<void *> dev_allocs; // everything freed on re-plan / destroy
+    LevelDev h_levels[kMaxLevels];
+    LevelDev *d_levels = nullptr;
+    CellRect *d_cells = nullptr;
+    BlurTile *d_tiles = nullptr;
+    int ntiles = 0;
+    int *d_counts = nullptr;        // [2][nlevels][batch]: cand_count then sel_count
+    int *d_overflow = nullptr;
+    int *d_slot = nullptr;          // [batch][total_out_cap]
+    KeypointRec *d_kp = nullptr;    // [batch][kp_cap]
+    uint8_t *d_desc = nullptr;      // [batch][kp_cap][32]
+    int *d_n = nullptr, *d_mono = nullptr;
+    uint8_t *l0_own = nullptr;      // arena copy of level 0 (host-input path)
+    size_t l0_own_fstride = 0;
+    int l0_own_pitch = 0;
+    // pinned host staging
+    uint8_t *h_in = nullptr; size_t h_in_bytes = 0;
+    KeypointRec *h_kp = nullptr; uint8_t *h_desc = nullptr; int *h_n = nullptr, *h_mono = nullptr, *h_overflow = nullptr;
+    int last_batch = 0;             // batch size of the most recent run (debug getters)
+};
+
+#define CU_TRY(h, expr)                                                                                         \
+    do {                                                                                                        \
+        cudaError_t e__ = (expr);                                                                               \
+        if (e__ != cudaSuccess) {                                                                               \
+            (h)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                                     \
+            return ORBX_E_CUDA;                                                                                 \
+        }                                                                                                       \
+    } while (0)
+
+static int fail(const orbx_handle *h, int code, const char *msg) {
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+
+static void free_plan(orbx_handle *h) {
+    for (void *p : h->dev_allocs) cudaFree(p);
+    h->dev_allocs.clear();
+    if (h->h_in) cudaFreeHost(h->h_in);
+    if (h->h_kp) cudaFreeHost(h->h_kp);
+    if (h->h_desc) cudaFreeHost(h->h_desc);
+    if (h->h_n) cudaFreeHost(h->h_n);
+    h->h_in = nullptr; h->h_kp = nullptr; h->h_desc = nullptr; h->h_n = nullptr; h->h_mono = nullptr; h->h_overflow = nullptr;
+    h->planned = false;
+}
+
+template <typename T>
+static cudaError_t dev_alloc(orbx_handle *h, T **out, size_t count) {
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(count * sizeof(T), 256));
+    if (e == cudaSuccess) { h->dev_allocs.push_back(p); *out = (T *)p; }
+    return e;
+}
+
+template <typename T>
+static cudaError_t dev_upload(orbx_handle *h, T **out, const std::vector<T> &v) {
+    cudaError_t e = dev_alloc(h, out, v.size());
+    if (e != cudaSuccess || v.empty()) return e;
+    return cudaMemcpy(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+// (Re)build the geometry plan and the workspace for w x h frames, `batch` frames per call.
+static int ensure_plan(orbx_handle *h, int w, int ht, int batch) {
+    if (w > h->cfg.max_width || ht > h->cfg.max_height) return fail(h, ORBX_E_CAPACITY, "frame larger than max_width x max_height");
+    if (batch > h->cfg.max_batch) return fail(h, ORBX_E_CAPACITY, "batch larger than max_batch");
+    if (h->planned && h->plan.width == w && h->plan.height == ht) return ORBX_OK;
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    free_plan(h);
+    std::string err;
+    if (!build_plan(h->P, w, ht, h->plan, err)) { h->err = err; return ORBX_E_INVALID; }
+    const Plan &pl = h->plan;
+    const int B = h->cfg.max_batch, nl = pl.nlevels;
+    h->batch_cap = B;
+    h->kp_cap = pl.total_out_cap;
+    CU_TRY(h, dev_alloc(h, &h->d_levels, (size_t)kMaxLevels));
+    CU_TRY(h, dev_upload(h, &h->d_cells, pl.cells));
+    CU_TRY(h, dev_alloc(h, &h->d_counts, (size_t)2 * nl * B));
+    CU_TRY(h, dev_alloc(h, &h->d_overflow, (size_t)1));
+    CU_TRY(h, dev_alloc(h, &h->d_slot, (size_t)B * pl.total_out_cap));
+    CU_TRY(h, dev_alloc(h, &h->d_kp, (size_t)B * h->kp_cap));
+    CU_TRY(h, dev_alloc(h, &h->d_desc, (size_t)B * h->kp_cap * 32));
+    CU_TRY(h, dev_alloc(h, &h->d_n, (size_t)B));
+    CU_TRY(h, dev_alloc(h, &h->d_mono, (size_t)B));
+    std::vector<BlurTile> tiles;
+    int out_base = 0;
+    std::memset(h->h_levels, 0, sizeof(h->h_levels));
+    for (int l = 0; l < nl; l++) {
+        const LevelPlan &LP = pl.lv[l];
+        LevelDev &D = h->h_levels[l];
+        D.w = LP.w; D.h = LP.h; D.pitch = LP.pitch; D.blur_pitch = LP.pitch;
+        D.img_fstride = LP.plane_bytes; D.blur_fstride = LP.plane_bytes;
+        CU_TRY(h, dev_alloc(h, &D.img, LP.plane_bytes * B + 64));
+        CU_TRY(h, dev_alloc(h, &D.blur, LP.plane_bytes * B + 64));
+        if (l == 0) { h->l0_own = D.img; h->l0_own_fstride = LP.plane_bytes; h->l0_own_pitch = LP.pitch; }
+        if (l > 0) {
+            ResizeTap *xt = nullptr, *yt = nullptr;
+            CU_TRY(h, dev_upload(h, &xt, LP.xtap));
+            CU_TRY(h, dev_upload(h, &yt, LP.ytap));
+            D.xtap = xt; D.ytap = yt;
+        }
+        uint32_t *t0 = nullptr, *t1 = nullptr, *t2 = nullptr, *t3 = nullptr;
+        CU_TRY(h, dev_upload(h, &t0, LP.xbin)); CU_TRY(h, dev_upload(h, &t1, LP.ybin));
+        CU_TRY(h, dev_upload(h, &t2, LP.xord)); CU_TRY(h, dev_upload(h, &t3, LP.yord));
+        D.xbin = t0; D.ybin = t1; D.xord = t2; D.yord = t3;
+        D.reg_w = LP.reg_w; D.reg_h = LP.reg_h; D.n_ini = LP.n_ini; D.depth0 = LP.depth0; D.nbins = LP.nbins;
+        D.quota = LP.quota; D.out_cap = LP.out_cap;
+        for (int r = 0; r < kMaxRoots; r++) { D.root_ulx[r] = LP.root_ulx[r]; D.root_brx[r] = LP.root_brx[r]; }
+        D.ord_cell_area = LP.ord_cell_area; D.ord_ncols = LP.ord_ncols; D.wcell = LP.wcell; D.hcell = LP.hcell;
+        D.cand_cap = LP.cand_cap;
+        CU_TRY(h, dev_alloc(h, &D.cand, (size_t)B * LP.cand_cap));
+        CU_TRY(h, dev_alloc(h, &D.sorted, (size_t)B * LP.cand_cap));
+        CU_TRY(h, dev_alloc(h, &D.bin_cursor, (size_t)B * std::max(LP.nbins, 1)));
+        D.cand_count = h->d_counts + (size_t)l * B;
+        D.sel_count = h->d_counts + (size_t)(nl + l) * B;
+        CU_TRY(h, dev_alloc(h, &D.sel, (size_t)B * LP.out_cap));
+        D.out_base = out_base; out_base += LP.out_cap;
+        D.scale = h->P.scale[l]; D.kp_size = LP.kp_size;
+        for (int ty = 0; ty * 64 < LP.h; ty++)
+            for (int tx = 0; tx * 64 < LP.w; tx++) tiles.push_back(BlurTile{(int16_t)l, (int16_t)tx, (int16_t)ty, 0});
+    }
+    h->ntiles = (int)tiles.size();
+    CU_TRY(h, dev_upload(h, &h->d_tiles, tiles));
+    CU_TRY(h, cudaMemcpy(h->d_levels, h->h_levels, sizeof(h->h_levels), cudaMemcpyHostToDevice));
+    // pinned staging
+    h->h_in_bytes = (size_t)B * pl.lv[0].plane_bytes;
+    CU_TRY(h, cudaMallocHost((void **)&h->h_in, h->h_in_bytes));
+    CU_TRY(h, cudaMallocHost((void **)&h->h_kp, (size_t)B * h->kp_cap * sizeof(KeypointRec)));
+    CU_TRY(h, cudaMallocHost((void **)&h->h_desc, (size_t)B * h->kp_cap * 32));
+    CU_TRY(h, cudaMallocHost((void **)&h->h_n, (size_t)(2 * B + 1) * sizeof(int)));
+    h->h_mono = h->h_n + B; h->h_overflow = h->h_n + 2 * B;
+    h->planned = true;
+    return ORBX_OK;
+}
+
+// Point level 0 at `img` (device memory) and refresh the device copy of the level table if it moved.
+static int set_level0(orbx_handle *h, const uint8_t *img, int pitch, size_t fstride) {
+    LevelDev &D = h->h_levels[0];
+    if (D.img == img && D.pitch == pitch && D.img_fstride == fstride) return ORBX_OK;
+    D.img = const_cast<uint8_t *>(img); D.pitch = pitch; D.img_fstride = fstride;
+    CU_TRY(h, cudaMemcpyAsync(h->d_levels, &h->h_levels[0], sizeof(LevelDev), cudaMemcpyHostToDevice, h->stream));
+    return ORBX_OK;
+}
+
+// The kernel pipeline for `batch` frames whose level 0 is already in place.
+static int run_pipeline(orbx_handle *h, int batch, int lap0, int lap1, KeypointRec *d_kp, uint8_t *d_desc, int cap,
+                        int *d_n, int *d_mono) {
+    const Plan &pl = h->plan;
+    const int nl = pl.nlevels;
+    CU_TRY(h, cudaMemsetAsync(h->d_counts, 0, sizeof(int) * 2 * nl * h->batch_cap, h->stream));
+    CU_TRY(h, cudaMemsetAsync(h->d_overflow, 0, sizeof(int), h->stream));
+    for (int l = 1; l < nl; l++) h->launches += launch_resize(h->d_levels, h->h_levels, l, batch, h->stream);
+    h->launches += launch_blur(h->d_levels, h->d_tiles, h->ntiles, batch, h->stream);
+    h->launches += launch_fast(h->d_levels, h->d_cells, (int)pl.cells.size(), batch, h->P.ini_th, h->P.min_th, h->d_overflow, h->stream);
+    h->launches += launch_octree(h->d_levels, h->h_levels, nl, batch, h->d_overflow, h->stream);
+    h->launches += launch_finalize(h->d_levels, nl, batch, pl.total_out_cap, lap0, lap1, d_kp, cap, h->d_slot, d_n, d_mono, h->d_overflow, h->stream);
+    h->launches += launch_describe(h->d_levels, nl, batch, pl.total_out_cap, h->d_slot, d_kp, d_desc, cap, h->stream);
+    CU_TRY(h, cudaGetLastError());
+    h->last_batch = batch;
+    return ORBX_OK;
+}
+
+// scratch device buffer helper for the stand-alone stage entry points
+struct Scratch {
+    std::vector<void *> p;
+    ~Scratch() { for (void *q : p) cudaFree(q); }
+    template <typename T> T *get(size_t n) { void *q = nullptr; if (cudaMalloc(&q, std::max<size_t>(n * sizeof(T), 256)) != cudaSuccess) return nullptr; p.push_back(q); return (T *)q; }
+};
+
+extern "C" {
+
+const char *orbx_version(void) { return "orbx 0.1 sm_100a"; }
+
+int orbx_create(const orbx_config *cfg, orbx_handle **out) {
+    if (!cfg || !out) return fail(nullptr, ORBX_E_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->max_width < 1 || cfg->max_height < 1 || cfg->max_width > 4095 || cfg->max_height > 4095 || cfg->max_batch < 1 || cfg->max_batch > 4096)
+        return fail(nullptr, ORBX_E_INVALID, "max_width/max_height must be 1..4095, max_batch 1..4096");
+    orbx_handle *h = new (std::nothrow) orbx_handle();
+    if (!h) return fail(nullptr, ORBX_E_INVALID, "out of host memory");
+    h->cfg = *cfg;
+    if (!init_params(h->P, cfg->nfeatures, cfg->scale_factor, cfg->nlevels, cfg->ini_th_fast, cfg->min_th_fast)) {
+        delete h;
+        return fail(nullptr, ORBX_E_INVALID, "unsupported extractor parameters (nlevels 1..16, 1 < scaleFactor < 2, 1 <= minTh <= iniTh <= 254)");
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev < 1) {
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (orbx has no CPU fallback)";
+        delete h; return ORBX_E_CUDA;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) { delete h; return fail(nullptr, ORBX_E_INVALID, "device ordinal out of range"); }
+    h->device = cfg->device;
+    if ((e = cudaSetDevice(h->device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_create_error = std::string("cuda init: ") + cudaGetErrorString(e);
+        delete h; return ORBX_E_CUDA;
+    }
+    upload_constants();
+    if ((e = cudaGetLastError()) != cudaSuccess) {
+        g_create_error = std::string("constant upload: ") + cudaGetErrorString(e);
+        cudaStreamDestroy(h->stream); delete h; return ORBX_E_CUDA;
+    }
+    *out = h;
+    return ORBX_OK;
+}
+
+void orbx_destroy(orbx_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    free_plan(h);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+const char *orbx_last_error(const orbx_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int orbx_keypoint_capacity(const orbx_handle *h) {
+    if (!h) return ORBX_E_INVALID;
+    // sum over levels of max(quota + 3, 4 * roots); roots <= 8
+    int cap = 0;
+    for (int l = 0; l < h->P.nlevels; l++) cap += std::max(h->P.quota[l] + 3, 4 * kMaxRoots);
+    return cap;
+}
+
+int orbx_get_tables(const orbx_handle *h, float *scale, float *inv_scale, float *sigma2, float *inv_sigma2, int *features_per_level) {
+    if (!h) return ORBX_E_INVALID;
+    for (int l = 0; l < h->P.nlevels; l++) {
+        if (scale) scale[l] = h->P.scale[l];
+        if (inv_scale) inv_scale[l] = h->P.inv_scale[l];
+        if (sigma2) sigma2[l] = h->P.sigma2[l];
+        if (inv_sigma2) inv_sigma2[l] = h->P.inv_sigma2[l];
+        if (features_per_level) features_per_level[l] = h->P.quota[l];
+    }
+    return h->P.nlevels;
+}
+
+int orbx_get_level_sizes(const orbx_handle *h, int width, int height, int *widths, int *heights) {
+    if (!h || width < 1 || height < 1) return ORBX_E_INVALID;
+    for (int l = 0; l < h->P.nlevels; l++) {
+        if (widths) widths[l] = (int)lrintf((float)width * h->P.inv_scale[l]);
+        if (heights) heights[l] = (int)lrintf((float)height * h->P.inv_scale[l]);
+    }
+    return h->P.nlevels;
+}
+
+long long orbx_launch_count(const orbx_handle *h) { return h ? h->launches : 0; }
+
+int orbx_sync(orbx_handle *h) {
+    if (!h) return ORBX_E_INVALID;
+    CU_TRY(h, cudaSetDevice(h->device));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    if (h->planned) {   // surface an internal overflow of the last device-resident batch
+        int ov = 0;
+        CU_TRY(h, cudaMemcpy(&ov, h->d_overflow, sizeof(int), cudaMemcpyDeviceToHost));
+        if (ov) {
+            char msg[96]; snprintf(msg, sizeof(msg), "internal buffer overflow (stage code %d)", ov);
+            return fail(h, ORBX_E_OVERFLOW, msg);
+        }
+    }
+    return ORBX_OK;
+}
+
+int orbx_extract_batch_device(orbx_handle *h, const uint8_t *d_frames, size_t frame_stride_bytes, int batch, int width,
+                              int height, int stride, int lap0, int lap1, orbx_keypoint *d_kp_out, uint8_t *d_desc_out,
+                              int cap, int *d_n_out, int *d_mono_out) {
+    if (!h) return ORBX_E_INVALID;
+    if (!d_frames || !d_kp_out || !d_desc_out || !d_n_out || !d_mono_out) return fail(h, ORBX_E_INVALID, "null argument");
+    if (width < 1 || height < 1) return fail(h, ORBX_E_EMPTY, "empty image");
+    if (batch < 1 || stride < width || frame_stride_bytes < (size_t)stride * (height - 1) + width) return fail(h, ORBX_E_INVALID, "bad batch / stride");
+    CU_TRY(h, cudaSetDevice(h->device));
+    int rc = ensure_plan(h, width, height, batch);
+    if (rc) return rc;
+    if (cap < h->plan.total_out_cap) return fail(h, ORBX_E_CAPACITY, "cap smaller than orbx_keypoint_capacity for this frame size");
+    if ((rc = set_level0(h, d_frames, stride, frame_stride_bytes))) return rc;
+    return run_pipeline(h, batch, lap0, lap1, reinterpret_cast<KeypointRec *>(d_kp_out), d_desc_out, cap, d_n_out, d_mono_out);
+}
+
+int orbx_extract_batch(orbx_handle *h, const uint8_t *const *frames, int batch, int width, int height, int stride, int lap0,
+                       int lap1, orbx_keypoint *kp_out, uint8_t *desc_out, int cap, int *n_out, int *mono_index_out) {
+    if (!h) return ORBX_E_INVALID;
+    if (!frames || !kp_out || !desc_out || !n_out || !mono_index_out) return fail(h, ORBX_E_INVALID, "null argument");
+    if (width < 1 || height < 1) {
+        for (int i = 0; i < batch; i++) { n_out[i] = 0; mono_index_out[i] = -1; }
+        return fail(h, ORBX_E_EMPTY, "empty image");
+    }
+    if (batch < 1 || stride < width) return fail(h, ORBX_E_INVALID, "bad batch / stride");
+    for (int i = 0; i < batch; i++) if (!frames[i]) return fail(h, ORBX_E_INVALID, "null frame pointer");
+    CU_TRY(h, cudaSetDevice(h->device));
+    int rc = ensure_plan(h, width, height, batch);
+    if (rc) return rc;
+    const int kc = h->kp_cap;
+    const int pitch0 = h->l0_own_pitch;
+    const size_t fstride0 = h->l0_own_fstride;
+    // host -> pinned -> device (one 2D copy), rows repacked to the plane pitch
+    for (int i = 0; i < batch; i++) {
+        uint8_t *dst = h->h_in + (size_t)i * fstride0;
+        const uint8_t *src = frames[i];
+        if (stride == pitch0) std::memcpy(dst, src, (size_t)stride * (height - 1) + width);
+        else for (int y = 0; y < height; y++) std::memcpy(dst + (size_t)y * pitch0, src + (size_t)y * stride, (size_t)width);
+    }
+    CU_TRY(h, cudaMemcpyAsync(h->l0_own, h->h_in, (size_t)batch * fstride0, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = set_level0(h, h->l0_own, pitch0, fstride0))) return rc;
+    if ((rc = run_pipeline(h, batch, lap0, lap1, h->d_kp, h->d_desc, kc, h->d_n, h->d_mono))) return rc;
+    CU_TRY(h, cudaMemcpyAsync(h->h_n, h->d_n, sizeof(int) * batch, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(h->h_mono, h->d_mono, sizeof(int) * batch, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(h->h_overflow, h->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(h->h_kp, h->d_kp, (size_t)batch * kc * sizeof(KeypointRec), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(h->h_desc, h->d_desc, (size_t)batch * kc * 32, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    if (*h->h_overflow) {
+        char msg[96]; snprintf(msg, sizeof(msg), "internal buffer overflow (stage code %d)", *h->h_overflow);
+        return fail(h, ORBX_E_OVERFLOW, msg);
+    }
+    for (int i = 0; i < batch; i++) {
+        const int n = h->h_n[i];
+        if (n > cap) return fail(h, ORBX_E_CAPACITY, "kp_out/desc_out capacity smaller than the number of keypoints");
+        n_out[i] = n; mono_index_out[i] = h->h_mono[i];
+        std::memcpy(kp_out + (size_t)i * cap, h->h_kp + (size_t)i * kc, (size_t)n * sizeof(KeypointRec));
+        std::memcpy(desc_out + (size_t)i * cap * 32, h->h_desc + (size_t)i * kc * 32, (size_t)n * 32);
+    }
+    return ORBX_OK;
+}
+
+int orbx_extract(orbx_handle *h, const uint8_t *gray, int width, int height, int stride, int lap0, int lap1,
+                 orbx_keypoint *kp_out, uint8_t *desc_out, int cap, int *n_out, int *mono_index_out) {
+    const uint8_t *frames[1] = {gray};
+    if (h && (!gray || width < 1 || height < 1)) {
+        if (n_out) *n_out = 0;
+        if (mono_index_out) *mono_index_out = -1;
+        return fail(h, ORBX_E_EMPTY, "empty image");
+    }
+    return orbx_extract_batch(h, frames, 1, width, height, stride, lap0, lap1, kp_out, desc_out, cap, n_out, mono_index_out);
+}
+
+// ---- stage inspection ------------------------------------------------------------------------------------------
+int orbx_debug_get_level(orbx_handle *h, int frame, int level, int blurred, uint8_t *out, int out_stride, int *width_out, int *height_out) {
+    if (!h || !out) return ORBX_E_INVALID;
+    if (!h->planned || frame < 0 || frame >= h->last_batch || level < 0 || level >= h->plan.nlevels) return fail(h, ORBX_E_INVALID, "no such frame / level");
+    CU_TRY(h, cudaSetDevice(h->device));
+    const LevelDev &D = h->h_levels[level];
+    if (out_stride < D.w) return fail(h, ORBX_E_CAPACITY, "out_stride < level width");
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    const uint8_t *src = blurred ? D.blur + (size_t)frame * D.blur_fstride : D.img + (size_t)frame * D.img_fstride;
+    CU_TRY(h, cudaMemcpy2D(out, out_stride, src, blurred ? D.blur_pitch : D.pitch, D.w, D.h, cudaMemcpyDeviceToHost));
+    if (width_out) *width_out = D.w;
+    if (height_out) *height_out = D.h;
+    return ORBX_OK;
+}
+
+int orbx_debug_get_candidates(orbx_handle *h, int frame, int level, float *xyr_out, int cap, int *n_out) {
+    if (!h || !xyr_out || !n_out) return ORBX_E_INVALID;
+    if (!h->planned || frame < 0 || frame >= h->last_batch || level < 0 || level >= h->plan.nlevels) return fail(h, ORBX_E_INVALID, "no such frame / level");
+    CU_TRY(h, cudaSetDevice(h->device));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    const LevelDev &D = h->h_levels[level];
+    int n = 0;
+    CU_TRY(h, cudaMemcpy(&n, D.cand_count + frame, sizeof(int), cudaMemcpyDeviceToHost));
+    *n_out = n;
+    if (n > cap) return fail(h, ORBX_E_CAPACITY, "candidate buffer too small");
+    std::vector<uint32_t> tmp((size_t)std::max(n, 1));
+    CU_TRY(h, cudaMemcpy(tmp.data(), D.cand + (size_t)frame * D.cand_cap, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; i++) {
+        xyr_out[3 * i] = (float)((tmp[i] >> 8) & 0xFFF); xyr_out[3 * i + 1] = (float)(tmp[i] >> 20); xyr_out[3 * i + 2] = (float)(tmp[i] & 0xFF);
+    }
+    return ORBX_OK;
+}
+
+int orbx_debug_get_level_keypoints(orbx_handle *h, int frame, int level, float *xyra_out, int cap, int *n_out) {
+    if (!h || !xyra_out || !n_out) return ORBX_E_INVALID;
+    if (!h->planned || frame < 0 || frame >= h->last_batch || level < 0 || level >= h->plan.nlevels) return fail(h, ORBX_E_INVALID, "no such frame / level");
+    CU_TRY(h, cudaSetDevice(h->device));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    const LevelDev &D = h->h_levels[level];
+    int n = 0;
+    CU_TRY(h, cudaMemcpy(&n, D.sel_count + frame, sizeof(int), cudaMemcpyDeviceToHost));
+    *n_out = n;
+    if (n > cap) return fail(h, ORBX_E_CAPACITY, "keypoint buffer too small");
+    std::vector<uint32_t> tmp((size_t)std::max(n, 1));
+    std::vector<int> slots((size_t)std::max(n, 1));
+    CU_TRY(h, cudaMemcpy(tmp.data(), D.sel + (size_t)frame * D.out_cap, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
+    CU_TRY(h, cudaMemcpy(slots.data(), h->d_slot + (size_t)frame * h->plan.total_out_cap + D.out_base, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; i++) {
+        KeypointRec r;
+        CU_TRY(h, cudaMemcpy(&r, h->d_kp + (size_t)frame * h->kp_cap + slots[i], sizeof(r), cudaMemcpyDeviceToHost));
+        xyra_out[4 * i] = (float)((tmp[i] >> 8) & 0xFFF); xyra_out[4 * i + 1] = (float)(tmp[i] >> 20);
+        xyra_out[4 * i + 2] = (float)(tmp[i] & 0xFF); xyra_out[4 * i + 3] = r.angle;
+    }
+    return ORBX_OK;
+}
+
+int orbx_debug_resize(orbx_handle *h, const uint8_t *src, int sw, int sh, int sstride, uint8_t *dst, int dw, int dh, int dstride) {
+    if (!h || !src || !dst || sw < 1 || sh < 1 || dw < 1 || dh < 1 || sstride < sw || dstride < dw) return ORBX_E_INVALID;
+    CU_TRY(h, cudaSetDevice(h->device));
+    // a two-level table built ad hoc: level 0 = src, level 1 = dst
+    Scratch S;
+    const int sp = (sw + 31) / 32 * 32, dp = (dw + 31) / 32 * 32;
+    uint8_t *d_src = S.get<uint8_t>((size_t)sp * sh + 64), *d_dst = S.get<uint8_t>((size_t)dp * dh + 64);
+    std::vector<ResizeTap> xt, yt;
+    build_resize_taps(dw, sw, true, xt);
+    build_resize_taps(dh, sh, false, yt);
+    ResizeTap *d_xt = S.get<ResizeTap>(dw), *d_yt = S.get<ResizeTap>(dh);
+    LevelDev lv[2]; std::memset(lv, 0, sizeof(lv));
+    LevelDev *d_lv = S.get<LevelDev>(2);
+    if (!d_src || !d_dst || !d_xt || !d_yt || !d_lv) return fail(h, ORBX_E_CUDA, "cudaMalloc failed");
+    lv[0].img = d_src; lv[0].w = sw; lv[0].h = sh; lv[0].pitch = sp; lv[0].img_fstride = (size_t)sp * sh;
+    lv[1].img = d_dst; lv[1].w = dw; lv[1].h = dh; lv[1].pitch = dp; lv[1].img_fstride = (size_t)dp * dh; lv[1].xtap = d_xt; lv[1].ytap = d_yt;
+    CU_TRY(h, cudaMemcpy2D(d_src, sp, src, sstride, sw, sh, cudaMemcpyHostToDevice));
+    CU_TRY(h, cudaMemcpy(d_xt, xt.data(), sizeof(ResizeTap) * dw, cudaMemcpyHostToDevice));
+    CU_TRY(h, cudaMemcpy(d_yt, yt.data(), sizeof(ResizeTap) * dh, cudaMemcpyHostToDevice));
+    CU_TRY(h, cudaMemcpy(d_lv, lv, sizeof(lv), cudaMemcpyHostToDevice));
+    h->launches += launch_resize(d_lv, lv, 1, 1, h->stream);
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    CU_TRY(h, cudaMemcpy2D(dst, dstride, d_dst, dp, dw, dh, cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+}
+
+int orbx_debug_blur(orbx_handle *h, const uint8_t *src, int w, int ht, int sstride, uint8_t *dst, int dstride) {
+    if (!h || !src || !dst || w < 1 || ht < 1 || sstride < w || dstride < w) return ORBX_E_INVALID;
+    CU_TRY(h, cudaSetDevice(h->device));
+    Scratch S;
+    const int p = (w + 31) / 32 * 32;
+    uint8_t *d_src = S.get<uint8_t>((size_t)p * ht + 64), *d_dst = S.get<uint8_t>((size_t)p * ht + 64);
+    std::vector<BlurTile> tiles;
+    for (int ty = 0; ty * 64 < ht; ty++) for (int tx = 0; tx * 64 < w; tx++) tiles.push_back(BlurTile{0, (int16_t)tx, (int16_t)ty, 0});
+    BlurTile *d_t = S.get<BlurTile>(tiles.size());
+    LevelDev lv; std::memset(&lv, 0, sizeof(lv));
+    LevelDev *d_lv = S.get<LevelDev>(1);
+    if (!d_src || !d_dst || !d_t || !d_lv) return fail(h, ORBX_E_CUDA, "cudaMalloc failed");
+    lv.img = d_src; lv.blur = d_dst; lv.w = w; lv.h = ht; lv.pitch = p; lv.blur_pitch = p; lv.img_fstride = lv.blur_fstride = (size_t)p * ht;
+    CU_TRY(h, cudaMemcpy2D(d_src, p, src, sstride, w, ht, cudaMemcpyHostToDevice));
+    CU_TRY(h, cudaMemcpy(d_t, tiles.data(), sizeof(BlurTile) * tiles.size(), cudaMemcpyHostToDevice));
+    CU_TRY(h, cudaMemcpy(d_lv, &lv, sizeof(lv), cudaMemcpyHostToDevice));
+    h->launches += launch_blur(d_lv, d_t, (int)tiles.size(), 1, h->stream);
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    CU_TRY(h, cudaMemcpy2D(dst, dstride, d_dst, p, w, ht, cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+}
+
+int orbx_debug_describe(orbx_handle *h, const uint8_t *img, const uint8_t *blurred, int w, int ht, int stride, const float *xy,
+                        int n, const float *angle_in, float *angle_out, uint8_t *desc_out) {
+    if (!h || !xy || n < 0 || w < 1 || ht < 1 || stride < w) return ORBX_E_INVALID;
+    if (!img && !angle_in) return fail(h, ORBX_E_INVALID, "need img or angle_in");
+    for (int i = 0; i < n; i++) {
+        const float x = xy[2 * i], y = xy[2 * i + 1];
+        if (!(x >= kEdge && x <= w - 1 - kEdge && y >= kEdge && y <= ht - 1 - kEdge)) return fail(h, ORBX_E_INVALID, "keypoint closer than 19 px to the border");
+    }
+    CU_TRY(h, cudaSetDevice(h->device));
+    Scratch S;
+    const int p = (w + 31) / 32 * 32;
+    uint8_t *d_img = img ? S.get<uint8_t>((size_t)p * ht + 64) : nullptr, *d_bl = blurred ? S.get<uint8_t>((size_t)p * ht + 64) : nullptr;
+    float *d_xy = S.get<float>((size_t)2 * std::max(n, 1)), *d_ai = angle_in ? S.get<float>(std::max(n, 1)) : nullptr, *d_ao = S.get<float>(std::max(n, 1));
+    uint8_t *d_desc = S.get<uint8_t>((size_t)32 * std::max(n, 1));
+    if ((img && !d_img) || (blurred && !d_bl) || !d_xy || !d_ao || !d_desc) return fail(h, ORBX_E_CUDA, "cudaMalloc failed");
+    if (img) CU_TRY(h, cudaMemcpy2D(d_img, p, img, stride, w, ht, cudaMemcpyHostToDevice));
+    if (blurred) CU_TRY(h, cudaMemcpy2D(d_bl, p, blurred, stride, w, ht, cudaMemcpyHostToDevice));
+    CU_TRY(h, cudaMemcpy(d_xy, xy, sizeof(float) * 2 * n, cudaMemcpyHostToDevice));
+    if (angle_in) CU_TRY(h, cudaMemcpy(d_ai, angle_in, sizeof(float) * n, cudaMemcpyHostToDevice));
+    h->launches += launch_describe_points(d_img, d_bl, p, d_xy, n, d_ai, d_ao, d_desc, h->stream);
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    if (angle_out) CU_TRY(h, cudaMemcpy(angle_out, d_ao, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    if (desc_out && blurred) CU_TRY(h, cudaMemcpy(desc_out, d_desc, (size_t)32 * n, cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+}
+
+int orbx_debug_octree(orbx_handle *h, const float *keys, int n, int minX, int maxX, int minY, int maxY, int N, int *out_idx,
+                      int cap, int *n_out) {
+    if (!h || (!keys && n > 0) || !out_idx || !n_out || n < 0 || N < 0) return ORBX_E_INVALID;
+    // The quadtree kernel needs the level LUTs: synthesise a one-level plan whose region is (maxX-minX) x (maxY-minY),
+    // i.e. a level of size (reg_w + 32) x (reg_h + 32) with minBorder 16.
+    if (minX != kMinBorder || minY != kMinBorder) return fail(h, ORBX_E_INVALID, "octree debug entry expects minX = minY = 16");
+    CU_TRY(h, cudaSetDevice(h->device));
+    ExtractorParams P1 = h->P;
+    P1.nlevels = 1; P1.quota[0] = N;
+    Plan pl; std::string err;
+    if (!build_plan(P1, maxX + kMinBorder, maxY + kMinBorder, pl, err)) { h->err = err; return ORBX_E_INVALID; }
+    const LevelPlan &LP = pl.lv[0];
+    if (LP.ncols <= 0 || LP.nrows <= 0) { *n_out = 0; return ORBX_OK; }
+    Scratch S;
+    LevelDev D; std::memset(&D, 0, sizeof(D));
+    uint32_t *t0 = S.get<uint32_t>(LP.xbin.size()), *t1 = S.get<uint32_t>(LP.ybin.size()), *t2 = S.get<uint32_t>(LP.xord.size()), *t3 = S.get<uint32_t>(LP.yord.size());
+    const int ccap = std::max(n, 1);
+    uint32_t *d_cand = S.get<uint32_t>(ccap), *d_sorted = S.get<uint32_t>(ccap), *d_cur = S.get<uint32_t>(std::max(LP.nbins, 1)), *d_sel = S.get<uint32_t>(LP.out_cap);
+    int *d_cnt = S.get<int>(4);
+    LevelDev *d_lv = S.get<LevelDev>(1);
+    if (!t0 || !t1 || !t2 || !t3 || !d_cand || !d_sorted || !d_cur || !d_sel || !d_cnt || !d_lv) return fail(h, ORBX_E_CUDA, "cudaMalloc failed");
+    CU_TRY(h, cudaMemcpy(t0, LP.xbin.data(), LP.xbin.size() * 4, cudaMemcpyHostToDevice));
+    CU_TRY(h, cudaMemcpy(t1, LP.ybin.data(), LP.ybin.size() * 4, cudaMemcpyHostToDevice));
+    CU_TRY(h, cudaMemcpy(t2, LP.xord.data(), LP.xord.size() * 4, cudaMemcpyHostToDevice));
+    CU_TRY(h, cudaMemcpy(t3, LP.yord.data(), LP.yord.size() * 4, cudaMemcpyHostToDevice));
+    // pack keys; remember the original index of every (x, y) to map the winners back
+    std::vector<uint32_t> packed((size_t)ccap);
+    std::vector<int> index_of((size_t)LP.reg_w * LP.reg_h, -1);
+    for (int i = 0; i < n; i++) {
+        const int x = (int)keys[3 * i], y = (int)keys[3 * i + 1], r = (int)keys[3 * i + 2];
+        if (x < 3 || y < 3 || x >= LP.reg_w - 3 || y >= LP.reg_h - 3 || r < 0 || r > 255 || (float)x != keys[3 * i] || (float)y != keys[3 * i + 1])
+            return fail(h, ORBX_E_INVALID, "octree debug entry: keys must be integer FAST candidates inside the tested region");
+        packed[i] = ((uint32_t)y << 20) | ((uint32_t)x << 8) | (uint32_t)r;
+        if (index_of[(size_t)y * LP.reg_w + x] >= 0) return fail(h, ORBX_E_INVALID, "duplicate key position");
+        index_of[(size_t)y * LP.reg_w + x] = i;
+    }
+    CU_TRY(h, cudaMemcpy(d_cand, packed.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice));
+    int counts[4] = {n, 0, 0, 0};
+    CU_TRY(h, cudaMemcpy(d_cnt, counts, sizeof(counts), cudaMemcpyHostToDevice));
+    D.xbin = t0; D.ybin = t1; D.xord = t2; D.yord = t3;
+    D.w = LP.w; D.h = LP.h;
+    D.reg_w = LP.reg_w; D.reg_h = LP.reg_h; D.n_ini = LP.n_ini; D.depth0 = LP.depth0; D.nbins = LP.nbins; D.quota = N; D.out_cap = LP.out_cap;
+    for (int r = 0; r < kMaxRoots; r++) { D.root_ulx[r] = LP.root_ulx[r]; D.root_brx[r] = LP.root_brx[r]; }
+    D.ord_cell_area = LP.ord_cell_area; D.ord_ncols = LP.ord_ncols; D.wcell = LP.wcell; D.hcell = LP.hcell;
+    D.cand = d_cand; D.sorted = d_sorted; D.bin_cursor = d_cur; D.cand_cap = ccap; D.cand_count = d_cnt; D.sel = d_sel; D.sel_count = d_cnt + 1;
+    CU_TRY(h, cudaMemcpy(d_lv, &D, sizeof(D), cudaMemcpyHostToDevice));
+    h->launches += launch_octree(d_lv, &D, 1, 1, d_cnt + 2, h->stream);
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    CU_TRY(h, cudaMemcpy(counts, d_cnt, sizeof(counts), cudaMemcpyDeviceToHost));
+    if (counts[2]) return fail(h, ORBX_E_OVERFLOW, "quadtree node buffer overflow");
+    const int m = counts[1];
+    *n_out = m;
+    if (m > cap) return fail(h, ORBX_E_CAPACITY, "out_idx too small");
+    std::vector<uint32_t> sel((size_t)std::max(m, 1));
+    CU_TRY(h, cudaMemcpy(sel.data(), d_sel, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < m; i++) {
+        const int x = (int)((sel[i] >> 8) & 0xFFF) - kMinBorder, y = (int)(sel[i] >> 20) - kMinBorder;
+        out_idx[i] = index_of[(size_t)y * LP.reg_w + x];
+    }
+    return ORBX_OK;
+}
+
+// ---- matching entry points on the extractor handle (kernels in orbx_match.cu) --------------------------------------
+int orbx_distance_batch(orbx_handle *h, const uint8_t *a, const uint8_t *b, int n, int32_t *dist_out) {
+    if (!h) return ORBX_E_INVALID;
+    if (!a || !b || !dist_out || n < 0) return fail(h, ORBX_E_INVALID, "null argument");
+    return match_distance_batch(h->device, h->stream, a, b, n, dist_out, h->err, h->launches);
+}
+
+int orbx_match_windowed(orbx_handle *h, const uint8_t *q_desc, const float *q_uvr, const int32_t *q_levels, int nq,
+                        const orbx_keypoint *t_kp, const uint8_t *t_desc, int nt, const float *bounds4, int32_t *best_idx,
+                        int32_t *best_dist, int32_t *second_idx, int32_t *second_dist) {
+    if (!h) return ORBX_E_INVALID;
+    if (!q_desc || !q_uvr || !q_levels || !bounds4 || !best_idx || !best_dist || !second_idx || !second_dist || nq < 0 || nt < 0 ||
+        (nt > 0 && (!t_kp || !t_desc)))
+        return fail(h, ORBX_E_INVALID, "null argument");
+    if (!(bounds4[2] > bounds4[0]) || !(bounds4[3] > bounds4[1])) return fail(h, ORBX_E_INVALID, "empty image bounds");
+    return match_windowed(h->device, h->stream, q_desc, q_uvr, q_levels, nq, t_kp, t_desc, nt, bounds4, best_idx, best_dist,
+                          second_idx, second_dist, h->err, h->launches);
+}
+
+// ---- plan inspection without a GPU (used by the CPU-only tests) --------------------------------------------------
+// Fills level sizes, cell counts, quotas and candidate capacities of the plan for (params, w, h); returns nlevels or < 0.
+int orbx_plan_probe(int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th, int width, int height,
+                    int *widths, int *heights, int *ncells, int *quota, int *n_ini, int *depth0, long long *algorithmic_bytes) {
+    ExtractorParams P;
+    if (!init_params(P, nfeatures, scale_factor, nlevels, ini_th, min_th)) return ORBX_E_INVALID;
+    Plan pl; std::string err;
+    if (!build_plan(P, width, height, pl, err)) { g_create_error = err; return ORBX_E_INVALID; }
+    for (int l = 0; l < nlevels; l++) {
+        if (widths) widths[l] = pl.lv[l].w;
+        if (heights) heights[l] = pl.lv[l].h;
+        if (ncells) ncells[l] = pl.lv[l].ncells;
+        if (quota) quota[l] = pl.lv[l].quota;
+        if (n_ini) n_ini[l] = pl.lv[l].n_ini;
+        if (depth0) depth0[l] = pl.lv[l].depth0;
+    }
+    if (algorithmic_bytes) *algorithmic_bytes = (long long)pl.algorithmic_bytes(nfeatures);
+    return nlevels;
+}
+
+}  // extern "C"

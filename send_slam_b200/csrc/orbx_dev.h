@@ -1,0 +1,68 @@
+// Device-side descriptors shared by the extraction kernels and the host runtime.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+#include "orbx_plan.h"
+
+namespace orbx {
+
+// One pyramid level as the kernels see it.  Planes are [batch][h][pitch] u8; level 0 may alias caller memory.
+struct LevelDev {
+    uint8_t *img;              // un-blurred plane (FAST, IC_Angle read this)
+    uint8_t *blur;             // 7x7 Gaussian of img (steered BRIEF reads this)
+    size_t img_fstride;        // bytes between consecutive frames in img
+    size_t blur_fstride;
+    int w, h, pitch, blur_pitch;
+    const ResizeTap *xtap, *ytap;                   // taps from level l-1
+    const uint32_t *xbin, *ybin, *xord, *yord;      // quadtree / order LUTs, indexed by (x-16), (y-16)
+    int reg_w, reg_h, n_ini, depth0, nbins, quota, out_cap;
+    int root_ulx[kMaxRoots], root_brx[kMaxRoots];
+    uint32_t ord_cell_area, ord_ncols;
+    int wcell, hcell;
+    uint32_t *cand;            // [batch][cand_cap]   (y-16)<<20 | (x-16)<<8 | score
+    uint32_t *sorted;          // [batch][cand_cap]   bin-sorted copy, built only when the tree goes below depth0
+    uint32_t *bin_cursor;      // [batch][nbins]      scratch for that copy
+    int *cand_count;           // [batch]
+    int cand_cap;
+    uint32_t *sel;             // [batch][out_cap]    y<<20 | x<<8 | score, level coordinates, quadtree list order
+    int *sel_count;            // [batch]
+    int out_base;              // prefix sum of out_cap over lower levels
+    float scale, kp_size;
+};
+
+struct BlurTile { int16_t level, tx, ty, pad; };   // one 64x64 output tile of the Gaussian pass
+
+struct KeypointRec {           // == orbx_keypoint == cv::KeyPoint
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+};
+
+// launch wrappers (orbx_kernels.cu); all asynchronous on `stream`, return the number of kernel launches issued
+int launch_resize(const LevelDev *d_levels, const LevelDev *h_levels, int level, int batch, cudaStream_t stream);
+int launch_blur(const LevelDev *d_levels, const BlurTile *d_tiles, int ntiles, int batch, cudaStream_t stream);
+int launch_fast(const LevelDev *d_levels, const CellRect *d_cells, int ncells, int batch, int ini_th, int min_th,
+                int *d_overflow, cudaStream_t stream);
+int launch_octree(const LevelDev *d_levels, const LevelDev *h_levels, int nlevels, int batch, int *d_overflow,
+                  cudaStream_t stream);
+int launch_finalize(const LevelDev *d_levels, int nlevels, int batch, int total_out_cap, int lap0, int lap1,
+                    KeypointRec *d_kp, int cap, int *d_slot, int *d_n, int *d_mono, int *d_overflow, cudaStream_t stream);
+int launch_describe(const LevelDev *d_levels, int nlevels, int batch, int total_out_cap, const int *d_slot,
+                    KeypointRec *d_kp, uint8_t *d_desc, int cap, cudaStream_t stream);
+// stand-alone stage launchers for the debug / parity entry points
+int launch_describe_points(const uint8_t *d_img, const uint8_t *d_blur, int pitch, const float *d_xy, int n,
+                           const float *d_angle_in, float *d_angle_out, uint8_t *d_desc, cudaStream_t stream);
+void upload_constants();
+}  // namespace orbx
+
+#include <string>
+struct orbx_keypoint;
+namespace orbx {
+// matching launchers that run on an extractor handle's stream (orbx_match.cu)
+int match_distance_batch(int device, cudaStream_t stream, const uint8_t *a, const uint8_t *b, int n, int32_t *dist_out,
+                         std::string &err, long long &launches);
+int match_windowed(int device, cudaStream_t stream, const uint8_t *q_desc, const float *q_uvr, const int32_t *q_levels, int nq,
+                   const orbx_keypoint *t_kp, const uint8_t *t_desc, int nt, const float *bounds4, int32_t *best_idx,
+                   int32_t *best_dist, int32_t *second_idx, int32_t *second_dist, std::string &err, long long &launches);       // pattern + umax to __constant__/__device__ memory (once per process per device)
+
+}  // namespace orbx

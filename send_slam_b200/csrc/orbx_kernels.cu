@@ -1,0 +1,852 @@
+// Extraction kernels of the B200-native ORB front end (sm_100a).
+//
+// Stage            replaces (UPSTREAM ORB-SLAM3 src/ORBextractor.cc, built per slam_backends/orb_slam_3/CMakeLists.txt:52)
+//   k_resize       ComputePyramid: cv::resize(INTER_LINEAR), level l-1 -> l               
+//   k_blur         GaussianBlur(7x7, sigma 2, REFLECT_101) of every level                  (A.2)
+//   k_fast_cells   ComputeKeyPointsOctTree cell loop: cv::FAST(iniTh) / per-cell minTh fallback + 3x3 NMS (A.3)
+//   k_octree       DistributeOctTree + DivideNode                                          (C.1)
+//   k_finalize     tail of operator(): level -> image scaling, mono/stereo slot order      (C.1)
+//   k_describe     computeOrientation (IC_Angle + fastAtan2) and computeOrbDescriptor      (A.4, A.5)
+//
+// All arithmetic is integer or individually rounded fp32 (no FMA contraction) so results are bit-identical to the
+// CPU oracle (oracle/orb_oracle.c).  Everything here is HBM/L2-resident byte work: no tensor cores on purpose.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "orbx_dev.h"
+
+namespace orbx {
+
+__device__ int8_t g_pattern[1024];
+__constant__ int c_umax[16];
+
+static const int8_t h_pattern[1024] = {
+#include "orb_pattern.inc"
+};
+
+void upload_constants() {
+    // umax for HALF_PATCH_SIZE 15 (ctor of ORBextractor; identical for every parameter set)
+    static const int umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+    cudaMemcpyToSymbol(g_pattern, h_pattern, sizeof(h_pattern));
+    cudaMemcpyToSymbol(c_umax, umax, sizeof(umax));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K1  pyramid resize: 4 destination pixels per thread, taps precomputed on the host (orbx_plan.cpp)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_resize(const LevelDev *__restrict__ lv, int level) {
+    const LevelDev &D = lv[level];
+    const LevelDev &S = lv[level - 1];
+    const int dx0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (dx0 >= D.w) return;
+    const int dy = blockIdx.y, f = blockIdx.z;
+    const ResizeTap ty = D.ytap[dy];
+    const uint8_t *__restrict__ s0 = S.img + (size_t)f * S.img_fstride + (size_t)ty.ofs * S.pitch;
+    const uint8_t *__restrict__ s1 = S.img + (size_t)f * S.img_fstride + (size_t)ty.ofs1 * S.pitch;
+    uint32_t packed = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int dx = dx0 + i;
+        if (dx < D.w) {
+            const ResizeTap tx = D.xtap[dx];
+            const int r0 = (int)s0[tx.ofs] * tx.c0 + (int)s0[tx.ofs1] * tx.c1;
+            const int r1 = (int)s1[tx.ofs] * tx.c0 + (int)s1[tx.ofs1] * tx.c1;
+            int v = ((((int)ty.c0 * (r0 >> 4)) >> 16) + (((int)ty.c1 * (r1 >> 4)) >> 16) + 2) >> 2;
+            v = min(max(v, 0), 255);
+            packed |= (uint32_t)v << (8 * i);
+        }
+    }
+    *reinterpret_cast<uint32_t *>(D.img + (size_t)f * D.img_fstride + (size_t)dy * D.pitch + dx0) = packed;
+}
+
+int launch_resize(const LevelDev *d_levels, const LevelDev *h_levels, int level, int batch, cudaStream_t stream) {
+    const LevelDev &D = h_levels[level];
+    dim3 grid((D.w + 4 * 128 - 1) / (4 * 128), D.h, batch);
+    k_resize<<<grid, 128, 0, stream>>>(d_levels, level);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K5  7x7 Gaussian, fixed point [18,34,48,56,48,34,18]/256 per axis, exact 16.16 accumulation, REFLECT_101
+//     tile 64x64: shared u8 halo tile -> horizontal pass (two pixels per IMAD, 16-bit lanes) -> vertical pass
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int BT = 64;                 // tile edge
+constexpr int BIN_PITCH = 80;          // bytes per staged input row (64 + 6 halo, padded to 16)
+constexpr int BROWS = BT + 6;
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+    return min(max(i, 0), n - 1);
+}
+
+__global__ void __launch_bounds__(256) k_blur(const LevelDev *__restrict__ lv, const BlurTile *__restrict__ tiles) {
+    __shared__ __align__(16) uint8_t s_in[BROWS * BIN_PITCH];
+    __shared__ __align__(16) uint32_t s_h[BROWS * (BT / 2)];   // horizontal sums, lanes = columns (c, c+2)
+    const BlurTile t = tiles[blockIdx.x];
+    const LevelDev &L = lv[t.level];
+    const int f = blockIdx.y;
+    const int x0 = t.tx * BT, y0 = t.ty * BT;
+    const uint8_t *__restrict__ src = L.img + (size_t)f * L.img_fstride;
+    for (int i = threadIdx.x; i < BROWS * BIN_PITCH; i += 256) {
+        const int r = i / BIN_PITCH, c = i - r * BIN_PITCH;
+        const int gx = reflect101(x0 - 3 + c, L.w), gy = reflect101(y0 - 3 + r, L.h);
+        s_in[i] = src[(size_t)gy * L.pitch + gx];
+    }
+    __syncthreads();
+    // horizontal: item = (row, group of 8 outputs)
+    for (int it = threadIdx.x; it < BROWS * (BT / 8); it += 256) {
+        const int r = it >> 3, g = it & 7;
+        const uint2 a = *reinterpret_cast<const uint2 *>(s_in + r * BIN_PITCH + 8 * g);
+        const uint2 b = *reinterpret_cast<const uint2 *>(s_in + r * BIN_PITCH + 8 * g + 8);
+        const uint32_t w0 = a.x, w1 = a.y, w2 = b.x, w3 = b.y;
+        // q[j] = (byte j+2) << 16 | byte j   for j = 0..11
+        uint32_t q[12];
+        const uint32_t s01 = __funnelshift_r(w0, w1, 16), s12 = __funnelshift_r(w1, w2, 16), s23 = __funnelshift_r(w2, w3, 16);
+        q[0] = w0 & 0x00FF00FFu;  q[1] = (w0 >> 8) & 0x00FF00FFu;  q[2] = s01 & 0x00FF00FFu;  q[3] = (s01 >> 8) & 0x00FF00FFu;
+        q[4] = w1 & 0x00FF00FFu;  q[5] = (w1 >> 8) & 0x00FF00FFu;  q[6] = s12 & 0x00FF00FFu;  q[7] = (s12 >> 8) & 0x00FF00FFu;
+        q[8] = w2 & 0x00FF00FFu;  q[9] = (w2 >> 8) & 0x00FF00FFu;  q[10] = s23 & 0x00FF00FFu; q[11] = (s23 >> 8) & 0x00FF00FFu;
+        uint32_t o[4];
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            const int i0 = (p & 1) + 4 * (p >> 1);   // output columns (i0, i0+2): 0,1,4,5
+            o[p] = 18u * (q[i0] + q[i0 + 6]) + 34u * (q[i0 + 1] + q[i0 + 5]) + 48u * (q[i0 + 2] + q[i0 + 4]) + 56u * q[i0 + 3];
+        }
+        *reinterpret_cast<uint4 *>(s_h + r * (BT / 2) + 4 * g) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    __syncthreads();
+    // vertical: item = (4-pixel column group, 4-row segment); words (2cg, 2cg+1) hold columns (0,2),(1,3) of the group
+    {
+        const int cg = threadIdx.x & 15, seg = threadIdx.x >> 4;
+        const int gx = x0 + 4 * cg;
+        if (gx < L.w) {
+            uint32_t lo[10], hi[10];
+#pragma unroll
+            for (int r = 0; r < 10; r++) {
+                const uint2 v = *reinterpret_cast<const uint2 *>(s_h + (4 * seg + r) * (BT / 2) + 2 * cg);
+                lo[r] = v.x; hi[r] = v.y;
+            }
+            uint8_t *__restrict__ dst = L.blur + (size_t)f * L.blur_fstride;
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const int gy = y0 + 4 * seg + r;
+                if (gy >= L.h) break;
+                uint32_t px[4];
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    // column c of the group: c=0 -> lo lane0, c=1 -> hi lane0, c=2 -> lo lane1, c=3 -> hi lane1
+                    uint32_t acc = 32768u;
+#pragma unroll
+                    for (int k = 0; k < 7; k++) {
+                        const uint32_t wv = (c & 1) ? hi[r + k] : lo[r + k];
+                        const uint32_t e = (c & 2) ? (wv >> 16) : (wv & 0xFFFFu);
+                        const uint32_t kk = (k == 0 || k == 6) ? 18u : (k == 1 || k == 5) ? 34u : (k == 2 || k == 4) ? 48u : 56u;
+                        acc += kk * e;
+                    }
+                    px[c] = acc >> 16;
+                }
+                *reinterpret_cast<uint32_t *>(dst + (size_t)gy * L.blur_pitch + gx) = px[0] | (px[1] << 8) | (px[2] << 16) | (px[3] << 24);
+            }
+        }
+    }
+}
+
+int launch_blur(const LevelDev *d_levels, const BlurTile *d_tiles, int ntiles, int batch, cudaStream_t stream) {
+    if (ntiles <= 0) return 0;
+    dim3 grid(ntiles, batch);
+    k_blur<<<grid, 256, 0, stream>>>(d_levels, d_tiles);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K2  FAST-9/16 score + per-cell NMS + per-cell threshold fallback.  One CTA per (cell, frame).
+//
+// score(p) = max(0, max over the 16 arcs of 9 ring pixels of max(min_k (v - r_k), min_k (r_k - v)))  (= cv's
+// cornerScore + 1, independent of the threshold).  Corner at threshold t <=> score > t; response = score - 1.
+// Per thread: 4 horizontally adjacent pixels x 2 rows.  The 16 ring windows are 4-byte slices of 3 staged words
+// per row; odd pixels use the slices as two u16 lanes (pixel in the high byte, neighbour as harmless junk in the
+// low byte), even pixels use the slices shifted by one byte.  Arc extrema use VIMNMX / VIMNMX3 .U16x2:
+//   min over arcs of (max over arc) = min_i max3(Q2[i], Q2[i+2], min(r[2i], r[2i+9])),  Q2 = maxima of 4 ring pixels.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int FT_PITCH = 84;           // staged ROI row pitch in bytes (ROI <= 76 wide, +4 guard, multiple of 4)
+constexpr int FT_ROWS = 80;
+constexpr int FS_PITCH = 80;           // score tile pitch (interior <= 70, +1 border each side, padded)
+
+__device__ __forceinline__ uint32_t umax2(uint32_t a, uint32_t b) { return __vmaxu2(a, b); }
+__device__ __forceinline__ uint32_t umin2(uint32_t a, uint32_t b) { return __vminu2(a, b); }
+__device__ __forceinline__ uint32_t umax3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_u16x2(a, b, c); }
+__device__ __forceinline__ uint32_t umin3(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u16x2(a, b, c); }
+
+// r[0..15] ring lanes, v centre lanes (pixel value in the high byte of each u16 lane).  Returns the two scores as
+// clean u16 lanes.
+__device__ __forceinline__ uint32_t fast_score_lanes(const uint32_t (&r)[16], uint32_t v) {
+    uint32_t qx[8], qn[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        qx[j] = umax2(r[2 * j + 1], r[(2 * j + 2) & 15]);
+        qn[j] = umin2(r[2 * j + 1], r[(2 * j + 2) & 15]);
+    }
+    uint32_t q2x[8], q2n[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        q2x[i] = umax2(qx[i], qx[(i + 1) & 7]);
+        q2n[i] = umin2(qn[i], qn[(i + 1) & 7]);
+    }
+    uint32_t fx[8], fn[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t a = r[2 * i], b = r[(2 * i + 9) & 15];
+        fx[i] = umax3(q2x[i], q2x[(i + 2) & 7], umin2(a, b));   // max over arc, smaller of the two arcs sharing 8 pixels
+        fn[i] = umin3(q2n[i], q2n[(i + 2) & 7], umax2(a, b));
+    }
+    uint32_t min_arc_max = umin3(umin3(fx[0], fx[1], fx[2]), umin3(fx[3], fx[4], fx[5]), umin2(fx[6], fx[7]));
+    uint32_t max_arc_min = umax3(umax3(fn[0], fn[1], fn[2]), umax3(fn[3], fn[4], fn[5]), umax2(fn[6], fn[7]));
+    // high bytes -> clean lanes; dark = v - min_arc_max, bright = max_arc_min - v, score = max(dark, bright, 0)
+    const uint32_t hv = __byte_perm(v, 0, 0x4341), hx = __byte_perm(min_arc_max, 0, 0x4341), hn = __byte_perm(max_arc_min, 0, 0x4341);
+    const uint32_t dark = hv + 0x01000100u - hx;       // 256 + (v - M) per lane, never borrows
+    const uint32_t bright = hn + 0x01000100u - hv;
+    return umax3(dark, bright, 0x01000100u) & 0x00FF00FFu;
+}
+
+// rows[7][3]: staged words of ROI rows y-3..y+3, bytes 4g..4g+11 (pixels of interest at bytes 3..6).
+__device__ __forceinline__ uint32_t fast_score4(const uint32_t (&w)[7][3]) {
+    // 4-byte slices at byte offset o of a row: o=0 w0, o=4 w1, else funnel shifts
+#define SL(row, o) ((o) == 0 ? w[row][0] : (o) == 4 ? w[row][1] : (o) < 4 ? __funnelshift_r(w[row][0], w[row][1], 8 * (o)) \
+                                                                   : __funnelshift_r(w[row][1], w[row][2], 8 * ((o)-4)))
+    uint32_t r[16];
+    r[0] = SL(6, 3);  r[1] = SL(6, 4);  r[2] = SL(5, 5);  r[3] = SL(4, 6);
+    r[4] = SL(3, 6);  r[5] = SL(2, 6);  r[6] = SL(1, 5);  r[7] = SL(0, 4);
+    r[8] = SL(0, 3);  r[9] = SL(0, 2);  r[10] = SL(1, 1); r[11] = SL(2, 0);
+    r[12] = SL(3, 0); r[13] = SL(4, 0); r[14] = SL(5, 1); r[15] = SL(6, 2);
+    const uint32_t c = SL(3, 3);
+#undef SL
+    const uint32_t odd = fast_score_lanes(r, c);          // pixels 1, 3
+    uint32_t re[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) re[k] = r[k] << 8;
+    const uint32_t even = fast_score_lanes(re, c << 8);   // pixels 0, 2
+    return even | (odd << 8);
+}
+
+__global__ void __launch_bounds__(192) k_fast_cells(const LevelDev *__restrict__ lv, const CellRect *__restrict__ cells,
+                                                    int ini_th, int min_th, int *__restrict__ overflow) {
+    __shared__ __align__(16) uint8_t s_roi[FT_ROWS * FT_PITCH];
+    __shared__ __align__(16) uint8_t s_sc[(FT_ROWS - 4) * FS_PITCH];   // interior scores with a 1-px zero ring
+    __shared__ uint32_t s_list[36 * 36 + 8];
+    __shared__ int s_n, s_base;
+    const CellRect cell = cells[blockIdx.x];
+    const LevelDev &L = lv[cell.level];
+    const int f = blockIdx.y;
+    const int rw = cell.x1 - cell.x0, rh = cell.y1 - cell.y0;   // ROI
+    const int iw = rw - 6, ih = rh - 6;                            // tested pixels
+    const uint8_t *__restrict__ src = L.img + (size_t)f * L.img_fstride + (size_t)cell.y0 * L.pitch + cell.x0;
+    // stage ROI (+ zero guard columns so that the last 4-pixel group may read past the ROI)
+    const int rw_pad = min((rw + 8) & ~3, FT_PITCH);
+    for (int i = threadIdx.x; i < (rh + 1) * rw_pad; i += blockDim.x) {
+        const int r = i / rw_pad, c = i - r * rw_pad;
+        s_roi[r * FT_PITCH + c] = (r < rh && c < rw) ? src[(size_t)r * L.pitch + c] : (uint8_t)0;
+    }
+    for (int i = threadIdx.x; i < (ih + 2) * FS_PITCH / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(s_sc)[i] = 0;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    // scores: item = (4-pixel group g, row pair s)
+    const int ng = (iw + 3) >> 2, ns = (ih + 1) >> 1;
+    for (int it = threadIdx.x; it < ng * ns; it += blockDim.x) {
+        const int s = it / ng, g = it - s * ng;
+        uint32_t w[8][3];
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const uint32_t *p = reinterpret_cast<const uint32_t *>(s_roi + (2 * s + r) * FT_PITCH + 4 * g);
+            w[r][0] = p[0]; w[r][1] = p[1]; w[r][2] = p[2];
+        }
+        uint32_t wa[7][3], wb[7][3];
+#pragma unroll
+        for (int r = 0; r < 7; r++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) { wa[r][k] = w[r][k]; wb[r][k] = w[r + 1][k]; }
+        uint32_t sa = fast_score4(wa), sb = fast_score4(wb);
+        // mask pixels beyond the interior (group / row-pair overhang)
+        const int valid = iw - 4 * g;
+        if (valid < 4) { const uint32_t m = 0xFFFFFFFFu >> (8 * (4 - valid)); sa &= m; sb &= m; }
+        // score tile: interior pixel (x, y) at [(y+1)*FS_PITCH + 4 + x]  (column 3 and row 0 are the zero ring)
+        *reinterpret_cast<uint32_t *>(s_sc + (2 * s + 1) * FS_PITCH + 4 + 4 * g) = sa;
+        if (2 * s + 1 < ih) *reinterpret_cast<uint32_t *>(s_sc + (2 * s + 2) * FS_PITCH + 4 + 4 * g) = sb;
+    }
+    __syncthreads();
+    // NMS (strict 8-neighbour maximum inside the cell) + count at the initial threshold
+    int n_ini_local = 0;
+    for (int i = threadIdx.x; i < iw * ih; i += blockDim.x) {
+        const int y = i / iw, x = i - y * iw;
+        const uint8_t *q = s_sc + (y + 1) * FS_PITCH + 4 + x;
+        const int m = q[0];
+        if (m > min_th) {
+            const bool ismax = m > q[-1] && m > q[1] && m > q[-FS_PITCH - 1] && m > q[-FS_PITCH] && m > q[-FS_PITCH + 1] &&
+                               m > q[FS_PITCH - 1] && m > q[FS_PITCH] && m > q[FS_PITCH + 1];
+            if (ismax) {
+                const int slot = atomicAdd(&s_n, 1);
+                // relative coordinates (x - 16, y - 16) of the reference's vToDistributeKeys entries
+                const uint32_t xr = (uint32_t)(cell.x0 + 3 + x - kMinBorder), yr = (uint32_t)(cell.y0 + 3 + y - kMinBorder);
+                s_list[slot] = (yr << 20) | (xr << 8) | (uint32_t)(m - 1);
+                if (m > ini_th) n_ini_local++;
+            }
+        }
+    }
+    const int n_ini_total = __syncthreads_count(n_ini_local > 0);
+    // per-cell fallback: if any corner passes iniThFAST keep only those, else keep everything above minThFAST
+    const int keep_th = n_ini_total > 0 ? ini_th : min_th;
+    const int n_all = s_n;
+    __syncthreads();
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    uint32_t mine[8];
+    int nmine = 0;
+    for (int i = threadIdx.x; i < n_all; i += blockDim.x) {
+        const uint32_t c = s_list[i];
+        if ((int)(c & 0xFF) + 1 > keep_th && nmine < 8) mine[nmine++] = c;
+    }
+    const int my_off = nmine ? atomicAdd(&s_n, nmine) : 0;
+    __syncthreads();
+    if (threadIdx.x == 0) s_base = s_n ? atomicAdd(&L.cand_count[f], s_n) : 0;
+    __syncthreads();
+    uint32_t *__restrict__ out = L.cand + (size_t)f * L.cand_cap;
+    for (int k = 0; k < nmine; k++) {
+        const int pos = s_base + my_off + k;
+        if (pos < L.cand_cap) out[pos] = mine[k]; else *overflow = 1;
+    }
+}
+
+int launch_fast(const LevelDev *d_levels, const CellRect *d_cells, int ncells, int batch, int ini_th, int min_th,
+                int *d_overflow, cudaStream_t stream) {
+    if (ncells <= 0) return 0;
+    dim3 grid(ncells, batch);
+    k_fast_cells<<<grid, 192, 0, stream>>>(d_levels, d_cells, ini_th, min_th, d_overflow);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K3  DistributeOctTree.  One CTA per (frame, level).
+//
+// The reference's list algorithm is replayed breadth-first with block-wide scans.  Its quadrants are fixed by the
+// root box (ceil-halving), so a key's path is a function of its integer coordinates: the host tabulates it
+// (LevelDev::xbin/ybin, depth0 levels, Morton order).  One histogram pass over the candidates then gives the key
+// count of EVERY node down to depth0 as a difference of two prefix sums; deeper nodes (only reached in sparse,
+// clustered frames) are split by partitioning their slice of a bin-sorted copy of the keys.  The winner of a leaf
+// (max response, first in the reference's emission order on ties) comes from a per-bin atomicMax of
+// (score << 24 | ~order).  List order, the (size, creation order) sort of the final phase and its early break are
+// reproduced with prefix sums over list positions.
+// ---------------------------------------------------------------------------------------------------------------
+struct __align__(8) QNode {
+    int16_t ulx, uly, brx, bry;
+    int lo, hi;            // key range (positions in bin-sorted order)
+    uint32_t prefix;       // root << 2*depth | Morton path
+    int depth;
+};
+
+constexpr int OT_THREADS = 256;
+
+// exclusive scan of a[0..n) in place; returns the total to every thread.  s_warp: 8 ints of scratch.
+__device__ int block_excl_scan(int *a, int n, int *s_warp) {
+    const int tid = threadIdx.x, per = (n + OT_THREADS - 1) / OT_THREADS;
+    const int b = tid * per, e = min(b + per, n);
+    int sum = 0;
+    for (int i = b; i < e; i++) sum += a[i];
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if ((tid & 31) >= o) inc += t; }
+    __syncthreads();           // s_warp may still be read from a previous call
+    if ((tid & 31) == 31) s_warp[tid >> 5] = inc;
+    __syncthreads();
+    int woff = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < OT_THREADS / 32; w++) { const int v = s_warp[w]; if (w < (tid >> 5)) woff += v; total += v; }
+    int run = woff + inc - sum;
+    for (int i = b; i < e; i++) { const int v = a[i]; a[i] = run; run += v; }
+    __syncthreads();
+    return total;
+}
+
+struct OctShared {
+    int len, phase, finish, need_sorted, sorted_done, cand_n, rstar, ctot;
+};
+
+__device__ __forceinline__ void child_box(const QNode &p, int q, QNode &c) {
+    const int mx = p.ulx + ((p.brx - p.ulx + 1) >> 1), my = p.uly + ((p.bry - p.uly + 1) >> 1);   // ceil(half)
+    c.ulx = (q & 1) ? mx : p.ulx; c.brx = (q & 1) ? p.brx : mx;
+    c.uly = (q & 2) ? my : p.uly; c.bry = (q & 2) ? p.bry : my;
+    c.prefix = p.prefix * 4u + (uint32_t)q;
+    c.depth = p.depth + 1;
+}
+
+// split points s[0..4] of node p (s[0]=lo, s[4]=hi): children q own [s[q], s[q+1]).
+__device__ void split_node(const LevelDev &L, const QNode &p, const int *bin_start, uint32_t *sorted, int *s, bool sorted_ok,
+                           int *need_sorted) {
+    s[0] = p.lo; s[4] = p.hi;
+    if (p.depth < L.depth0) {
+        const int sh = 2 * (L.depth0 - p.depth - 1);
+        const uint32_t b = p.prefix * 4u;
+        s[1] = bin_start[(b + 1) << sh]; s[2] = bin_start[(b + 2) << sh]; s[3] = bin_start[(b + 3) << sh];
+        return;
+    }
+    if (!sorted_ok) { *need_sorted = 1; s[1] = s[2] = s[3] = p.lo; return; }
+    // below the tabulated depth: 4-way in-place partition of this node's slice (small by construction)
+    const int mx = p.ulx + ((p.brx - p.ulx + 1) >> 1), my = p.uly + ((p.bry - p.uly + 1) >> 1);
+    int c0 = 0, c1 = 0, c2 = 0;
+    for (int k = p.lo; k < p.hi; k++) {
+        const uint32_t key = sorted[k];
+        const int x = (key >> 8) & 0xFFF, y = key >> 20;
+        const int q = (x < mx ? 0 : 1) | (y < my ? 0 : 2);
+        c0 += q == 0; c1 += q == 1; c2 += q == 2;
+    }
+    s[1] = p.lo + c0; s[2] = s[1] + c1; s[3] = s[2] + c2;
+    int cur0 = s[0], cur1 = s[1], cur2 = s[2], cur3 = s[3];
+    for (int b = 0; b < 3; b++) {
+        const int end = s[b + 1];
+        int &cur = b == 0 ? cur0 : b == 1 ? cur1 : cur2;
+        while (cur < end) {
+            const uint32_t key = sorted[cur];
+            const int x = (key >> 8) & 0xFFF, y = key >> 20;
+            const int q = (x < mx ? 0 : 1) | (y < my ? 0 : 2);
+            if (q == b) { cur++; continue; }
+            int &dst = q == 1 ? cur1 : q == 2 ? cur2 : cur3;   // q > b always here
+            const uint32_t other = sorted[dst];
+            sorted[dst] = key; sorted[cur] = other; dst++;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(OT_THREADS) k_octree(const LevelDev *__restrict__ lv, int nlevels, int cap_nodes,
+                                                       int *__restrict__ overflow) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int level = blockIdx.x, f = blockIdx.y;
+    const LevelDev &L = lv[level];
+    const int tid = threadIdx.x;
+    __shared__ OctShared S;
+    __shared__ int s_warp[8];
+    if (L.n_ini <= 0 || L.nbins <= 0) { if (tid == 0) L.sel_count[f] = 0; return; }
+    int n = L.cand_count[f];
+    if (n > L.cand_cap) n = L.cand_cap;
+    const int N = L.quota;
+    // shared carve-up
+    QNode *cur = reinterpret_cast<QNode *>(smem_raw);
+    QNode *nxt = cur + cap_nodes;
+    int *bin_start = reinterpret_cast<int *>(nxt + cap_nodes);             // [nbins + 1]
+    uint32_t *best = reinterpret_cast<uint32_t *>(bin_start + L.nbins + 1);   // [nbins]
+    int *a_cc = reinterpret_cast<int *>(best + L.nbins);      // [cap] children count -> offsets
+    int *a_kp = a_cc + cap_nodes;                              // [cap] kept / processed flags -> offsets
+    int *a_s1 = a_kp + cap_nodes, *a_s2 = a_s1 + cap_nodes, *a_s3 = a_s2 + cap_nodes;   // split points
+    int *a_rank = a_s3 + cap_nodes;                            // [cap] processing rank of a candidate / order
+    int *a_ord = a_rank + cap_nodes;                           // [cap] list position by rank
+    const uint32_t *__restrict__ cand = L.cand + (size_t)f * L.cand_cap;
+    uint32_t *sorted = L.sorted + (size_t)f * L.cand_cap;
+
+    for (int i = tid; i < L.nbins; i += OT_THREADS) { bin_start[i] = 0; best[i] = 0; }
+    if (tid == 0) { bin_start[L.nbins] = 0; S.len = 0; S.phase = 0; S.finish = 0; S.need_sorted = 0; S.sorted_done = 0; }
+    __syncthreads();
+    // pass A: histogram + per-bin winner
+    for (int k = tid; k < n; k += OT_THREADS) {
+        const uint32_t c = cand[k];
+        const uint32_t xr = (c >> 8) & 0xFFF, yr = c >> 20;
+        const uint32_t b = L.xbin[xr] | L.ybin[yr];
+        atomicAdd(&bin_start[b], 1);
+        atomicMax(&best[b], ((c & 0xFFu) << 24) | (0xFFFFFFu - (L.xord[xr] + L.yord[yr])));
+    }
+    __syncthreads();
+    block_excl_scan(bin_start, L.nbins + 1, s_warp);   // bin_start[b] = first key of bin b, bin_start[nbins] = n
+    // roots (push_back order), empty ones erased
+    if (tid == 0) {
+        int len = 0;
+        for (int r = 0; r < L.n_ini; r++) {
+            QNode q;
+            q.ulx = (int16_t)L.root_ulx[r]; q.brx = (int16_t)L.root_brx[r]; q.uly = 0; q.bry = (int16_t)L.reg_h;
+            q.lo = bin_start[r << (2 * L.depth0)]; q.hi = bin_start[(r + 1) << (2 * L.depth0)];
+            q.prefix = (uint32_t)r; q.depth = 0;
+            if (q.hi > q.lo) cur[len++] = q;
+        }
+        S.len = len; S.cand_n = 0;
+    }
+    __syncthreads();
+
+    while (true) {
+        const int len = S.len;
+        const bool final_phase = S.phase != 0;
+        // region of nodes to divide: every non-single node (full round) or the candidates created by the last step
+        const int region = final_phase ? S.cand_n : len;
+        if (tid == 0) S.need_sorted = 0;
+        __syncthreads();
+        const bool sorted_ok = S.sorted_done != 0;
+        for (int i = tid; i < len; i += OT_THREADS) {
+            int cc = 0;
+            a_kp[i] = 0;
+            if (i < region) {
+                const QNode p = cur[i];
+                if (p.hi - p.lo > 1) {
+                    int s[5];
+                    split_node(L, p, bin_start, sorted, s, sorted_ok, &S.need_sorted);
+                    a_s1[i] = s[1]; a_s2[i] = s[2]; a_s3[i] = s[3];
+                    cc = (s[1] > s[0]) + (s[2] > s[1]) + (s[3] > s[2]) + (s[4] > s[3]);
+                }
+            }
+            a_cc[i] = cc;       // 0 => not divided in this step
+        }
+        __syncthreads();
+        if (S.need_sorted) {
+            // the tree wants to go below depth0: build the bin-sorted key copy once, then redo this step
+            uint32_t *cursor = L.bin_cursor + (size_t)f * L.nbins;
+            for (int i = tid; i < L.nbins; i += OT_THREADS) cursor[i] = 0;
+            __syncthreads();
+            for (int k = tid; k < n; k += OT_THREADS) {
+                const uint32_t c = cand[k];
+                const uint32_t b = L.xbin[(c >> 8) & 0xFFF] | L.ybin[c >> 20];
+                sorted[bin_start[b] + atomicAdd(&cursor[b], 1u)] = c;
+            }
+            __threadfence_block();
+            __syncthreads();
+            if (tid == 0) S.sorted_done = 1;
+            __syncthreads();
+            continue;
+        }
+
+        int new_len, ctot, expandable = 0;
+        if (!final_phase) {
+            // ---- full round: every divided node is replaced by its non-empty children (pushed to the front in
+            //      creation order => reversed), single-key nodes keep their relative order behind them
+            for (int i = tid; i < len; i += OT_THREADS) a_kp[i] = (a_cc[i] == 0) ? 1 : 0;
+            __syncthreads();
+            ctot = block_excl_scan(a_cc, len, s_warp);
+            const int kept = block_excl_scan(a_kp, len, s_warp);
+            new_len = ctot + kept;
+            if (new_len > cap_nodes) { if (tid == 0) { *overflow = 2; L.sel_count[f] = 0; } return; }
+            for (int i = tid; i < len; i += OT_THREADS) {
+                const QNode p = cur[i];
+                if (p.hi - p.lo <= 1) { nxt[ctot + a_kp[i]] = p; continue; }
+                const int s[5] = {p.lo, a_s1[i], a_s2[i], a_s3[i], p.hi};
+                int k = a_cc[i];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    if (s[q + 1] > s[q]) {
+                        QNode c; child_box(p, q, c); c.lo = s[q]; c.hi = s[q + 1];
+                        nxt[ctot - 1 - k] = c; k++;
+                        if (c.hi - c.lo > 1) expandable++;
+                    }
+                }
+            }
+        } else {
+            // ---- final phase: candidates (count > 1, created by the previous step = list positions [0, region))
+            //      are divided largest first, ties by creation order descending = list position ascending, until
+            //      the list holds N nodes
+            for (int i = tid; i < region; i += OT_THREADS) {
+                int rank = -1;
+                if (a_cc[i] > 0) {
+                    const int sz = cur[i].hi - cur[i].lo;
+                    rank = 0;
+                    for (int j = 0; j < region; j++) {
+                        if (a_cc[j] > 0) {
+                            const int sj = cur[j].hi - cur[j].lo;
+                            rank += (sj > sz) || (sj == sz && j < i);
+                        }
+                    }
+                }
+                a_rank[i] = rank;
+            }
+            __syncthreads();
+            // number of candidates
+            for (int i = tid; i < region; i += OT_THREADS) if (a_rank[i] >= 0) a_ord[a_rank[i]] = i;
+            if (tid == 0) { S.rstar = 0x7FFFFFFF; S.ctot = 0; }
+            __syncthreads();
+            // total candidates via scan of flags
+            for (int i = tid; i < region; i += OT_THREADS) a_kp[i] = a_rank[i] >= 0 ? 1 : 0;
+            __syncthreads();
+            const int ncand = block_excl_scan(a_kp, region, s_warp);
+            // growth in processing order: a_s? reused as scratch is not possible (split points live there) -> use a_kp
+            for (int r = tid; r < ncand; r += OT_THREADS) a_kp[r] = a_cc[a_ord[r]] - 1;
+            __syncthreads();
+            block_excl_scan(a_kp, ncand, s_warp);          // a_kp[r] = growth before rank r
+            for (int r = tid; r < ncand; r += OT_THREADS) {
+                const int after = len + a_kp[r] + a_cc[a_ord[r]] - 1;
+                if (after >= N) atomicMin(&S.rstar, r);
+            }
+            __syncthreads();
+            const int rstar = min(S.rstar, ncand - 1);     // last processed rank (-1 if no candidates)
+            const int nproc = rstar + 1;
+            // children offsets in processing order
+            for (int r = tid; r < ncand; r += OT_THREADS) a_kp[r] = (r < nproc) ? a_cc[a_ord[r]] : 0;
+            __syncthreads();
+            ctot = block_excl_scan(a_kp, ncand, s_warp);   // a_kp[r] = children created before rank r
+            // a_rank[i] (list position) -> child offset, or -1 if the node is not processed
+            for (int i = tid; i < len; i += OT_THREADS) {
+                int v = -1;
+                if (i < region && a_rank[i] >= 0 && a_rank[i] < nproc) v = a_kp[a_rank[i]];
+                a_ord[i] = v;      // a_ord no longer needed as rank->position map
+            }
+            __syncthreads();
+            for (int i = tid; i < len; i += OT_THREADS) a_kp[i] = a_ord[i] >= 0 ? 1 : 0;
+            __syncthreads();
+            block_excl_scan(a_kp, len, s_warp);            // a_kp[i] = processed nodes before list position i
+            new_len = len - nproc + ctot;
+            if (new_len > cap_nodes) { if (tid == 0) { *overflow = 2; L.sel_count[f] = 0; } return; }
+            for (int i = tid; i < len; i += OT_THREADS) {
+                const QNode p = cur[i];
+                if (a_ord[i] < 0) { nxt[ctot + i - a_kp[i]] = p; continue; }
+                const int s[5] = {p.lo, a_s1[i], a_s2[i], a_s3[i], p.hi};
+                int k = a_ord[i];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    if (s[q + 1] > s[q]) {
+                        QNode c; child_box(p, q, c); c.lo = s[q]; c.hi = s[q + 1];
+                        nxt[ctot - 1 - k] = c; k++;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // reduce `expandable` (full round only)
+        if (!final_phase) {
+            if (tid == 0) S.ctot = 0;
+            __syncthreads();
+            if (expandable) atomicAdd(&S.ctot, expandable);
+            __syncthreads();
+            expandable = S.ctot;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const int prev = S.len;
+            S.len = new_len;
+            S.cand_n = ctot;                 // nodes created by this step sit at list positions [0, ctot)
+            if (new_len >= N || new_len == prev) S.finish = 1;
+            else if (!final_phase && new_len + 3 * expandable > N) S.phase = 1;
+        }
+        { QNode *t = cur; cur = nxt; nxt = t; }
+        __syncthreads();
+        if (S.finish) break;
+    }
+
+    // ---- leaves -> keypoints: best response per node, reference emission order on ties
+    const int len = S.len;
+    uint32_t *__restrict__ sel = L.sel + (size_t)f * L.out_cap;
+    if (len > L.out_cap) { if (tid == 0) { *overflow = 3; L.sel_count[f] = 0; } return; }
+    for (int i = tid; i < len; i += OT_THREADS) {
+        const QNode p = cur[i];
+        uint32_t bv = 0;
+        if (p.depth <= L.depth0) {
+            const int sh = 2 * (L.depth0 - p.depth);
+            const uint32_t b0 = p.prefix << sh, b1 = (p.prefix + 1u) << sh;
+            for (uint32_t b = b0; b < b1; b++) bv = max(bv, best[b]);
+        } else {
+            for (int k = p.lo; k < p.hi; k++) {
+                const uint32_t c = sorted[k];
+                const uint32_t xr = (c >> 8) & 0xFFF, yr = c >> 20;
+                bv = max(bv, ((c & 0xFFu) << 24) | (0xFFFFFFu - (L.xord[xr] + L.yord[yr])));
+            }
+        }
+        const uint32_t ord = 0xFFFFFFu - (bv & 0xFFFFFFu), score = bv >> 24;
+        const uint32_t cellid = ord / L.ord_cell_area, rem = ord - cellid * L.ord_cell_area;
+        const uint32_t yin = rem / (uint32_t)L.wcell, xin = rem - yin * (uint32_t)L.wcell;
+        const uint32_t ci = cellid / L.ord_ncols, cj = cellid - ci * L.ord_ncols;
+        const uint32_t x = cj * (uint32_t)L.wcell + xin + 3u + kMinBorder, y = ci * (uint32_t)L.hcell + yin + 3u + kMinBorder;
+        sel[i] = (y << 20) | (x << 8) | score;
+    }
+    if (tid == 0) L.sel_count[f] = len;
+}
+
+static size_t octree_smem_bytes(int nbins, int cap) {
+    return (size_t)2 * cap * sizeof(QNode) + (size_t)(2 * nbins + 1) * 4 + (size_t)7 * cap * 4 + 16;
+}
+
+int launch_octree(const LevelDev *d_levels, const LevelDev *h_levels, int nlevels, int batch, int *d_overflow,
+                  cudaStream_t stream) {
+    // one launch for all levels: size the node arrays for the largest quota and the bins for the finest table
+    int cap = 0, nbins = 0;
+    for (int l = 0; l < nlevels; l++) {
+        if (h_levels[l].out_cap + 8 > cap) cap = h_levels[l].out_cap + 8;
+        if (h_levels[l].nbins > nbins) nbins = h_levels[l].nbins;
+    }
+    cap = (cap + 1) & ~1;
+    const size_t smem = octree_smem_bytes(nbins, cap);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    dim3 grid(nlevels, batch);
+    k_octree<<<grid, OT_THREADS, smem, stream>>>(d_levels, nlevels, cap, d_overflow);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K7  output slots.  One CTA per frame: walks levels 0..L-1 in list order, scales to image coordinates and assigns
+//     the reference's slot (lapping-area keypoints fill from the back, the rest from the front).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_finalize(const LevelDev *__restrict__ lv, int nlevels, int total_out_cap, int lap0,
+                                                  int lap1, KeypointRec *__restrict__ kp, int cap, int *__restrict__ slot,
+                                                  int *__restrict__ n_out, int *__restrict__ mono_out, int *__restrict__ overflow) {
+    const int f = blockIdx.x, tid = threadIdx.x;
+    __shared__ int s_cnt[kMaxLevels + 1];
+    __shared__ int s_warp[8];
+    __shared__ int s_run;
+    if (tid == 0) {
+        int acc = 0;
+        for (int l = 0; l < nlevels; l++) { s_cnt[l] = acc; acc += lv[l].sel_count[f]; }
+        s_cnt[nlevels] = acc; s_run = 0;
+    }
+    __syncthreads();
+    const int ntot = s_cnt[nlevels];
+    if (ntot > cap) { if (tid == 0) { *overflow = 4; n_out[f] = 0; mono_out[f] = 0; } return; }
+    const float flap0 = (float)lap0, flap1 = (float)lap1;
+    // chunks of 256 keypoints in sequence order; running count of lapping-area keypoints carried across chunks
+    for (int base = 0; base < ntot; base += 256) {
+        const int i = base + tid;
+        int l = 0, inlap = 0;
+        float x = 0.f, y = 0.f, resp = 0.f;
+        if (i < ntot) {
+            while (i >= s_cnt[l + 1]) l++;
+            const uint32_t c = lv[l].sel[(size_t)f * lv[l].out_cap + (i - s_cnt[l])];
+            x = (float)((c >> 8) & 0xFFF); y = (float)(c >> 20); resp = (float)(c & 0xFF);
+            if (l != 0) { x = __fmul_rn(x, lv[l].scale); y = __fmul_rn(y, lv[l].scale); }
+            inlap = (x >= flap0 && x <= flap1) ? 1 : 0;
+        }
+        // block exclusive scan of inlap
+        int inc = inlap;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if ((tid & 31) >= o) inc += t; }
+        if ((tid & 31) == 31) s_warp[tid >> 5] = inc;
+        __syncthreads();
+        int woff = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) { const int v = s_warp[w]; if (w < (tid >> 5)) woff += v; tot += v; }
+        const int before = s_run + woff + inc - inlap;     // lapping keypoints before i
+        if (i < ntot) {
+            const int sl = inlap ? (ntot - 1 - before) : (i - before);
+            KeypointRec r;
+            r.x = x; r.y = y; r.size = lv[l].kp_size; r.angle = -1.f; r.response = resp; r.octave = l; r.class_id = -1;
+            kp[(size_t)f * cap + sl] = r;
+            slot[(size_t)f * total_out_cap + lv[l].out_base + (i - s_cnt[l])] = sl;
+        }
+        __syncthreads();
+        if (tid == 0) s_run += tot;
+        __syncthreads();
+    }
+    if (tid == 0) { n_out[f] = ntot; mono_out[f] = ntot - s_run; }
+}
+
+int launch_finalize(const LevelDev *d_levels, int nlevels, int batch, int total_out_cap, int lap0, int lap1,
+                    KeypointRec *d_kp, int cap, int *d_slot, int *d_n, int *d_mono, int *d_overflow, cudaStream_t stream) {
+    k_finalize<<<batch, 256, 0, stream>>>(d_levels, nlevels, total_out_cap, lap0, lap1, d_kp, cap, d_slot, d_n, d_mono, d_overflow);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K4 + K6  one warp per keypoint: IC_Angle moments by warp reduction, cv::fastAtan2 in individually rounded fp32,
+//          then 256 steered BRIEF tests (8 per lane) on the blurred plane.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+    const float s = 57.29577951308232f;   // (float)(180 / CV_PI)
+    const float p1 = __fmul_rn(0.9997878412794807f, s), p3 = __fmul_rn(-0.3258083974640975f, s);
+    const float p5 = __fmul_rn(0.1555786518463281f, s), p7 = __fmul_rn(-0.04432655554792128f, s);
+    const float eps = 2.220446049250313e-16f;   // (float)DBL_EPSILON
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0.f) a = __fsub_rn(180.f, a);
+    if (y < 0.f) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+__device__ __forceinline__ float warp_ic_angle(const uint8_t *__restrict__ center, int pitch, int lane) {
+    int m10 = 0, m01 = 0;
+    const int u = lane - kHalfPatch;
+    if (lane <= 2 * kHalfPatch) {
+#pragma unroll 1
+        for (int v = -kHalfPatch; v <= kHalfPatch; v++) {
+            const int d = c_umax[v < 0 ? -v : v];
+            if (u >= -d && u <= d) {
+                const int val = center[v * pitch + u];
+                m10 += u * val; m01 += v * val;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xFFFFFFFFu, m10, o); m01 += __shfl_xor_sync(0xFFFFFFFFu, m01, o); }
+    return fast_atan2_deg((float)m01, (float)m10);
+}
+
+__device__ __forceinline__ uint8_t warp_brief_byte(const uint8_t *__restrict__ center, int pitch, float angle_deg, int lane) {
+    const float factor = 0.017453292519943295f;   // (float)(CV_PI / 180.f)
+    const float ang = __fmul_rn(angle_deg, factor);
+    // cosf / sinf of the reference are modelled as the correctly rounded fp32 value (DESIGN.md "trig rule")
+    const float a = __double2float_rn(cos((double)ang)), b = __double2float_rn(sin((double)ang));
+    const char4 *pat = reinterpret_cast<const char4 *>(g_pattern) + lane * 8;
+    uint32_t val = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const char4 p = pat[j];
+        const float x0 = (float)p.x, y0 = (float)p.y, x1 = (float)p.z, y1 = (float)p.w;
+        const int ix0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+        const int iy0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+        const int ix1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+        const int iy1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+        const int t0 = center[iy0 * pitch + ix0], t1 = center[iy1 * pitch + ix1];
+        val |= (uint32_t)(t0 < t1) << j;
+    }
+    return (uint8_t)val;
+}
+
+__global__ void __launch_bounds__(256) k_describe(const LevelDev *__restrict__ lv, int nlevels, int total_out_cap,
+                                                  const int *__restrict__ slot, KeypointRec *__restrict__ kp,
+                                                  uint8_t *__restrict__ desc, int cap) {
+    const int f = blockIdx.y, lane = threadIdx.x & 31;
+    const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (item >= total_out_cap) return;
+    int l = 0;
+    while (l + 1 < nlevels && item >= lv[l + 1].out_base) l++;
+    const LevelDev &L = lv[l];
+    const int idx = item - L.out_base;
+    if (idx >= L.sel_count[f]) return;
+    const uint32_t c = L.sel[(size_t)f * L.out_cap + idx];
+    const int x = (c >> 8) & 0xFFF, y = c >> 20;
+    const uint8_t *img = L.img + (size_t)f * L.img_fstride + (size_t)y * L.pitch + x;
+    const float angle = warp_ic_angle(img, L.pitch, lane);
+    const uint8_t *bl = L.blur + (size_t)f * L.blur_fstride + (size_t)y * L.blur_pitch + x;
+    const uint8_t byte = warp_brief_byte(bl, L.blur_pitch, angle, lane);
+    const int sl = slot[(size_t)f * total_out_cap + item];
+    desc[((size_t)f * cap + sl) * 32 + lane] = byte;
+    if (lane == 0) kp[(size_t)f * cap + sl].angle = angle;
+}
+
+int launch_describe(const LevelDev *d_levels, int nlevels, int batch, int total_out_cap, const int *d_slot,
+                    KeypointRec *d_kp, uint8_t *d_desc, int cap, cudaStream_t stream) {
+    dim3 grid((total_out_cap + 7) / 8, batch);
+    k_describe<<<grid, 256, 0, stream>>>(d_levels, nlevels, total_out_cap, d_slot, d_kp, d_desc, cap);
+    return 1;
+}
+
+__global__ void __launch_bounds__(256) k_describe_points(const uint8_t *__restrict__ img, const uint8_t *__restrict__ blur, int pitch,
+                                                         const float *__restrict__ xy, int n, const float *__restrict__ angle_in,
+                                                         float *__restrict__ angle_out, uint8_t *__restrict__ desc) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const int x = __float2int_rn(xy[2 * i]), y = __float2int_rn(xy[2 * i + 1]);
+    float angle;
+    if (angle_in) angle = angle_in[i];
+    else angle = warp_ic_angle(img + (size_t)y * pitch + x, pitch, lane);
+    if (angle_out && lane == 0) angle_out[i] = angle;
+    if (desc && blur) desc[(size_t)i * 32 + lane] = warp_brief_byte(blur + (size_t)y * pitch + x, pitch, angle, lane);
+}
+
+int launch_describe_points(const uint8_t *d_img, const uint8_t *d_blur, int pitch, const float *d_xy, int n,
+                           const float *d_angle_in, float *d_angle_out, uint8_t *d_desc, cudaStream_t stream) {
+    if (n <= 0) return 0;
+    k_describe_points<<<(n + 7) / 8, 256, 0, stream>>>(d_img, d_blur, pitch, d_xy, n, d_angle_in, d_angle_out, d_desc);
+    return 1;
+}
+
+}  // namespace orbx

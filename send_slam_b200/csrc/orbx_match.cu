@@ -1,0 +1,385 @@
+// Hamming matching kernels + their C ABI (include/orbx.h "matching").
+//
+//   k_distance_batch   ORBmatcher::DescriptorDistance over n pairs                         
+//   k_match_windowed   Frame::GetFeaturesInArea + best / second-best distance per query   (C.2, SearchByProjection /
+//                      SearchForInitialization inner loops)
+//   k_knn2             brute-force k=2 nearest neighbours of nq queries in a row shard     (cv::BFMatcher NORM_HAMMING)
+//   k_knn2_merge       top-2 merge of per-chunk / per-rank partial results
+//
+// Distances are XOR + POPC on eight 32-bit words (exact integers).  The kNN kernel keeps queries in registers and
+// streams database rows through shared memory (broadcast reads), so the POPC pipe is the bound.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/orbx.h"
+#include "orbx_dev.h"
+
+using namespace orbx;
+
+namespace {
+
+__device__ __forceinline__ int hamming256(const uint4 &a0, const uint4 &a1, const uint4 &b0, const uint4 &b1) {
+    return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+           __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+__global__ void __launch_bounds__(256) k_distance_batch(const uint4 *__restrict__ a, const uint4 *__restrict__ b, int n,
+                                                        int32_t *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = hamming256(a[2 * i], a[2 * i + 1], b[2 * i], b[2 * i + 1]);
+}
+
+// ---- windowed search -------------------------------------------------------------------------------------------
+constexpr int GRID_COLS = 64, GRID_ROWS = 48;   // FRAME_GRID_COLS / FRAME_GRID_ROWS of UPSTREAM Frame.h
+constexpr unsigned long long NONE64 = ~0ull;
+
+__global__ void __launch_bounds__(256) k_match_windowed(const uint4 *__restrict__ qdesc, const float *__restrict__ quvr,
+                                                        const int32_t *__restrict__ qlev, int nq,
+                                                        const KeypointRec *__restrict__ tkp, const uint4 *__restrict__ tdesc, int nt,
+                                                        float minX, float minY, float invW, float invH,
+                                                        int32_t *__restrict__ best_idx, int32_t *__restrict__ best_dist,
+                                                        int32_t *__restrict__ second_idx, int32_t *__restrict__ second_dist) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const uint4 q0 = qdesc[2 * q], q1 = qdesc[2 * q + 1];
+    const float x = quvr[3 * q], y = quvr[3 * q + 1], r = quvr[3 * q + 2];
+    const int minLevel = qlev[2 * q], maxLevel = qlev[2 * q + 1];
+    const bool check = (minLevel > 0) || (maxLevel >= 0);
+    const int cx0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, minX), r), invW)));
+    const int cx1 = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, minX), r), invW)));
+    const int cy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, minY), r), invH)));
+    const int cy1 = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, minY), r), invH)));
+    unsigned long long k1 = NONE64, k2 = NONE64;
+    for (int t = lane; t < nt; t += 32) {
+        const KeypointRec kp = tkp[t];
+        const int px = (int)roundf(__fmul_rn(__fsub_rn(kp.x, minX), invW)), py = (int)roundf(__fmul_rn(__fsub_rn(kp.y, minY), invH));
+        if (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) continue;   // Frame::PosInGrid rejected it
+        if (px < cx0 || px > cx1 || py < cy0 || py > cy1) continue;
+        if (check) {
+            if (kp.octave < minLevel) continue;
+            if (maxLevel >= 0 && kp.octave > maxLevel) continue;
+        }
+        if (!(fabsf(__fsub_rn(kp.x, x)) < r && fabsf(__fsub_rn(kp.y, y)) < r)) continue;
+        const int d = hamming256(q0, q1, tdesc[2 * t], tdesc[2 * t + 1]);
+        // ties resolve in the reference's visiting order: grid column, grid row, train index
+        const unsigned long long key = ((unsigned long long)d << 40) | ((unsigned long long)(px * GRID_ROWS + py) << 24) | (unsigned long long)t;
+        if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
+    }
+    unsigned long long b = k1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(0xFFFFFFFFu, b, o); b = v < b ? v : b; }
+    unsigned long long s = (k1 == b) ? k2 : k1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(0xFFFFFFFFu, s, o); s = v < s ? v : s; }
+    if (lane == 0) {
+        best_idx[q] = b == NONE64 ? -1 : (int32_t)(b & 0xFFFFFFull);  best_dist[q] = b == NONE64 ? 256 : (int32_t)(b >> 40);
+        second_idx[q] = s == NONE64 ? -1 : (int32_t)(s & 0xFFFFFFull); second_dist[q] = s == NONE64 ? 256 : (int32_t)(s >> 40);
+    }
+}
+
+// ---- brute-force kNN, k = 2 -----------------------------------------------------------------------------------
+constexpr int KQ_THREADS = 128;    // threads per CTA
+constexpr int KQ_QPT = 2;          // queries per thread (registers)
+constexpr int KQ_TILE = 128;       // database rows staged per step
+constexpr int KQ_ROW_BITS = 23;    // row-in-chunk bits of the packed (distance, row) key
+
+__global__ void __launch_bounds__(KQ_THREADS) k_knn2(const uint4 *__restrict__ db, long long nrows, long long row_offset,
+                                                     const uint4 *__restrict__ queries, int nq, int rows_per_chunk,
+                                                     unsigned long long *__restrict__ partial) {
+    __shared__ uint4 s_db[2][KQ_TILE * 2];
+    const int tid = threadIdx.x;
+    const int qa = blockIdx.x * (KQ_THREADS * KQ_QPT) + tid, qb = qa + KQ_THREADS;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    const uint4 a0 = qa < nq ? queries[2 * qa] : z, a1 = qa < nq ? queries[2 * qa + 1] : z;
+    const uint4 b0 = qb < nq ? queries[2 * qb] : z, b1 = qb < nq ? queries[2 * qb + 1] : z;
+    const long long r0 = (long long)blockIdx.y * rows_per_chunk;
+    const long long r1 = min(r0 + (long long)rows_per_chunk, nrows);
+    uint32_t ka1 = 0xFFFFFFFFu, ka2 = 0xFFFFFFFFu, kb1 = 0xFFFFFFFFu, kb2 = 0xFFFFFFFFu;
+    const int ntiles = (int)((r1 - r0 + KQ_TILE - 1) / KQ_TILE);
+    // prologue: stage tile 0
+    if (ntiles > 0) {
+        const int cnt = (int)min((long long)KQ_TILE, r1 - r0);
+        for (int i = tid; i < cnt * 2; i += KQ_THREADS) s_db[0][i] = db[r0 * 2 + i];
+    }
+    __syncthreads();
+    for (int t = 0; t < ntiles; t++) {
+        const long long base = r0 + (long long)t * KQ_TILE;
+        const int cnt = (int)min((long long)KQ_TILE, r1 - base);
+        // prefetch the next tile into registers while this one is consumed
+        uint4 pre[2]; int npre = 0;
+        if (t + 1 < ntiles) {
+            const long long nb = base + KQ_TILE;
+            const int ncnt = (int)min((long long)KQ_TILE, r1 - nb);
+            for (int i = tid, k = 0; i < ncnt * 2; i += KQ_THREADS, k++) { pre[k] = db[nb * 2 + i]; npre = k + 1; }
+        }
+        const uint4 *__restrict__ rows = s_db[t & 1];
+        uint32_t rowkey = (uint32_t)(base - r0);
+#pragma unroll 4
+        for (int r = 0; r < cnt; r++, rowkey++) {
+            const uint4 d0 = rows[2 * r], d1 = rows[2 * r + 1];
+            const uint32_t da = (uint32_t)hamming256(a0, a1, d0, d1), dbb = (uint32_t)hamming256(b0, b1, d0, d1);
+            const uint32_t keya = (da << KQ_ROW_BITS) + rowkey, keyb = (dbb << KQ_ROW_BITS) + rowkey;
+            ka2 = min(ka2, max(ka1, keya)); ka1 = min(ka1, keya);
+            kb2 = min(kb2, max(kb1, keyb)); kb1 = min(kb1, keyb);
+        }
+        if (t + 1 < ntiles) {
+            for (int k = 0; k < npre; k++) s_db[(t + 1) & 1][tid + k * KQ_THREADS] = pre[k];
+        }
+        __syncthreads();
+    }
+    auto emit = [&](int q, uint32_t k1, uint32_t k2) {
+        if (q >= nq) return;
+        unsigned long long *o = partial + ((size_t)blockIdx.y * nq + q) * 2;
+        const uint32_t m = (1u << KQ_ROW_BITS) - 1;
+        o[0] = k1 == 0xFFFFFFFFu ? NONE64 : (((unsigned long long)(k1 >> KQ_ROW_BITS) << 32) | (unsigned long long)(row_offset + r0 + (k1 & m)));
+        o[1] = k2 == 0xFFFFFFFFu ? NONE64 : (((unsigned long long)(k2 >> KQ_ROW_BITS) << 32) | (unsigned long long)(row_offset + r0 + (k2 & m)));
+    };
+    emit(qa, ka1, ka2);
+    emit(qb, kb1, kb2);
+}
+
+__global__ void __launch_bounds__(256) k_knn2_merge(const unsigned long long *__restrict__ partial, int nparts, int nq,
+                                                    unsigned long long *__restrict__ out) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    unsigned long long k1 = NONE64, k2 = NONE64;
+    for (int p = 0; p < nparts; p++) {
+        const unsigned long long *v = partial + ((size_t)p * nq + q) * 2;
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const unsigned long long key = v[j];
+            if (key < k1) { k2 = k1; k1 = key; } else if (key < k2 && key != k1) k2 = key;
+        }
+    }
+    out[2 * q] = k1; out[2 * q + 1] = k2;
+}
+
+thread_local std::string g_db_error;
+
+}  // namespace
+
+struct orbx_db {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    const uint8_t *d_rows = nullptr;
+    bool owns_rows = false;
+    long long nrows = 0, row_offset = 0;
+    int nchunks = 0, rows_per_chunk = 0;
+    uint8_t *d_q = nullptr; int q_cap = 0;
+    unsigned long long *d_partial = nullptr; size_t partial_cap = 0;
+    unsigned long long *d_out = nullptr;
+    unsigned long long *h_out = nullptr;
+    mutable std::string err;
+    long long launches = 0;
+};
+
+#define DB_TRY(db, expr)                                                                       \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess) { (db)->err = std::string(#expr) + ": " + cudaGetErrorString(e__); return ORBX_E_CUDA; } \
+    } while (0)
+
+static int db_reserve(orbx_db *db, int nq) {
+    if (nq <= db->q_cap) return ORBX_OK;
+    if (db->d_q) cudaFree(db->d_q);
+    if (db->d_partial) cudaFree(db->d_partial);
+    if (db->d_out) cudaFree(db->d_out);
+    if (db->h_out) cudaFreeHost(db->h_out);
+    db->d_q = nullptr; db->d_partial = nullptr; db->d_out = nullptr; db->h_out = nullptr; db->q_cap = 0;
+    DB_TRY(db, cudaMalloc((void **)&db->d_q, (size_t)nq * 32));
+    DB_TRY(db, cudaMalloc((void **)&db->d_partial, (size_t)db->nchunks * nq * 2 * sizeof(unsigned long long)));
+    DB_TRY(db, cudaMalloc((void **)&db->d_out, (size_t)nq * 2 * sizeof(unsigned long long)));
+    DB_TRY(db, cudaMallocHost((void **)&db->h_out, (size_t)nq * 2 * sizeof(unsigned long long)));
+    db->q_cap = nq;
+    return ORBX_OK;
+}
+
+static int db_create_common(int device, long long nrows, long long row_offset, orbx_db **out) {
+    if (!out) { g_db_error = "null argument"; return ORBX_E_INVALID; }
+    *out = nullptr;
+    if (nrows < 0 || row_offset < 0 || row_offset + nrows >= (1ll << 32)) { g_db_error = "row count / offset out of range"; return ORBX_E_INVALID; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev < 1) { g_db_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (orbx has no CPU fallback)"; return ORBX_E_CUDA; }
+    if (device < 0 || device >= ndev) { g_db_error = "device ordinal out of range"; return ORBX_E_INVALID; }
+    orbx_db *db = new (std::nothrow) orbx_db();
+    if (!db) { g_db_error = "out of host memory"; return ORBX_E_INVALID; }
+    db->device = device; db->nrows = nrows; db->row_offset = row_offset;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_db_error = std::string("cuda init: ") + cudaGetErrorString(e); delete db; return ORBX_E_CUDA;
+    }
+    // chunking: enough CTAs to fill 148 SMs a few times for ~2k queries, chunk <= 2^23 rows (packed key)
+    cudaDeviceProp prop; cudaGetDeviceProperties(&prop, device);
+    int chunks = std::max(1, prop.multiProcessorCount * 4 / 8);
+    long long rpc = (nrows + chunks - 1) / std::max(chunks, 1);
+    rpc = std::max<long long>(rpc, KQ_TILE * 8);
+    rpc = (rpc + KQ_TILE - 1) / KQ_TILE * KQ_TILE;
+    rpc = std::min<long long>(rpc, (1ll << KQ_ROW_BITS) - KQ_TILE);
+    db->rows_per_chunk = (int)rpc;
+    db->nchunks = (int)std::max<long long>(1, (nrows + rpc - 1) / rpc);
+    *out = db;
+    return ORBX_OK;
+}
+
+extern "C" {
+
+int orbx_knn2_create_db(int device, const uint8_t *rows, long long nrows, long long row_offset, orbx_db **out) {
+    if (!rows && nrows > 0) { g_db_error = "null rows"; return ORBX_E_INVALID; }
+    int rc = db_create_common(device, nrows, row_offset, out);
+    if (rc) return rc;
+    orbx_db *db = *out;
+    uint8_t *d = nullptr;
+    cudaError_t e = cudaMalloc((void **)&d, std::max<size_t>((size_t)nrows * 32, 256));
+    if (e == cudaSuccess && nrows > 0) e = cudaMemcpy(d, rows, (size_t)nrows * 32, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        g_db_error = std::string("db upload: ") + cudaGetErrorString(e);
+        if (d) cudaFree(d);
+        cudaStreamDestroy(db->stream); delete db; *out = nullptr; return ORBX_E_CUDA;
+    }
+    db->d_rows = d; db->owns_rows = true;
+    return ORBX_OK;
+}
+
+int orbx_knn2_create_db_device(int device, const uint8_t *d_rows, long long nrows, long long row_offset, orbx_db **out) {
+    if (!d_rows && nrows > 0) { g_db_error = "null rows"; return ORBX_E_INVALID; }
+    if (((uintptr_t)d_rows & 15) != 0) { g_db_error = "device rows must be 16-byte aligned"; return ORBX_E_INVALID; }
+    int rc = db_create_common(device, nrows, row_offset, out);
+    if (rc) return rc;
+    (*out)->d_rows = d_rows; (*out)->owns_rows = false;
+    return ORBX_OK;
+}
+
+void orbx_knn2_destroy_db(orbx_db *db) {
+    if (!db) return;
+    cudaSetDevice(db->device);
+    if (db->stream) cudaStreamSynchronize(db->stream);
+    if (db->owns_rows && db->d_rows) cudaFree(const_cast<uint8_t *>(db->d_rows));
+    if (db->d_q) cudaFree(db->d_q);
+    if (db->d_partial) cudaFree(db->d_partial);
+    if (db->d_out) cudaFree(db->d_out);
+    if (db->h_out) cudaFreeHost(db->h_out);
+    if (db->stream) cudaStreamDestroy(db->stream);
+    delete db;
+}
+
+const char *orbx_knn2_last_error(const orbx_db *db) { return db ? db->err.c_str() : g_db_error.c_str(); }
+long long orbx_knn2_launch_count(const orbx_db *db) { return db ? db->launches : 0; }
+
+int orbx_knn2_sync(orbx_db *db) {
+    if (!db) return ORBX_E_INVALID;
+    DB_TRY(db, cudaSetDevice(db->device));
+    DB_TRY(db, cudaStreamSynchronize(db->stream));
+    return ORBX_OK;
+}
+
+int orbx_knn2_query_device(orbx_db *db, const uint8_t *d_queries, int nq, unsigned long long *d_packed_out) {
+    if (!db || !d_queries || !d_packed_out || nq < 1) return ORBX_E_INVALID;
+    if (((uintptr_t)d_queries & 15) != 0) { db->err = "device queries must be 16-byte aligned"; return ORBX_E_INVALID; }
+    DB_TRY(db, cudaSetDevice(db->device));
+    int rc = db_reserve(db, nq);
+    if (rc) return rc;
+    dim3 grid((nq + KQ_THREADS * KQ_QPT - 1) / (KQ_THREADS * KQ_QPT), db->nchunks);
+    k_knn2<<<grid, KQ_THREADS, 0, db->stream>>>(reinterpret_cast<const uint4 *>(db->d_rows), db->nrows, db->row_offset,
+                                                reinterpret_cast<const uint4 *>(d_queries), nq, db->rows_per_chunk, db->d_partial);
+    k_knn2_merge<<<(nq + 255) / 256, 256, 0, db->stream>>>(db->d_partial, db->nchunks, nq, d_packed_out);
+    db->launches += 2;
+    DB_TRY(db, cudaGetLastError());
+    return ORBX_OK;
+}
+
+int orbx_knn2_merge_device(orbx_db *db, const unsigned long long *d_partials, int nparts, int nq, unsigned long long *d_packed_out) {
+    if (!db || !d_partials || !d_packed_out || nparts < 1 || nq < 1) return ORBX_E_INVALID;
+    DB_TRY(db, cudaSetDevice(db->device));
+    k_knn2_merge<<<(nq + 255) / 256, 256, 0, db->stream>>>(d_partials, nparts, nq, d_packed_out);
+    db->launches += 1;
+    DB_TRY(db, cudaGetLastError());
+    return ORBX_OK;
+}
+
+int orbx_knn2_query(orbx_db *db, const uint8_t *queries, int nq, int32_t *idx_out, int32_t *dist_out) {
+    if (!db || !queries || !idx_out || !dist_out || nq < 1) return ORBX_E_INVALID;
+    DB_TRY(db, cudaSetDevice(db->device));
+    int rc = db_reserve(db, nq);
+    if (rc) return rc;
+    DB_TRY(db, cudaMemcpyAsync(db->d_q, queries, (size_t)nq * 32, cudaMemcpyHostToDevice, db->stream));
+    if ((rc = orbx_knn2_query_device(db, db->d_q, nq, db->d_out))) return rc;
+    DB_TRY(db, cudaMemcpyAsync(db->h_out, db->d_out, (size_t)nq * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, db->stream));
+    DB_TRY(db, cudaStreamSynchronize(db->stream));
+    for (int i = 0; i < 2 * nq; i++) {
+        const unsigned long long k = db->h_out[i];
+        if (k == NONE64) { idx_out[i] = -1; dist_out[i] = -1; }
+        else { idx_out[i] = (int32_t)(k & 0xFFFFFFFFull); dist_out[i] = (int32_t)(k >> 32); }
+    }
+    return ORBX_OK;
+}
+
+}  // extern "C"
+
+// ---- entry points that live on the extractor handle --------------------------------------------------------------
+// (the handle type is opaque here; only its stream/device/launch counter are needed, passed through small accessors)
+namespace orbx {
+int match_distance_batch(int device, cudaStream_t stream, const uint8_t *a, const uint8_t *b, int n, int32_t *dist_out, std::string &err,
+                         long long &launches) {
+    if (n <= 0) return ORBX_OK;
+    uint8_t *d_a = nullptr, *d_b = nullptr; int32_t *d_o = nullptr;
+    cudaError_t e = cudaSetDevice(device);
+    auto cleanup = [&]() { if (d_a) cudaFree(d_a); if (d_b) cudaFree(d_b); if (d_o) cudaFree(d_o); };
+#define M_TRY(expr) do { e = (expr); if (e != cudaSuccess) { err = std::string(#expr) + ": " + cudaGetErrorString(e); cleanup(); return ORBX_E_CUDA; } } while (0)
+    M_TRY(cudaMalloc((void **)&d_a, (size_t)n * 32)); M_TRY(cudaMalloc((void **)&d_b, (size_t)n * 32)); M_TRY(cudaMalloc((void **)&d_o, (size_t)n * 4));
+    M_TRY(cudaMemcpyAsync(d_a, a, (size_t)n * 32, cudaMemcpyHostToDevice, stream));
+    M_TRY(cudaMemcpyAsync(d_b, b, (size_t)n * 32, cudaMemcpyHostToDevice, stream));
+    k_distance_batch<<<(n + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const uint4 *>(d_a), reinterpret_cast<const uint4 *>(d_b), n, d_o);
+    launches++;
+    M_TRY(cudaGetLastError());
+    M_TRY(cudaMemcpyAsync(dist_out, d_o, (size_t)n * 4, cudaMemcpyDeviceToHost, stream));
+    M_TRY(cudaStreamSynchronize(stream));
+    cleanup();
+    return ORBX_OK;
+}
+
+int match_windowed(int device, cudaStream_t stream, const uint8_t *q_desc, const float *q_uvr, const int32_t *q_levels, int nq,
+                   const orbx_keypoint *t_kp, const uint8_t *t_desc, int nt, const float *bounds4, int32_t *best_idx,
+                   int32_t *best_dist, int32_t *second_idx, int32_t *second_dist, std::string &err, long long &launches) {
+    if (nq <= 0) return ORBX_OK;
+    if (nt >= (1 << 24)) { err = "too many train keypoints"; return ORBX_E_INVALID; }
+    cudaError_t e = cudaSetDevice(device);
+    std::vector<void *> allocs;
+    auto cleanup = [&]() { for (void *p : allocs) cudaFree(p); };
+    auto dalloc = [&](size_t bytes) -> void * { void *p = nullptr; if (cudaMalloc(&p, std::max<size_t>(bytes, 256)) != cudaSuccess) return nullptr; allocs.push_back(p); return p; };
+    uint8_t *d_qd = (uint8_t *)dalloc((size_t)nq * 32); float *d_uvr = (float *)dalloc((size_t)nq * 12); int32_t *d_lev = (int32_t *)dalloc((size_t)nq * 8);
+    KeypointRec *d_tkp = (KeypointRec *)dalloc((size_t)std::max(nt, 1) * sizeof(KeypointRec)); uint8_t *d_td = (uint8_t *)dalloc((size_t)std::max(nt, 1) * 32);
+    int32_t *d_out = (int32_t *)dalloc((size_t)nq * 16);
+    if (!d_qd || !d_uvr || !d_lev || !d_tkp || !d_td || !d_out) { err = "cudaMalloc failed"; cleanup(); return ORBX_E_CUDA; }
+    M_TRY(cudaMemcpyAsync(d_qd, q_desc, (size_t)nq * 32, cudaMemcpyHostToDevice, stream));
+    M_TRY(cudaMemcpyAsync(d_uvr, q_uvr, (size_t)nq * 12, cudaMemcpyHostToDevice, stream));
+    M_TRY(cudaMemcpyAsync(d_lev, q_levels, (size_t)nq * 8, cudaMemcpyHostToDevice, stream));
+    if (nt > 0) {
+        M_TRY(cudaMemcpyAsync(d_tkp, t_kp, (size_t)nt * sizeof(KeypointRec), cudaMemcpyHostToDevice, stream));
+        M_TRY(cudaMemcpyAsync(d_td, t_desc, (size_t)nt * 32, cudaMemcpyHostToDevice, stream));
+    }
+    const float minX = bounds4[0], minY = bounds4[1], maxX = bounds4[2], maxY = bounds4[3];
+    const float invW = (float)GRID_COLS / (maxX - minX), invH = (float)GRID_ROWS / (maxY - minY);
+    k_match_windowed<<<(nq + 7) / 8, 256, 0, stream>>>(reinterpret_cast<const uint4 *>(d_qd), d_uvr, d_lev, nq, d_tkp,
+                                                       reinterpret_cast<const uint4 *>(d_td), nt, minX, minY, invW, invH,
+                                                       d_out, d_out + nq, d_out + 2 * nq, d_out + 3 * nq);
+    launches++;
+    M_TRY(cudaGetLastError());
+    M_TRY(cudaMemcpyAsync(best_idx, d_out, (size_t)nq * 4, cudaMemcpyDeviceToHost, stream));
+    M_TRY(cudaMemcpyAsync(best_dist, d_out + nq, (size_t)nq * 4, cudaMemcpyDeviceToHost, stream));
+    M_TRY(cudaMemcpyAsync(second_idx, d_out + 2 * nq, (size_t)nq * 4, cudaMemcpyDeviceToHost, stream));
+    M_TRY(cudaMemcpyAsync(second_dist, d_out + 3 * nq, (size_t)nq * 4, cudaMemcpyDeviceToHost, stream));
+    M_TRY(cudaStreamSynchronize(stream));
+    cleanup();
+#undef M_TRY
+    return ORBX_OK;
+}
+}  // namespace orbx

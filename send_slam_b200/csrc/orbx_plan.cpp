@@ -1,0 +1,197 @@
+// Host geometry plan (see orbx_plan.h).  Pure C++, no CUDA: unit-testable without a GPU through the
+// orbx_plan_* debug exports at the bottom of orbx_api.cu.
+#include "orbx_plan.h"
+
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+namespace orbx {
+
+static inline int cv_round(float v) { return (int)lrintf(v); }
+static inline int cv_round(double v) { return (int)lrint(v); }
+
+// ORBextractor::ORBextractor (UPSTREAM src/ORBextractor.cc ctor; SURVEY.md C.1 "Constructor")
+bool init_params(ExtractorParams &p, int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th) {
+    if (nlevels < 1 || nlevels > kMaxLevels || nfeatures < 0 || nfeatures > (1 << 20)) return false;
+    if (!(scale_factor > 1.0f) || !(scale_factor < 2.0f)) return false;   // == 2 would take cv::resize's INTER_AREA path
+    if (ini_th < 1 || ini_th > 254 || min_th < 1 || min_th > ini_th) return false;
+    p.nfeatures = nfeatures; p.scale_factor_f = scale_factor; p.nlevels = nlevels; p.ini_th = ini_th; p.min_th = min_th;
+    const double sf = (double)scale_factor;   // float ctor argument stored in a double member
+    p.scale[0] = 1.0f; p.sigma2[0] = 1.0f;
+    for (int i = 1; i < nlevels; i++) {
+        p.scale[i] = (float)((double)p.scale[i - 1] * sf);
+        p.sigma2[i] = p.scale[i] * p.scale[i];
+    }
+    for (int i = 0; i < nlevels; i++) { p.inv_scale[i] = 1.0f / p.scale[i]; p.inv_sigma2[i] = 1.0f / p.sigma2[i]; }
+    const float factor = (float)(1.0 / sf);
+    float want = (float)nfeatures * (1.0f - factor) / (1.0f - (float)std::pow((double)factor, (double)nlevels));
+    int sum = 0;
+    for (int l = 0; l < nlevels - 1; l++) { p.quota[l] = cv_round(want); sum += p.quota[l]; want *= factor; }
+    p.quota[nlevels - 1] = nfeatures - sum > 0 ? nfeatures - sum : 0;
+    // umax: quarter-circle half-widths of the 31-px patch
+    std::memset(p.umax, 0, sizeof(p.umax));
+    const int vmax = (int)std::floor(kHalfPatch * std::sqrt(2.0) / 2 + 1), vmin = (int)std::ceil(kHalfPatch * std::sqrt(2.0) / 2);
+    for (int v = 0; v <= vmax; v++) p.umax[v] = cv_round(std::sqrt((double)(kHalfPatch * kHalfPatch - v * v)));
+    for (int v = kHalfPatch, v0 = 0; v >= vmin; --v) {
+        while (p.umax[v0] == p.umax[v0 + 1]) ++v0;
+        p.umax[v] = v0; ++v0;
+    }
+    return true;
+}
+
+// cv::resize INTER_LINEAR coefficient tables, 8UC1.  is_x: the x axis clamps the fraction at the
+// borders, the y axis clips the row index on access instead.
+void build_resize_taps(int dst, int src, bool is_x, std::vector<ResizeTap> &taps) {
+    taps.resize(dst);
+    const double scale = 1.0 / ((double)dst / (double)src);
+    for (int d = 0; d < dst; d++) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = (int)std::floor(f);
+        f -= (float)s;
+        if (is_x) {
+            if (s < 0) { f = 0.f; s = 0; }
+            if (s >= src - 1) { f = 0.f; s = src - 1; }
+        }
+        auto sat16 = [](int v) { return (int16_t)(v < -32768 ? -32768 : v > 32767 ? 32767 : v); };
+        ResizeTap t;
+        t.c0 = sat16(cv_round((1.f - f) * 2048.f));
+        t.c1 = sat16(cv_round(f * 2048.f));
+        int s0 = s < 0 ? 0 : (s > src - 1 ? src - 1 : s);
+        int s1 = s + 1 < 0 ? 0 : (s + 1 > src - 1 ? src - 1 : s + 1);
+        t.ofs = (int16_t)s0; t.ofs1 = (int16_t)s1;
+        taps[d] = t;
+    }
+}
+
+static inline uint32_t spread_bits(uint32_t v) {   // bit i -> bit 2i
+    uint32_t r = 0;
+    for (int i = 0; i < 16; i++) r |= ((v >> i) & 1u) << (2 * i);
+    return r;
+}
+
+bool build_plan(const ExtractorParams &p, int width, int height, Plan &plan, std::string &err) {
+    if (width < 1 || height < 1 || width > 4095 || height > 4095) { err = "frame size out of range (1..4095)"; return false; }
+    plan = Plan();
+    plan.width = width; plan.height = height; plan.nlevels = p.nlevels;
+    plan.lv.resize(p.nlevels);
+    for (int l = 0; l < p.nlevels; l++) {
+        LevelPlan &L = plan.lv[l];
+        // ComputePyramid: Size(cvRound((float)cols*scale), cvRound((float)rows*scale)), scale = mvInvScaleFactor[l]
+        L.w = cv_round((float)width * p.inv_scale[l]);
+        L.h = cv_round((float)height * p.inv_scale[l]);
+        if (L.w < 1 || L.h < 1) { err = "pyramid level collapses to zero size"; return false; }
+        L.pitch = (L.w + kPitchAlign - 1) / kPitchAlign * kPitchAlign;
+        L.plane_bytes = (size_t)L.pitch * L.h;
+        if (l > 0) {
+            build_resize_taps(L.w, plan.lv[l - 1].w, true, L.xtap);
+            build_resize_taps(L.h, plan.lv[l - 1].h, false, L.ytap);
+        }
+        L.quota = p.quota[l];
+        L.kp_size = (float)(int)((float)kPatchSize * p.scale[l]);
+
+        // ---- ComputeKeyPointsOctTree cell grid ----
+        const int maxBX = L.w - kEdge + 3, maxBY = L.h - kEdge + 3;
+        L.reg_w = maxBX - kMinBorder; L.reg_h = maxBY - kMinBorder;
+        L.first_cell = (int)plan.cells.size();
+        L.cand_cap = 0;
+        if (L.reg_w > 0 && L.reg_h > 0) {
+            const float W = 35.f;
+            const float fw = (float)L.reg_w, fh = (float)L.reg_h;
+            L.ncols = (int)(fw / W); L.nrows = (int)(fh / W);
+            if (L.ncols > 0 && L.nrows > 0) {
+                L.wcell = (int)std::ceil(fw / (float)L.ncols);
+                L.hcell = (int)std::ceil(fh / (float)L.nrows);
+                if (L.wcell + 6 > 80 || L.hcell + 6 > 80) { err = "FAST cell larger than the kernel tile"; return false; }
+                for (int i = 0; i < L.nrows; i++) {
+                    const int iniY = kMinBorder + i * L.hcell;
+                    int maxY = iniY + L.hcell + 6;
+                    if (iniY >= maxBY - 3) continue;
+                    if (maxY > maxBY) maxY = maxBY;
+                    for (int j = 0; j < L.ncols; j++) {
+                        const int iniX = kMinBorder + j * L.wcell;
+                        int maxX = iniX + L.wcell + 6;
+                        if (iniX >= maxBX - 6) continue;
+                        if (maxX > maxBX) maxX = maxBX;
+                        const int a = maxX - iniX - 6, b = maxY - iniY - 6;   // tested pixels
+                        if (a <= 0 || b <= 0) continue;                          // cv::FAST finds nothing in such a ROI
+                        CellRect c{};
+                        c.level = (int16_t)l; c.x0 = (int16_t)iniX; c.y0 = (int16_t)iniY; c.x1 = (int16_t)maxX; c.y1 = (int16_t)maxY;
+                        plan.cells.push_back(c);
+                        L.cand_cap += ((a + 1) / 2) * ((b + 1) / 2);
+                    }
+                }
+            }
+        }
+        L.ncells = (int)plan.cells.size() - L.first_cell;
+        L.cand_cap = (L.cand_cap + 63) / 64 * 64 + 64;
+
+        // ---- DistributeOctTree set-up ----
+        L.n_ini = 0; L.depth0 = 0; L.nbins = 0;
+        if (L.reg_w > 0 && L.reg_h > 0) {
+            L.n_ini = (int)std::round((float)L.reg_w / (float)L.reg_h);
+            if (L.n_ini < 1 || L.n_ini > kMaxRoots) { err = "unsupported aspect ratio (quadtree roots outside 1..8)"; return false; }
+            const float hX = (float)L.reg_w / (float)L.n_ini;
+            for (int i = 0; i < L.n_ini; i++) {
+                L.root_ulx[i] = (int)(hX * (float)i);
+                L.root_brx[i] = (int)(hX * (float)(i + 1));
+            }
+            int d0 = 6;
+            while (d0 > 1 && (L.n_ini << (2 * d0)) > kMaxBins) d0--;
+            L.depth0 = d0;
+            L.nbins = L.n_ini << (2 * d0);
+            L.xbin.assign(L.reg_w, 0); L.ybin.assign(L.reg_h, 0);
+            L.xord.assign(L.reg_w, 0); L.yord.assign(L.reg_h, 0);
+            for (int x = 0; x < L.reg_w; x++) {
+                int r = (int)((float)x / hX);
+                if (r >= L.n_ini) r = L.n_ini - 1;   // cannot happen for key coordinates (x <= reg_w - 4)
+                int ul = L.root_ulx[r], br = L.root_brx[r];
+                uint32_t path = 0;
+                for (int d = 0; d < d0; d++) {
+                    const int half = (int)std::ceil((float)(br - ul) / 2);
+                    const int mx = ul + half;
+                    if (x < mx) { path = path << 1; br = mx; } else { path = (path << 1) | 1u; ul = mx; }
+                }
+                L.xbin[x] = ((uint32_t)r << (2 * d0)) | spread_bits(path);
+            }
+            for (int y = 0; y < L.reg_h; y++) {
+                int ul = 0, br = L.reg_h;
+                uint32_t path = 0;
+                for (int d = 0; d < d0; d++) {
+                    const int half = (int)std::ceil((float)(br - ul) / 2);
+                    const int my = ul + half;
+                    if (y < my) { path = path << 1; br = my; } else { path = (path << 1) | 1u; ul = my; }
+                }
+                L.ybin[y] = spread_bits(path) << 1;
+            }
+            if (L.ncols > 0 && L.nrows > 0) {
+                const uint32_t area = (uint32_t)L.wcell * (uint32_t)L.hcell;
+                L.ord_cell_area = area; L.ord_ncols = (uint32_t)L.ncols;
+                if ((uint64_t)area * (uint64_t)L.ncols * (uint64_t)L.nrows >= (1u << 24)) { err = "frame too large for the 24-bit order key"; return false; }
+                for (int x = 0; x < L.reg_w; x++) {
+                    int xi = x - 3; if (xi < 0) xi = 0;
+                    int j = xi / L.wcell; if (j > L.ncols - 1) j = L.ncols - 1;
+                    L.xord[x] = (uint32_t)j * area + (uint32_t)(xi - j * L.wcell);
+                }
+                for (int y = 0; y < L.reg_h; y++) {
+                    int yi = y - 3; if (yi < 0) yi = 0;
+                    int i = yi / L.hcell; if (i > L.nrows - 1) i = L.nrows - 1;
+                    L.yord[y] = (uint32_t)i * (uint32_t)L.ncols * area + (uint32_t)(yi - i * L.hcell) * (uint32_t)L.wcell;
+                }
+            }
+        }
+        const int minout = 4 * (L.n_ini > 0 ? L.n_ini : 1);
+        L.out_cap = (L.quota + 3 > minout ? L.quota + 3 : minout);
+        plan.total_out_cap += L.out_cap;
+    }
+    return true;
+}
+
+size_t Plan::algorithmic_bytes(int nkeypoints) const {
+    size_t S = 0;
+    for (const auto &L : lv) S += (size_t)L.w * L.h;
+    const size_t P0 = (size_t)lv.front().w * lv.front().h, PL = (size_t)lv.back().w * lv.back().h;
+    return 5 * S - P0 - PL + (size_t)1321 * (size_t)nkeypoints;
+}
+
+}  // namespace orbx

@@ -1,0 +1,398 @@
+"""Host-side mirror of the reference's operator interface for the ORB hot path, on top of the C ABI (include/orbx.h).
+
+`ORBextractor` / `ORBmatcher` keep the names, argument meaning and error behaviour of UPSTREAM ORB-SLAM3
+include/ORBextractor.h / include/ORBmatcher.h (the classes the reference builds from src/ORBextractor.cc and
+src/ORBmatcher.cc, slam_backends/orb_slam_3/CMakeLists.txt:52-53,80-81, and drives from
+orbslam3_mono_networked.cc:594).  Everything that computes goes through liborbx.so (hand-written CUDA, sm_100a);
+there is no CPU fallback: importing works without a GPU, constructing an extractor without one raises OrbxError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liborbx.so")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])  # == cv::KeyPoint == orbx_keypoint
+
+ORBX_OK, ORBX_E_INVALID, ORBX_E_CUDA, ORBX_E_CAPACITY, ORBX_E_EMPTY, ORBX_E_OVERFLOW = 0, -1, -2, -3, -4, -5
+
+
+class OrbxError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"orbx error {code}: {msg}")
+        self.code = code
+
+
+class _Config(C.Structure):
+    _fields_ = [("nfeatures", C.c_int), ("scale_factor", C.c_float), ("nlevels", C.c_int), ("ini_th_fast", C.c_int),
+                ("min_th_fast", C.c_int), ("device", C.c_int), ("max_width", C.c_int), ("max_height", C.c_int),
+                ("max_batch", C.c_int)]
+
+
+# every symbol include/orbx.h declares (tests check the library exports all of them)
+EXPORTS = [
+    "orbx_create", "orbx_destroy", "orbx_last_error", "orbx_keypoint_capacity", "orbx_get_tables", "orbx_get_level_sizes",
+    "orbx_extract", "orbx_extract_batch", "orbx_extract_batch_device", "orbx_sync", "orbx_launch_count",
+    "orbx_debug_get_level", "orbx_debug_get_candidates", "orbx_debug_get_level_keypoints", "orbx_debug_resize",
+    "orbx_debug_blur", "orbx_debug_octree", "orbx_debug_describe", "orbx_distance_batch", "orbx_match_windowed",
+    "orbx_knn2_create_db", "orbx_knn2_create_db_device", "orbx_knn2_destroy_db", "orbx_knn2_last_error", "orbx_knn2_query",
+    "orbx_knn2_query_device", "orbx_knn2_merge_device", "orbx_knn2_sync", "orbx_knn2_launch_count", "orbx_plan_probe",
+    "orbx_version",
+]
+
+_lib = None
+
+
+def lib():
+    """Loads liborbx.so (built in-tree by __graft_entry__.build()); fails loudly if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        raise OrbxError(ORBX_E_CUDA, f"{_SO} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                     "(there is no CPU fallback)")
+    L = C.CDLL(_SO)
+    vp, ip, fp = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float)
+    L.orbx_create.argtypes = [C.POINTER(_Config), C.POINTER(vp)]
+    L.orbx_destroy.argtypes = [vp]
+    L.orbx_destroy.restype = None
+    L.orbx_last_error.argtypes = [vp]
+    L.orbx_last_error.restype = C.c_char_p
+    L.orbx_keypoint_capacity.argtypes = [vp]
+    L.orbx_get_tables.argtypes = [vp, fp, fp, fp, fp, ip]
+    L.orbx_get_level_sizes.argtypes = [vp, C.c_int, C.c_int, ip, ip]
+    L.orbx_extract.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, ip, ip]
+    L.orbx_extract_batch.argtypes = [vp, C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp,
+                                     C.c_int, vp, vp]
+    L.orbx_extract_batch_device.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp,
+                                            vp, C.c_int, vp, vp]
+    L.orbx_sync.argtypes = [vp]
+    L.orbx_launch_count.argtypes = [vp]
+    L.orbx_launch_count.restype = C.c_longlong
+    L.orbx_debug_get_level.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, ip, ip]
+    L.orbx_debug_get_candidates.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, ip]
+    L.orbx_debug_get_level_keypoints.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, ip]
+    L.orbx_debug_resize.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int]
+    L.orbx_debug_blur.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int]
+    L.orbx_debug_octree.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, ip]
+    L.orbx_debug_describe.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp]
+    L.orbx_distance_batch.argtypes = [vp, vp, vp, C.c_int, vp]
+    L.orbx_match_windowed.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp, vp]
+    L.orbx_knn2_create_db.argtypes = [C.c_int, vp, C.c_longlong, C.c_longlong, C.POINTER(vp)]
+    L.orbx_knn2_create_db_device.argtypes = [C.c_int, vp, C.c_longlong, C.c_longlong, C.POINTER(vp)]
+    L.orbx_knn2_destroy_db.argtypes = [vp]
+    L.orbx_knn2_destroy_db.restype = None
+    L.orbx_knn2_last_error.argtypes = [vp]
+    L.orbx_knn2_last_error.restype = C.c_char_p
+    L.orbx_knn2_query.argtypes = [vp, vp, C.c_int, vp, vp]
+    L.orbx_knn2_query_device.argtypes = [vp, vp, C.c_int, vp]
+    L.orbx_knn2_merge_device.argtypes = [vp, vp, C.c_int, C.c_int, vp]
+    L.orbx_knn2_sync.argtypes = [vp]
+    L.orbx_knn2_launch_count.argtypes = [vp]
+    L.orbx_knn2_launch_count.restype = C.c_longlong
+    L.orbx_plan_probe.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, ip, ip, ip, ip, ip, ip,
+                                  C.POINTER(C.c_longlong)]
+    L.orbx_version.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def plan_probe(nfeatures, scale_factor, nlevels, ini_th, min_th, width, height):
+    """Geometry plan of the library for one frame size; needs no GPU."""
+    L = lib()
+    arrs = [np.zeros(nlevels, np.int32) for _ in range(6)]
+    ab = C.c_longlong()
+    ip = C.POINTER(C.c_int)
+    rc = L.orbx_plan_probe(nfeatures, scale_factor, nlevels, ini_th, min_th, width, height,
+                           *[a.ctypes.data_as(ip) for a in arrs], C.byref(ab))
+    if rc < 0:
+        raise OrbxError(rc, (L.orbx_last_error(None) or b"").decode())
+    keys = ["widths", "heights", "ncells", "quota", "n_ini", "depth0"]
+    out = dict(zip(keys, arrs))
+    out["algorithmic_bytes"] = ab.value
+    return out
+
+
+class ORBextractor:
+    """ORB_SLAM3::ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST) on one B200.
+
+    Extra keyword arguments size the GPU workspace (device ordinal, largest frame, frames per batch call)."""
+
+    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, *, device=0, max_width=1920,
+                 max_height=1080, max_batch=1):
+        self._L = lib()
+        self._h = C.c_void_p()
+        cfg = _Config(int(nfeatures), float(scaleFactor), int(nlevels), int(iniThFAST), int(minThFAST), int(device),
+                      int(max_width), int(max_height), int(max_batch))
+        rc = self._L.orbx_create(C.byref(cfg), C.byref(self._h))
+        if rc != ORBX_OK:
+            raise OrbxError(rc, (self._L.orbx_last_error(None) or b"").decode())
+        self.nfeatures, self.nlevels, self.max_batch, self.device = int(nfeatures), int(nlevels), int(max_batch), int(device)
+        n = self.nlevels
+        self._scale, self._inv, self._s2, self._is2 = (np.zeros(n, np.float32) for _ in range(4))
+        self._quota = np.zeros(n, np.int32)
+        fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int)
+        self._L.orbx_get_tables(self._h, self._scale.ctypes.data_as(fp), self._inv.ctypes.data_as(fp),
+                                self._s2.ctypes.data_as(fp), self._is2.ctypes.data_as(fp), self._quota.ctypes.data_as(ip))
+        self.capacity = int(self._L.orbx_keypoint_capacity(self._h))
+        self.mvImagePyramid = []  # as in the shim: left empty for mono (only stereo matching reads it)
+
+    # -- lifecycle
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.orbx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != ORBX_OK:
+            raise OrbxError(rc, (self._L.orbx_last_error(self._h) or b"").decode())
+
+    # -- getters of include/ORBextractor.h
+    def GetLevels(self):
+        return self.nlevels
+
+    def GetScaleFactor(self):
+        return float(self._scale[1]) if self.nlevels > 1 else 1.0
+
+    def GetScaleFactors(self):
+        return self._scale.copy()
+
+    def GetInverseScaleFactors(self):
+        return self._inv.copy()
+
+    def GetScaleSigmaSquares(self):
+        return self._s2.copy()
+
+    def GetInverseScaleSigmaSquares(self):
+        return self._is2.copy()
+
+    def features_per_level(self):
+        return self._quota.copy()
+
+    def level_sizes(self, width, height):
+        w, h = np.zeros(self.nlevels, np.int32), np.zeros(self.nlevels, np.int32)
+        ip = C.POINTER(C.c_int)
+        self._L.orbx_get_level_sizes(self._h, width, height, w.ctypes.data_as(ip), h.ctypes.data_as(ip))
+        return list(zip(w.tolist(), h.tolist()))
+
+    # -- operator()
+    def __call__(self, image, mask=None, vLappingArea=(0, 1000)):
+        """Returns (monoIndex, keypoints, descriptors).  Empty image: (-1, empty, empty) like the reference."""
+        if image is None or image.size == 0:
+            return -1, np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8)
+        if image.dtype != np.uint8 or image.ndim != 2:
+            raise OrbxError(ORBX_E_INVALID, "image must be CV_8UC1 (the reference asserts image.type() == CV_8UC1)")
+        if image.strides[1] != 1:
+            image = np.ascontiguousarray(image)
+        h, w = image.shape
+        kps = np.zeros(self.capacity, KP_DTYPE)
+        desc = np.zeros((self.capacity, 32), np.uint8)
+        n, mono = C.c_int(), C.c_int()
+        rc = self._L.orbx_extract(self._h, _p(image), w, h, image.strides[0], int(vLappingArea[0]), int(vLappingArea[1]),
+                                  _p(kps), _p(desc), self.capacity, C.byref(n), C.byref(mono))
+        self._check(rc)
+        return mono.value, kps[:n.value].copy(), desc[:n.value].copy()
+
+    def extract_batch(self, frames, vLappingArea=(0, 1000)):
+        """frames: uint8 [B,H,W] (C-contiguous rows).  Returns (mono[B], n[B], kps[B,cap], desc[B,cap,32])."""
+        frames = np.asarray(frames)
+        if frames.dtype != np.uint8 or frames.ndim != 3:
+            raise OrbxError(ORBX_E_INVALID, "frames must be uint8 [B,H,W]")
+        if frames.strides[2] != 1:
+            frames = np.ascontiguousarray(frames)
+        B, h, w = frames.shape
+        ptrs = (C.c_void_p * B)(*[frames[i].ctypes.data for i in range(B)])
+        kps = np.zeros((B, self.capacity), KP_DTYPE)
+        desc = np.zeros((B, self.capacity, 32), np.uint8)
+        n, mono = np.zeros(B, np.int32), np.zeros(B, np.int32)
+        rc = self._L.orbx_extract_batch(self._h, ptrs, B, w, h, frames.strides[1], int(vLappingArea[0]),
+                                        int(vLappingArea[1]), _p(kps), _p(desc), self.capacity, _p(n), _p(mono))
+        self._check(rc)
+        return mono, n, kps, desc
+
+    def extract_batch_device(self, d_frames_ptr, frame_stride, batch, width, height, stride, d_kp_ptr, d_desc_ptr, cap,
+                             d_n_ptr, d_mono_ptr, vLappingArea=(0, 1000)):
+        """Device-resident batch: raw device pointers (e.g. torch.Tensor.data_ptr()); asynchronous, see sync()."""
+        rc = self._L.orbx_extract_batch_device(self._h, C.c_void_p(d_frames_ptr), frame_stride, batch, width, height, stride,
+                                               int(vLappingArea[0]), int(vLappingArea[1]), C.c_void_p(d_kp_ptr),
+                                               C.c_void_p(d_desc_ptr), cap, C.c_void_p(d_n_ptr), C.c_void_p(d_mono_ptr))
+        self._check(rc)
+
+    def sync(self):
+        self._check(self._L.orbx_sync(self._h))
+
+    def launch_count(self):
+        return int(self._L.orbx_launch_count(self._h))
+
+    # -- stage inspection (parity tests)
+    def debug_level(self, frame, level, blurred=False):
+        """Pyramid plane (or its blurred copy) of a frame of the last extract call."""
+        w, h = C.c_int(), C.c_int()
+        tmp = np.zeros((4095, 4096), np.uint8)   # the library checks out_stride >= level width
+        rc = self._L.orbx_debug_get_level(self._h, frame, level, int(blurred), _p(tmp), 4096, C.byref(w), C.byref(h))
+        self._check(rc)
+        return tmp[:h.value, :w.value].copy()
+
+    def debug_candidates(self, frame, level, cap=1 << 20):
+        out = np.zeros((cap, 3), np.float32)
+        n = C.c_int()
+        self._check(self._L.orbx_debug_get_candidates(self._h, frame, level, _p(out), cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    def debug_level_keypoints(self, frame, level, cap=1 << 16):
+        out = np.zeros((cap, 4), np.float32)
+        n = C.c_int()
+        self._check(self._L.orbx_debug_get_level_keypoints(self._h, frame, level, _p(out), cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    def debug_resize(self, src, dw, dh):
+        src = np.ascontiguousarray(src, np.uint8)
+        dst = np.zeros((dh, dw), np.uint8)
+        self._check(self._L.orbx_debug_resize(self._h, _p(src), src.shape[1], src.shape[0], src.shape[1], _p(dst), dw, dh, dw))
+        return dst
+
+    def debug_blur(self, src):
+        src = np.ascontiguousarray(src, np.uint8)
+        dst = np.zeros_like(src)
+        self._check(self._L.orbx_debug_blur(self._h, _p(src), src.shape[1], src.shape[0], src.shape[1], _p(dst), src.shape[1]))
+        return dst
+
+    def debug_octree(self, keys, minX, maxX, minY, maxY, N):
+        keys = np.ascontiguousarray(keys, np.float32).reshape(-1, 3)
+        out = np.zeros(max(len(keys), 64), np.int32)
+        n = C.c_int()
+        self._check(self._L.orbx_debug_octree(self._h, _p(keys), len(keys), minX, maxX, minY, maxY, N, _p(out), len(out), C.byref(n)))
+        return out[:n.value].copy()
+
+    def debug_describe(self, img, blurred, xy, angles=None):
+        ref = img if img is not None else blurred
+        h, w = ref.shape
+        img_c = None if img is None else np.ascontiguousarray(img, np.uint8)
+        bl_c = None if blurred is None else np.ascontiguousarray(blurred, np.uint8)
+        xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+        n = len(xy)
+        ang_in = None if angles is None else np.ascontiguousarray(angles, np.float32)
+        ang_out = np.zeros(n, np.float32)
+        desc = np.zeros((n, 32), np.uint8)
+        self._check(self._L.orbx_debug_describe(self._h, _p(img_c), _p(bl_c), w, h, w, _p(xy), n, _p(ang_in), _p(ang_out), _p(desc)))
+        return ang_out, desc
+
+    # -- matching entry points that live on the extractor handle
+    def distance_batch(self, a, b):
+        a = np.ascontiguousarray(a, np.uint8).reshape(-1, 32)
+        b = np.ascontiguousarray(b, np.uint8).reshape(-1, 32)
+        if a.shape != b.shape:
+            raise OrbxError(ORBX_E_INVALID, "descriptor arrays differ in shape")
+        out = np.zeros(len(a), np.int32)
+        self._check(self._L.orbx_distance_batch(self._h, _p(a), _p(b), len(a), _p(out)))
+        return out
+
+    def match_windowed(self, q_desc, q_uvr, q_levels, t_kp, t_desc, bounds):
+        q_desc = np.ascontiguousarray(q_desc, np.uint8).reshape(-1, 32)
+        q_uvr = np.ascontiguousarray(q_uvr, np.float32).reshape(-1, 3)
+        q_levels = np.ascontiguousarray(q_levels, np.int32).reshape(-1, 2)
+        t_kp = np.ascontiguousarray(t_kp, KP_DTYPE)
+        t_desc = np.ascontiguousarray(t_desc, np.uint8).reshape(-1, 32)
+        bounds = np.ascontiguousarray(bounds, np.float32)
+        nq = len(q_desc)
+        outs = [np.zeros(nq, np.int32) for _ in range(4)]
+        self._check(self._L.orbx_match_windowed(self._h, _p(q_desc), _p(q_uvr), _p(q_levels), nq, _p(t_kp), _p(t_desc), len(t_kp),
+                                                _p(bounds), *[_p(o) for o in outs]))
+        return tuple(outs)  # best_idx, best_dist, second_idx, second_dist
+
+
+class ORBmatcher:
+    """The arithmetic core of ORB_SLAM3::ORBmatcher: DescriptorDistance and the windowed candidate search.
+    TH_HIGH / TH_LOW / HISTO_LENGTH and the nnratio ctor argument are kept for the callers that gate on them."""
+    TH_HIGH, TH_LOW, HISTO_LENGTH = 100, 50, 30
+
+    def __init__(self, nnratio=0.6, checkOri=True, *, extractor: ORBextractor):
+        self.mfNNratio, self.mbCheckOrientation, self._ex = float(nnratio), bool(checkOri), extractor
+
+    def DescriptorDistance(self, a, b) -> int:
+        return int(self._ex.distance_batch(np.asarray(a).reshape(1, 32), np.asarray(b).reshape(1, 32))[0])
+
+    def DescriptorDistances(self, a, b):
+        return self._ex.distance_batch(a, b)
+
+    def SearchInWindows(self, q_desc, q_uvr, q_levels, t_kp, t_desc, bounds):
+        """GetFeaturesInArea + best / second-best per query (the loop body of SearchByProjection /
+        SearchForInitialization); thresholds, ratio test and rotation histogram stay with the caller."""
+        return self._ex.match_windowed(q_desc, q_uvr, q_levels, t_kp, t_desc, bounds)
+
+
+class Knn2Index:
+    """One row shard of a descriptor database resident in HBM: cv::BFMatcher(NORM_HAMMING).knnMatch(k=2)."""
+
+    def __init__(self, rows=None, *, device=0, row_offset=0, device_ptr=None, nrows=None):
+        self._L = lib()
+        self._db = C.c_void_p()
+        if device_ptr is not None:
+            rc = self._L.orbx_knn2_create_db_device(device, C.c_void_p(device_ptr), int(nrows), int(row_offset), C.byref(self._db))
+            self.nrows = int(nrows)
+        else:
+            rows = np.ascontiguousarray(rows, np.uint8).reshape(-1, 32)
+            rc = self._L.orbx_knn2_create_db(device, _p(rows), len(rows), int(row_offset), C.byref(self._db))
+            self.nrows = len(rows)
+        if rc != ORBX_OK:
+            raise OrbxError(rc, (self._L.orbx_knn2_last_error(None) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_db", None) and self._db.value:
+            self._L.orbx_knn2_destroy_db(self._db)
+            self._db = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != ORBX_OK:
+            raise OrbxError(rc, (self._L.orbx_knn2_last_error(self._db) or b"").decode())
+
+    def knnMatch(self, queries):
+        """Returns (idx [nq,2] int32 global rows, dist [nq,2] int32); -1 where the shard has fewer than 2 rows."""
+        q = np.ascontiguousarray(queries, np.uint8).reshape(-1, 32)
+        idx, dist = np.zeros((len(q), 2), np.int32), np.zeros((len(q), 2), np.int32)
+        self._check(self._L.orbx_knn2_query(self._db, _p(q), len(q), _p(idx), _p(dist)))
+        return idx, dist
+
+    def query_device(self, d_queries_ptr, nq, d_packed_out_ptr):
+        self._check(self._L.orbx_knn2_query_device(self._db, C.c_void_p(d_queries_ptr), nq, C.c_void_p(d_packed_out_ptr)))
+
+    def merge_device(self, d_partials_ptr, nparts, nq, d_packed_out_ptr):
+        self._check(self._L.orbx_knn2_merge_device(self._db, C.c_void_p(d_partials_ptr), nparts, nq, C.c_void_p(d_packed_out_ptr)))
+
+    def sync(self):
+        self._check(self._L.orbx_knn2_sync(self._db))
+
+    def launch_count(self):
+        return int(self._L.orbx_knn2_launch_count(self._db))
+
+
+def unpack_knn(packed: np.ndarray):
+    """(dist << 32 | row) uint64 [nq,2] -> (idx int64, dist int32), -1 where missing."""
+    packed = np.asarray(packed, np.uint64).reshape(-1, 2)
+    none = packed == np.uint64(0xFFFFFFFFFFFFFFFF)
+    idx = (packed & np.uint64(0xFFFFFFFF)).astype(np.int64)
+    dist = (packed >> np.uint64(32)).astype(np.int64).astype(np.int32)
+    idx[none] = -1
+    dist[none] = -1
+    return idx, dist
