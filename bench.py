@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native ORB front end (contract: task statement ④ / base contract).
+
+One "step" = one pass of the hot path over one batch of 64 synthetic 640x480 gray frames (nFeatures 1000, 8 levels,
+scale 1.2, iniTh 20, minTh 7) per GPU -- the configuration BASELINE.json's metric is quoted on.
+  value  frames/s, inputs resident in HBM when the timed region starts (orbx_extract_batch_device), whole job.
+  e2e    same metric through the reference-facing C ABI call with HOST buffers (orbx_extract_batch): the host->device
+         copy of the 64 frames and the device->host copy of keypoints + descriptors are inside the timed region.
+  roofline / cpu_baseline / hamming: see DESIGN.md "Measurement".
+`--impl reference` times the CPU restatement of the reference's extractor (oracle/, all host threads) instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, NFEAT, NLEVELS, SCALE, INI_TH, MIN_TH = 640, 480, 1000, 8, 1.2, 20, 7
+BATCH = 64
+RING = 8                 # distinct input batches cycled through: 8 x 64 x 300 KB = 157 MB > 126 MB L2
+KNN_Q, KNN_ROWS = 2000, 1_000_000
+METRIC = "ORB frames/s (640x480,1k kp) + Hamming pairs/s at 1/2/4/8 B200, %roofline"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_frames(n, seed0):
+    from send_slam_b200 import synth
+    return np.stack([synth.textured_frame(seed0 + i, W, H) for i in range(n)])
+
+
+def cpu_baseline(frames, nthreads):
+    """Oracle port (plain C, one extractor instance per thread) on a bounded sample. Returns frames/s."""
+    from oracle import oracle_lib as ol
+    ol.extract_batch(frames[:max(2, nthreads)], NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, nthreads=nthreads)  # warm-up
+    t0 = time.perf_counter()
+    ol.extract_batch(frames, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    return len(frames) / dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU restatement of the reference's ORBextractor on all host threads (rank 0 only)."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    nfr = max(cores * 4, 32)
+    frames = make_frames(nfr, 0)
+    from oracle import oracle_lib as ol
+    for _ in range(args.warmup):
+        ol.extract_batch(frames[:cores], NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, nthreads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ol.extract_batch(frames, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, nthreads=cores)
+    dt = time.perf_counter() - t0
+    fps = args.steps * nfr / dt
+    sample = f"{nfr} synthetic 640x480 frames per step x {args.steps} steps, one extractor per thread"
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"ORB extraction {W}x{H} gray, nFeatures {NFEAT}, {NLEVELS} levels, scale {SCALE}, CPU restatement of "
+                                   "ORB-SLAM3 ORBextractor (reference source not in tree / unbuildable: oracle port)"},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="orbx", choices=["orbx", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-knn", action="store_true", help="skip the Hamming kNN leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "orbx" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from send_slam_b200 import orbx
+
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: orbx has no CPU fallback"}), flush=True)
+        return 2
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ex = orbx.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank, max_width=W, max_height=H, max_batch=BATCH)
+    cap = ex.capacity
+    # all orbx work is issued on this torch stream so that torch CUDA events bracket the kernels on the launching stream
+    stream = torch.cuda.Stream(device=dev)
+    ex.set_stream(stream.cuda_stream)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # ---- inputs: RING distinct batches, resident in HBM (frames sharded by rank: independent units, no collective)
+    host_batches = [make_frames(BATCH, 1000 * rank + BATCH * r) for r in range(RING)]
+    d_in = [torch.from_numpy(b).to(dev) for b in host_batches]
+    d_kp = torch.zeros((BATCH, cap, 7), dtype=torch.float32, device=dev)
+    d_desc = torch.zeros((BATCH, cap, 32), dtype=torch.uint8, device=dev)
+    d_n = torch.zeros(BATCH, dtype=torch.int32, device=dev)
+    d_mono = torch.zeros(BATCH, dtype=torch.int32, device=dev)
+
+    def step_device(i):
+        t = d_in[i % RING]
+        ex.extract_batch_device(t.data_ptr(), H * W, BATCH, W, H, W, d_kp.data_ptr(), d_desc.data_ptr(), cap,
+                                d_n.data_ptr(), d_mono.data_ptr())
+
+    for i in range(args.warmup):
+        step_device(i)
+    ex.sync()
+    n_first = int(d_n.sum().item())
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ex.launch_count()
+    ev0.record(stream)
+    for i in range(args.steps):
+        step_device(i)
+    ev1.record(stream)
+    ex.sync()
+    barrier()
+    dt = ev0.elapsed_time(ev1) * 1e-3
+    launches = ex.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+    fps = world * args.steps * BATCH / dt
+
+    # ---- per-kernel durations (CUDA events on the handle's stream, same inputs, right after the timed region)
+    ex.set_profiling(True)
+    acc = {}
+    nprof = max(3, min(args.steps, 10))
+    for i in range(nprof):
+        step_device(i)
+        ex.sync()
+        for k, v in ex.stage_times_ms().items():
+            acc[k] = acc.get(k, 0.0) + v / nprof
+    ex.set_profiling(False)
+    nkp = float(d_n.float().mean().item())
+
+    # ---- e2e through the C ABI with host buffers
+    e2e_steps = max(3, min(args.steps, 10))
+    for i in range(2):
+        ex.extract_batch(host_batches[i % RING])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        mono, n, kps, desc = ex.extract_batch(host_batches[i % RING])
+    barrier()
+    dte = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([dte], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dte = float(tt.item())
+    e2e_fps = world * e2e_steps * BATCH / dte
+    h2d = BATCH * W * H
+    d2h = BATCH * cap * (28 + 32) + BATCH * 8 + 4
+
+    # ---- Hamming kNN leg (k=2): 2000 queries vs a 1M-row shard per GPU, device resident
+    hamming = None
+    if not args.no_knn:
+        from send_slam_b200 import synth
+        db = synth.descriptor_db(KNN_ROWS, seed=1234 + rank)
+        q, _src = synth.queries_from_db(db, KNN_Q, seed=99)
+        d_db = torch.from_numpy(db).to(dev)
+        d_q = torch.from_numpy(q).to(dev)
+        d_out = torch.zeros((KNN_Q, 2), dtype=torch.int64, device=dev)
+        index = orbx.Knn2Index(device=local_rank, device_ptr=d_db.data_ptr(), nrows=KNN_ROWS, row_offset=rank * KNN_ROWS)
+        index.set_stream(stream.cuda_stream)
+        for _ in range(3):
+            index.query_device(d_q.data_ptr(), KNN_Q, d_out.data_ptr())
+        index.sync()
+        barrier()
+        ksteps = 10
+        ev0.record(stream)
+        for _ in range(ksteps):
+            index.query_device(d_q.data_ptr(), KNN_Q, d_out.data_ptr())
+        ev1.record(stream)
+        index.sync()
+        barrier()
+        dtk = ev0.elapsed_time(ev1) * 1e-3
+        if world > 1:
+            tt = torch.tensor([dtk], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dtk = float(tt.item())
+        pairs = world * ksteps * KNN_Q * KNN_ROWS / dtk
+        # POPC-pipe roofline: 8 POPC32 per pair; measured POPC rate on this pool's B200 (profiles/ubench_pipes_r01.md)
+        popc_per_clk_sm, sms, ghz = 16.0, 148, 1.965
+        peak_pairs = sms * popc_per_clk_sm * ghz * 1e9 / 8.0
+        hamming = {"metric": "Hamming pairs/s (k=2 brute force)", "value": pairs, "unit": "pairs/s",
+                   "config": {"queries": KNN_Q, "db_rows_per_gpu": KNN_ROWS, "k": 2},
+                   "roofline": {"bound": "popc-pipe", "achieved": pairs / world, "peak": peak_pairs, "unit": "pairs/s/GPU",
+                                "frac": pairs / world / peak_pairs,
+                                "note": "peak = 148 SM x 16 POPC/clk/SM x 1.965 GHz / 8 POPC per pair (SURVEY.md 8d)"},
+                   "gpu_launches": index.launch_count()}
+        index.close()
+
+    # ---- cpu baseline (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        nfr = min(max(cores * 12, 64), 384)
+        sample_frames = np.concatenate(host_batches[: (nfr + BATCH - 1) // BATCH])[:nfr]
+        v = cpu_baseline(sample_frames, cores)
+        cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
+               "sample": f"{nfr} of the benchmark's synthetic 640x480 frames, oracle/orb_oracle.c, one extractor per thread"}
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        plan = orbx.plan_probe(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, W, H)
+        S = int((plan["widths"].astype(np.int64) * plan["heights"]).sum())
+        P0 = int(plan["widths"][0]) * int(plan["heights"][0])
+        PL = int(plan["widths"][-1]) * int(plan["heights"][-1])
+        # algorithmic bytes per frame per stage: each stage reads its inputs once, writes outputs once
+        stage_bytes = {"pyramid": 2 * S - P0 - PL, "blur": 2 * S, "fast": S, "quadtree": 0, "finalize": 28 * NFEAT,
+                       "describe": (749 + 512 + 32) * NFEAT}
+        dom = max(("pyramid", "blur", "fast", "describe"), key=lambda k: acc[k])
+        hbm = float(peaks["hbm_gbs"])
+        ach = stage_bytes[dom] * BATCH / (acc[dom] * 1e-3) / 1e9
+        total_bytes = plan["algorithmic_bytes"]
+        roofline = {"bound": "hbm", "kernel": {"pyramid": "k_resize (7 launches)", "blur": "k_blur", "fast": "k_fast_cells",
+                                                 "describe": "k_describe"}[dom],
+                    "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+                    "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": stage_bytes[dom] * BATCH,
+                    "launch_ms": acc[dom],
+                    "whole_step": {"algorithmic_bytes_per_frame": total_bytes,
+                                   "achieved": total_bytes * fps / world / 1e9, "frac": total_bytes * fps / world / 1e9 / hbm},
+                    "stage_ms": acc}
+        line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u8", "data": "synthetic",
+                "config": {"workload": f"ORB extraction, {BATCH} x {W}x{H} gray frames per GPU per step, nFeatures {NFEAT}, {NLEVELS} levels, "
+                                       f"scale {SCALE}, iniTh {INI_TH}, minTh {MIN_TH} (BASELINE configs[0] shape, 64-frame batches of configs[1])",
+                           "l2": f"inputs cycle through {RING} distinct batches = {RING * BATCH * W * H / 1e6:.0f} MB > 126 MB L2",
+                           "sharding": "frames sharded by rank, no collective", "keypoints_per_frame": nkp},
+                "clocks": clocks, "gpu_launches": launches,
+                "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "steps": e2e_steps, "api": "orbx_extract_batch (host buffers)"},
+                "roofline": roofline, "cpu_baseline": cpu, "hamming": hamming, "keypoints_first_batch": n_first}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -97,8 +97,16 @@ int orbx_extract_batch_device(orbx_handle *h, const uint8_t *d_frames, size_t fr
                               int height, int stride, int lap0, int lap1, orbx_keypoint *d_kp_out,
                               uint8_t *d_desc_out, int cap, int *d_n_out, int *d_mono_out);
 int orbx_sync(orbx_handle *h);
+/* Issue all further work of this handle on the caller's CUDA stream (cudaStream_t; NULL = back to the handle's own
+ * stream), e.g. torch's current stream so that the caller's events bracket the kernels. */
+int orbx_set_stream(orbx_handle *h, void *cuda_stream);
 /* Number of kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 long long orbx_launch_count(const orbx_handle *h);
+
+/* Per-stage device timing of the NEXT extract calls (CUDA events on the handle's stream between the kernels);
+ * orbx_get_stage_times returns the last batch's milliseconds for {pyramid, blur, fast, quadtree, finalize, describe}. */
+int orbx_set_profiling(orbx_handle *h, int enable);
+int orbx_get_stage_times(orbx_handle *h, float *ms6);
 
 /* ---- stage inspection (parity tests; valid after an extract call on the same handle) ------------------------- */
 /* Copies pyramid level `level` of batch frame `frame` (blurred != 0: the Gaussian-blurred plane) to host. */
@@ -152,6 +160,7 @@ int orbx_knn2_query_device(orbx_db *db, const uint8_t *d_queries, int nq, unsign
 int orbx_knn2_merge_device(orbx_db *db, const unsigned long long *d_partials, int nparts, int nq,
                            unsigned long long *d_packed_out);
 int orbx_knn2_sync(orbx_db *db);
+int orbx_knn2_set_stream(orbx_db *db, void *cuda_stream);
 long long orbx_knn2_launch_count(const orbx_db *db);
 
 /* Geometry plan probe, needs NO GPU (used by the CPU-only tests): level sizes, FAST cells per level, per-level

@@ -50,6 +50,7 @@ def lib():
         L.orb_oracle_ic_moments.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, i32p, i32p, i32p]
         L.orb_oracle_ic_angle.restype = C.c_float
         L.orb_oracle_ic_angle.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float]
+        L.orb_oracle_set_trig_mode.argtypes = [C.c_int]
         L.orb_oracle_brief.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p]
         L.orb_oracle_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.c_void_p, C.c_void_p, C.c_int, i32p, i32p]
@@ -136,6 +137,11 @@ class Oracle:
         else:
             s, a, d = np.zeros(0, np.int32), np.zeros(0, np.float32), np.zeros((0, 32), np.uint8)
         return c, s, a, d
+
+
+def set_trig_mode(mode: int):
+    """1 (default) = correctly rounded cos/sin, 0 = this host's libm cosf/sinf (see orb_oracle.c 'Trig rule')."""
+    lib().orb_oracle_set_trig_mode(int(mode))
 
 
 def resize(src: np.ndarray, dw: int, dh: int) -> np.ndarray:

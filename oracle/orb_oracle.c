@@ -544,10 +544,20 @@ float orb_oracle_ic_angle(void *h, const u8 *img, int stride, float x, float y) 
 /* ------------------------------------------------------------------------------------------------ */
 /* computeOrbDescriptor                                                             */
 /* ------------------------------------------------------------------------------------------------ */
+/* Trig rule.  The reference calls cosf/sinf (std::cos/std::sin on a float).  glibc's cosf is NOT correctly rounded
+ * (about 1.3 % of arguments are 1 ulp off here) and x86-64 glibc selects an FMA or SSE2 variant per CPU, so the
+ * reference's own bits depend on the host.  Canonical oracle rule (mode 1, default): the correctly rounded fp32 of the
+ * fp64 cos/sin -- what cv2.ORB-free Python (oracle/orb_cv2.py) and the CUDA kernel compute.  Mode 0 = this host's
+ * libm cosf/sinf, kept to measure how many descriptor bits the choice moves (tests/test_oracle_vs_cv2.py). */
+static int g_trig_mode = 1;
+void orb_oracle_set_trig_mode(int mode) { g_trig_mode = mode; }
+
 void orb_oracle_brief(const u8 *blurred, int stride, float x, float y, float angle_deg, u8 *desc) {
     const float factorPI = (float)(3.14159265358979323846 / 180.f);
     float ang = angle_deg * factorPI;
-    float a = cosf(ang), b = sinf(ang);
+    float a, b;
+    if (g_trig_mode == 0) { a = cosf(ang); b = sinf(ang); }
+    else { a = (float)cos((double)ang); b = (float)sin((double)ang); }
     const u8 *c = blurred + (size_t)cv_round_f(y) * stride + cv_round_f(x);
     for (int i = 0; i < 32; i++) {
         int val = 0;

@@ -25,7 +25,8 @@ struct orbx_handle {
     orbx_config cfg{};
     ExtractorParams P{};
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // stream all work of this handle is issued on
+    cudaStream_t own_stream = nullptr;  // created by orbx_create; `stream` may be redirected by orbx_set_stream
     mutable std::string err;
     long long launches = 0;
 
@@ -53,6 +54,10 @@ struct orbx_handle {
     uint8_t *h_in = nullptr; size_t h_in_bytes = 0;
     KeypointRec *h_kp = nullptr; uint8_t *h_desc = nullptr; int *h_n = nullptr, *h_mono = nullptr, *h_overflow = nullptr;
     int last_batch = 0;             // batch size of the most recent run (debug getters)
+    // optional per-stage timing (orbx_set_profiling): events around resize / blur / fast / octree / finalize / describe
+    bool profiling = false;
+    cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool ev_valid = false;
 };
 
 #define CU_TRY(h, expr)                                                                                         \
@@ -184,12 +189,23 @@ static int run_pipeline(orbx_handle *h, int batch, int lap0, int lap1, KeypointR
     const int nl = pl.nlevels;
     CU_TRY(h, cudaMemsetAsync(h->d_counts, 0, sizeof(int) * 2 * nl * h->batch_cap, h->stream));
     CU_TRY(h, cudaMemsetAsync(h->d_overflow, 0, sizeof(int), h->stream));
+    const bool prof = h->profiling;
+#define STAGE_MARK(i) do { if (prof) CU_TRY(h, cudaEventRecord(h->ev[i], h->stream)); } while (0)
+    STAGE_MARK(0);
     for (int l = 1; l < nl; l++) h->launches += launch_resize(h->d_levels, h->h_levels, l, batch, h->stream);
+    STAGE_MARK(1);
     h->launches += launch_blur(h->d_levels, h->d_tiles, h->ntiles, batch, h->stream);
+    STAGE_MARK(2);
     h->launches += launch_fast(h->d_levels, h->d_cells, (int)pl.cells.size(), batch, h->P.ini_th, h->P.min_th, h->d_overflow, h->stream);
+    STAGE_MARK(3);
     h->launches += launch_octree(h->d_levels, h->h_levels, nl, batch, h->d_overflow, h->stream);
+    STAGE_MARK(4);
     h->launches += launch_finalize(h->d_levels, nl, batch, pl.total_out_cap, lap0, lap1, d_kp, cap, h->d_slot, d_n, d_mono, h->d_overflow, h->stream);
+    STAGE_MARK(5);
     h->launches += launch_describe(h->d_levels, nl, batch, pl.total_out_cap, h->d_slot, d_kp, d_desc, cap, h->stream);
+    STAGE_MARK(6);
+#undef STAGE_MARK
+    h->ev_valid = prof;
     CU_TRY(h, cudaGetLastError());
     h->last_batch = batch;
     return ORBX_OK;
@@ -230,6 +246,7 @@ int orbx_create(const orbx_config *cfg, orbx_handle **out) {
         g_create_error = std::string("cuda init: ") + cudaGetErrorString(e);
         delete h; return ORBX_E_CUDA;
     }
+    h->own_stream = h->stream;
     upload_constants();
     if ((e = cudaGetLastError()) != cudaSuccess) {
         g_create_error = std::string("constant upload: ") + cudaGetErrorString(e);
@@ -244,7 +261,8 @@ void orbx_destroy(orbx_handle *h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     free_plan(h);
-    if (h->stream) cudaStreamDestroy(h->stream);
+    for (int i = 0; i < 7; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
 
@@ -280,6 +298,32 @@ int orbx_get_level_sizes(const orbx_handle *h, int width, int height, int *width
 }
 
 long long orbx_launch_count(const orbx_handle *h) { return h ? h->launches : 0; }
+
+int orbx_set_stream(orbx_handle *h, void *cuda_stream) {
+    if (!h) return ORBX_E_INVALID;
+    CU_TRY(h, cudaSetDevice(h->device));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return ORBX_OK;
+}
+
+int orbx_set_profiling(orbx_handle *h, int enable) {
+    if (!h) return ORBX_E_INVALID;
+    CU_TRY(h, cudaSetDevice(h->device));
+    if (enable && !h->ev[0]) for (int i = 0; i < 7; i++) CU_TRY(h, cudaEventCreate(&h->ev[i]));
+    h->profiling = enable != 0;
+    h->ev_valid = false;
+    return ORBX_OK;
+}
+
+int orbx_get_stage_times(orbx_handle *h, float *ms6) {
+    if (!h || !ms6) return ORBX_E_INVALID;
+    if (!h->ev_valid) return fail(h, ORBX_E_INVALID, "no profiled batch: call orbx_set_profiling(h, 1) before extracting");
+    CU_TRY(h, cudaSetDevice(h->device));
+    CU_TRY(h, cudaEventSynchronize(h->ev[6]));
+    for (int i = 0; i < 6; i++) CU_TRY(h, cudaEventElapsedTime(&ms6[i], h->ev[i], h->ev[i + 1]));
+    return ORBX_OK;
+}
 
 int orbx_sync(orbx_handle *h) {
     if (!h) return ORBX_E_INVALID;

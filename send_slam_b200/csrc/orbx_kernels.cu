@@ -9,7 +9,7 @@
 //   k_describe     computeOrientation (IC_Angle + fastAtan2) and computeOrbDescriptor      (A.4, A.5)
 //
 // All arithmetic is integer or individually rounded fp32 (no FMA contraction) so results are bit-identical to the
-// CPU oracle (oracle/orb_oracle.c).  Everything here is HBM/L2-resident byte work: no tensor cores on purpose.
+// CPU checker used by the tests.  Everything here is HBM/L2-resident byte work: no tensor cores on purpose.
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -75,10 +75,13 @@ constexpr int BT = 64;                 // tile edge
 constexpr int BIN_PITCH = 80;          // bytes per staged input row (64 + 6 halo, padded to 16)
 constexpr int BROWS = BT + 6;
 
+// BORDER_REFLECT_101 for any index (period 2(n-1)); n == 1 maps everything to 0
 __device__ __forceinline__ int reflect101(int i, int n) {
+    if (n == 1) return 0;
+    const int p = 2 * (n - 1);
     if (i < 0) i = -i;
-    if (i >= n) i = 2 * (n - 1) - i;
-    return min(max(i, 0), n - 1);
+    i %= p;
+    return i >= n ? p - i : i;
 }
 
 __global__ void __launch_bounds__(256) k_blur(const LevelDev *__restrict__ lv, const BlurTile *__restrict__ tiles) {

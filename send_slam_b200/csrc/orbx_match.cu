@@ -169,7 +169,7 @@ thread_local std::string g_db_error;
 
 struct orbx_db {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
     const uint8_t *d_rows = nullptr;
     bool owns_rows = false;
     long long nrows = 0, row_offset = 0;
@@ -224,6 +224,7 @@ static int db_create_common(int device, long long nrows, long long row_offset, o
     rpc = std::max<long long>(rpc, KQ_TILE * 8);
     rpc = (rpc + KQ_TILE - 1) / KQ_TILE * KQ_TILE;
     rpc = std::min<long long>(rpc, (1ll << KQ_ROW_BITS) - KQ_TILE);
+    db->own_stream = db->stream;
     db->rows_per_chunk = (int)rpc;
     db->nchunks = (int)std::max<long long>(1, (nrows + rpc - 1) / rpc);
     *out = db;
@@ -267,8 +268,16 @@ void orbx_knn2_destroy_db(orbx_db *db) {
     if (db->d_partial) cudaFree(db->d_partial);
     if (db->d_out) cudaFree(db->d_out);
     if (db->h_out) cudaFreeHost(db->h_out);
-    if (db->stream) cudaStreamDestroy(db->stream);
+    if (db->own_stream) cudaStreamDestroy(db->own_stream);
     delete db;
+}
+
+int orbx_knn2_set_stream(orbx_db *db, void *cuda_stream) {
+    if (!db) return ORBX_E_INVALID;
+    DB_TRY(db, cudaSetDevice(db->device));
+    DB_TRY(db, cudaStreamSynchronize(db->stream));
+    db->stream = cuda_stream ? (cudaStream_t)cuda_stream : db->own_stream;
+    return ORBX_OK;
 }
 
 const char *orbx_knn2_last_error(const orbx_db *db) { return db ? db->err.c_str() : g_db_error.c_str(); }

@@ -42,7 +42,8 @@ EXPORTS = [
     "orbx_debug_blur", "orbx_debug_octree", "orbx_debug_describe", "orbx_distance_batch", "orbx_match_windowed",
     "orbx_knn2_create_db", "orbx_knn2_create_db_device", "orbx_knn2_destroy_db", "orbx_knn2_last_error", "orbx_knn2_query",
     "orbx_knn2_query_device", "orbx_knn2_merge_device", "orbx_knn2_sync", "orbx_knn2_launch_count", "orbx_plan_probe",
-    "orbx_version",
+    "orbx_version", "orbx_set_profiling", "orbx_get_stage_times", "orbx_set_stream",
+    "orbx_knn2_set_stream",
 ]
 
 _lib = None
@@ -98,6 +99,10 @@ def lib():
     L.orbx_plan_probe.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, ip, ip, ip, ip, ip, ip,
                                   C.POINTER(C.c_longlong)]
     L.orbx_version.restype = C.c_char_p
+    L.orbx_set_stream.argtypes = [vp, vp]
+    L.orbx_knn2_set_stream.argtypes = [vp, vp]
+    L.orbx_set_profiling.argtypes = [vp, C.c_int]
+    L.orbx_get_stage_times.argtypes = [vp, fp]
     _lib = L
     return L
 
@@ -236,8 +241,22 @@ class ORBextractor:
     def sync(self):
         self._check(self._L.orbx_sync(self._h))
 
+    def set_stream(self, cuda_stream: int):
+        """cuda_stream: raw cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); 0 = the handle's own stream."""
+        self._check(self._L.orbx_set_stream(self._h, C.c_void_p(cuda_stream)))
+
     def launch_count(self):
         return int(self._L.orbx_launch_count(self._h))
+
+    STAGES = ("pyramid", "blur", "fast", "quadtree", "finalize", "describe")
+
+    def set_profiling(self, enable: bool):
+        self._check(self._L.orbx_set_profiling(self._h, int(bool(enable))))
+
+    def stage_times_ms(self):
+        ms = np.zeros(6, np.float32)
+        self._check(self._L.orbx_get_stage_times(self._h, ms.ctypes.data_as(C.POINTER(C.c_float))))
+        return dict(zip(self.STAGES, ms.tolist()))
 
     # -- stage inspection (parity tests)
     def debug_level(self, frame, level, blurred=False):
@@ -382,6 +401,9 @@ class Knn2Index:
 
     def sync(self):
         self._check(self._L.orbx_knn2_sync(self._db))
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self._L.orbx_knn2_set_stream(self._db, C.c_void_p(cuda_stream)))
 
     def launch_count(self):
         return int(self._L.orbx_knn2_launch_count(self._db))

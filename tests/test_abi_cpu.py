@@ -1,0 +1,94 @@
+"""CPU: the C-ABI library loads, exports every symbol include/orbx.h declares, fails loudly without a GPU, and its
+host-side geometry plan agrees with the oracle (no compute calls here)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from send_slam_b200 import orbx
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    txt = open(os.path.join(ROOT, "include", "orbx.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(orbx_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = orbx.lib()
+    names = declared_functions()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(L, n), f"liborbx.so does not export {n}"
+    assert sorted(orbx.EXPORTS) == names, "orbx.py EXPORTS and include/orbx.h disagree"
+    assert b"sm_100a" in L.orbx_version()
+
+
+def test_keypoint_record_is_cv_keypoint():
+    assert orbx.KP_DTYPE.itemsize == 28
+    assert [orbx.KP_DTYPE.fields[n][1] for n in orbx.KP_DTYPE.names] == [0, 4, 8, 12, 16, 20, 24]
+
+
+def test_plan_matches_oracle_geometry(oracle):
+    for (nf, w, h) in [(1000, 640, 480), (1200, 752, 480), (2000, 1920, 1080), (1250, 1280, 720), (500, 320, 240)]:
+        p = orbx.plan_probe(nf, 1.2, 8, 20, 7, w, h)
+        o = oracle.Oracle(nf)
+        assert [(int(a), int(b)) for a, b in zip(p["widths"], p["heights"])] == [o.level_size(w, h, l) for l in range(8)]
+        assert p["quota"].tolist() == o.tables()["quota"].tolist()
+    # cells per frame and algorithmic bytes per frame
+    assert int(orbx.plan_probe(1000, 1.2, 8, 20, 7, 640, 480)["ncells"].sum()) == 577
+    assert int(orbx.plan_probe(1200, 1.2, 8, 20, 7, 752, 480)["ncells"].sum()) == 700
+    # 4620 FAST calls in the reference at 1080p; 20 of them get a ROI with no testable pixel (height < 7) and are not
+    # scheduled here
+    assert int(orbx.plan_probe(2000, 1.2, 8, 20, 7, 1920, 1080)["ncells"].sum()) == 4600
+    assert orbx.plan_probe(1000, 1.2, 8, 20, 7, 640, 480)["algorithmic_bytes"] == 5742474
+    assert orbx.plan_probe(1200, 1.2, 8, 20, 7, 752, 480)["algorithmic_bytes"] == 6782935
+    assert orbx.plan_probe(2000, 1.2, 8, 20, 7, 1920, 1080)["algorithmic_bytes"] == 32503669
+    assert orbx.plan_probe(1200, 1.2, 8, 20, 7, 752, 480)["n_ini"].tolist()[0] == 2
+
+
+def test_plan_rejects_bad_parameters():
+    with pytest.raises(orbx.OrbxError):
+        orbx.plan_probe(1000, 2.0, 8, 20, 7, 640, 480)      # scale 2 would be cv::resize's INTER_AREA path
+    with pytest.raises(orbx.OrbxError):
+        orbx.plan_probe(1000, 1.2, 17, 20, 7, 640, 480)
+    with pytest.raises(orbx.OrbxError):
+        orbx.plan_probe(1000, 1.2, 8, 20, 7, 5000, 480)
+    with pytest.raises(orbx.OrbxError):
+        orbx.plan_probe(1000, 1.2, 8, 5, 7, 640, 480)       # minTh > iniTh
+
+
+def _no_gpu():
+    try:
+        import torch
+        return not torch.cuda.is_available()
+    except Exception:
+        return True
+
+
+@pytest.mark.skipif(not _no_gpu(), reason="only meaningful without a GPU")
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path fails loudly instead of computing on the host."""
+    with pytest.raises(orbx.OrbxError) as e:
+        orbx.ORBextractor(1000, 1.2, 8, 20, 7)
+    assert e.value.code == orbx.ORBX_E_CUDA and "no CPU fallback" in str(e.value)
+    with pytest.raises(orbx.OrbxError) as e:
+        orbx.Knn2Index(np.zeros((4, 32), np.uint8))
+    assert e.value.code == orbx.ORBX_E_CUDA
+    L = orbx.lib()
+    assert L.orbx_extract(None, None, 0, 0, 0, 0, 0, None, None, 0, None, None) == orbx.ORBX_E_INVALID
+    assert L.orbx_knn2_query(None, None, 0, None, None) == orbx.ORBX_E_INVALID
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under send_slam_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "send_slam_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle_lib" not in txt and "orb_oracle" not in txt and "from oracle" not in txt, f

@@ -1,0 +1,356 @@
+"""GPU parity tests: every call goes through the C ABI (liborbx.so); the CPU oracle and the golden fixtures are the checker.
+
+Bars (BASELINE.json north_star): pyramid pixels, blurred pixels, FAST keypoint sets, quadtree selection + order and Hamming
+distances bit-exact; orientation within 1e-3 degrees (here: bit-exact, both sides evaluate the same fp32 sequence);
+descriptors bit-exact under the canonical trig rule.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from send_slam_b200 import orbx, synth
+
+pytestmark = pytest.mark.gpu
+
+ANGLE_TOL_DEG = 1e-3        # north_star tolerance; observed difference is 0
+
+
+@pytest.fixture(scope="module")
+def ex():
+    e = orbx.ORBextractor(1000, 1.2, 8, 20, 7, device=0, max_width=1920, max_height=1080, max_batch=8)
+    yield e
+    e.close()
+
+
+def assert_same_extraction(got, want, what=""):
+    mono, kps, desc = got
+    kps_o, desc_o, mono_o = want
+    assert mono == mono_o, what
+    assert len(kps) == len(kps_o), (what, len(kps), len(kps_o))
+    for name in ("x", "y", "size", "response", "octave", "class_id"):
+        assert np.array_equal(kps[name], kps_o[name]), (what, name)
+    if len(kps):
+        d = np.abs(kps["angle"] - kps_o["angle"])
+        d = np.minimum(d, 360 - d)
+        assert float(d.max()) <= ANGLE_TOL_DEG, (what, float(d.max()))
+    assert np.array_equal(desc, desc_o), (what, int(np.unpackbits(desc ^ desc_o).sum()))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# stage by stage
+# ---------------------------------------------------------------------------------------------------------------------
+def test_resize_bit_exact(ex, oracle):
+    rng = np.random.default_rng(1)
+    for (w, h) in [(640, 480), (752, 480), (333, 217), (1920, 1080), (97, 61), (36, 40)]:
+        src = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        for s in (1.2, 1.0001, 1.97):
+            dw, dh = max(1, int(round(w / s))), max(1, int(round(h / s)))
+            assert np.array_equal(ex.debug_resize(src, dw, dh), oracle.resize(src, dw, dh)), (w, h, s)
+
+
+def test_blur_bit_exact(ex, oracle):
+    rng = np.random.default_rng(2)
+    for (w, h) in [(640, 480), (179, 134), (65, 64), (64, 65), (1920, 1080), (8, 8), (5, 300)]:
+        src = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        assert np.array_equal(ex.debug_blur(src), oracle.blur7(src)), (w, h)
+    sat = np.full((70, 70), 255, np.uint8)
+    assert np.array_equal(ex.debug_blur(sat), sat)
+
+
+def test_pyramid_fast_quadtree_stages(ex, oracle):
+    for kind, (w, h), nf in [("textured", (640, 480), 1000), ("mixed", (752, 480), 1200), ("sparse", (640, 480), 1000),
+                             ("lowcontrast", (640, 480), 1000), ("textured", (1280, 720), 1250)]:
+        e = ex if nf == 1000 else orbx.ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h)
+        frame = synth.textured_frame(31, w, h, kind)
+        o = oracle.Oracle(nf)
+        want = o.extract(frame)
+        got = e(frame)
+        for l in range(8):
+            lv_o, bl_o = o.stage_level(l)
+            assert np.array_equal(e.debug_level(0, l), lv_o), (kind, "pyramid", l)
+            if bl_o is not None:
+                assert np.array_equal(e.debug_level(0, l, blurred=True), bl_o), (kind, "blur", l)
+            c_o, s_o, a_o, _ = o.stage_keys(l)
+            c = e.debug_candidates(0, l)
+            assert len(c) == len(c_o), (kind, "FAST count", l)
+            assert set(map(tuple, c.tolist())) == set(map(tuple, c_o.tolist())), (kind, "FAST set", l)
+            k = e.debug_level_keypoints(0, l)
+            sel_o = c_o[s_o] + np.array([16, 16, 0], np.float32) if len(s_o) else np.zeros((0, 3), np.float32)
+            assert np.array_equal(k[:, :3], sel_o), (kind, "quadtree selection/order", l)
+            if len(k):
+                assert float(np.abs(k[:, 3] - a_o).max()) <= ANGLE_TOL_DEG, (kind, "angle", l)
+        assert_same_extraction(got, want, kind)
+        if e is not ex:
+            e.close()
+
+
+def test_quadtree_standalone(ex, oracle):
+    """DistributeOctTree on hand-made key sets: clustered (forces the below-depth0 path), ties in response, N edge cases."""
+    rng = np.random.default_rng(5)
+    W, H = 640 - 32, 480 - 32
+
+    def keys_from(xs, ys, rs, w=W, h=H):
+        """Unique integer keys in the order the reference's cell loop emits them (cell row, cell column, y, x): the
+        list order decides response ties, and the library assumes that order for candidates (it produces them itself)."""
+        pts = {}
+        for x, y, r in zip(xs, ys, rs):
+            pts[(int(x), int(y))] = int(r)
+        ncols, nrows = int(w / 35), int(h / 35)
+        wcell, hcell = int(np.ceil(w / ncols)), int(np.ceil(h / nrows))
+        order = sorted(pts, key=lambda p: ((p[1] - 3) // hcell, (p[0] - 3) // wcell, p[1], p[0]))
+        return np.array([(x, y, pts[(x, y)]) for (x, y) in order], np.float32).reshape(-1, 3)
+
+    cases = []
+    cases.append((keys_from(rng.integers(3, W - 3, 5000), rng.integers(3, H - 3, 5000), rng.integers(7, 120, 5000)), 217))
+    cases.append((keys_from(rng.integers(3, W - 3, 300), rng.integers(3, H - 3, 300), np.full(300, 30)), 500))        # N > keys
+    cx, cy = rng.normal(300, 6, 3000), rng.normal(200, 5, 3000)                                                       # tight cluster
+    cases.append((keys_from(np.clip(cx, 3, W - 4), np.clip(cy, 3, H - 4), rng.integers(7, 60, 3000)), 400))
+    cases.append((keys_from(rng.integers(3, 40, 800), rng.integers(3, 40, 800), rng.integers(7, 9, 800)), 150))       # corner + ties
+    cases.append((keys_from([10], [10], [50]), 10))
+    cases.append((keys_from(rng.integers(3, W - 3, 2000), rng.integers(3, H - 3, 2000), rng.integers(7, 200, 2000)), 0))
+    cases.append((keys_from(rng.integers(3, W - 3, 2000), rng.integers(3, H - 3, 2000), rng.integers(7, 200, 2000)), 1))
+    cases.append((np.zeros((0, 3), np.float32), 50))
+    for i, (keys, N) in enumerate(cases):
+        want = oracle.octree(keys, 16, 16 + W, 16, 16 + H, N)
+        got = ex.debug_octree(keys, 16, 16 + W, 16, 16 + H, N)
+        assert np.array_equal(got, want), (i, len(keys), N, len(got), len(want))
+    # 752x480-shaped region: two root nodes
+    W2, H2 = 752 - 32, 480 - 32
+    keys = keys_from(rng.integers(3, W2 - 3, 9000), rng.integers(3, H2 - 3, 9000), rng.integers(7, 100, 9000), W2, H2)
+    for N in (5, 261, 1300):
+        assert np.array_equal(ex.debug_octree(keys, 16, 16 + W2, 16, 16 + H2, N), oracle.octree(keys, 16, 16 + W2, 16, 16 + H2, N)), N
+
+
+def test_orientation_and_descriptor_standalone(ex, oracle):
+    frame = synth.textured_frame(8, 400, 300)
+    bl = oracle.blur7(frame)
+    rng = np.random.default_rng(9)
+    xy = np.stack([rng.integers(19, 400 - 19, 500), rng.integers(19, 300 - 19, 500)], 1).astype(np.float32)
+    xy[0] = (19, 19)
+    xy[1] = (400 - 20, 300 - 20)
+    ang, desc = ex.debug_describe(frame, bl, xy)
+    o = oracle.Oracle(500)
+    a_o = np.array([o.L.orb_oracle_ic_angle(o.h, oracle._p(frame), 400, float(x), float(y)) for x, y in xy], np.float32)
+    assert float(np.abs(ang - a_o).max()) <= ANGLE_TOL_DEG
+    assert np.array_equal(ang, a_o)         # in fact bit-identical
+    d_o = np.stack([oracle.brief(bl, x, y, a) for (x, y), a in zip(xy, a_o)])
+    assert np.array_equal(desc, d_o)
+    # descriptors for given angles, including the axis-aligned ones
+    given = np.linspace(0, 359.9, 500).astype(np.float32)
+    given[:4] = (0, 90, 180, 270)
+    _, desc2 = ex.debug_describe(None, bl, xy, angles=given)
+    assert np.array_equal(desc2, np.stack([oracle.brief(bl, x, y, a) for (x, y), a in zip(xy, given)]))
+    with pytest.raises(orbx.OrbxError):
+        ex.debug_describe(frame, bl, np.array([[5, 5]], np.float32))     # closer than 19 px to the border
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# whole operator(), golden fixtures, batches
+# ---------------------------------------------------------------------------------------------------------------------
+def test_golden_fixtures(golden_dir):
+    for path in sorted(glob.glob(os.path.join(golden_dir, "*.npz"))):
+        if os.path.basename(path).startswith("knn2"):
+            continue
+        g = np.load(path)
+        w, h, nf = int(g["width"]), int(g["height"]), int(g["nfeatures"])
+        frame = synth.textured_frame(int(g["seed"]), w, h, str(g["kind"]))
+        e = orbx.ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h)
+        mono, kps, desc = e(frame, None, tuple(int(v) for v in g["lap"]))
+        ref = g["kps"]
+        assert mono == int(g["mono_index"]) and len(kps) == len(ref), path
+        for i, name in enumerate(["x", "y", "size", "angle", "response", "octave", "class_id"]):
+            assert np.array_equal(kps[name].astype(np.float32), ref[:, i]), (path, name)
+        assert np.array_equal(desc, g["desc"]), path
+        e.close()
+
+
+def test_operator_all_configs(oracle):
+    """BASELINE.json configs as parity cases: 640x480/1000, 752x480/1200, 1920x1080/2000 (lapping split), 1280x720/1250."""
+    for (w, h, nf) in [(640, 480, 1000), (752, 480, 1200), (1920, 1080, 2000), (1280, 720, 1250)]:
+        e = orbx.ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h)
+        o = oracle.Oracle(nf)
+        for seed, kind in [(40, "textured"), (41, "mixed")]:
+            frame = synth.textured_frame(seed, w, h, kind)
+            assert_same_extraction(e(frame), o.extract(frame), (w, h, kind))
+        if w > 1000:
+            mono, kps, _ = e(synth.textured_frame(40, w, h))
+            assert 0 < mono < len(kps)
+            assert np.all(kps["x"][:mono] > 1000) and np.all(kps["x"][mono:] <= 1000)
+        e.close()
+
+
+def test_operator_edge_cases(ex, oracle):
+    mono, kps, desc = ex(np.full((480, 640), 9, np.uint8))
+    assert (mono, len(kps), desc.shape) == (0, 0, (0, 32))
+    assert ex(np.zeros((0, 0), np.uint8))[0] == -1                       # empty image: the reference returns -1
+    with pytest.raises(orbx.OrbxError):
+        ex(np.zeros((480, 640), np.float32))                             # reference asserts CV_8UC1
+    with pytest.raises(orbx.OrbxError) as e:
+        ex(np.zeros((1200, 2000), np.uint8))
+    assert e.value.code == orbx.ORBX_E_CAPACITY
+    # strided (non-contiguous rows) input and a custom lapping area
+    big = synth.textured_frame(50, 700, 500)
+    view = big[10:490, 20:660]
+    o = oracle.Oracle(1000)
+    assert_same_extraction(ex(view, None, (100, 300)), o.extract(np.ascontiguousarray(view), lap=(100, 300)), "strided")
+    # tiny frames: upper levels have no FAST cell at all
+    small = synth.textured_frame(51, 120, 100)
+    assert_same_extraction(ex(small), o.extract(small), "120x100")
+    # initialisation extractor of the reference (5 x nFeatures = 6250, orbslam3_mono_networked.cc:193 + UPSTREAM Tracking)
+    e5 = orbx.ORBextractor(6250, 1.2, 8, 20, 7, max_width=1280, max_height=800)
+    f = synth.textured_frame(52, 1280, 800)
+    assert_same_extraction(e5(f), oracle.Oracle(6250).extract(f), "ini extractor 6250 @1280x800")
+    e5.close()
+    # different pyramid parameters
+    e2 = orbx.ORBextractor(800, 1.5, 5, 25, 10, max_width=640, max_height=480)
+    f = synth.textured_frame(53, 640, 480, "mixed")
+    assert_same_extraction(e2(f), oracle.Oracle(800, 1.5, 5, 25, 10).extract(f), "scale 1.5, 5 levels")
+    e2.close()
+
+
+def test_batch_equals_per_frame(oracle):
+    """64-frame batch through orbx_extract_batch == per-frame oracle (frames are independent units)."""
+    B, w, h, nf = 64, 752, 480, 1200
+    frames = np.stack([synth.textured_frame(s, w, h, "textured" if s % 3 else "mixed") for s in range(B)])
+    frames[5] = 128                                                      # a constant frame inside the batch
+    e = orbx.ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=B)
+    mono, n, kps, desc = e.extract_batch(frames)
+    ref = oracle.extract_batch(frames, nf, nthreads=os.cpu_count() or 1)
+    kps_o, desc_o, n_o, mono_o = ref
+    assert np.array_equal(n, n_o) and np.array_equal(mono, mono_o) and n[5] == 0
+    for i in range(B):
+        k = int(n[i])
+        for name in kps.dtype.names:
+            assert np.array_equal(kps[i, :k][name], kps_o[i, :k][name]), (i, name)
+        assert np.array_equal(desc[i, :k], desc_o[i, :k]), i
+    # a second, smaller batch on the same handle (workspace reuse) and a different frame size (re-plan)
+    mono2, n2, kps2, desc2 = e.extract_batch(frames[:3])
+    assert np.array_equal(n2, n[:3]) and np.array_equal(desc2[0, :n2[0]], desc[0, :n[0]])
+    small = np.stack([synth.textured_frame(70 + s, 320, 240) for s in range(4)])
+    mono3, n3, kps3, desc3 = e.extract_batch(small)
+    o = oracle.Oracle(nf)
+    for i in range(4):
+        k_o, d_o, m_o = o.extract(small[i])
+        assert n3[i] == len(k_o) and np.array_equal(desc3[i, :n3[i]], d_o)
+    e.close()
+
+
+def test_device_resident_batch(oracle):
+    import torch
+    B, w, h, nf = 8, 640, 480, 1000
+    frames = np.stack([synth.textured_frame(200 + s, w, h) for s in range(B)])
+    e = orbx.ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=B)
+    cap = e.capacity
+    d_in = torch.from_numpy(frames).cuda()
+    d_kp = torch.zeros((B, cap, 7), dtype=torch.float32, device="cuda")
+    d_desc = torch.zeros((B, cap, 32), dtype=torch.uint8, device="cuda")
+    d_n = torch.zeros(B, dtype=torch.int32, device="cuda")
+    d_mono = torch.zeros(B, dtype=torch.int32, device="cuda")
+    e.set_stream(torch.cuda.current_stream().cuda_stream)
+    e.extract_batch_device(d_in.data_ptr(), w * h, B, w, h, w, d_kp.data_ptr(), d_desc.data_ptr(), cap, d_n.data_ptr(), d_mono.data_ptr())
+    e.sync()
+    n = d_n.cpu().numpy()
+    desc = d_desc.cpu().numpy()
+    kp = d_kp.cpu().numpy()
+    o = oracle.Oracle(nf)
+    for i in range(B):
+        k_o, d_o, m_o = o.extract(frames[i])
+        assert n[i] == len(k_o) and np.array_equal(desc[i, :n[i]], d_o)
+        assert np.array_equal(kp[i, :n[i], 0], k_o["x"]) and np.array_equal(kp[i, :n[i], 3], k_o["angle"])
+    assert e.launch_count() >= 12
+    e.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# matching
+# ---------------------------------------------------------------------------------------------------------------------
+def test_distance_batch(ex, oracle):
+    rng = np.random.default_rng(3)
+    a = rng.integers(0, 256, (5000, 32), dtype=np.uint8)
+    b = rng.integers(0, 256, (5000, 32), dtype=np.uint8)
+    b[:10] = a[:10]
+    b[10:20] = ~a[10:20]
+    d = ex.distance_batch(a, b)
+    assert d[:10].tolist() == [0] * 10 and d[10:20].tolist() == [256] * 10
+    assert np.array_equal(d, np.unpackbits(a ^ b, axis=1).sum(1).astype(np.int32))
+    assert all(int(d[i]) == oracle.distance(a[i], b[i]) for i in range(0, 5000, 97))
+    m = orbx.ORBmatcher(0.9, True, extractor=ex)
+    assert m.DescriptorDistance(a[33], b[33]) == int(d[33])
+
+
+def test_knn2_golden_and_oracle(oracle, golden_dir):
+    g = np.load(os.path.join(golden_dir, "knn2_4096x128.npz"))
+    db = synth.descriptor_db(4096, seed=int(g["db_seed"]))
+    q, _ = synth.queries_from_db(db, 128, seed=int(g["q_seed"]))
+    db[100] = db[7]
+    db[2000] = db[7]
+    idx, dist = orbx.Knn2Index(db).knnMatch(q)
+    assert np.array_equal(idx, g["idx"]) and np.array_equal(dist, g["dist"])
+    # ragged sizes: rows not a multiple of the tile, queries not a multiple of the CTA, tiny shards, row offset
+    rng = np.random.default_rng(4)
+    for nrows, nq in [(1, 3), (2, 1), (127, 5), (129, 257), (70001, 300), (300000, 2000)]:
+        db = rng.integers(0, 256, (nrows, 32), dtype=np.uint8)
+        q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+        q[0] = db[nrows // 2]
+        idx, dist = orbx.Knn2Index(db, row_offset=1000).knnMatch(q)
+        idx_o, dist_o = oracle.knn2(q, db, nthreads=os.cpu_count() or 1)
+        idx_o = np.where(idx_o >= 0, idx_o + 1000, idx_o)
+        assert np.array_equal(idx, idx_o) and np.array_equal(dist, dist_o), (nrows, nq)
+        assert dist[0, 0] == 0
+
+
+def test_knn2_full_size_properties():
+    """2000 queries x 1M rows per shard (config 4's per-GPU share at 8+ GPUs is 1.25M): known answers instead of an
+    oracle pass -- queries are database rows with <= 40 flipped bits, so the nearest row and its distance are known and
+    the ratio test passes; merging the two half-shard results equals the whole-shard result (checksum of checksums)."""
+    import torch
+    db = synth.descriptor_db(1_000_000, seed=1234)
+    q, src = synth.queries_from_db(db, 2000, seed=99)
+    flips = np.unpackbits(q ^ db[src], axis=1).sum(1)
+    whole = orbx.Knn2Index(db)
+    idx, dist = whole.knnMatch(q)
+    assert np.array_equal(idx[:, 0], src) and np.array_equal(dist[:, 0], flips)
+    assert np.all(dist[:, 1] > 60) and np.all(dist[:, 0] < 0.7 * dist[:, 1])
+    lo, hi = orbx.Knn2Index(db[:500_000]), orbx.Knn2Index(db[500_000:], row_offset=500_000)
+    d_q = torch.from_numpy(q).cuda()
+    parts = torch.zeros((2, 2000, 2), dtype=torch.int64, device="cuda")
+    lo.query_device(d_q.data_ptr(), 2000, parts[0].data_ptr()); lo.sync()
+    hi.query_device(d_q.data_ptr(), 2000, parts[1].data_ptr()); hi.sync()
+    out = torch.zeros((2000, 2), dtype=torch.int64, device="cuda")
+    lo.merge_device(parts.data_ptr(), 2, 2000, out.data_ptr()); lo.sync()
+    midx, mdist = orbx.unpack_knn(out.cpu().numpy().view(np.uint64))
+    assert np.array_equal(midx, idx) and np.array_equal(mdist, dist)
+
+
+def test_windowed_matching(ex, oracle):
+    """Previous-frame windowed search (config 3 shape): extract two shifted 1080p frames, search every keypoint of the
+    first in a window of the second."""
+    w, h, nf = 1920, 1080, 2000
+    e = orbx.ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h)
+    f0 = synth.textured_frame(60, w, h)
+    f1 = synth.shifted_frame(f0, 4, -3, seed=1)
+    _, k0, d0 = e(f0)
+    _, k1, d1 = e(f1)
+    bounds = np.array([0, 0, w, h], np.float32)
+    scale = e.GetScaleFactors()
+    rng = np.random.default_rng(6)
+    quvr = np.stack([k0["x"] + 4, k0["y"] - 3, 15.0 * scale[k0["octave"]]], 1).astype(np.float32)
+    qlev = np.stack([k0["octave"] - 1, k0["octave"] + 1], 1).astype(np.int32)
+    # a few special windows: no level check, level 0 only, off-image, huge radius
+    qlev[:50] = (-1, -1)
+    qlev[50:100] = (0, 0)
+    quvr[100:110, 0] = -500
+    quvr[110:120, 2] = 400
+    got = e.match_windowed(d0, quvr, qlev, k1, d1, bounds)
+    want = oracle.match_windowed(d0, quvr, qlev, k1, d1, bounds)
+    for g_, w_, name in zip(got, want, ["best_idx", "best_dist", "second_idx", "second_dist"]):
+        assert np.array_equal(g_, w_), name
+    matched = (got[0] >= 0) & (got[1] <= orbx.ORBmatcher.TH_HIGH)
+    assert matched.mean() > 0.5
+    assert np.all(got[0][100:110] == -1) and np.all(got[1][100:110] == 256)
+    # empty train set / empty query set
+    z = e.match_windowed(d0[:5], quvr[:5], qlev[:5], k1[:0], d1[:0], bounds)
+    assert np.all(z[0] == -1) and np.all(z[3] == 256)
+    e.close()
