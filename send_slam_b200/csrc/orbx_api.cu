@@ -138,6 +138,7 @@ static int ensure_plan(orbx_handle *h, int w, int ht, int batch) {
             CU_TRY(h, dev_upload(h, &xt, LP.xtap));
             CU_TRY(h, dev_upload(h, &yt, LP.ytap));
             D.xtap = xt; D.ytap = yt;
+            if (!LP.xpack.empty()) { uint32_t *xp = nullptr; CU_TRY(h, dev_upload(h, &xp, LP.xpack)); D.xpack = xp; }
         }
         uint32_t *t0 = nullptr, *t1 = nullptr, *t2 = nullptr, *t3 = nullptr;
         CU_TRY(h, dev_upload(h, &t0, LP.xbin)); CU_TRY(h, dev_upload(h, &t1, LP.ybin));
@@ -484,6 +485,23 @@ int orbx_debug_resize(orbx_handle *h, const uint8_t *src, int sw, int sh, int ss
     if (!d_src || !d_dst || !d_xt || !d_yt || !d_lv) return fail(h, ORBX_E_CUDA, "cudaMalloc failed");
     lv[0].img = d_src; lv[0].w = sw; lv[0].h = sh; lv[0].pitch = sp; lv[0].img_fstride = (size_t)sp * sh;
     lv[1].img = d_dst; lv[1].w = dw; lv[1].h = dh; lv[1].pitch = dp; lv[1].img_fstride = (size_t)dp * dh; lv[1].xtap = d_xt; lv[1].ytap = d_yt;
+    {   // compact taps when they fit (same rule as build_plan)
+        bool ok = true;
+        for (int d = 0; d < dw && ok; d++) {
+            const ResizeTap &tp = xt[d];
+            ok = (tp.c0 + tp.c1 == 2048) && tp.c1 >= 0 && (tp.ofs1 == tp.ofs + 1 || tp.c1 == 0);
+            if (ok && (d & 3) == 0) { const int last = d + 3 < dw ? d + 3 : dw - 1; ok = xt[last].ofs - tp.ofs <= 6 && xt[last].ofs >= tp.ofs; }
+        }
+        for (int d = 0; d < dh && ok; d++) ok = yt[d].c0 >= 0 && yt[d].c1 >= 0;
+        if (ok) {
+            std::vector<uint32_t> xp((size_t)(dw + 3) / 4 * 4);
+            for (size_t d = 0; d < xp.size(); d++) { const ResizeTap &tp = xt[d < (size_t)dw ? d : (size_t)dw - 1]; xp[d] = ((uint32_t)tp.ofs << 16) | (uint32_t)tp.c1; }
+            uint32_t *d_xp = S.get<uint32_t>(xp.size());
+            if (!d_xp) return fail(h, ORBX_E_CUDA, "cudaMalloc failed");
+            CU_TRY(h, cudaMemcpy(d_xp, xp.data(), xp.size() * 4, cudaMemcpyHostToDevice));
+            lv[1].xpack = d_xp;
+        }
+    }
     CU_TRY(h, cudaMemcpy2D(d_src, sp, src, sstride, sw, sh, cudaMemcpyHostToDevice));
     CU_TRY(h, cudaMemcpy(d_xt, xt.data(), sizeof(ResizeTap) * dw, cudaMemcpyHostToDevice));
     CU_TRY(h, cudaMemcpy(d_yt, yt.data(), sizeof(ResizeTap) * dh, cudaMemcpyHostToDevice));

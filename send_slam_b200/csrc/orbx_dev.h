@@ -15,6 +15,7 @@ struct LevelDev {
     size_t blur_fstride;
     int w, h, pitch, blur_pitch;
     const ResizeTap *xtap, *ytap;                   // taps from level l-1
+    const uint32_t *xpack;                          // x taps as ofs << 16 | c1 (c0 = 2048 - c1), padded to 4; may be null
     const uint32_t *xbin, *ybin, *xord, *yord;      // quadtree / order LUTs, indexed by (x-16), (y-16)
     int reg_w, reg_h, n_ini, depth0, nbins, quota, out_cap;
     int root_ulx[kMaxRoots], root_brx[kMaxRoots];

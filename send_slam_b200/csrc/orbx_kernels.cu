@@ -33,9 +33,13 @@ void upload_constants() {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K1  pyramid resize: 4 destination pixels per thread, taps precomputed on the host (orbx_plan.cpp)
+// K1  pyramid resize (cv::resize INTER_LINEAR, 8UC1).  Taps are tabulated on the host (orbx_plan.cpp).
+//     k_resize: 4 destination pixels x 2 destination rows per thread.  The <= 8 source bytes a 4-pixel group needs are
+//     fetched as three aligned words per source row and realigned once; each pixel then costs one PRMT (its two
+//     neighbouring source bytes) and one IDP.2A (s0*c0 + s1*c1) per source row.
+//     k_resize_generic: byte-wise fallback for source planes that are not 4-byte aligned (caller-owned level 0).
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_resize(const LevelDev *__restrict__ lv, int level) {
+__global__ void __launch_bounds__(128) k_resize_generic(const LevelDev *__restrict__ lv, int level) {
     const LevelDev &D = lv[level];
     const LevelDev &S = lv[level - 1];
     const int dx0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -60,10 +64,66 @@ __global__ void __launch_bounds__(128) k_resize(const LevelDev *__restrict__ lv,
     *reinterpret_cast<uint32_t *>(D.img + (size_t)f * D.img_fstride + (size_t)dy * D.pitch + dx0) = packed;
 }
 
+// xpack[dx] = ofs << 16 | c1 (c0 = 2048 - c1), padded to a multiple of 4 entries
+__global__ void __launch_bounds__(128) k_resize(const LevelDev *__restrict__ lv, int level) {
+    const LevelDev &D = lv[level];
+    const LevelDev &S = lv[level - 1];
+    const int dx0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (dx0 >= D.w) return;
+    const int dy0 = blockIdx.y * 2, f = blockIdx.z;
+    const uint4 tp = __ldg(reinterpret_cast<const uint4 *>(D.xpack + dx0));
+    const uint32_t t[4] = {tp.x, tp.y, tp.z, tp.w};
+    const int ofs0 = (int)(t[0] >> 16);
+    const int base = ofs0 & ~3;
+    const uint32_t mis8 = 8u * (uint32_t)(ofs0 & 3);
+    const int lastw = (S.w - 1) & ~3;                       // last word that still starts inside the row
+    const int o0 = base, o1 = min(base + 4, lastw), o2 = min(base + 8, lastw);
+    uint32_t sel[4], coef[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint32_t d = (t[i] >> 16) - (uint32_t)ofs0;   // 0..6: byte offset of the first tap inside the window
+        sel[i] = d | ((d + 1) << 4);                          // PRMT: bytes d, d+1 -> result bytes 0, 1
+        const uint32_t c1 = t[i] & 0xFFFFu;
+        coef[i] = (c1 << 16) | (2048u - c1);                  // IDP.2A: lo16 * byte0 + hi16 * byte1
+    }
+    const uint8_t *__restrict__ sbase = S.img + (size_t)f * S.img_fstride;
+#pragma unroll
+    for (int rr = 0; rr < 2; rr++) {
+        const int dy = dy0 + rr;
+        if (dy >= D.h) break;
+        const ResizeTap ty = D.ytap[dy];
+        uint32_t r[2][4];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const uint8_t *row = sbase + (size_t)(k ? ty.ofs1 : ty.ofs) * S.pitch;
+            const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t *>(row + o0));
+            const uint32_t w1 = __ldg(reinterpret_cast<const uint32_t *>(row + o1));
+            const uint32_t w2 = __ldg(reinterpret_cast<const uint32_t *>(row + o2));
+            const uint32_t a = __funnelshift_r(w0, w1, mis8), b = __funnelshift_r(w1, w2, mis8);   // bytes ofs0 .. ofs0+7
+#pragma unroll
+            for (int i = 0; i < 4; i++) r[k][i] = __dp2a_lo(coef[i], __byte_perm(a, b, sel[i]), 0u);
+        }
+        uint32_t packed = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int v = ((((int)ty.c0 * (int)(r[0][i] >> 4)) >> 16) + (((int)ty.c1 * (int)(r[1][i] >> 4)) >> 16) + 2) >> 2;
+            packed |= (uint32_t)min(v, 255) << (8 * i);
+        }
+        *reinterpret_cast<uint32_t *>(D.img + (size_t)f * D.img_fstride + (size_t)dy * D.pitch + dx0) = packed;
+    }
+}
+
 int launch_resize(const LevelDev *d_levels, const LevelDev *h_levels, int level, int batch, cudaStream_t stream) {
     const LevelDev &D = h_levels[level];
-    dim3 grid((D.w + 4 * 128 - 1) / (4 * 128), D.h, batch);
-    k_resize<<<grid, 128, 0, stream>>>(d_levels, level);
+    const LevelDev &S = h_levels[level - 1];
+    const bool aligned = ((reinterpret_cast<uintptr_t>(S.img) | (uintptr_t)S.pitch | (uintptr_t)S.img_fstride) & 3) == 0 && D.xpack != nullptr;
+    if (aligned) {
+        dim3 grid((D.w + 4 * 128 - 1) / (4 * 128), (D.h + 1) / 2, batch);
+        k_resize<<<grid, 128, 0, stream>>>(d_levels, level);
+    } else {
+        dim3 grid((D.w + 4 * 128 - 1) / (4 * 128), D.h, batch);
+        k_resize_generic<<<grid, 128, 0, stream>>>(d_levels, level);
+    }
     return 1;
 }
 
@@ -72,7 +132,7 @@ int launch_resize(const LevelDev *d_levels, const LevelDev *h_levels, int level,
 //     tile 64x64: shared u8 halo tile -> horizontal pass (two pixels per IMAD, 16-bit lanes) -> vertical pass
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int BT = 64;                 // tile edge
-constexpr int BIN_PITCH = 80;          // bytes per staged input row (64 + 6 halo, padded to 16)
+constexpr int BIN_PITCH = 80;          // bytes per staged input row: image columns x0-4 .. x0+75
 constexpr int BROWS = BT + 6;
 
 // BORDER_REFLECT_101 for any index (period 2(n-1)); n == 1 maps everything to 0
@@ -92,10 +152,21 @@ __global__ void __launch_bounds__(256) k_blur(const LevelDev *__restrict__ lv, c
     const int f = blockIdx.y;
     const int x0 = t.tx * BT, y0 = t.ty * BT;
     const uint8_t *__restrict__ src = L.img + (size_t)f * L.img_fstride;
-    for (int i = threadIdx.x; i < BROWS * BIN_PITCH; i += 256) {
-        const int r = i / BIN_PITCH, c = i - r * BIN_PITCH;
-        const int gx = reflect101(x0 - 3 + c, L.w), gy = reflect101(y0 - 3 + r, L.h);
-        s_in[i] = src[(size_t)gy * L.pitch + gx];
+    // stage rows y0-3 .. y0+66, columns x0-4 .. x0+75 (20 words per row): aligned word loads where the word lies inside
+    // the image, per-byte BORDER_REFLECT_101 elsewhere
+    const bool word_ok = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)L.pitch) & 3) == 0;
+    for (int i = threadIdx.x; i < BROWS * (BIN_PITCH / 4); i += 256) {
+        const int r = i / (BIN_PITCH / 4), c = i - r * (BIN_PITCH / 4);
+        const int gy = y0 - 3 + r, gx = x0 - 4 + 4 * c;
+        uint32_t v;
+        if (word_ok && gy >= 0 && gy < L.h && gx >= 0 && gx + 3 < L.w) {
+            v = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)gy * L.pitch + gx));
+        } else {
+            const uint8_t *row = src + (size_t)reflect101(gy, L.h) * L.pitch;
+            v = (uint32_t)row[reflect101(gx, L.w)] | ((uint32_t)row[reflect101(gx + 1, L.w)] << 8) |
+                ((uint32_t)row[reflect101(gx + 2, L.w)] << 16) | ((uint32_t)row[reflect101(gx + 3, L.w)] << 24);
+        }
+        reinterpret_cast<uint32_t *>(s_in)[i] = v;
     }
     __syncthreads();
     // horizontal: item = (row, group of 8 outputs)
@@ -104,12 +175,13 @@ __global__ void __launch_bounds__(256) k_blur(const LevelDev *__restrict__ lv, c
         const uint2 a = *reinterpret_cast<const uint2 *>(s_in + r * BIN_PITCH + 8 * g);
         const uint2 b = *reinterpret_cast<const uint2 *>(s_in + r * BIN_PITCH + 8 * g + 8);
         const uint32_t w0 = a.x, w1 = a.y, w2 = b.x, w3 = b.y;
-        // q[j] = (byte j+2) << 16 | byte j   for j = 0..11
+        // staged column c is image column x0-4+c, so output 8g+i reads bytes i+1 .. i+7 of these 16:
+        // q[j] = (byte j+3) << 16 | byte j+1   for j = 0..11
         uint32_t q[12];
         const uint32_t s01 = __funnelshift_r(w0, w1, 16), s12 = __funnelshift_r(w1, w2, 16), s23 = __funnelshift_r(w2, w3, 16);
-        q[0] = w0 & 0x00FF00FFu;  q[1] = (w0 >> 8) & 0x00FF00FFu;  q[2] = s01 & 0x00FF00FFu;  q[3] = (s01 >> 8) & 0x00FF00FFu;
-        q[4] = w1 & 0x00FF00FFu;  q[5] = (w1 >> 8) & 0x00FF00FFu;  q[6] = s12 & 0x00FF00FFu;  q[7] = (s12 >> 8) & 0x00FF00FFu;
-        q[8] = w2 & 0x00FF00FFu;  q[9] = (w2 >> 8) & 0x00FF00FFu;  q[10] = s23 & 0x00FF00FFu; q[11] = (s23 >> 8) & 0x00FF00FFu;
+        q[0] = (w0 >> 8) & 0x00FF00FFu;  q[1] = s01 & 0x00FF00FFu;  q[2] = (s01 >> 8) & 0x00FF00FFu;  q[3] = w1 & 0x00FF00FFu;
+        q[4] = (w1 >> 8) & 0x00FF00FFu;  q[5] = s12 & 0x00FF00FFu;  q[6] = (s12 >> 8) & 0x00FF00FFu;  q[7] = w2 & 0x00FF00FFu;
+        q[8] = (w2 >> 8) & 0x00FF00FFu;  q[9] = s23 & 0x00FF00FFu;  q[10] = (s23 >> 8) & 0x00FF00FFu; q[11] = w3 & 0x00FF00FFu;
         uint32_t o[4];
 #pragma unroll
         for (int p = 0; p < 4; p++) {
@@ -244,11 +316,34 @@ __global__ void __launch_bounds__(192) k_fast_cells(const LevelDev *__restrict__
     const int rw = cell.x1 - cell.x0, rh = cell.y1 - cell.y0;   // ROI
     const int iw = rw - 6, ih = rh - 6;                            // tested pixels
     const uint8_t *__restrict__ src = L.img + (size_t)f * L.img_fstride + (size_t)cell.y0 * L.pitch + cell.x0;
-    // stage ROI (+ zero guard columns so that the last 4-pixel group may read past the ROI)
-    const int rw_pad = min((rw + 8) & ~3, FT_PITCH);
-    for (int i = threadIdx.x; i < (rh + 1) * rw_pad; i += blockDim.x) {
-        const int r = i / rw_pad, c = i - r * rw_pad;
-        s_roi[r * FT_PITCH + c] = (r < rh && c < rw) ? src[(size_t)r * L.pitch + c] : (uint8_t)0;
+    // stage ROI rows 0..rh (one extra row for the row-pair overhang) and rw+8 columns (4-pixel group overhang): one
+    // warp per row, one aligned 32-bit word pair per lane realigned with a funnel shift.  All of it lies inside the
+    // level plane because a ROI ends at least 16 px before the right / bottom edge; the overhang is masked later.
+    {
+        const int nwords = min((rw + 8) >> 2, FT_PITCH / 4);
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        if (lane < nwords) {
+            const size_t off0 = (size_t)f * L.img_fstride + (size_t)cell.y0 * L.pitch + cell.x0 + 4 * lane;
+            constexpr int RB = 7;   // rows in flight per lane (6 warps x 7 rows covers a 42-row ROI in one round)
+            for (int r0 = wid; r0 <= rh; r0 += nwarps * RB) {
+                uint32_t lo[RB], hi[RB], sh[RB];
+#pragma unroll
+                for (int k = 0; k < RB; k++) {
+                    const int r = r0 + k * nwarps;
+                    if (r <= rh) {
+                        const size_t off = off0 + (size_t)r * L.pitch;
+                        const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(L.img) + off) & 3);
+                        const uint32_t *q = reinterpret_cast<const uint32_t *>(L.img + (off - mis));
+                        lo[k] = __ldg(q); hi[k] = __ldg(q + 1); sh[k] = 8 * mis;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < RB; k++) {
+                    const int r = r0 + k * nwarps;
+                    if (r <= rh) *reinterpret_cast<uint32_t *>(s_roi + r * FT_PITCH + 4 * lane) = __funnelshift_r(lo[k], hi[k], sh[k]);
+                }
+            }
+        }
     }
     for (int i = threadIdx.x; i < (ih + 2) * FS_PITCH / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(s_sc)[i] = 0;
     if (threadIdx.x == 0) s_n = 0;
@@ -277,20 +372,40 @@ __global__ void __launch_bounds__(192) k_fast_cells(const LevelDev *__restrict__
         if (2 * s + 1 < ih) *reinterpret_cast<uint32_t *>(s_sc + (2 * s + 2) * FS_PITCH + 4 + 4 * g) = sb;
     }
     __syncthreads();
-    // NMS (strict 8-neighbour maximum inside the cell) + count at the initial threshold
+    // NMS (strict 8-neighbour maximum inside the cell, neighbours outside count 0) + count at the initial threshold.
+    // Same 4-pixel items as the scores; u16 lanes again: max over the 3x3 ring = max3(T(x-1), T(x+1), V(x)) with
+    // V = max(up, down), T = max(V, mid); strict compare via (s & 0xFF00) > (m | 0x00FF) per lane.
     int n_ini_local = 0;
-    for (int i = threadIdx.x; i < iw * ih; i += blockDim.x) {
-        const int y = i / iw, x = i - y * iw;
-        const uint8_t *q = s_sc + (y + 1) * FS_PITCH + 4 + x;
-        const int m = q[0];
-        if (m > min_th) {
-            const bool ismax = m > q[-1] && m > q[1] && m > q[-FS_PITCH - 1] && m > q[-FS_PITCH] && m > q[-FS_PITCH + 1] &&
-                               m > q[FS_PITCH - 1] && m > q[FS_PITCH] && m > q[FS_PITCH + 1];
-            if (ismax) {
-                const int slot = atomicAdd(&s_n, 1);
+    {
+        const uint32_t thr = ((uint32_t)min_th << 8) | ((uint32_t)min_th << 24);
+        for (int it = threadIdx.x; it < ng * ih; it += blockDim.x) {
+            const int y = it / ng, g = it - y * ng;
+            const uint32_t *ru = reinterpret_cast<const uint32_t *>(s_sc + y * FS_PITCH) + g;   // words g, g+1, g+2: x-4.., x.., x+4..
+            const uint32_t *rm = ru + FS_PITCH / 4, *rd = rm + FS_PITCH / 4;
+            const uint32_t c_m = rm[1];
+            if (c_m == 0) continue;
+            const uint32_t u0 = ru[0], u1 = ru[1], u2 = ru[2], m0 = rm[0], m2 = rm[2], d0 = rd[0], d1 = rd[1], d2 = rd[2];
+            // columns x-1 / x+1 of the four pixels
+            const uint32_t lu = __funnelshift_r(u0, u1, 24), lm = __funnelshift_r(m0, c_m, 24), ld = __funnelshift_r(d0, d1, 24);
+            const uint32_t ruu = __funnelshift_r(u1, u2, 8), rmm = __funnelshift_r(c_m, m2, 8), rdd = __funnelshift_r(d1, d2, 8);
+            // odd pixels (1, 3): high bytes of the lanes as they are
+            uint32_t mo = umax3(umax3(lu, ld, lm), umax3(ruu, rdd, rmm), umax3(u1, d1, thr));
+            // even pixels (0, 2): shift everything by one byte
+            uint32_t me = umax3(umax3(lu << 8, ld << 8, lm << 8), umax3(ruu << 8, rdd << 8, rmm << 8), umax3(u1 << 8, d1 << 8, thr));
+            const uint32_t so = c_m & 0xFF00FF00u, se = (c_m << 8) & 0xFF00FF00u;
+            mo |= 0x00FF00FFu; me |= 0x00FF00FFu;
+            const uint32_t fo = umax2(so, mo) ^ mo, fe = umax2(se, me) ^ me;   // non-zero lane <=> strict maximum above minTh
+            // flagged pixels of this item (at most 2: neighbours cannot both be strict maxima)
+            uint32_t mask = ((fe & 0xFFFFu) ? 1u : 0u) | ((fo & 0xFFFFu) ? 2u : 0u) | ((fe >> 16) ? 4u : 0u) | ((fo >> 16) ? 8u : 0u);
+            if (mask == 0) continue;
+            int slot = atomicAdd(&s_n, __popc(mask));
+            while (mask) {
+                const int k = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const int m = (c_m >> (8 * k)) & 0xFF, x = 4 * g + k;
                 // relative coordinates (x - 16, y - 16) of the reference's vToDistributeKeys entries
                 const uint32_t xr = (uint32_t)(cell.x0 + 3 + x - kMinBorder), yr = (uint32_t)(cell.y0 + 3 + y - kMinBorder);
-                s_list[slot] = (yr << 20) | (xr << 8) | (uint32_t)(m - 1);
+                s_list[slot++] = (yr << 20) | (xr << 8) | (uint32_t)(m - 1);
                 if (m > ini_th) n_ini_local++;
             }
         }

@@ -86,6 +86,26 @@ bool build_plan(const ExtractorParams &p, int width, int height, Plan &plan, std
         if (l > 0) {
             build_resize_taps(L.w, plan.lv[l - 1].w, true, L.xtap);
             build_resize_taps(L.h, plan.lv[l - 1].h, false, L.ytap);
+            // compact form: needs c0 + c1 == 2048, second tap = first + 1 (or weight 0) and <= 6 source bytes between
+            // the first taps of 4 neighbouring outputs (always true for scale factors in (1, 2))
+            bool ok = true;
+            const int sw = plan.lv[l - 1].w;
+            for (int d = 0; d < L.w && ok; d++) {
+                const ResizeTap &t = L.xtap[d];
+                ok = (t.c0 + t.c1 == 2048) && t.c1 >= 0 && (t.ofs1 == t.ofs + 1 || t.c1 == 0) && t.ofs >= 0 && t.ofs < sw;
+                if (ok && (d & 3) == 0) {
+                    const int last = d + 3 < L.w ? d + 3 : L.w - 1;
+                    ok = L.xtap[last].ofs - t.ofs <= 6 && L.xtap[last].ofs >= t.ofs;
+                }
+            }
+            for (int d = 0; d < L.h && ok; d++) ok = L.ytap[d].c0 >= 0 && L.ytap[d].c1 >= 0;
+            if (ok) {
+                L.xpack.resize((size_t)(L.w + 3) / 4 * 4);
+                for (size_t d = 0; d < L.xpack.size(); d++) {
+                    const ResizeTap &t = L.xtap[d < (size_t)L.w ? d : (size_t)L.w - 1];
+                    L.xpack[d] = ((uint32_t)t.ofs << 16) | (uint32_t)t.c1;
+                }
+            }
         }
         L.quota = p.quota[l];
         L.kp_size = (float)(int)((float)kPatchSize * p.scale[l]);

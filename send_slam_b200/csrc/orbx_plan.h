@@ -50,6 +50,7 @@ struct LevelPlan {
     size_t plane_bytes = 0;          // pitch * h
     // resize taps from level l-1 (empty for level 0)
     std::vector<ResizeTap> xtap, ytap;
+    std::vector<uint32_t> xpack;      // compact x taps for the fast kernel; empty if the taps do not fit that form
     // FAST cell grid
     int ncols = 0, nrows = 0, wcell = 0, hcell = 0;
     int first_cell = 0, ncells = 0;  // range in Plan::cells
