@@ -138,9 +138,10 @@ constexpr int BROWS = BT + 6;
 // BORDER_REFLECT_101 for any index (period 2(n-1)); n == 1 maps everything to 0
 __device__ __forceinline__ int reflect101(int i, int n) {
     if (n == 1) return 0;
-    const int p = 2 * (n - 1);
     if (i < 0) i = -i;
-    i %= p;
+    if (i < n) return i;
+    const int p = 2 * (n - 1);
+    if (i >= p) i %= p;          // only for images narrower than the staging halo
     return i >= n ? p - i : i;
 }
 
@@ -155,18 +156,35 @@ __global__ void __launch_bounds__(256) k_blur(const LevelDev *__restrict__ lv, c
     // stage rows y0-3 .. y0+66, columns x0-4 .. x0+75 (20 words per row): aligned word loads where the word lies inside
     // the image, per-byte BORDER_REFLECT_101 elsewhere
     const bool word_ok = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)L.pitch) & 3) == 0;
-    for (int i = threadIdx.x; i < BROWS * (BIN_PITCH / 4); i += 256) {
-        const int r = i / (BIN_PITCH / 4), c = i - r * (BIN_PITCH / 4);
-        const int gy = y0 - 3 + r, gx = x0 - 4 + 4 * c;
-        uint32_t v;
-        if (word_ok && gy >= 0 && gy < L.h && gx >= 0 && gx + 3 < L.w) {
-            v = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)gy * L.pitch + gx));
-        } else {
-            const uint8_t *row = src + (size_t)reflect101(gy, L.h) * L.pitch;
-            v = (uint32_t)row[reflect101(gx, L.w)] | ((uint32_t)row[reflect101(gx + 1, L.w)] << 8) |
-                ((uint32_t)row[reflect101(gx + 2, L.w)] << 16) | ((uint32_t)row[reflect101(gx + 3, L.w)] << 24);
+    {
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        if (lane < BIN_PITCH / 4) {
+            const int gx = x0 - 4 + 4 * lane;
+            const bool col_in = gx >= 0 && gx + 3 < L.w;
+            constexpr int RB = 3;    // rows in flight per lane: 8 warps x 3 rows per round, 3 rounds cover the 70 rows
+            for (int r0 = wid; r0 < BROWS; r0 += 8 * RB) {
+                uint32_t v[RB];
+#pragma unroll
+                for (int k = 0; k < RB; k++) {
+                    const int r = r0 + 8 * k;
+                    if (r < BROWS) {
+                        const int gy = y0 - 3 + r;
+                        if (word_ok && col_in && gy >= 0 && gy < L.h) {
+                            v[k] = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)gy * L.pitch + gx));
+                        } else {
+                            const uint8_t *row = src + (size_t)reflect101(gy, L.h) * L.pitch;
+                            v[k] = (uint32_t)row[reflect101(gx, L.w)] | ((uint32_t)row[reflect101(gx + 1, L.w)] << 8) |
+                                   ((uint32_t)row[reflect101(gx + 2, L.w)] << 16) | ((uint32_t)row[reflect101(gx + 3, L.w)] << 24);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < RB; k++) {
+                    const int r = r0 + 8 * k;
+                    if (r < BROWS) reinterpret_cast<uint32_t *>(s_in)[r * (BIN_PITCH / 4) + lane] = v[k];
+                }
+            }
         }
-        reinterpret_cast<uint32_t *>(s_in)[i] = v;
     }
     __syncthreads();
     // horizontal: item = (row, group of 8 outputs)
@@ -323,24 +341,31 @@ __global__ void __launch_bounds__(192) k_fast_cells(const LevelDev *__restrict__
         const int nwords = min((rw + 8) >> 2, FT_PITCH / 4);
         const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
         if (lane < nwords) {
-            const size_t off0 = (size_t)f * L.img_fstride + (size_t)cell.y0 * L.pitch + cell.x0 + 4 * lane;
+            const uint8_t *p0 = src + 4 * lane;
             constexpr int RB = 7;   // rows in flight per lane (6 warps x 7 rows covers a 42-row ROI in one round)
-            for (int r0 = wid; r0 <= rh; r0 += nwarps * RB) {
-                uint32_t lo[RB], hi[RB], sh[RB];
+            if ((L.pitch & 3) == 0) {
+                // every row has the same misalignment: one aligned base pointer, rows are pitch/4 words apart
+                const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(p0) & 3), sh = 8 * mis;
+                const uint32_t *q0 = reinterpret_cast<const uint32_t *>(p0 - mis);
+                const int pw = L.pitch >> 2;
+                for (int r0 = wid; r0 <= rh; r0 += nwarps * RB) {
+                    uint32_t lo[RB], hi[RB];
 #pragma unroll
-                for (int k = 0; k < RB; k++) {
-                    const int r = r0 + k * nwarps;
-                    if (r <= rh) {
-                        const size_t off = off0 + (size_t)r * L.pitch;
-                        const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(L.img) + off) & 3);
-                        const uint32_t *q = reinterpret_cast<const uint32_t *>(L.img + (off - mis));
-                        lo[k] = __ldg(q); hi[k] = __ldg(q + 1); sh[k] = 8 * mis;
+                    for (int k = 0; k < RB; k++) {
+                        const int r = r0 + k * nwarps;
+                        if (r <= rh) { const uint32_t *q = q0 + r * pw; lo[k] = __ldg(q); hi[k] = __ldg(q + 1); }
+                    }
+#pragma unroll
+                    for (int k = 0; k < RB; k++) {
+                        const int r = r0 + k * nwarps;
+                        if (r <= rh) *reinterpret_cast<uint32_t *>(s_roi + r * FT_PITCH + 4 * lane) = __funnelshift_r(lo[k], hi[k], sh);
                     }
                 }
-#pragma unroll
-                for (int k = 0; k < RB; k++) {
-                    const int r = r0 + k * nwarps;
-                    if (r <= rh) *reinterpret_cast<uint32_t *>(s_roi + r * FT_PITCH + 4 * lane) = __funnelshift_r(lo[k], hi[k], sh[k]);
+            } else {
+                for (int r = wid; r <= rh; r += nwarps) {
+                    const uint8_t *p = p0 + (size_t)r * L.pitch;
+                    *reinterpret_cast<uint32_t *>(s_roi + r * FT_PITCH + 4 * lane) =
+                        (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
                 }
             }
         }
@@ -351,7 +376,7 @@ __global__ void __launch_bounds__(192) k_fast_cells(const LevelDev *__restrict__
     // scores: item = (4-pixel group g, row pair s)
     const int ng = (iw + 3) >> 2, ns = (ih + 1) >> 1;
     for (int it = threadIdx.x; it < ng * ns; it += blockDim.x) {
-        const int s = it / ng, g = it - s * ng;
+        const int s = (int)(((uint32_t)it * (65536u / (uint32_t)ng + 1u)) >> 16), g = it - s * ng;
         uint32_t w[8][3];
 #pragma unroll
         for (int r = 0; r < 8; r++) {
@@ -378,8 +403,9 @@ __global__ void __launch_bounds__(192) k_fast_cells(const LevelDev *__restrict__
     int n_ini_local = 0;
     {
         const uint32_t thr = ((uint32_t)min_th << 8) | ((uint32_t)min_th << 24);
+        const uint32_t inv_ng = 65536u / (uint32_t)ng + 1u;   // exact floor(it / ng) for it < 65536 / ... (it < 18 * 74)
         for (int it = threadIdx.x; it < ng * ih; it += blockDim.x) {
-            const int y = it / ng, g = it - y * ng;
+            const int y = (int)(((uint32_t)it * inv_ng) >> 16), g = it - y * ng;
             const uint32_t *ru = reinterpret_cast<const uint32_t *>(s_sc + y * FS_PITCH) + g;   // words g, g+1, g+2: x-4.., x.., x+4..
             const uint32_t *rm = ru + FS_PITCH / 4, *rd = rm + FS_PITCH / 4;
             const uint32_t c_m = rm[1];
@@ -879,18 +905,19 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 }
 
 __device__ __forceinline__ float warp_ic_angle(const uint8_t *__restrict__ center, int pitch, int lane) {
-    int m10 = 0, m01 = 0;
-    const int u = lane - kHalfPatch;
-    if (lane <= 2 * kHalfPatch) {
-#pragma unroll 1
-        for (int v = -kHalfPatch; v <= kHalfPatch; v++) {
-            const int d = c_umax[v < 0 ? -v : v];
-            if (u >= -d && u <= d) {
-                const int val = center[v * pitch + u];
-                m10 += u * val; m01 += v * val;
-            }
-        }
+    // lane <-> column u = lane - 15; all 31 row loads of a lane are independent (fully unrolled, predicated by the
+    // circular patch mask umax[|v|] = 15,15,15,15,14,14,14,13,13,12,11,10,9,8,6,3)
+    constexpr int UM[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+    const int u = lane - kHalfPatch, au = u < 0 ? -u : u;
+    int sum = 0, m01 = 0;
+    const uint8_t *p = center + u;
+#pragma unroll
+    for (int v = -kHalfPatch; v <= kHalfPatch; v++) {
+        const int d = UM[v < 0 ? -v : v];
+        const int val = (au <= d) ? (int)__ldg(p + v * pitch) : 0;
+        sum += val; m01 += v * val;
     }
+    int m10 = u * sum;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xFFFFFFFFu, m10, o); m01 += __shfl_xor_sync(0xFFFFFFFFu, m01, o); }
     return fast_atan2_deg((float)m01, (float)m10);
