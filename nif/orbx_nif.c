@@ -1,0 +1,128 @@
+/* erl_nif wrapper of liborbx.so for the Elixir side of SEND-SLAM (seam b3).
+ *
+ * The reference has no NIF: a process registered in CameraRegistry receives {:camera_frame, {:ok, opts}}
+ * (send_slam/lib/send_slam/camera_producer.ex:190-208; consumers register like send_slam/lib/send_slam/timer.ex:24-27)
+ * and SlamHandler ships every frame as PPM over TCP (send_slam/lib/send_slam/slam_handler.ex:59-88).  With this NIF a
+ * consumer can extract in-VM: `SendSlam.OrbNif.extract(handle, Evision.Mat.to_binary(gray), w, h)`.
+ * All calls block on the GPU for 100s of microseconds or more => ERL_NIF_DIRTY_JOB_IO_BOUND.  Errors come back as
+ * {:error, reason}; nothing here raises or crashes the VM.
+ * Build (where Erlang is installed): cc -shared -fPIC -I$ERL_INCLUDE -I../include orbx_nif.c -L../send_slam_b200 -lorbx
+ * Compile-check here (no erl_nif.h in this image): cc -DORBX_NIF_MIN -I../include -c orbx_nif.c
+ */
+#ifdef ORBX_NIF_MIN
+#include "erl_nif_min.h"
+#else
+#include <erl_nif.h>
+#endif
+#include <string.h>
+
+#include "orbx.h"
+
+static ErlNifResourceType *g_handle_type;
+
+typedef struct { orbx_handle *h; int cap; } nif_handle;
+
+static void handle_dtor(ErlNifEnv *env, void *obj) {
+    (void)env;
+    nif_handle *nh = (nif_handle *)obj;
+    if (nh->h) orbx_destroy(nh->h);
+    nh->h = NULL;
+}
+
+static ERL_NIF_TERM mk_error(ErlNifEnv *env, const char *reason) {
+    return enif_make_tuple2(env, enif_make_atom(env, "error"), enif_make_atom(env, reason));
+}
+
+static const char *code_atom(int rc) {
+    switch (rc) {
+        case ORBX_E_INVALID: return "invalid_argument";
+        case ORBX_E_CUDA: return "cuda_error";
+        case ORBX_E_CAPACITY: return "capacity";
+        case ORBX_E_EMPTY: return "empty_image";
+        case ORBX_E_OVERFLOW: return "overflow";
+        default: return "unknown";
+    }
+}
+
+/* create(%{nfeatures, scale_factor, nlevels, ini_th, min_th, device, max_width, max_height}) as an 8-tuple */
+static ERL_NIF_TERM nif_create(ErlNifEnv *env, int argc, const ERL_NIF_TERM argv[]) {
+    int nf, nl, ini, mn, dev, mw, mh;
+    double sf;
+    if (argc != 8 || !enif_get_int(env, argv[0], &nf) || !enif_get_double(env, argv[1], &sf) || !enif_get_int(env, argv[2], &nl) ||
+        !enif_get_int(env, argv[3], &ini) || !enif_get_int(env, argv[4], &mn) || !enif_get_int(env, argv[5], &dev) ||
+        !enif_get_int(env, argv[6], &mw) || !enif_get_int(env, argv[7], &mh))
+        return enif_make_badarg(env);
+    orbx_config cfg;
+    cfg.nfeatures = nf; cfg.scale_factor = (float)sf; cfg.nlevels = nl; cfg.ini_th_fast = ini; cfg.min_th_fast = mn;
+    cfg.device = dev; cfg.max_width = mw; cfg.max_height = mh; cfg.max_batch = 1;
+    orbx_handle *h = NULL;
+    int rc = orbx_create(&cfg, &h);
+    if (rc != ORBX_OK) return mk_error(env, code_atom(rc));
+    nif_handle *nh = (nif_handle *)enif_alloc_resource(g_handle_type, sizeof(nif_handle));
+    nh->h = h; nh->cap = orbx_keypoint_capacity(h);
+    ERL_NIF_TERM term = enif_make_resource(env, nh);
+    enif_release_resource(nh);
+    return enif_make_tuple2(env, enif_make_atom(env, "ok"), term);
+}
+
+/* extract(handle, gray_binary, width, height) -> {:ok, n, mono_index, keypoints_binary (n*28 B), descriptors_binary (n*32 B)} */
+static ERL_NIF_TERM nif_extract(ErlNifEnv *env, int argc, const ERL_NIF_TERM argv[]) {
+    nif_handle *nh;
+    ErlNifBinary img;
+    int w, h;
+    if (argc != 4 || !enif_get_resource(env, argv[0], g_handle_type, (void **)&nh) || !enif_inspect_binary(env, argv[1], &img) ||
+        !enif_get_int(env, argv[2], &w) || !enif_get_int(env, argv[3], &h))
+        return enif_make_badarg(env);
+    if (!nh->h) return mk_error(env, "closed");
+    if (w < 1 || h < 1 || (size_t)w * (size_t)h != img.size) return mk_error(env, "size_mismatch");
+    ERL_NIF_TERM kp_term, desc_term;
+    unsigned char *kp = enif_make_new_binary(env, (size_t)nh->cap * sizeof(orbx_keypoint), &kp_term);
+    unsigned char *desc = enif_make_new_binary(env, (size_t)nh->cap * ORBX_DESC_BYTES, &desc_term);
+    if (!kp || !desc) return mk_error(env, "enomem");
+    int n = 0, mono = -1;
+    int rc = orbx_extract(nh->h, img.data, w, h, w, 0, 1000, (orbx_keypoint *)kp, desc, nh->cap, &n, &mono);
+    if (rc != ORBX_OK) return mk_error(env, code_atom(rc));
+    return enif_make_tuple5(env, enif_make_atom(env, "ok"), enif_make_int(env, n), enif_make_int(env, mono),
+                            enif_make_sub_binary(env, kp_term, 0, (size_t)n * sizeof(orbx_keypoint)),
+                            enif_make_sub_binary(env, desc_term, 0, (size_t)n * ORBX_DESC_BYTES));
+}
+
+/* match_windowed(handle, q_desc, q_uvr, q_levels, t_kp, t_desc, {minx, miny, maxx, maxy}) -> {:ok, best_idx, best_dist, second_idx, second_dist} (int32 binaries) */
+static ERL_NIF_TERM nif_match_windowed(ErlNifEnv *env, int argc, const ERL_NIF_TERM argv[]) {
+    nif_handle *nh;
+    ErlNifBinary qd, quvr, qlev, tkp, td;
+    const ERL_NIF_TERM *b;
+    int arity;
+    double bd[4];
+    if (argc != 7 || !enif_get_resource(env, argv[0], g_handle_type, (void **)&nh) || !enif_inspect_binary(env, argv[1], &qd) ||
+        !enif_inspect_binary(env, argv[2], &quvr) || !enif_inspect_binary(env, argv[3], &qlev) || !enif_inspect_binary(env, argv[4], &tkp) ||
+        !enif_inspect_binary(env, argv[5], &td) || !enif_get_tuple(env, argv[6], &arity, &b) || arity != 4)
+        return enif_make_badarg(env);
+    for (int i = 0; i < 4; i++) if (!enif_get_double(env, b[i], &bd[i])) return enif_make_badarg(env);
+    if (!nh->h) return mk_error(env, "closed");
+    const int nq = (int)(qd.size / 32), nt = (int)(td.size / 32);
+    if (qd.size % 32 || td.size % 32 || quvr.size != (size_t)nq * 12 || qlev.size != (size_t)nq * 8 || tkp.size != (size_t)nt * sizeof(orbx_keypoint))
+        return mk_error(env, "size_mismatch");
+    float bounds[4] = {(float)bd[0], (float)bd[1], (float)bd[2], (float)bd[3]};
+    ERL_NIF_TERM t[4];
+    int32_t *o[4];
+    for (int i = 0; i < 4; i++) { o[i] = (int32_t *)enif_make_new_binary(env, (size_t)nq * 4, &t[i]); if (!o[i]) return mk_error(env, "enomem"); }
+    int rc = orbx_match_windowed(nh->h, qd.data, (const float *)quvr.data, (const int32_t *)qlev.data, nq, (const orbx_keypoint *)tkp.data,
+                                 td.data, nt, bounds, o[0], o[1], o[2], o[3]);
+    if (rc != ORBX_OK) return mk_error(env, code_atom(rc));
+    return enif_make_tuple5(env, enif_make_atom(env, "ok"), t[0], t[1], t[2], t[3]);
+}
+
+static int on_load(ErlNifEnv *env, void **priv, ERL_NIF_TERM info) {
+    (void)priv; (void)info;
+    g_handle_type = enif_open_resource_type(env, NULL, "orbx_handle", handle_dtor, ERL_NIF_RT_CREATE, NULL);
+    return g_handle_type ? 0 : 1;
+}
+
+static ErlNifFunc nif_funcs[] = {
+    {"create", 8, nif_create, ERL_NIF_DIRTY_JOB_IO_BOUND},
+    {"extract", 4, nif_extract, ERL_NIF_DIRTY_JOB_IO_BOUND},
+    {"match_windowed", 7, nif_match_windowed, ERL_NIF_DIRTY_JOB_IO_BOUND},
+};
+
+ERL_NIF_INIT(Elixir.SendSlam.OrbNif, nif_funcs, on_load, NULL, NULL, NULL)
