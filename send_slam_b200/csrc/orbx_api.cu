@@ -27,6 +27,8 @@ struct orbx_handle {
     int device = 0;
     cudaStream_t stream = nullptr;      // stream all work of this handle is issued on
     cudaStream_t own_stream = nullptr;  // created by orbx_create; `stream` may be redirected by orbx_set_stream
+    cudaStream_t side_stream = nullptr; // the Gaussian pass runs here, concurrently with FAST + quadtree
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     mutable std::string err;
     long long launches = 0;
 
@@ -195,14 +197,27 @@ static int run_pipeline(orbx_handle *h, int batch, int lap0, int lap1, KeypointR
     STAGE_MARK(0);
     for (int l = 1; l < nl; l++) h->launches += launch_resize(h->d_levels, h->h_levels, l, batch, h->stream);
     STAGE_MARK(1);
-    h->launches += launch_blur(h->d_levels, h->d_tiles, h->ntiles, batch, h->stream);
+    // The blurred planes are only needed by the descriptor stage, and the quadtree kernel (one CTA per frame x level,
+    // latency-bound) cannot fill the machine: outside profiling mode the Gaussian pass runs on a side stream next to
+    // quadtree + slot assignment.  It is forked after FAST because two machine-filling kernels gain nothing from
+    // running side by side.
+    if (prof) h->launches += launch_blur(h->d_levels, h->d_tiles, h->ntiles, batch, h->stream);
     STAGE_MARK(2);
     h->launches += launch_fast(h->d_levels, h->d_cells, (int)pl.cells.size(), batch, h->P.ini_th, h->P.min_th, h->d_overflow, h->stream);
     STAGE_MARK(3);
+    if (!prof) {
+        CU_TRY(h, cudaEventRecord(h->ev_fork, h->stream));
+        CU_TRY(h, cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+    }
     h->launches += launch_octree(h->d_levels, h->h_levels, nl, batch, h->d_overflow, h->stream);
+    if (!prof) {
+        h->launches += launch_blur(h->d_levels, h->d_tiles, h->ntiles, batch, h->side_stream);
+        CU_TRY(h, cudaEventRecord(h->ev_join, h->side_stream));
+    }
     STAGE_MARK(4);
     h->launches += launch_finalize(h->d_levels, nl, batch, pl.total_out_cap, lap0, lap1, d_kp, cap, h->d_slot, d_n, d_mono, h->d_overflow, h->stream);
     STAGE_MARK(5);
+    if (!prof) CU_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     h->launches += launch_describe(h->d_levels, nl, batch, pl.total_out_cap, h->d_slot, d_kp, d_desc, cap, h->stream);
     STAGE_MARK(6);
 #undef STAGE_MARK
@@ -248,6 +263,12 @@ int orbx_create(const orbx_config *cfg, orbx_handle **out) {
         delete h; return ORBX_E_CUDA;
     }
     h->own_stream = h->stream;
+    if ((e = cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming)) != cudaSuccess) {
+        g_create_error = std::string("cuda init: ") + cudaGetErrorString(e);
+        cudaStreamDestroy(h->stream); delete h; return ORBX_E_CUDA;
+    }
     upload_constants();
     if ((e = cudaGetLastError()) != cudaSuccess) {
         g_create_error = std::string("constant upload: ") + cudaGetErrorString(e);
@@ -264,6 +285,9 @@ void orbx_destroy(orbx_handle *h) {
     free_plan(h);
     for (int i = 0; i < 7; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     delete h;
 }
 
