@@ -71,6 +71,13 @@ struct orbx_handle {
         }                                                                                                       \
     } while (0)
 
+// true for cudaHostAlloc'd / cudaHostRegister'ed memory (DMA-able without staging)
+static bool is_pinned_host(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 static int fail(const orbx_handle *h, int code, const char *msg) {
     if (h) h->err = msg; else g_create_error = msg;
     return code;
@@ -396,21 +403,43 @@ int orbx_extract_batch(orbx_handle *h, const uint8_t *const *frames, int batch, 
     const int kc = h->kp_cap;
     const int pitch0 = h->l0_own_pitch;
     const size_t fstride0 = h->l0_own_fstride;
-    // host -> pinned -> device (one 2D copy), rows repacked to the plane pitch
-    for (int i = 0; i < batch; i++) {
-        uint8_t *dst = h->h_in + (size_t)i * fstride0;
-        const uint8_t *src = frames[i];
-        if (stride == pitch0) std::memcpy(dst, src, (size_t)stride * (height - 1) + width);
-        else for (int y = 0; y < height; y++) std::memcpy(dst + (size_t)y * pitch0, src + (size_t)y * stride, (size_t)width);
+    // Input: page-locked caller memory is DMA'd straight into the level-0 planes (one strided 2D copy per frame, or a
+    // single one when the frames are evenly spaced); pageable memory is first repacked into the handle's pinned staging.
+    const bool in_pinned = is_pinned_host(frames[0]) && is_pinned_host(frames[batch - 1] + (size_t)stride * (height - 1));
+    if (in_pinned) {
+        bool even = true;
+        const ptrdiff_t step = batch > 1 ? frames[1] - frames[0] : (ptrdiff_t)stride * height;
+        for (int i = 1; i < batch && even; i++) even = (frames[i] - frames[i - 1]) == step;
+        if (even && step == (ptrdiff_t)stride * height && fstride0 == (size_t)pitch0 * height) {
+            CU_TRY(h, cudaMemcpy2DAsync(h->l0_own, pitch0, frames[0], stride, width, (size_t)height * batch, cudaMemcpyHostToDevice, h->stream));
+        } else {
+            for (int i = 0; i < batch; i++)
+                CU_TRY(h, cudaMemcpy2DAsync(h->l0_own + (size_t)i * fstride0, pitch0, frames[i], stride, width, height, cudaMemcpyHostToDevice, h->stream));
+        }
+    } else {
+        for (int i = 0; i < batch; i++) {
+            uint8_t *dst = h->h_in + (size_t)i * fstride0;
+            const uint8_t *src = frames[i];
+            if (stride == pitch0) std::memcpy(dst, src, (size_t)stride * (height - 1) + width);
+            else for (int y = 0; y < height; y++) std::memcpy(dst + (size_t)y * pitch0, src + (size_t)y * stride, (size_t)width);
+        }
+        CU_TRY(h, cudaMemcpyAsync(h->l0_own, h->h_in, (size_t)batch * fstride0, cudaMemcpyHostToDevice, h->stream));
     }
-    CU_TRY(h, cudaMemcpyAsync(h->l0_own, h->h_in, (size_t)batch * fstride0, cudaMemcpyHostToDevice, h->stream));
     if ((rc = set_level0(h, h->l0_own, pitch0, fstride0))) return rc;
     if ((rc = run_pipeline(h, batch, lap0, lap1, h->d_kp, h->d_desc, kc, h->d_n, h->d_mono))) return rc;
     CU_TRY(h, cudaMemcpyAsync(h->h_n, h->d_n, sizeof(int) * batch, cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(h, cudaMemcpyAsync(h->h_mono, h->d_mono, sizeof(int) * batch, cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(h, cudaMemcpyAsync(h->h_overflow, h->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CU_TRY(h, cudaMemcpyAsync(h->h_kp, h->d_kp, (size_t)batch * kc * sizeof(KeypointRec), cudaMemcpyDeviceToHost, h->stream));
-    CU_TRY(h, cudaMemcpyAsync(h->h_desc, h->d_desc, (size_t)batch * kc * 32, cudaMemcpyDeviceToHost, h->stream));
+    // Output: page-locked caller buffers of the internal record capacity receive the result blocks directly
+    const bool out_direct = cap >= kc && is_pinned_host(kp_out) && is_pinned_host(desc_out);
+    if (out_direct) {
+        CU_TRY(h, cudaMemcpy2DAsync(kp_out, (size_t)cap * sizeof(KeypointRec), h->d_kp, (size_t)kc * sizeof(KeypointRec),
+                                    (size_t)kc * sizeof(KeypointRec), batch, cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(h, cudaMemcpy2DAsync(desc_out, (size_t)cap * 32, h->d_desc, (size_t)kc * 32, (size_t)kc * 32, batch, cudaMemcpyDeviceToHost, h->stream));
+    } else {
+        CU_TRY(h, cudaMemcpyAsync(h->h_kp, h->d_kp, (size_t)batch * kc * sizeof(KeypointRec), cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(h, cudaMemcpyAsync(h->h_desc, h->d_desc, (size_t)batch * kc * 32, cudaMemcpyDeviceToHost, h->stream));
+    }
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     if (*h->h_overflow) {
         char msg[96]; snprintf(msg, sizeof(msg), "internal buffer overflow (stage code %d)", *h->h_overflow);
@@ -420,8 +449,10 @@ int orbx_extract_batch(orbx_handle *h, const uint8_t *const *frames, int batch, 
         const int n = h->h_n[i];
         if (n > cap) return fail(h, ORBX_E_CAPACITY, "kp_out/desc_out capacity smaller than the number of keypoints");
         n_out[i] = n; mono_index_out[i] = h->h_mono[i];
-        std::memcpy(kp_out + (size_t)i * cap, h->h_kp + (size_t)i * kc, (size_t)n * sizeof(KeypointRec));
-        std::memcpy(desc_out + (size_t)i * cap * 32, h->h_desc + (size_t)i * kc * 32, (size_t)n * 32);
+        if (!out_direct) {
+            std::memcpy(kp_out + (size_t)i * cap, h->h_kp + (size_t)i * kc, (size_t)n * sizeof(KeypointRec));
+            std::memcpy(desc_out + (size_t)i * cap * 32, h->h_desc + (size_t)i * kc * 32, (size_t)n * 32);
+        }
     }
     return ORBX_OK;
 }

@@ -213,8 +213,9 @@ class ORBextractor:
         self._check(rc)
         return mono.value, kps[:n.value].copy(), desc[:n.value].copy()
 
-    def extract_batch(self, frames, vLappingArea=(0, 1000)):
-        """frames: uint8 [B,H,W] (C-contiguous rows).  Returns (mono[B], n[B], kps[B,cap], desc[B,cap,32])."""
+    def extract_batch(self, frames, vLappingArea=(0, 1000), out=None):
+        """frames: uint8 [B,H,W] (C-contiguous rows).  Returns (mono[B], n[B], kps[B,cap], desc[B,cap,32]).
+        out = (kps, desc) lets the caller supply (e.g. page-locked) result arrays of shape [B,cap] / [B,cap,32]."""
         frames = np.asarray(frames)
         if frames.dtype != np.uint8 or frames.ndim != 3:
             raise OrbxError(ORBX_E_INVALID, "frames must be uint8 [B,H,W]")
@@ -222,8 +223,13 @@ class ORBextractor:
             frames = np.ascontiguousarray(frames)
         B, h, w = frames.shape
         ptrs = (C.c_void_p * B)(*[frames[i].ctypes.data for i in range(B)])
-        kps = np.zeros((B, self.capacity), KP_DTYPE)
-        desc = np.zeros((B, self.capacity, 32), np.uint8)
+        if out is None:
+            kps = np.zeros((B, self.capacity), KP_DTYPE)
+            desc = np.zeros((B, self.capacity, 32), np.uint8)
+        else:
+            kps, desc = out
+            if kps.shape != (B, self.capacity) or desc.shape != (B, self.capacity, 32) or kps.dtype != KP_DTYPE or desc.dtype != np.uint8:
+                raise OrbxError(ORBX_E_INVALID, "out arrays must be [B,cap] KP_DTYPE and [B,cap,32] uint8")
         n, mono = np.zeros(B, np.int32), np.zeros(B, np.int32)
         rc = self._L.orbx_extract_batch(self._h, ptrs, B, w, h, frames.strides[1], int(vLappingArea[0]),
                                         int(vLappingArea[1]), _p(kps), _p(desc), self.capacity, _p(n), _p(mono))
