@@ -31,6 +31,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <float.h>
+#ifdef __AVX2__
+#include <immintrin.h>
+#endif
 
 typedef unsigned char u8;
 
@@ -246,9 +249,38 @@ static int fast_score(const u8 *p, const int *off, int t) {
     return -b0 - 1;
 }
 
-/* Runs FAST+NMS on the ROI [x0,x1)x[y0,y1) of img; appends (x+ox, y+oy, score) (ROI-relative coords plus
- * offsets) row-major.  score buffer sc is (x1-x0)*(y1-y0) bytes of scratch.  Returns number appended. */
-static int fast_roi(const u8 *img, int stride, int x0, int y0, int x1, int y1, int t, u8 *sc,
+#ifdef __AVX2__
+/* 32 pixels at once: m = max(v - min_arcs(max_arc r), max_arcs(min_arc r) - v, 0), the same value fast_score() derives
+ * from d = v - r (min_k (v - r_k) = v - max_k r_k).  Arc extrema of the 16 arcs of 9: pairs Q[j] = (r[2j+1], r[2j+2]),
+ * quads Q2[i] = Q[i] u Q[i+1]; the two arcs starting at 2i and 2i+1 share r[2i+1..2i+8] = Q2[i] u Q2[i+2]. */
+static inline __m256i fast_m32(const u8 *p, const int *off) {
+    __m256i r[16], qx[8], qn[8], q2x[8], q2n[8];
+    for (int k = 0; k < 16; k++) r[k] = _mm256_loadu_si256((const __m256i *)(p + off[k]));
+    const __m256i v = _mm256_loadu_si256((const __m256i *)p);
+    for (int j = 0; j < 8; j++) {
+        qx[j] = _mm256_max_epu8(r[2 * j + 1], r[(2 * j + 2) & 15]);
+        qn[j] = _mm256_min_epu8(r[2 * j + 1], r[(2 * j + 2) & 15]);
+    }
+    for (int i = 0; i < 8; i++) {
+        q2x[i] = _mm256_max_epu8(qx[i], qx[(i + 1) & 7]);
+        q2n[i] = _mm256_min_epu8(qn[i], qn[(i + 1) & 7]);
+    }
+    __m256i min_arc_max = _mm256_set1_epi8((char)0xFF), max_arc_min = _mm256_setzero_si256();
+    for (int i = 0; i < 8; i++) {
+        const __m256i a = r[2 * i], b = r[(2 * i + 9) & 15];
+        const __m256i fx = _mm256_max_epu8(_mm256_max_epu8(q2x[i], q2x[(i + 2) & 7]), _mm256_min_epu8(a, b));
+        const __m256i fn = _mm256_min_epu8(_mm256_min_epu8(q2n[i], q2n[(i + 2) & 7]), _mm256_max_epu8(a, b));
+        min_arc_max = _mm256_min_epu8(min_arc_max, fx);
+        max_arc_min = _mm256_max_epu8(max_arc_min, fn);
+    }
+    return _mm256_max_epu8(_mm256_subs_epu8(v, min_arc_max), _mm256_subs_epu8(max_arc_min, v));
+}
+#endif
+
+/* Runs FAST+NMS on the ROI [x0,x1)x[y0,y1) of img (img_w = full row width, bounds the vector loads); appends
+ * (x+ox, y+oy, score) (ROI-relative coords plus offsets) row-major.  score buffer sc is (x1-x0)*(y1-y0) bytes of scratch.
+ * Returns number appended.  score = cv's cornerScore = m - 1 for m > t. */
+static int fast_roi(const u8 *img, int stride, int img_w, int x0, int y0, int x1, int y1, int t, u8 *sc,
                     float ox, float oy, float **out, int *n, int *cap) {
     int cw = x1 - x0, chh = y1 - y0, added = 0;
     if (cw < 7 || chh < 7) return 0;
@@ -257,7 +289,16 @@ static int fast_roi(const u8 *img, int stride, int x0, int y0, int x1, int y1, i
     memset(sc, 0, (size_t)cw * chh);
     for (int y = 3; y < chh - 3; y++) {
         const u8 *row = img + (size_t)(y0 + y) * stride + x0;
-        for (int x = 3; x < cw - 3; x++) {
+        int x = 3;
+#ifdef __AVX2__
+        for (; x < cw - 3 && x0 + x + 3 + 32 <= img_w; x += 32) {
+            u8 m[32];
+            _mm256_storeu_si256((__m256i *)m, fast_m32(row + x, off));
+            const int cnt = cw - 3 - x < 32 ? cw - 3 - x : 32;
+            for (int i = 0; i < cnt; i++) if (m[i] > t) sc[y * cw + x + i] = (u8)(m[i] - 1);
+        }
+#endif
+        for (; x < cw - 3; x++) {
             const u8 *p = row + x;
             int v = p[0], lo = v - t, hi = v + t;
             /* exact necessary condition: every opposite pair must hold one darker / one brighter pixel */
@@ -292,7 +333,7 @@ static int fast_roi(const u8 *img, int stride, int x0, int y0, int x1, int y1, i
 int orb_oracle_fast(const u8 *img, int w, int h, int stride, int t, float *out, int cap) {
     u8 *sc = (u8 *)malloc((size_t)w * h);
     float *buf = NULL; int n = 0, c = 0;
-    fast_roi(img, stride, 0, 0, w, h, t, sc, 0.f, 0.f, &buf, &n, &c);
+    fast_roi(img, stride, w, 0, 0, w, h, t, sc, 0.f, 0.f, &buf, &n, &c);
     int m = n < cap ? n : cap;
     if (m > 0) memcpy(out, buf, sizeof(float) * 3 * (size_t)m);
     free(buf); free(sc);
@@ -318,8 +359,8 @@ static void fast_cells(const u8 *img, int w, int h, int stride, int ini_th, int 
             int iniX = minBX + j * wCell, maxX = iniX + wCell + 6;
             if (iniX >= maxBX - 6) continue;
             if (maxX > maxBX) maxX = maxBX;
-            int got = fast_roi(img, stride, iniX, iniY, maxX, maxY, ini_th, sc, (float)(j * wCell), (float)(i * hCell), out, n, cap);
-            if (!got) fast_roi(img, stride, iniX, iniY, maxX, maxY, min_th, sc, (float)(j * wCell), (float)(i * hCell), out, n, cap);
+            int got = fast_roi(img, stride, w, iniX, iniY, maxX, maxY, ini_th, sc, (float)(j * wCell), (float)(i * hCell), out, n, cap);
+            if (!got) fast_roi(img, stride, w, iniX, iniY, maxX, maxY, min_th, sc, (float)(j * wCell), (float)(i * hCell), out, n, cap);
         }
     }
     free(sc);
