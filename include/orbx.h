@@ -159,6 +159,11 @@ int orbx_knn2_query_device(orbx_db *db, const uint8_t *d_queries, int nq, unsign
  * orbx_knn2_query_device output) into d_packed_out[nq*2]; all pointers in HBM on the db's device. */
 int orbx_knn2_merge_device(orbx_db *db, const unsigned long long *d_partials, int nparts, int nq,
                            unsigned long long *d_packed_out);
+/* Distance backend of a shard: ORBX_KNN_TENSOR (default) = descriptors expanded to {-1,+1} int8, q.d = 256 - 2H on
+ * tcgen05.mma kind::i8 with the top-2 taken from TMEM; ORBX_KNN_POPC = XOR + POPC on the CUDA cores.  Identical results. */
+#define ORBX_KNN_POPC 0
+#define ORBX_KNN_TENSOR 1
+int orbx_knn2_set_backend(orbx_db *db, int backend);
 int orbx_knn2_sync(orbx_db *db);
 int orbx_knn2_set_stream(orbx_db *db, void *cuda_stream);
 long long orbx_knn2_launch_count(const orbx_db *db);

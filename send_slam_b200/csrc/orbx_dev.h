@@ -57,6 +57,17 @@ void upload_constants();
 }  // namespace orbx
 
 #include <string>
+namespace orbx {
+// tensor-core kNN (orbx_knn_tc.cu)
+size_t knn_tc_smem_bytes();
+int knn_tc_max_queries();
+long long knn_tc_padded_rows(long long nrows);
+int knn_tc_padded_queries(int nq);
+int launch_expand_pm1(const uint8_t *d_bits, long long nrows, long long nrows_pad, int8_t *d_out, cudaStream_t stream);
+int launch_knn2_tc(const int8_t *d_qe, int nq, const int8_t *d_dbe, long long nrows, long long row_offset, int sm_count,
+                   unsigned long long *d_partial, int *grid_out, cudaStream_t stream, std::string &err);
+}  // namespace orbx
+
 struct orbx_keypoint;
 namespace orbx {
 // matching launchers that run on an extractor handle's stream (orbx_match.cu)

@@ -180,6 +180,12 @@ struct orbx_db {
     unsigned long long *h_out = nullptr;
     mutable std::string err;
     long long launches = 0;
+    // tensor-core backend (orbx_knn_tc.cu): {-1,+1} int8 expansion of the shard (built on first use) and of the queries
+    int backend = 1;                 // ORBX_KNN_TENSOR
+    int sm_count = 0;
+    int8_t *d_dbe = nullptr;
+    int8_t *d_qe = nullptr; int qe_cap = 0;
+    unsigned long long *d_partial_tc = nullptr; size_t partial_tc_cap = 0;
 };
 
 #define DB_TRY(db, expr)                                                                       \
@@ -219,6 +225,7 @@ static int db_create_common(int device, long long nrows, long long row_offset, o
     }
     // chunking: enough CTAs to fill 148 SMs a few times for ~2k queries, chunk <= 2^23 rows (packed key)
     cudaDeviceProp prop; cudaGetDeviceProperties(&prop, device);
+    db->sm_count = prop.multiProcessorCount;
     int chunks = std::max(1, prop.multiProcessorCount * 4 / 8);
     long long rpc = (nrows + chunks - 1) / std::max(chunks, 1);
     rpc = std::max<long long>(rpc, KQ_TILE * 8);
@@ -268,6 +275,9 @@ void orbx_knn2_destroy_db(orbx_db *db) {
     if (db->d_partial) cudaFree(db->d_partial);
     if (db->d_out) cudaFree(db->d_out);
     if (db->h_out) cudaFreeHost(db->h_out);
+    if (db->d_dbe) cudaFree(db->d_dbe);
+    if (db->d_qe) cudaFree(db->d_qe);
+    if (db->d_partial_tc) cudaFree(db->d_partial_tc);
     if (db->own_stream) cudaStreamDestroy(db->own_stream);
     delete db;
 }
@@ -290,10 +300,53 @@ int orbx_knn2_sync(orbx_db *db) {
     return ORBX_OK;
 }
 
+int orbx_knn2_set_backend(orbx_db *db, int backend) {
+    if (!db || (backend != ORBX_KNN_POPC && backend != ORBX_KNN_TENSOR)) return ORBX_E_INVALID;
+    db->backend = backend;
+    return ORBX_OK;
+}
+
+// tensor-core path: expand (once) the shard and (per call) the queries to {-1,+1} int8, GEMM tiles + top-2 in TMEM
+static int query_device_tensor(orbx_db *db, const uint8_t *d_queries, int nq, unsigned long long *d_packed_out) {
+    if (!db->d_dbe) {
+        const long long rows_pad = knn_tc_padded_rows(db->nrows);
+        DB_TRY(db, cudaMalloc((void **)&db->d_dbe, (size_t)rows_pad * 256));
+        db->launches += launch_expand_pm1(db->d_rows, db->nrows, rows_pad, db->d_dbe, db->stream);
+        DB_TRY(db, cudaGetLastError());
+    }
+    const int maxq = knn_tc_max_queries();
+    const int qcap = knn_tc_padded_queries(std::min(nq, maxq));
+    if (qcap > db->qe_cap) {
+        if (db->d_qe) cudaFree(db->d_qe);
+        db->d_qe = nullptr; db->qe_cap = 0;
+        DB_TRY(db, cudaMalloc((void **)&db->d_qe, (size_t)qcap * 256));
+        db->qe_cap = qcap;
+    }
+    const size_t need = (size_t)db->sm_count * std::min(nq, maxq) * 2;
+    if (need > db->partial_tc_cap) {
+        if (db->d_partial_tc) cudaFree(db->d_partial_tc);
+        db->d_partial_tc = nullptr; db->partial_tc_cap = 0;
+        DB_TRY(db, cudaMalloc((void **)&db->d_partial_tc, need * sizeof(unsigned long long)));
+        db->partial_tc_cap = need;
+    }
+    for (int q0 = 0; q0 < nq; q0 += maxq) {
+        const int n = std::min(maxq, nq - q0);
+        db->launches += launch_expand_pm1(d_queries + (size_t)q0 * 32, n, knn_tc_padded_queries(n), db->d_qe, db->stream);
+        int grid = 0;
+        const int l = launch_knn2_tc(db->d_qe, n, db->d_dbe, db->nrows, db->row_offset, db->sm_count, db->d_partial_tc, &grid, db->stream, db->err);
+        if (!l) return ORBX_E_CUDA;
+        k_knn2_merge<<<(n + 255) / 256, 256, 0, db->stream>>>(db->d_partial_tc, grid, n, d_packed_out + (size_t)q0 * 2);
+        db->launches += l + 1;
+        DB_TRY(db, cudaGetLastError());
+    }
+    return ORBX_OK;
+}
+
 int orbx_knn2_query_device(orbx_db *db, const uint8_t *d_queries, int nq, unsigned long long *d_packed_out) {
     if (!db || !d_queries || !d_packed_out || nq < 1) return ORBX_E_INVALID;
     if (((uintptr_t)d_queries & 15) != 0) { db->err = "device queries must be 16-byte aligned"; return ORBX_E_INVALID; }
     DB_TRY(db, cudaSetDevice(db->device));
+    if (db->backend == ORBX_KNN_TENSOR && db->nrows > 0) return query_device_tensor(db, d_queries, nq, d_packed_out);
     int rc = db_reserve(db, nq);
     if (rc) return rc;
     dim3 grid((nq + KQ_THREADS * KQ_QPT - 1) / (KQ_THREADS * KQ_QPT), db->nchunks);

@@ -43,7 +43,7 @@ EXPORTS = [
     "orbx_knn2_create_db", "orbx_knn2_create_db_device", "orbx_knn2_destroy_db", "orbx_knn2_last_error", "orbx_knn2_query",
     "orbx_knn2_query_device", "orbx_knn2_merge_device", "orbx_knn2_sync", "orbx_knn2_launch_count", "orbx_plan_probe",
     "orbx_version", "orbx_set_profiling", "orbx_get_stage_times", "orbx_set_stream",
-    "orbx_knn2_set_stream",
+    "orbx_knn2_set_stream", "orbx_knn2_set_backend",
 ]
 
 _lib = None
@@ -101,6 +101,7 @@ def lib():
     L.orbx_version.restype = C.c_char_p
     L.orbx_set_stream.argtypes = [vp, vp]
     L.orbx_knn2_set_stream.argtypes = [vp, vp]
+    L.orbx_knn2_set_backend.argtypes = [vp, C.c_int]
     L.orbx_set_profiling.argtypes = [vp, C.c_int]
     L.orbx_get_stage_times.argtypes = [vp, fp]
     _lib = L
@@ -410,6 +411,12 @@ class Knn2Index:
 
     def set_stream(self, cuda_stream: int):
         self._check(self._L.orbx_knn2_set_stream(self._db, C.c_void_p(cuda_stream)))
+
+    POPC, TENSOR = 0, 1
+
+    def set_backend(self, backend: int):
+        """Knn2Index.TENSOR (default: tcgen05 int8 GEMM tiles) or Knn2Index.POPC (CUDA-core XOR + POPC)."""
+        self._check(self._L.orbx_knn2_set_backend(self._db, int(backend)))
 
     def launch_count(self):
         return int(self._L.orbx_knn2_launch_count(self._db))
