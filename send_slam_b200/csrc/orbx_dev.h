@@ -65,7 +65,9 @@ long long knn_tc_padded_rows(long long nrows);
 int knn_tc_padded_queries(int nq);
 int launch_expand_pm1(const uint8_t *d_bits, long long nrows, long long nrows_pad, int8_t *d_out, cudaStream_t stream);
 int launch_knn2_tc(const int8_t *d_qe, int nq, const int8_t *d_dbe, long long nrows, long long row_offset, int sm_count,
-                   unsigned long long *d_partial, int *grid_out, cudaStream_t stream, std::string &err);
+                   unsigned long long *d_partial, int *nparts_out,
+                   void (*merge)(const unsigned long long *, int, int, unsigned long long *, cudaStream_t), cudaStream_t stream,
+                   std::string &err);
 }  // namespace orbx
 
 struct orbx_keypoint;

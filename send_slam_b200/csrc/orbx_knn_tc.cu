@@ -26,7 +26,8 @@ constexpr int TC_QT = 128;            // queries per tile (UMMA M)
 constexpr int TC_DT = 256;            // database rows per tile (UMMA N)
 constexpr int TC_K = 256;             // expanded descriptor length (bytes, int8)
 constexpr int TC_MAX_QTILES = 16;     // 2048 queries per launch
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;        // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+constexpr uint32_t TC_SENTINEL = 0x7FFFFFu;   // row field of a seeded (virtual) key
 constexpr uint32_t TC_A_BYTES = TC_QT * TC_K;          // 32 KB per query tile (two 128 x 128 B swizzle boxes)
 constexpr uint32_t TC_B_BYTES = TC_DT * TC_K;          // 64 KB per database tile (two 256 x 128 B boxes)
 constexpr unsigned long long TC_NONE64 = ~0ull;
@@ -105,12 +106,13 @@ struct TcShared {
     uint64_t full_a[2], empty_a[2], full_b[2], empty_b[2], tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
     uint32_t pad;
-    uint32_t top[TC_MAX_QTILES][TC_QT][2];   // running (H << 23 | row-in-CTA) keys, best and second best
+    uint32_t top[TC_MAX_QTILES][2][TC_QT][2];   // [query tile][column half][row]: running (H << 23 | row-in-CTA) keys
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const __grid_constant__ CUtensorMap map_q,
                                                            const __grid_constant__ CUtensorMap map_db, int nq, int nqt,
-                                                           long long nrows, int ntiles, long long row_offset,
+                                                           long long nrows, int tile0, int ntiles, long long row_offset,
+                                                           const unsigned long long *__restrict__ seed,
                                                            unsigned long long *__restrict__ partial) {
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment: round the dynamic shared-memory base up (1 KB of slack is requested)
@@ -123,12 +125,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const __grid_constant
     const int cta = blockIdx.x, G = gridDim.x;
     const int my_tiles = cta < ntiles ? (ntiles - cta + G - 1) / G : 0;
 
-    for (int i = threadIdx.x; i < TC_MAX_QTILES * TC_QT * 2; i += TC_THREADS) (&S.top[0][0][0])[i] = 0xFFFFFFFFu;
+    // running top-2 state; with a seed (top-2 of an earlier pass over lower rows) only strictly closer rows can matter,
+    // so both slots start at the virtual key (seed second-best distance, sentinel row)
+    for (int i = threadIdx.x; i < TC_MAX_QTILES * 2 * TC_QT; i += TC_THREADS) {
+        const int q = i / (2 * TC_QT), r = i % TC_QT, qi = q * TC_QT + r;
+        uint32_t v = 0xFFFFFFFFu;
+        if (seed && qi < nq) {
+            const unsigned long long s2 = seed[2 * (size_t)qi + 1];
+            if (s2 != TC_NONE64) v = ((uint32_t)(s2 >> 32) << 23) | TC_SENTINEL;
+        }
+        (&S.top[0][0][0][0])[2 * i] = v; (&S.top[0][0][0][0])[2 * i + 1] = v;
+    }
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; s++) {
             mbar_init(&S.full_a[s], 1); mbar_init(&S.empty_a[s], 1);
             mbar_init(&S.full_b[s], 1); mbar_init(&S.empty_b[s], 1);
-            mbar_init(&S.tmem_full[s], 1); mbar_init(&S.tmem_empty[s], 4);   // one arrival per epilogue warp
+            mbar_init(&S.tmem_full[s], 1); mbar_init(&S.tmem_empty[s], 8);   // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -146,7 +158,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const __grid_constant
         if (lane == 0) {
             uint32_t it = 0;
             for (int k = 0; k < my_tiles; k++) {
-                const int t = cta + k * G, bs = k & 1;
+                const int t = tile0 + cta + k * G, bs = k & 1;
                 mbar_wait(&S.empty_b[bs], ((k >> 1) & 1) ^ 1);
                 mbar_expect_tx(&S.full_b[bs], TC_B_BYTES);
                 tma_load_2d(smem_b + bs * TC_B_BYTES, &map_db, 0, t * TC_DT, &S.full_b[bs]);
@@ -190,22 +202,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const __grid_constant
             }
         }
     } else {
-        // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
-        const int quarter = warp & 3;
+        // ===== epilogue: warps 2..9; TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
+        const int quarter = warp & 3, half = (warp - 2) >> 2;
         const int row_in_tile = quarter * 32 + lane;
         uint32_t it = 0;
         for (int k = 0; k < my_tiles; k++) {
-            const int t = cta + k * G;
+            const int t = tile0 + cta + k * G;
             const long long tile_row0 = (long long)t * TC_DT;
             const int valid_cols = (int)min((long long)TC_DT, nrows - tile_row0);
             for (int q = 0; q < nqt; q++, it++) {
                 const int acc = it & 1;
-                uint32_t k1 = S.top[q][row_in_tile][0], k2 = S.top[q][row_in_tile][1];
+                uint32_t k1 = S.top[q][half][row_in_tile][0], k2 = S.top[q][half][row_in_tile][1];
                 int thr = 256 - 2 * (int)(k2 >> 23);          // a dot product must exceed this to enter the top 2
                 mbar_wait(&S.tmem_full[acc], (it >> 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-                for (int c0 = 0; c0 < TC_DT; c0 += 64) {
+                for (int c0 = half * (TC_DT / 2); c0 < (half + 1) * (TC_DT / 2); c0 += 64) {
                     uint32_t v[64];
                     TMEM_LD64(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TC_DT + c0), v);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -227,24 +239,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const __grid_constant
                         }
                     }
                 }
-                S.top[q][row_in_tile][0] = k1; S.top[q][row_in_tile][1] = k2;
+                S.top[q][half][row_in_tile][0] = k1; S.top[q][half][row_in_tile][1] = k2;
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&S.tmem_empty[acc]);
             }
         }
-        // this CTA's partial result
-        for (int q = 0; q < nqt; q++) {
-            const int qi = q * TC_QT + row_in_tile;
-            if (qi < nq) {
-                unsigned long long *o = partial + ((size_t)cta * nq + qi) * 2;
+        // merge the two column halves and write this CTA's partial result
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (half == 0) {
+            for (int q = 0; q < nqt; q++) {
+                const int qi = q * TC_QT + row_in_tile;
+                if (qi < nq) {
+                    uint32_t k1 = S.top[q][0][row_in_tile][0], k2 = S.top[q][0][row_in_tile][1];
 #pragma unroll
-                for (int j = 0; j < 2; j++) {
-                    const uint32_t key = S.top[q][row_in_tile][j];
-                    if (key == 0xFFFFFFFFu) { o[j] = TC_NONE64; continue; }
-                    const uint32_t local = key & 0x7FFFFFu;
-                    const long long grow = row_offset + (long long)(cta + (int)(local >> 8) * G) * TC_DT + (local & 255u);
-                    o[j] = ((unsigned long long)(key >> 23) << 32) | (unsigned long long)grow;
+                    for (int j = 0; j < 2; j++) {
+                        const uint32_t key = S.top[q][1][row_in_tile][j];
+                        k2 = min(k2, max(k1, key)); k1 = min(k1, key);
+                    }
+                    unsigned long long *o = partial + ((size_t)cta * nq + qi) * 2;
+                    const uint32_t keys[2] = {k1, k2};
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
+                        const uint32_t key = keys[j], local = key & 0x7FFFFFu;
+                        if (key == 0xFFFFFFFFu || local == TC_SENTINEL) { o[j] = TC_NONE64; continue; }
+                        const long long grow = row_offset + (long long)(tile0 + cta + (int)(local >> 8) * G) * TC_DT + (local & 255u);
+                        o[j] = ((unsigned long long)(key >> 23) << 32) | (unsigned long long)grow;
+                    }
                 }
             }
         }
@@ -300,17 +321,21 @@ int launch_expand_pm1(const uint8_t *d_bits, long long nrows, long long nrows_pa
     return 1;
 }
 
-// d_qe: expanded queries [nq_pad][256], d_dbe: expanded database [rows_pad][256]; partial: [grid][nq][2].
-// Returns the number of launches (0 on failure with err set); *grid_out = number of partial blocks written.
+// d_qe: expanded queries [nq_pad][256], d_dbe: expanded database [rows_pad][256]; partial: [sm_count + 1][nq][2].
+// Two passes when the shard has more tiles than CTAs: pass A takes the top-2 over the first `grid` tiles (merged into
+// partial slot `grid` by the caller-supplied merge), pass B covers the rest seeded with pass A's second-best distances,
+// which keeps its epilogue on the cheap filter path.  Returns launches issued (0 = failure, err set);
+// *nparts_out = number of partial blocks to merge at the end.
 int launch_knn2_tc(const int8_t *d_qe, int nq, const int8_t *d_dbe, long long nrows, long long row_offset, int sm_count,
-                   unsigned long long *d_partial, int *grid_out, cudaStream_t stream, std::string &err) {
+                   unsigned long long *d_partial, int *nparts_out, void (*merge)(const unsigned long long *, int, int, unsigned long long *, cudaStream_t),
+                   cudaStream_t stream, std::string &err) {
     const int nqt = (nq + TC_QT - 1) / TC_QT;
     if (nqt < 1 || nqt > TC_MAX_QTILES) { err = "tensor-core kNN handles 1..2048 queries per launch"; return 0; }
     const long long ntiles_ll = (nrows + TC_DT - 1) / TC_DT;
     if (ntiles_ll < 1 || ntiles_ll > (1ll << 30)) { err = "bad database size"; return 0; }
     const int ntiles = (int)ntiles_ll;
     const int grid = ntiles < sm_count ? ntiles : sm_count;
-    if ((long long)((ntiles + grid - 1) / grid) * TC_DT >= (1ll << 23)) { err = "database shard too large for the packed key"; return 0; }
+    if ((long long)((ntiles + grid - 1) / grid + 1) * TC_DT >= (1ll << 23) - TC_DT) { err = "database shard too large for the packed key"; return 0; }
     CUtensorMap mq, mdb;
     if (!make_map(&mq, d_qe, (long long)nqt * TC_QT, TC_QT, err)) return 0;
     if (!make_map(&mdb, d_dbe, ntiles_ll * TC_DT, TC_DT, err)) return 0;
@@ -322,9 +347,17 @@ int launch_knn2_tc(const int8_t *d_qe, int nq, const int8_t *d_dbe, long long nr
         }
         configured = true;
     }
-    k_knn2_tc<<<grid, TC_THREADS, smem, stream>>>(mq, mdb, nq, nqt, nrows, ntiles, row_offset, d_partial);
-    *grid_out = grid;
-    return 1;
+    if (ntiles <= 2 * grid) {   // small shard: one pass
+        k_knn2_tc<<<grid, TC_THREADS, smem, stream>>>(mq, mdb, nq, nqt, nrows, 0, ntiles, row_offset, nullptr, d_partial);
+        *nparts_out = grid;
+        return 1;
+    }
+    unsigned long long *seed = d_partial + (size_t)grid * nq * 2;
+    k_knn2_tc<<<grid, TC_THREADS, smem, stream>>>(mq, mdb, nq, nqt, nrows, 0, grid, row_offset, nullptr, d_partial);
+    merge(d_partial, grid, nq, seed, stream);
+    k_knn2_tc<<<grid, TC_THREADS, smem, stream>>>(mq, mdb, nq, nqt, nrows, grid, ntiles - grid, row_offset, seed, d_partial);
+    *nparts_out = grid + 1;
+    return 3;
 }
 
 }  // namespace orbx

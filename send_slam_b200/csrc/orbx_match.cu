@@ -165,6 +165,10 @@ __global__ void __launch_bounds__(256) k_knn2_merge(const unsigned long long *__
 
 thread_local std::string g_db_error;
 
+void merge_launch(const unsigned long long *parts, int nparts, int nq, unsigned long long *out, cudaStream_t stream) {
+    k_knn2_merge<<<(nq + 255) / 256, 256, 0, stream>>>(parts, nparts, nq, out);
+}
+
 }  // namespace
 
 struct orbx_db {
@@ -322,7 +326,7 @@ static int query_device_tensor(orbx_db *db, const uint8_t *d_queries, int nq, un
         DB_TRY(db, cudaMalloc((void **)&db->d_qe, (size_t)qcap * 256));
         db->qe_cap = qcap;
     }
-    const size_t need = (size_t)db->sm_count * std::min(nq, maxq) * 2;
+    const size_t need = (size_t)(db->sm_count + 1) * std::min(nq, maxq) * 2;
     if (need > db->partial_tc_cap) {
         if (db->d_partial_tc) cudaFree(db->d_partial_tc);
         db->d_partial_tc = nullptr; db->partial_tc_cap = 0;
@@ -332,10 +336,11 @@ static int query_device_tensor(orbx_db *db, const uint8_t *d_queries, int nq, un
     for (int q0 = 0; q0 < nq; q0 += maxq) {
         const int n = std::min(maxq, nq - q0);
         db->launches += launch_expand_pm1(d_queries + (size_t)q0 * 32, n, knn_tc_padded_queries(n), db->d_qe, db->stream);
-        int grid = 0;
-        const int l = launch_knn2_tc(db->d_qe, n, db->d_dbe, db->nrows, db->row_offset, db->sm_count, db->d_partial_tc, &grid, db->stream, db->err);
+        int nparts = 0;
+        const int l = launch_knn2_tc(db->d_qe, n, db->d_dbe, db->nrows, db->row_offset, db->sm_count, db->d_partial_tc, &nparts,
+                                     merge_launch, db->stream, db->err);
         if (!l) return ORBX_E_CUDA;
-        k_knn2_merge<<<(n + 255) / 256, 256, 0, db->stream>>>(db->d_partial_tc, grid, n, d_packed_out + (size_t)q0 * 2);
+        k_knn2_merge<<<(n + 255) / 256, 256, 0, db->stream>>>(db->d_partial_tc, nparts, n, d_packed_out + (size_t)q0 * 2);
         db->launches += l + 1;
         DB_TRY(db, cudaGetLastError());
     }
