@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -21,6 +22,23 @@ static_assert(sizeof(orbx_keypoint) == 28 && sizeof(KeypointRec) == 28, "keypoin
 
 static thread_local std::string g_create_error;
 
+// Identity of a host-buffer batch call for CUDA-graph replay: buffers (null = the handle's own staging), geometry, stream.
+struct GraphKey {
+    const void *in, *kp, *desc;
+    cudaStream_t stream;
+    int batch, width, height, stride, lap0, lap1, cap, chunk;
+    bool operator==(const GraphKey &o) const {
+        return in == o.in && kp == o.kp && desc == o.desc && stream == o.stream && batch == o.batch && width == o.width &&
+               height == o.height && stride == o.stride && lap0 == o.lap0 && lap1 == o.lap1 && cap == o.cap && chunk == o.chunk;
+    }
+};
+struct GraphEntry { GraphKey key; cudaGraphExec_t exec; long long launches; };
+
+static bool graphs_enabled() {
+    static const bool on = [] { const char *e = getenv("ORBX_GRAPHS"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 struct orbx_handle {
     orbx_config cfg{};
     ExtractorParams P{};
@@ -29,6 +47,13 @@ struct orbx_handle {
     cudaStream_t own_stream = nullptr;  // created by orbx_create; `stream` may be redirected by orbx_set_stream
     cudaStream_t side_stream = nullptr; // the Gaussian pass runs here, concurrently with FAST + quadtree
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // software pipeline of the host-buffer batch entry point (created on first use)
+    static constexpr int kMaxChunks = 32;
+    static constexpr int kComputeStreams = 8;
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr, cs[kComputeStreams] = {};
+    int ncs = 4;                        // compute streams in use
+    cudaEvent_t ev_start = nullptr, ev_end = nullptr, ev_in[kMaxChunks] = {}, ev_done[kMaxChunks] = {};
+    std::vector<GraphEntry> graphs;   // captured call shapes of orbx_extract_batch (dropped on re-plan)
     mutable std::string err;
     long long launches = 0;
 
@@ -84,6 +109,8 @@ static int fail(const orbx_handle *h, int code, const char *msg) {
 }
 
 static void free_plan(orbx_handle *h) {
+    for (auto &g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    h->graphs.clear();
     for (void *p : h->dev_allocs) cudaFree(p);
     h->dev_allocs.clear();
     if (h->h_in) cudaFreeHost(h->h_in);
@@ -192,45 +219,75 @@ static int set_level0(orbx_handle *h, const uint8_t *img, int pitch, size_t fstr
     return ORBX_OK;
 }
 
-// The kernel pipeline for `batch` frames whose level 0 is already in place.
-static int run_pipeline(orbx_handle *h, int batch, int lap0, int lap1, KeypointRec *d_kp, uint8_t *d_desc, int cap,
-                        int *d_n, int *d_mono) {
+// Frames per range of the host-buffer software pipeline (ORBX_CHUNK overrides; >= batch disables pipelining).
+static int pipeline_chunk(int batch) {
+    static const int env = [] { const char *e = getenv("ORBX_CHUNK"); return e ? atoi(e) : 0; }();
+    int c = env > 0 ? env : 8;
+    if (batch < 2 * c) return batch;
+    while ((batch + c - 1) / c > orbx_handle::kMaxChunks) c *= 2;
+    return c;
+}
+
+static int ensure_pipeline(orbx_handle *h) {
+    if (h->h2d_stream) return ORBX_OK;
+    CU_TRY(h, cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
+    CU_TRY(h, cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+    { const char *e = getenv("ORBX_STREAMS"); if (e && atoi(e) >= 1 && atoi(e) <= orbx_handle::kComputeStreams) h->ncs = atoi(e); }
+    for (int i = 0; i < orbx_handle::kComputeStreams; i++) CU_TRY(h, cudaStreamCreateWithFlags(&h->cs[i], cudaStreamNonBlocking));
+    CU_TRY(h, cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
+    CU_TRY(h, cudaEventCreateWithFlags(&h->ev_end, cudaEventDisableTiming));
+    for (int i = 0; i < orbx_handle::kMaxChunks; i++) {
+        CU_TRY(h, cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+        CU_TRY(h, cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+    }
+    return ORBX_OK;
+}
+
+// Clears the per-frame counters of the whole workspace (must precede the kernels of every frame range of a call).
+static int reset_counters(orbx_handle *h, cudaStream_t stream) {
+    CU_TRY(h, cudaMemsetAsync(h->d_counts, 0, sizeof(int) * 2 * h->plan.nlevels * h->batch_cap, stream));
+    CU_TRY(h, cudaMemsetAsync(h->d_overflow, 0, sizeof(int), stream));
+    return ORBX_OK;
+}
+
+// The kernel pipeline for frames [f0, f0 + batch) of the workspace, whose level 0 is already in place.  Everything is
+// issued on `stream`; with a `side` stream the Gaussian pass is forked onto it (ev_fork / ev_join order it).
+static int run_pipeline(orbx_handle *h, int f0, int batch, int lap0, int lap1, KeypointRec *d_kp, uint8_t *d_desc, int cap,
+                        int *d_n, int *d_mono, cudaStream_t stream, cudaStream_t side, cudaEvent_t ev_fork, cudaEvent_t ev_join) {
     const Plan &pl = h->plan;
     const int nl = pl.nlevels;
-    CU_TRY(h, cudaMemsetAsync(h->d_counts, 0, sizeof(int) * 2 * nl * h->batch_cap, h->stream));
-    CU_TRY(h, cudaMemsetAsync(h->d_overflow, 0, sizeof(int), h->stream));
-    const bool prof = h->profiling;
-#define STAGE_MARK(i) do { if (prof) CU_TRY(h, cudaEventRecord(h->ev[i], h->stream)); } while (0)
+    const bool prof = h->profiling && stream == h->stream;
+    const bool fork = !prof && side != nullptr;
+#define STAGE_MARK(i) do { if (prof) CU_TRY(h, cudaEventRecord(h->ev[i], stream)); } while (0)
     STAGE_MARK(0);
-    for (int l = 1; l < nl; l++) h->launches += launch_resize(h->d_levels, h->h_levels, l, batch, h->stream);
+    for (int l = 1; l < nl; l++) h->launches += launch_resize(h->d_levels, h->h_levels, l, f0, batch, stream);
     STAGE_MARK(1);
     // The blurred planes are only needed by the descriptor stage, and the quadtree kernel (one CTA per frame x level,
     // latency-bound) cannot fill the machine: outside profiling mode the Gaussian pass runs on a side stream next to
     // quadtree + slot assignment.  It is forked after FAST because two machine-filling kernels gain nothing from
     // running side by side.
-    if (prof) h->launches += launch_blur(h->d_levels, h->d_tiles, h->ntiles, batch, h->stream);
+    if (!fork) h->launches += launch_blur(h->d_levels, h->d_tiles, h->ntiles, f0, batch, stream);
     STAGE_MARK(2);
-    h->launches += launch_fast(h->d_levels, h->d_cells, (int)pl.cells.size(), batch, h->P.ini_th, h->P.min_th, h->d_overflow, h->stream);
+    h->launches += launch_fast(h->d_levels, h->d_cells, (int)pl.cells.size(), f0, batch, h->P.ini_th, h->P.min_th, h->d_overflow, stream);
     STAGE_MARK(3);
-    if (!prof) {
-        CU_TRY(h, cudaEventRecord(h->ev_fork, h->stream));
-        CU_TRY(h, cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+    if (fork) {
+        CU_TRY(h, cudaEventRecord(ev_fork, stream));
+        CU_TRY(h, cudaStreamWaitEvent(side, ev_fork, 0));
     }
-    h->launches += launch_octree(h->d_levels, h->h_levels, nl, batch, h->d_overflow, h->stream);
-    if (!prof) {
-        h->launches += launch_blur(h->d_levels, h->d_tiles, h->ntiles, batch, h->side_stream);
-        CU_TRY(h, cudaEventRecord(h->ev_join, h->side_stream));
+    h->launches += launch_octree(h->d_levels, h->h_levels, nl, f0, batch, h->d_overflow, stream);
+    if (fork) {
+        h->launches += launch_blur(h->d_levels, h->d_tiles, h->ntiles, f0, batch, side);
+        CU_TRY(h, cudaEventRecord(ev_join, side));
     }
     STAGE_MARK(4);
-    h->launches += launch_finalize(h->d_levels, nl, batch, pl.total_out_cap, lap0, lap1, d_kp, cap, h->d_slot, d_n, d_mono, h->d_overflow, h->stream);
+    h->launches += launch_finalize(h->d_levels, nl, f0, batch, pl.total_out_cap, lap0, lap1, d_kp, cap, h->d_slot, d_n, d_mono, h->d_overflow, stream);
     STAGE_MARK(5);
-    if (!prof) CU_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
-    h->launches += launch_describe(h->d_levels, nl, batch, pl.total_out_cap, h->d_slot, d_kp, d_desc, cap, h->stream);
+    if (fork) CU_TRY(h, cudaStreamWaitEvent(stream, ev_join, 0));
+    h->launches += launch_describe(h->d_levels, nl, f0, batch, pl.total_out_cap, h->d_slot, d_kp, d_desc, cap, stream);
     STAGE_MARK(6);
 #undef STAGE_MARK
-    h->ev_valid = prof;
+    if (stream == h->stream) h->ev_valid = prof;
     CU_TRY(h, cudaGetLastError());
-    h->last_batch = batch;
     return ORBX_OK;
 }
 
@@ -295,6 +352,15 @@ void orbx_destroy(orbx_handle *h) {
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
+    if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
+    for (int i = 0; i < orbx_handle::kComputeStreams; i++) if (h->cs[i]) cudaStreamDestroy(h->cs[i]);
+    if (h->ev_start) cudaEventDestroy(h->ev_start);
+    if (h->ev_end) cudaEventDestroy(h->ev_end);
+    for (int i = 0; i < orbx_handle::kMaxChunks; i++) {
+        if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
+        if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+    }
     delete h;
 }
 
@@ -384,7 +450,10 @@ int orbx_extract_batch_device(orbx_handle *h, const uint8_t *d_frames, size_t fr
     if (rc) return rc;
     if (cap < h->plan.total_out_cap) return fail(h, ORBX_E_CAPACITY, "cap smaller than orbx_keypoint_capacity for this frame size");
     if ((rc = set_level0(h, d_frames, stride, frame_stride_bytes))) return rc;
-    return run_pipeline(h, batch, lap0, lap1, reinterpret_cast<KeypointRec *>(d_kp_out), d_desc_out, cap, d_n_out, d_mono_out);
+    if ((rc = reset_counters(h, h->stream))) return rc;
+    h->last_batch = batch;
+    return run_pipeline(h, 0, batch, lap0, lap1, reinterpret_cast<KeypointRec *>(d_kp_out), d_desc_out, cap, d_n_out, d_mono_out,
+                        h->stream, h->side_stream, h->ev_fork, h->ev_join);
 }
 
 int orbx_extract_batch(orbx_handle *h, const uint8_t *const *frames, int batch, int width, int height, int stride, int lap0,
@@ -404,41 +473,124 @@ int orbx_extract_batch(orbx_handle *h, const uint8_t *const *frames, int batch, 
     const int pitch0 = h->l0_own_pitch;
     const size_t fstride0 = h->l0_own_fstride;
     // Input: page-locked caller memory is DMA'd straight into the level-0 planes (one strided 2D copy per frame, or a
-    // single one when the frames are evenly spaced); pageable memory is first repacked into the handle's pinned staging.
+    // single one per frame range when the frames are evenly spaced); pageable memory is first repacked into the
+    // handle's pinned staging.  Output: page-locked caller buffers of the internal record capacity receive the
+    // result blocks directly.
     const bool in_pinned = is_pinned_host(frames[0]) && is_pinned_host(frames[batch - 1] + (size_t)stride * (height - 1));
-    if (in_pinned) {
-        bool even = true;
-        const ptrdiff_t step = batch > 1 ? frames[1] - frames[0] : (ptrdiff_t)stride * height;
-        for (int i = 1; i < batch && even; i++) even = (frames[i] - frames[i - 1]) == step;
-        if (even && step == (ptrdiff_t)stride * height && fstride0 == (size_t)pitch0 * height) {
-            CU_TRY(h, cudaMemcpy2DAsync(h->l0_own, pitch0, frames[0], stride, width, (size_t)height * batch, cudaMemcpyHostToDevice, h->stream));
-        } else {
-            for (int i = 0; i < batch; i++)
-                CU_TRY(h, cudaMemcpy2DAsync(h->l0_own + (size_t)i * fstride0, pitch0, frames[i], stride, width, height, cudaMemcpyHostToDevice, h->stream));
-        }
-    } else {
-        for (int i = 0; i < batch; i++) {
+    const bool out_direct = cap >= kc && is_pinned_host(kp_out) && is_pinned_host(desc_out);
+    bool even = in_pinned && fstride0 == (size_t)pitch0 * height;
+    for (int i = 1; i < batch && even; i++) even = (frames[i] - frames[i - 1]) == (ptrdiff_t)stride * height;
+    // CPU half of the input path (pageable memory only): repack frames [f0, f0 + n) into the pinned staging
+    auto stage_in = [&](int f0, int n) {
+        if (in_pinned) return;
+        for (int i = f0; i < f0 + n; i++) {
             uint8_t *dst = h->h_in + (size_t)i * fstride0;
             const uint8_t *src = frames[i];
             if (stride == pitch0) std::memcpy(dst, src, (size_t)stride * (height - 1) + width);
             else for (int y = 0; y < height; y++) std::memcpy(dst + (size_t)y * pitch0, src + (size_t)y * stride, (size_t)width);
         }
-        CU_TRY(h, cudaMemcpyAsync(h->l0_own, h->h_in, (size_t)batch * fstride0, cudaMemcpyHostToDevice, h->stream));
-    }
+    };
+    auto copy_in = [&](int f0, int n, cudaStream_t st) -> int {
+        if (!in_pinned) {
+            CU_TRY(h, cudaMemcpyAsync(h->l0_own + (size_t)f0 * fstride0, h->h_in + (size_t)f0 * fstride0, (size_t)n * fstride0, cudaMemcpyHostToDevice, st));
+        } else if (even) {
+            CU_TRY(h, cudaMemcpy2DAsync(h->l0_own + (size_t)f0 * fstride0, pitch0, frames[f0], stride, width, (size_t)height * n, cudaMemcpyHostToDevice, st));
+        } else {
+            for (int i = f0; i < f0 + n; i++)
+                CU_TRY(h, cudaMemcpy2DAsync(h->l0_own + (size_t)i * fstride0, pitch0, frames[i], stride, width, height, cudaMemcpyHostToDevice, st));
+        }
+        return ORBX_OK;
+    };
+    auto download = [&](int f0, int n, cudaStream_t st) -> int {
+        if (out_direct) {
+            CU_TRY(h, cudaMemcpy2DAsync(kp_out + (size_t)f0 * cap, (size_t)cap * sizeof(KeypointRec), h->d_kp + (size_t)f0 * kc, (size_t)kc * sizeof(KeypointRec),
+                                        (size_t)kc * sizeof(KeypointRec), n, cudaMemcpyDeviceToHost, st));
+            CU_TRY(h, cudaMemcpy2DAsync(desc_out + (size_t)f0 * cap * 32, (size_t)cap * 32, h->d_desc + (size_t)f0 * kc * 32, (size_t)kc * 32, (size_t)kc * 32, n, cudaMemcpyDeviceToHost, st));
+        } else {
+            CU_TRY(h, cudaMemcpyAsync(h->h_kp + (size_t)f0 * kc, h->d_kp + (size_t)f0 * kc, (size_t)n * kc * sizeof(KeypointRec), cudaMemcpyDeviceToHost, st));
+            CU_TRY(h, cudaMemcpyAsync(h->h_desc + (size_t)f0 * kc * 32, h->d_desc + (size_t)f0 * kc * 32, (size_t)n * kc * 32, cudaMemcpyDeviceToHost, st));
+        }
+        return ORBX_OK;
+    };
+    h->last_batch = batch;
     if ((rc = set_level0(h, h->l0_own, pitch0, fstride0))) return rc;
-    if ((rc = run_pipeline(h, batch, lap0, lap1, h->d_kp, h->d_desc, kc, h->d_n, h->d_mono))) return rc;
-    CU_TRY(h, cudaMemcpyAsync(h->h_n, h->d_n, sizeof(int) * batch, cudaMemcpyDeviceToHost, h->stream));
-    CU_TRY(h, cudaMemcpyAsync(h->h_mono, h->d_mono, sizeof(int) * batch, cudaMemcpyDeviceToHost, h->stream));
-    CU_TRY(h, cudaMemcpyAsync(h->h_overflow, h->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    // Output: page-locked caller buffers of the internal record capacity receive the result blocks directly
-    const bool out_direct = cap >= kc && is_pinned_host(kp_out) && is_pinned_host(desc_out);
-    if (out_direct) {
-        CU_TRY(h, cudaMemcpy2DAsync(kp_out, (size_t)cap * sizeof(KeypointRec), h->d_kp, (size_t)kc * sizeof(KeypointRec),
-                                    (size_t)kc * sizeof(KeypointRec), batch, cudaMemcpyDeviceToHost, h->stream));
-        CU_TRY(h, cudaMemcpy2DAsync(desc_out, (size_t)cap * 32, h->d_desc, (size_t)kc * 32, (size_t)kc * 32, batch, cudaMemcpyDeviceToHost, h->stream));
+    const int chunk = h->profiling ? batch : pipeline_chunk(batch);
+    if (chunk < batch && (rc = ensure_pipeline(h))) return rc;
+    // Everything the device does for this call, issued relative to the handle's stream.  `cpu_stage` = do the pageable
+    // repacking inline (false when it was done up front because the device work is replayed from a CUDA graph).
+    auto enqueue = [&](bool cpu_stage) -> int {
+        int rc2;
+        if ((rc2 = reset_counters(h, h->stream))) return rc2;
+        if (chunk >= batch) {
+            // one frame range: copy in, compute, copy out, all on the handle's stream (+ its side stream)
+            if (cpu_stage) stage_in(0, batch);
+            if ((rc2 = copy_in(0, batch, h->stream))) return rc2;
+            if ((rc2 = run_pipeline(h, 0, batch, lap0, lap1, h->d_kp, h->d_desc, kc, h->d_n, h->d_mono, h->stream, h->side_stream, h->ev_fork, h->ev_join))) return rc2;
+            if ((rc2 = download(0, batch, h->stream))) return rc2;
+        } else {
+            // Software pipeline over frame ranges: the copy engines stream range k+1 in and range k-1 out while the SMs
+            // work on range k.  Ranges alternate between two compute streams so that the latency-bound quadtree kernel
+            // of one range overlaps the machine-filling kernels of the next.
+            CU_TRY(h, cudaEventRecord(h->ev_start, h->stream));
+            CU_TRY(h, cudaStreamWaitEvent(h->h2d_stream, h->ev_start, 0));
+            const int nchunks = (batch + chunk - 1) / chunk, ncs = std::min(h->ncs, nchunks);
+            for (int i = 0; i < ncs; i++) CU_TRY(h, cudaStreamWaitEvent(h->cs[i], h->ev_start, 0));
+            int k = 0;
+            for (int f0 = 0; f0 < batch; f0 += chunk, k++) {
+                const int n = std::min(chunk, batch - f0);
+                cudaStream_t cs = h->cs[k % ncs];
+                if (cpu_stage) stage_in(f0, n);
+                if ((rc2 = copy_in(f0, n, h->h2d_stream))) return rc2;
+                CU_TRY(h, cudaEventRecord(h->ev_in[k], h->h2d_stream));
+                CU_TRY(h, cudaStreamWaitEvent(cs, h->ev_in[k], 0));
+                if ((rc2 = run_pipeline(h, f0, n, lap0, lap1, h->d_kp, h->d_desc, kc, h->d_n, h->d_mono, cs, nullptr, nullptr, nullptr))) return rc2;
+                CU_TRY(h, cudaEventRecord(h->ev_done[k], cs));
+                CU_TRY(h, cudaStreamWaitEvent(h->d2h_stream, h->ev_done[k], 0));
+                if ((rc2 = download(f0, n, h->d2h_stream))) return rc2;
+            }
+            CU_TRY(h, cudaEventRecord(h->ev_end, h->d2h_stream));
+            CU_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_end, 0));
+        }
+        CU_TRY(h, cudaMemcpyAsync(h->h_n, h->d_n, sizeof(int) * batch, cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(h, cudaMemcpyAsync(h->h_mono, h->d_mono, sizeof(int) * batch, cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(h, cudaMemcpyAsync(h->h_overflow, h->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        return ORBX_OK;
+    };
+    // CUDA-graph replay: a call shape seen before (same buffers, same geometry) is captured once and replayed, which
+    // removes the ~100 API calls of the pipelined flow from the critical path.  Pageable input is graphed only in the
+    // single-range form (the repacking then happens up front); page-locked buffers are part of the key.
+    const bool graphable = graphs_enabled() && !h->profiling && (in_pinned ? even : chunk >= batch);
+    if (!graphable) {
+        if ((rc = enqueue(true))) return rc;
     } else {
-        CU_TRY(h, cudaMemcpyAsync(h->h_kp, h->d_kp, (size_t)batch * kc * sizeof(KeypointRec), cudaMemcpyDeviceToHost, h->stream));
-        CU_TRY(h, cudaMemcpyAsync(h->h_desc, h->d_desc, (size_t)batch * kc * 32, cudaMemcpyDeviceToHost, h->stream));
+        GraphKey key{in_pinned ? frames[0] : nullptr, out_direct ? (const void *)kp_out : nullptr, out_direct ? (const void *)desc_out : nullptr,
+                     h->stream, batch, width, height, stride, lap0, lap1, out_direct ? cap : 0, chunk};
+        GraphEntry *e = nullptr;
+        for (auto &g : h->graphs) if (g.key == key) { e = &g; break; }
+        if (!e) {
+            // first sighting: run directly (this also performs every lazy one-time initialisation outside a capture)
+            if (h->graphs.size() >= 16) { if (h->graphs.front().exec) cudaGraphExecDestroy(h->graphs.front().exec); h->graphs.erase(h->graphs.begin()); }
+            h->graphs.push_back(GraphEntry{key, nullptr, 0});
+            if ((rc = enqueue(true))) return rc;
+        } else {
+            if (!e->exec) {
+                const long long l0 = h->launches;
+                CU_TRY(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+                rc = enqueue(false);
+                cudaGraph_t graph = nullptr;
+                const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+                e->launches = h->launches - l0;
+                h->launches = l0;
+                if (rc) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
+                CU_TRY(h, ce);
+                const cudaError_t ie = cudaGraphInstantiate(&e->exec, graph, 0);
+                cudaGraphDestroy(graph);
+                CU_TRY(h, ie);
+            }
+            stage_in(0, batch);
+            CU_TRY(h, cudaGraphLaunch(e->exec, h->stream));
+            h->launches += e->launches;
+        }
     }
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     if (*h->h_overflow) {
@@ -561,7 +713,7 @@ int orbx_debug_resize(orbx_handle *h, const uint8_t *src, int sw, int sh, int ss
     CU_TRY(h, cudaMemcpy(d_xt, xt.data(), sizeof(ResizeTap) * dw, cudaMemcpyHostToDevice));
     CU_TRY(h, cudaMemcpy(d_yt, yt.data(), sizeof(ResizeTap) * dh, cudaMemcpyHostToDevice));
     CU_TRY(h, cudaMemcpy(d_lv, lv, sizeof(lv), cudaMemcpyHostToDevice));
-    h->launches += launch_resize(d_lv, lv, 1, 1, h->stream);
+    h->launches += launch_resize(d_lv, lv, 1, 0, 1, h->stream);
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     CU_TRY(h, cudaMemcpy2D(dst, dstride, d_dst, dp, dw, dh, cudaMemcpyDeviceToHost));
@@ -584,7 +736,7 @@ int orbx_debug_blur(orbx_handle *h, const uint8_t *src, int w, int ht, int sstri
     CU_TRY(h, cudaMemcpy2D(d_src, p, src, sstride, w, ht, cudaMemcpyHostToDevice));
     CU_TRY(h, cudaMemcpy(d_t, tiles.data(), sizeof(BlurTile) * tiles.size(), cudaMemcpyHostToDevice));
     CU_TRY(h, cudaMemcpy(d_lv, &lv, sizeof(lv), cudaMemcpyHostToDevice));
-    h->launches += launch_blur(d_lv, d_t, (int)tiles.size(), 1, h->stream);
+    h->launches += launch_blur(d_lv, d_t, (int)tiles.size(), 0, 1, h->stream);
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     CU_TRY(h, cudaMemcpy2D(dst, dstride, d_dst, p, w, ht, cudaMemcpyDeviceToHost));
@@ -664,7 +816,7 @@ int orbx_debug_octree(orbx_handle *h, const float *keys, int n, int minX, int ma
     D.ord_cell_area = LP.ord_cell_area; D.ord_ncols = LP.ord_ncols; D.wcell = LP.wcell; D.hcell = LP.hcell;
     D.cand = d_cand; D.sorted = d_sorted; D.bin_cursor = d_cur; D.cand_cap = ccap; D.cand_count = d_cnt; D.sel = d_sel; D.sel_count = d_cnt + 1;
     CU_TRY(h, cudaMemcpy(d_lv, &D, sizeof(D), cudaMemcpyHostToDevice));
-    h->launches += launch_octree(d_lv, &D, 1, 1, d_cnt + 2, h->stream);
+    h->launches += launch_octree(d_lv, &D, 1, 0, 1, d_cnt + 2, h->stream);
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     CU_TRY(h, cudaMemcpy(counts, d_cnt, sizeof(counts), cudaMemcpyDeviceToHost));

@@ -39,16 +39,17 @@ struct KeypointRec {           // == orbx_keypoint == cv::KeyPoint
     int32_t octave, class_id;
 };
 
-// launch wrappers (orbx_kernels.cu); all asynchronous on `stream`, return the number of kernel launches issued
-int launch_resize(const LevelDev *d_levels, const LevelDev *h_levels, int level, int batch, cudaStream_t stream);
-int launch_blur(const LevelDev *d_levels, const BlurTile *d_tiles, int ntiles, int batch, cudaStream_t stream);
-int launch_fast(const LevelDev *d_levels, const CellRect *d_cells, int ncells, int batch, int ini_th, int min_th,
+// launch wrappers (orbx_kernels.cu); all asynchronous on `stream`, return the number of kernel launches issued.
+// They process frames [f0, f0 + batch) of the workspace.
+int launch_resize(const LevelDev *d_levels, const LevelDev *h_levels, int level, int f0, int batch, cudaStream_t stream);
+int launch_blur(const LevelDev *d_levels, const BlurTile *d_tiles, int ntiles, int f0, int batch, cudaStream_t stream);
+int launch_fast(const LevelDev *d_levels, const CellRect *d_cells, int ncells, int f0, int batch, int ini_th, int min_th,
                 int *d_overflow, cudaStream_t stream);
-int launch_octree(const LevelDev *d_levels, const LevelDev *h_levels, int nlevels, int batch, int *d_overflow,
+int launch_octree(const LevelDev *d_levels, const LevelDev *h_levels, int nlevels, int f0, int batch, int *d_overflow,
                   cudaStream_t stream);
-int launch_finalize(const LevelDev *d_levels, int nlevels, int batch, int total_out_cap, int lap0, int lap1,
+int launch_finalize(const LevelDev *d_levels, int nlevels, int f0, int batch, int total_out_cap, int lap0, int lap1,
                     KeypointRec *d_kp, int cap, int *d_slot, int *d_n, int *d_mono, int *d_overflow, cudaStream_t stream);
-int launch_describe(const LevelDev *d_levels, int nlevels, int batch, int total_out_cap, const int *d_slot,
+int launch_describe(const LevelDev *d_levels, int nlevels, int f0, int batch, int total_out_cap, const int *d_slot,
                     KeypointRec *d_kp, uint8_t *d_desc, int cap, cudaStream_t stream);
 // stand-alone stage launchers for the debug / parity entry points
 int launch_describe_points(const uint8_t *d_img, const uint8_t *d_blur, int pitch, const float *d_xy, int n,

@@ -39,12 +39,12 @@ void upload_constants() {
 //     neighbouring source bytes) and one IDP.2A (s0*c0 + s1*c1) per source row.
 //     k_resize_generic: byte-wise fallback for source planes that are not 4-byte aligned (caller-owned level 0).
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_resize_generic(const LevelDev *__restrict__ lv, int level) {
+__global__ void __launch_bounds__(128) k_resize_generic(const LevelDev *__restrict__ lv, int level, int f0) {
     const LevelDev &D = lv[level];
     const LevelDev &S = lv[level - 1];
     const int dx0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (dx0 >= D.w) return;
-    const int dy = blockIdx.y, f = blockIdx.z;
+    const int dy = blockIdx.y, f = f0 + blockIdx.z;
     const ResizeTap ty = D.ytap[dy];
     const uint8_t *__restrict__ s0 = S.img + (size_t)f * S.img_fstride + (size_t)ty.ofs * S.pitch;
     const uint8_t *__restrict__ s1 = S.img + (size_t)f * S.img_fstride + (size_t)ty.ofs1 * S.pitch;
@@ -65,12 +65,12 @@ __global__ void __launch_bounds__(128) k_resize_generic(const LevelDev *__restri
 }
 
 // xpack[dx] = ofs << 16 | c1 (c0 = 2048 - c1), padded to a multiple of 4 entries
-__global__ void __launch_bounds__(128) k_resize(const LevelDev *__restrict__ lv, int level) {
+__global__ void __launch_bounds__(128) k_resize(const LevelDev *__restrict__ lv, int level, int f0) {
     const LevelDev &D = lv[level];
     const LevelDev &S = lv[level - 1];
     const int dx0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (dx0 >= D.w) return;
-    const int dy0 = blockIdx.y * 2, f = blockIdx.z;
+    const int dy0 = blockIdx.y * 2, f = f0 + blockIdx.z;
     const uint4 tp = __ldg(reinterpret_cast<const uint4 *>(D.xpack + dx0));
     const uint32_t t[4] = {tp.x, tp.y, tp.z, tp.w};
     const int ofs0 = (int)(t[0] >> 16);
@@ -113,16 +113,16 @@ __global__ void __launch_bounds__(128) k_resize(const LevelDev *__restrict__ lv,
     }
 }
 
-int launch_resize(const LevelDev *d_levels, const LevelDev *h_levels, int level, int batch, cudaStream_t stream) {
+int launch_resize(const LevelDev *d_levels, const LevelDev *h_levels, int level, int f0, int batch, cudaStream_t stream) {
     const LevelDev &D = h_levels[level];
     const LevelDev &S = h_levels[level - 1];
     const bool aligned = ((reinterpret_cast<uintptr_t>(S.img) | (uintptr_t)S.pitch | (uintptr_t)S.img_fstride) & 3) == 0 && D.xpack != nullptr;
     if (aligned) {
         dim3 grid((D.w + 4 * 128 - 1) / (4 * 128), (D.h + 1) / 2, batch);
-        k_resize<<<grid, 128, 0, stream>>>(d_levels, level);
+        k_resize<<<grid, 128, 0, stream>>>(d_levels, level, f0);
     } else {
         dim3 grid((D.w + 4 * 128 - 1) / (4 * 128), D.h, batch);
-        k_resize_generic<<<grid, 128, 0, stream>>>(d_levels, level);
+        k_resize_generic<<<grid, 128, 0, stream>>>(d_levels, level, f0);
     }
     return 1;
 }
@@ -145,12 +145,12 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return i >= n ? p - i : i;
 }
 
-__global__ void __launch_bounds__(256) k_blur(const LevelDev *__restrict__ lv, const BlurTile *__restrict__ tiles) {
+__global__ void __launch_bounds__(256) k_blur(const LevelDev *__restrict__ lv, const BlurTile *__restrict__ tiles, int f0) {
     __shared__ __align__(16) uint8_t s_in[BROWS * BIN_PITCH];
     __shared__ __align__(16) uint32_t s_h[BROWS * (BT / 2)];   // horizontal sums, lanes = columns (c, c+2)
     const BlurTile t = tiles[blockIdx.x];
     const LevelDev &L = lv[t.level];
-    const int f = blockIdx.y;
+    const int f = f0 + blockIdx.y;
     const int x0 = t.tx * BT, y0 = t.ty * BT;
     const uint8_t *__restrict__ src = L.img + (size_t)f * L.img_fstride;
     // stage rows y0-3 .. y0+66, columns x0-4 .. x0+75 (20 words per row): aligned word loads where the word lies inside
@@ -245,10 +245,10 @@ __global__ void __launch_bounds__(256) k_blur(const LevelDev *__restrict__ lv, c
     }
 }
 
-int launch_blur(const LevelDev *d_levels, const BlurTile *d_tiles, int ntiles, int batch, cudaStream_t stream) {
+int launch_blur(const LevelDev *d_levels, const BlurTile *d_tiles, int ntiles, int f0, int batch, cudaStream_t stream) {
     if (ntiles <= 0) return 0;
     dim3 grid(ntiles, batch);
-    k_blur<<<grid, 256, 0, stream>>>(d_levels, d_tiles);
+    k_blur<<<grid, 256, 0, stream>>>(d_levels, d_tiles, f0);
     return 1;
 }
 
@@ -323,14 +323,14 @@ __device__ __forceinline__ uint32_t fast_score4(const uint32_t (&w)[7][3]) {
 }
 
 __global__ void __launch_bounds__(192) k_fast_cells(const LevelDev *__restrict__ lv, const CellRect *__restrict__ cells,
-                                                    int ini_th, int min_th, int *__restrict__ overflow) {
+                                                    int ini_th, int min_th, int f0, int *__restrict__ overflow) {
     __shared__ __align__(16) uint8_t s_roi[FT_ROWS * FT_PITCH];
     __shared__ __align__(16) uint8_t s_sc[(FT_ROWS - 4) * FS_PITCH];   // interior scores with a 1-px zero ring
     __shared__ uint32_t s_list[36 * 36 + 8];
     __shared__ int s_n, s_base;
     const CellRect cell = cells[blockIdx.x];
     const LevelDev &L = lv[cell.level];
-    const int f = blockIdx.y;
+    const int f = f0 + blockIdx.y;
     const int rw = cell.x1 - cell.x0, rh = cell.y1 - cell.y0;   // ROI
     const int iw = rw - 6, ih = rh - 6;                            // tested pixels
     const uint8_t *__restrict__ src = L.img + (size_t)f * L.img_fstride + (size_t)cell.y0 * L.pitch + cell.x0;
@@ -460,11 +460,11 @@ __global__ void __launch_bounds__(192) k_fast_cells(const LevelDev *__restrict__
     }
 }
 
-int launch_fast(const LevelDev *d_levels, const CellRect *d_cells, int ncells, int batch, int ini_th, int min_th,
+int launch_fast(const LevelDev *d_levels, const CellRect *d_cells, int ncells, int f0, int batch, int ini_th, int min_th,
                 int *d_overflow, cudaStream_t stream) {
     if (ncells <= 0) return 0;
     dim3 grid(ncells, batch);
-    k_fast_cells<<<grid, 192, 0, stream>>>(d_levels, d_cells, ini_th, min_th, d_overflow);
+    k_fast_cells<<<grid, 192, 0, stream>>>(d_levels, d_cells, ini_th, min_th, f0, d_overflow);
     return 1;
 }
 
@@ -560,9 +560,9 @@ __device__ void split_node(const LevelDev &L, const QNode &p, const int *bin_sta
 }
 
 __global__ void __launch_bounds__(OT_THREADS) k_octree(const LevelDev *__restrict__ lv, int nlevels, int cap_nodes,
-                                                       int *__restrict__ overflow) {
+                                                       int f0, int *__restrict__ overflow) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int level = blockIdx.x, f = blockIdx.y;
+    const int level = blockIdx.x, f = f0 + blockIdx.y;
     const LevelDev &L = lv[level];
     const int tid = threadIdx.x;
     __shared__ OctShared S;
@@ -797,7 +797,7 @@ static size_t octree_smem_bytes(int nbins, int cap) {
     return (size_t)2 * cap * sizeof(QNode) + (size_t)(2 * nbins + 1) * 4 + (size_t)7 * cap * 4 + 16;
 }
 
-int launch_octree(const LevelDev *d_levels, const LevelDev *h_levels, int nlevels, int batch, int *d_overflow,
+int launch_octree(const LevelDev *d_levels, const LevelDev *h_levels, int nlevels, int f0, int batch, int *d_overflow,
                   cudaStream_t stream) {
     // one launch for all levels: size the node arrays for the largest quota and the bins for the finest table
     int cap = 0, nbins = 0;
@@ -813,7 +813,7 @@ int launch_octree(const LevelDev *d_levels, const LevelDev *h_levels, int nlevel
         configured = smem;
     }
     dim3 grid(nlevels, batch);
-    k_octree<<<grid, OT_THREADS, smem, stream>>>(d_levels, nlevels, cap, d_overflow);
+    k_octree<<<grid, OT_THREADS, smem, stream>>>(d_levels, nlevels, cap, f0, d_overflow);
     return 1;
 }
 
@@ -823,8 +823,8 @@ int launch_octree(const LevelDev *d_levels, const LevelDev *h_levels, int nlevel
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_finalize(const LevelDev *__restrict__ lv, int nlevels, int total_out_cap, int lap0,
                                                   int lap1, KeypointRec *__restrict__ kp, int cap, int *__restrict__ slot,
-                                                  int *__restrict__ n_out, int *__restrict__ mono_out, int *__restrict__ overflow) {
-    const int f = blockIdx.x, tid = threadIdx.x;
+                                                  int *__restrict__ n_out, int *__restrict__ mono_out, int f0, int *__restrict__ overflow) {
+    const int f = f0 + blockIdx.x, tid = threadIdx.x;
     __shared__ int s_cnt[kMaxLevels + 1];
     __shared__ int s_warp[8];
     __shared__ int s_run;
@@ -873,9 +873,9 @@ __global__ void __launch_bounds__(256) k_finalize(const LevelDev *__restrict__ l
     if (tid == 0) { n_out[f] = ntot; mono_out[f] = ntot - s_run; }
 }
 
-int launch_finalize(const LevelDev *d_levels, int nlevels, int batch, int total_out_cap, int lap0, int lap1,
+int launch_finalize(const LevelDev *d_levels, int nlevels, int f0, int batch, int total_out_cap, int lap0, int lap1,
                     KeypointRec *d_kp, int cap, int *d_slot, int *d_n, int *d_mono, int *d_overflow, cudaStream_t stream) {
-    k_finalize<<<batch, 256, 0, stream>>>(d_levels, nlevels, total_out_cap, lap0, lap1, d_kp, cap, d_slot, d_n, d_mono, d_overflow);
+    k_finalize<<<batch, 256, 0, stream>>>(d_levels, nlevels, total_out_cap, lap0, lap1, d_kp, cap, d_slot, d_n, d_mono, f0, d_overflow);
     return 1;
 }
 
@@ -946,8 +946,8 @@ __device__ __forceinline__ uint8_t warp_brief_byte(const uint8_t *__restrict__ c
 
 __global__ void __launch_bounds__(256) k_describe(const LevelDev *__restrict__ lv, int nlevels, int total_out_cap,
                                                   const int *__restrict__ slot, KeypointRec *__restrict__ kp,
-                                                  uint8_t *__restrict__ desc, int cap) {
-    const int f = blockIdx.y, lane = threadIdx.x & 31;
+                                                  uint8_t *__restrict__ desc, int cap, int f0) {
+    const int f = f0 + blockIdx.y, lane = threadIdx.x & 31;
     const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (item >= total_out_cap) return;
     int l = 0;
@@ -966,10 +966,10 @@ __global__ void __launch_bounds__(256) k_describe(const LevelDev *__restrict__ l
     if (lane == 0) kp[(size_t)f * cap + sl].angle = angle;
 }
 
-int launch_describe(const LevelDev *d_levels, int nlevels, int batch, int total_out_cap, const int *d_slot,
+int launch_describe(const LevelDev *d_levels, int nlevels, int f0, int batch, int total_out_cap, const int *d_slot,
                     KeypointRec *d_kp, uint8_t *d_desc, int cap, cudaStream_t stream) {
     dim3 grid((total_out_cap + 7) / 8, batch);
-    k_describe<<<grid, 256, 0, stream>>>(d_levels, nlevels, total_out_cap, d_slot, d_kp, d_desc, cap);
+    k_describe<<<grid, 256, 0, stream>>>(d_levels, nlevels, total_out_cap, d_slot, d_kp, d_desc, cap, f0);
     return 1;
 }
 

@@ -223,7 +223,8 @@ class ORBextractor:
         if frames.strides[2] != 1:
             frames = np.ascontiguousarray(frames)
         B, h, w = frames.shape
-        ptrs = (C.c_void_p * B)(*[frames[i].ctypes.data for i in range(B)])
+        base, step = frames.ctypes.data, frames.strides[0]
+        ptrs = (C.c_void_p * B)(*range(base, base + B * step, step)) if step > 0 else (C.c_void_p * B)(*[base] * B)
         if out is None:
             kps = np.zeros((B, self.capacity), KP_DTYPE)
             desc = np.zeros((B, self.capacity, 32), np.uint8)
