@@ -252,32 +252,44 @@ def main():
         d_out = torch.zeros((KNN_Q, 2), dtype=torch.int64, device=dev)
         index = orbx.Knn2Index(device=local_rank, device_ptr=d_db.data_ptr(), nrows=KNN_ROWS, row_offset=rank * KNN_ROWS)
         index.set_stream(stream.cuda_stream)
-        for _ in range(3):
-            index.query_device(d_q.data_ptr(), KNN_Q, d_out.data_ptr())
-        index.sync()
-        barrier()
+        def time_backend(backend):
+            index.set_backend(backend)
+            for _ in range(3):
+                index.query_device(d_q.data_ptr(), KNN_Q, d_out.data_ptr())
+            index.sync()
+            barrier()
+            l0 = index.launch_count()
+            ev0.record(stream)
+            for _ in range(ksteps):
+                index.query_device(d_q.data_ptr(), KNN_Q, d_out.data_ptr())
+            ev1.record(stream)
+            index.sync()
+            barrier()
+            t = ev0.elapsed_time(ev1) * 1e-3
+            if world > 1:
+                tt = torch.tensor([t], dtype=torch.float64, device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                t = float(tt.item())
+            return world * ksteps * KNN_Q * KNN_ROWS / t, index.launch_count() - l0
+
         ksteps = 10
-        ev0.record(stream)
-        for _ in range(ksteps):
-            index.query_device(d_q.data_ptr(), KNN_Q, d_out.data_ptr())
-        ev1.record(stream)
-        index.sync()
-        barrier()
-        dtk = ev0.elapsed_time(ev1) * 1e-3
-        if world > 1:
-            tt = torch.tensor([dtk], dtype=torch.float64, device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dtk = float(tt.item())
-        pairs = world * ksteps * KNN_Q * KNN_ROWS / dtk
-        # POPC-pipe roofline: 8 POPC32 per pair; measured POPC rate on this pool's B200 (profiles/ubench_pipes_r01.md)
-        popc_per_clk_sm, sms, ghz = 16.0, 148, 1.965
-        peak_pairs = sms * popc_per_clk_sm * ghz * 1e9 / 8.0
+        pairs_popc, _ = time_backend(orbx.Knn2Index.POPC)
+        pairs, klaunches = time_backend(orbx.Knn2Index.TENSOR)
+        peaks_k, _src_k = measured_peaks()
+        # tensor route: descriptors expanded to {-1,+1} int8, q.d = 256 - 2H by tcgen05.mma kind::i8 = 2 x 256 int8 ops per
+        # pair; kind::i8 issues at twice the dense bf16 rate, so the peak is 2 x the measured cuBLAS bf16 figure
+        tensor_peak_ops = 2.0 * float(peaks_k["bf16_tflops"]) * 1e12
+        tensor_pairs_peak = tensor_peak_ops / 512.0
+        # CUDA-core route: 8 POPC32 per pair on the POPC pipe (16 / clk / SM)
+        popc_pairs_peak = 148 * 16.0 * 1.965e9 / 8.0
         hamming = {"metric": "Hamming pairs/s (k=2 brute force)", "value": pairs, "unit": "pairs/s",
-                   "config": {"queries": KNN_Q, "db_rows_per_gpu": KNN_ROWS, "k": 2},
-                   "roofline": {"bound": "popc-pipe", "achieved": pairs / world, "peak": peak_pairs, "unit": "pairs/s/GPU",
-                                "frac": pairs / world / peak_pairs,
-                                "note": "peak = 148 SM x 16 POPC/clk/SM x 1.965 GHz / 8 POPC per pair (SURVEY.md 8d)"},
-                   "gpu_launches": index.launch_count()}
+                   "config": {"queries": KNN_Q, "db_rows_per_gpu": KNN_ROWS, "k": 2, "backend": "tcgen05.mma kind::i8 on {-1,+1} expansion"},
+                   "roofline": {"bound": "tensor", "achieved": pairs / world * 512.0 / 1e12, "peak": tensor_peak_ops / 1e12, "unit": "TOP/s (int8)",
+                                "frac": pairs / world / tensor_pairs_peak,
+                                "note": "512 int8 ops per pair; peak = 2 x measured dense bf16 TFLOP/s (MEASURED_PEAKS.json); nominal int8 dense 4500 TOP/s"},
+                   "popc_backend": {"value": pairs_popc, "unit": "pairs/s", "roofline": {"bound": "popc-pipe", "peak": popc_pairs_peak,
+                                    "frac": pairs_popc / world / popc_pairs_peak, "note": "148 SM x 16 POPC/clk/SM x 1.965 GHz / 8 POPC per pair"}},
+                   "gpu_launches": klaunches}
         index.close()
 
     # ---- cpu baseline (rank 0, N=1 only)

@@ -193,8 +193,8 @@ static int ensure_plan(orbx_handle *h, int w, int ht, int batch) {
         CU_TRY(h, dev_alloc(h, &D.sel, (size_t)B * LP.out_cap));
         D.out_base = out_base; out_base += LP.out_cap;
         D.scale = h->P.scale[l]; D.kp_size = LP.kp_size;
-        for (int ty = 0; ty * 64 < LP.h; ty++)
-            for (int tx = 0; tx * 64 < LP.w; tx++) tiles.push_back(BlurTile{(int16_t)l, (int16_t)tx, (int16_t)ty, 0});
+        for (int ty = 0; ty * kBlurTileH < LP.h; ty++)
+            for (int tx = 0; tx * kBlurTileW < LP.w; tx++) tiles.push_back(BlurTile{(int16_t)l, (int16_t)tx, (int16_t)ty, 0});
     }
     h->ntiles = (int)tiles.size();
     CU_TRY(h, dev_upload(h, &h->d_tiles, tiles));
@@ -222,7 +222,7 @@ static int set_level0(orbx_handle *h, const uint8_t *img, int pitch, size_t fstr
 // Frames per range of the host-buffer software pipeline (ORBX_CHUNK overrides; >= batch disables pipelining).
 static int pipeline_chunk(int batch) {
     static const int env = [] { const char *e = getenv("ORBX_CHUNK"); return e ? atoi(e) : 0; }();
-    int c = env > 0 ? env : 8;
+    int c = env > 0 ? env : 16;
     if (batch < 2 * c) return batch;
     while ((batch + c - 1) / c > orbx_handle::kMaxChunks) c *= 2;
     return c;
@@ -727,7 +727,7 @@ int orbx_debug_blur(orbx_handle *h, const uint8_t *src, int w, int ht, int sstri
     const int p = (w + 31) / 32 * 32;
     uint8_t *d_src = S.get<uint8_t>((size_t)p * ht + 64), *d_dst = S.get<uint8_t>((size_t)p * ht + 64);
     std::vector<BlurTile> tiles;
-    for (int ty = 0; ty * 64 < ht; ty++) for (int tx = 0; tx * 64 < w; tx++) tiles.push_back(BlurTile{0, (int16_t)tx, (int16_t)ty, 0});
+    for (int ty = 0; ty * kBlurTileH < ht; ty++) for (int tx = 0; tx * kBlurTileW < w; tx++) tiles.push_back(BlurTile{0, (int16_t)tx, (int16_t)ty, 0});
     BlurTile *d_t = S.get<BlurTile>(tiles.size());
     LevelDev lv; std::memset(&lv, 0, sizeof(lv));
     LevelDev *d_lv = S.get<LevelDev>(1);

@@ -32,7 +32,8 @@ struct LevelDev {
     float scale, kp_size;
 };
 
-struct BlurTile { int16_t level, tx, ty, pad; };   // one 64x64 output tile of the Gaussian pass
+constexpr int kBlurTileW = 64, kBlurTileH = 56;
+struct BlurTile { int16_t level, tx, ty, pad; };   // one kBlurTileW x kBlurTileH output tile of the Gaussian pass
 
 struct KeypointRec {           // == orbx_keypoint == cv::KeyPoint
     float x, y, size, angle, response;

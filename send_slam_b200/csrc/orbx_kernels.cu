@@ -64,13 +64,17 @@ __global__ void __launch_bounds__(128) k_resize_generic(const LevelDev *__restri
     *reinterpret_cast<uint32_t *>(D.img + (size_t)f * D.img_fstride + (size_t)dy * D.pitch + dx0) = packed;
 }
 
-// xpack[dx] = ofs << 16 | c1 (c0 = 2048 - c1), padded to a multiple of 4 entries
-__global__ void __launch_bounds__(128) k_resize(const LevelDev *__restrict__ lv, int level, int f0) {
+// xpack[dx] = ofs << 16 | c1 (c0 = 2048 - c1), padded to a multiple of 4 entries.
+// Work item = (4-pixel group, block of RR destination rows), flattened so that every lane of every warp has work on
+// the narrow upper levels too; all 6*RR source words of an item are requested before the first one is used (the kernel
+// is latency-bound otherwise: a level is a few MB).
+constexpr int RR = 4;
+__global__ void __launch_bounds__(128) k_resize(const LevelDev *__restrict__ lv, int level, int f0, int ngx, int nitems) {
     const LevelDev &D = lv[level];
     const LevelDev &S = lv[level - 1];
-    const int dx0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (dx0 >= D.w) return;
-    const int dy0 = blockIdx.y * 2, f = f0 + blockIdx.z;
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= nitems) return;
+    const int ry = item / ngx, dx0 = (item - ry * ngx) * 4, dy0 = ry * RR, f = f0 + blockIdx.y;
     const uint4 tp = __ldg(reinterpret_cast<const uint4 *>(D.xpack + dx0));
     const uint32_t t[4] = {tp.x, tp.y, tp.z, tp.w};
     const int ofs0 = (int)(t[0] >> 16);
@@ -78,6 +82,21 @@ __global__ void __launch_bounds__(128) k_resize(const LevelDev *__restrict__ lv,
     const uint32_t mis8 = 8u * (uint32_t)(ofs0 & 3);
     const int lastw = (S.w - 1) & ~3;                       // last word that still starts inside the row
     const int o0 = base, o1 = min(base + 4, lastw), o2 = min(base + 8, lastw);
+    const uint8_t *__restrict__ sbase = S.img + (size_t)f * S.img_fstride;
+    const int spitch = S.pitch, dh = D.h;
+    ResizeTap ty[RR];
+    uint32_t w[RR][2][3];
+#pragma unroll
+    for (int rr = 0; rr < RR; rr++) ty[rr] = D.ytap[min(dy0 + rr, dh - 1)];
+#pragma unroll
+    for (int rr = 0; rr < RR; rr++)
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const uint8_t *row = sbase + (size_t)(k ? ty[rr].ofs1 : ty[rr].ofs) * spitch;
+            w[rr][k][0] = __ldg(reinterpret_cast<const uint32_t *>(row + o0));
+            w[rr][k][1] = __ldg(reinterpret_cast<const uint32_t *>(row + o1));
+            w[rr][k][2] = __ldg(reinterpret_cast<const uint32_t *>(row + o2));
+        }
     uint32_t sel[4], coef[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -86,30 +105,23 @@ __global__ void __launch_bounds__(128) k_resize(const LevelDev *__restrict__ lv,
         const uint32_t c1 = t[i] & 0xFFFFu;
         coef[i] = (c1 << 16) | (2048u - c1);                  // IDP.2A: lo16 * byte0 + hi16 * byte1
     }
-    const uint8_t *__restrict__ sbase = S.img + (size_t)f * S.img_fstride;
+    uint8_t *__restrict__ drow = D.img + (size_t)f * D.img_fstride + (size_t)dy0 * D.pitch + dx0;
 #pragma unroll
-    for (int rr = 0; rr < 2; rr++) {
-        const int dy = dy0 + rr;
-        if (dy >= D.h) break;
-        const ResizeTap ty = D.ytap[dy];
+    for (int rr = 0; rr < RR; rr++) {
         uint32_t r[2][4];
 #pragma unroll
         for (int k = 0; k < 2; k++) {
-            const uint8_t *row = sbase + (size_t)(k ? ty.ofs1 : ty.ofs) * S.pitch;
-            const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t *>(row + o0));
-            const uint32_t w1 = __ldg(reinterpret_cast<const uint32_t *>(row + o1));
-            const uint32_t w2 = __ldg(reinterpret_cast<const uint32_t *>(row + o2));
-            const uint32_t a = __funnelshift_r(w0, w1, mis8), b = __funnelshift_r(w1, w2, mis8);   // bytes ofs0 .. ofs0+7
+            const uint32_t a = __funnelshift_r(w[rr][k][0], w[rr][k][1], mis8), b = __funnelshift_r(w[rr][k][1], w[rr][k][2], mis8);   // bytes ofs0 .. ofs0+7
 #pragma unroll
             for (int i = 0; i < 4; i++) r[k][i] = __dp2a_lo(coef[i], __byte_perm(a, b, sel[i]), 0u);
         }
         uint32_t packed = 0;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            const int v = ((((int)ty.c0 * (int)(r[0][i] >> 4)) >> 16) + (((int)ty.c1 * (int)(r[1][i] >> 4)) >> 16) + 2) >> 2;
+            const int v = ((((int)ty[rr].c0 * (int)(r[0][i] >> 4)) >> 16) + (((int)ty[rr].c1 * (int)(r[1][i] >> 4)) >> 16) + 2) >> 2;
             packed |= (uint32_t)min(v, 255) << (8 * i);
         }
-        *reinterpret_cast<uint32_t *>(D.img + (size_t)f * D.img_fstride + (size_t)dy * D.pitch + dx0) = packed;
+        if (dy0 + rr < dh) *reinterpret_cast<uint32_t *>(drow + (size_t)rr * D.pitch) = packed;
     }
 }
 
@@ -118,8 +130,9 @@ int launch_resize(const LevelDev *d_levels, const LevelDev *h_levels, int level,
     const LevelDev &S = h_levels[level - 1];
     const bool aligned = ((reinterpret_cast<uintptr_t>(S.img) | (uintptr_t)S.pitch | (uintptr_t)S.img_fstride) & 3) == 0 && D.xpack != nullptr;
     if (aligned) {
-        dim3 grid((D.w + 4 * 128 - 1) / (4 * 128), (D.h + 1) / 2, batch);
-        k_resize<<<grid, 128, 0, stream>>>(d_levels, level, f0);
+        const int ngx = (D.w + 3) / 4, nitems = ngx * ((D.h + RR - 1) / RR);
+        dim3 grid((nitems + 127) / 128, batch);
+        k_resize<<<grid, 128, 0, stream>>>(d_levels, level, f0, ngx, nitems);
     } else {
         dim3 grid((D.w + 4 * 128 - 1) / (4 * 128), D.h, batch);
         k_resize_generic<<<grid, 128, 0, stream>>>(d_levels, level, f0);
@@ -128,12 +141,15 @@ int launch_resize(const LevelDev *d_levels, const LevelDev *h_levels, int level,
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K5  7x7 Gaussian, fixed point [18,34,48,56,48,34,18]/256 per axis, exact 16.16 accumulation, REFLECT_101
-//     tile 64x64: shared u8 halo tile -> horizontal pass (two pixels per IMAD, 16-bit lanes) -> vertical pass
+// K5  7x7 Gaussian, fixed point [18,34,48,56,48,34,18]/256 per axis, exact 16.16 accumulation, REFLECT_101.
+//     Output tile 64 x 56 per CTA.  The halo tile (62 rows x 80 bytes) is staged with word loads; the horizontal pass is
+//     two IDP.4A per pixel on byte-aligned word slices (sums <= 65280 fit 16 bits) and leaves its sums packed as
+//     (row 2p, row 2p+1) pairs, so that the vertical pass is four IDP.2A per pixel (16-bit sums x 8-bit taps, 32-bit acc).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int BT = 64;                 // tile edge
+constexpr int BTW = kBlurTileW, BTH = kBlurTileH;   // 64 x 56
 constexpr int BIN_PITCH = 80;          // bytes per staged input row: image columns x0-4 .. x0+75
-constexpr int BROWS = BT + 6;
+constexpr int BROWS = BTH + 6;         // 62 staged rows = 31 row pairs
+static_assert(BTW == 64 && BTH == 56, "k_blur's thread mapping is written for 64 x 56 tiles");
 
 // BORDER_REFLECT_101 for any index (period 2(n-1)); n == 1 maps everything to 0
 __device__ __forceinline__ int reflect101(int i, int n) {
@@ -147,99 +163,98 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 
 __global__ void __launch_bounds__(256) k_blur(const LevelDev *__restrict__ lv, const BlurTile *__restrict__ tiles, int f0) {
     __shared__ __align__(16) uint8_t s_in[BROWS * BIN_PITCH];
-    __shared__ __align__(16) uint32_t s_h[BROWS * (BT / 2)];   // horizontal sums, lanes = columns (c, c+2)
+    __shared__ __align__(16) uint32_t s_h[(BROWS / 2) * BTW];   // [row pair][column]: H(2p, c) | H(2p+1, c) << 16
     const BlurTile t = tiles[blockIdx.x];
     const LevelDev &L = lv[t.level];
     const int f = f0 + blockIdx.y;
-    const int x0 = t.tx * BT, y0 = t.ty * BT;
+    const int x0 = t.tx * BTW, y0 = t.ty * BTH;
+    const int w = L.w, h = L.h, pitch = L.pitch;
     const uint8_t *__restrict__ src = L.img + (size_t)f * L.img_fstride;
-    // stage rows y0-3 .. y0+66, columns x0-4 .. x0+75 (20 words per row): aligned word loads where the word lies inside
-    // the image, per-byte BORDER_REFLECT_101 elsewhere
-    const bool word_ok = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)L.pitch) & 3) == 0;
+    // stage rows y0-3 .. y0+58, columns x0-4 .. x0+75 (20 words per row): aligned word loads where the word lies inside
+    // the image, per-byte BORDER_REFLECT_101 elsewhere.  1240 words, 5 per thread, all requested before the first store.
+    const bool word_ok = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)pitch) & 3) == 0;
     {
-        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        if (lane < BIN_PITCH / 4) {
-            const int gx = x0 - 4 + 4 * lane;
-            const bool col_in = gx >= 0 && gx + 3 < L.w;
-            constexpr int RB = 3;    // rows in flight per lane: 8 warps x 3 rows per round, 3 rounds cover the 70 rows
-            for (int r0 = wid; r0 < BROWS; r0 += 8 * RB) {
-                uint32_t v[RB];
+        constexpr int NW = BROWS * (BIN_PITCH / 4), PER = (NW + 255) / 256;
+        uint32_t v[PER];
 #pragma unroll
-                for (int k = 0; k < RB; k++) {
-                    const int r = r0 + 8 * k;
-                    if (r < BROWS) {
-                        const int gy = y0 - 3 + r;
-                        if (word_ok && col_in && gy >= 0 && gy < L.h) {
-                            v[k] = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)gy * L.pitch + gx));
-                        } else {
-                            const uint8_t *row = src + (size_t)reflect101(gy, L.h) * L.pitch;
-                            v[k] = (uint32_t)row[reflect101(gx, L.w)] | ((uint32_t)row[reflect101(gx + 1, L.w)] << 8) |
-                                   ((uint32_t)row[reflect101(gx + 2, L.w)] << 16) | ((uint32_t)row[reflect101(gx + 3, L.w)] << 24);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < RB; k++) {
-                    const int r = r0 + 8 * k;
-                    if (r < BROWS) reinterpret_cast<uint32_t *>(s_in)[r * (BIN_PITCH / 4) + lane] = v[k];
+        for (int k = 0; k < PER; k++) {
+            const int it = threadIdx.x + 256 * k;
+            if (it < NW) {
+                const int r = it / (BIN_PITCH / 4), wc = it - r * (BIN_PITCH / 4);
+                const int gy = y0 - 3 + r, gx = x0 - 4 + 4 * wc;
+                if (word_ok && gx >= 0 && gx + 3 < w && gy >= 0 && gy < h) {
+                    v[k] = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)gy * pitch + gx));
+                } else {
+                    const uint8_t *row = src + (size_t)reflect101(gy, h) * pitch;
+                    v[k] = (uint32_t)row[reflect101(gx, w)] | ((uint32_t)row[reflect101(gx + 1, w)] << 8) |
+                           ((uint32_t)row[reflect101(gx + 2, w)] << 16) | ((uint32_t)row[reflect101(gx + 3, w)] << 24);
                 }
             }
         }
-    }
-    __syncthreads();
-    // horizontal: item = (row, group of 8 outputs)
-    for (int it = threadIdx.x; it < BROWS * (BT / 8); it += 256) {
-        const int r = it >> 3, g = it & 7;
-        const uint2 a = *reinterpret_cast<const uint2 *>(s_in + r * BIN_PITCH + 8 * g);
-        const uint2 b = *reinterpret_cast<const uint2 *>(s_in + r * BIN_PITCH + 8 * g + 8);
-        const uint32_t w0 = a.x, w1 = a.y, w2 = b.x, w3 = b.y;
-        // staged column c is image column x0-4+c, so output 8g+i reads bytes i+1 .. i+7 of these 16:
-        // q[j] = (byte j+3) << 16 | byte j+1   for j = 0..11
-        uint32_t q[12];
-        const uint32_t s01 = __funnelshift_r(w0, w1, 16), s12 = __funnelshift_r(w1, w2, 16), s23 = __funnelshift_r(w2, w3, 16);
-        q[0] = (w0 >> 8) & 0x00FF00FFu;  q[1] = s01 & 0x00FF00FFu;  q[2] = (s01 >> 8) & 0x00FF00FFu;  q[3] = w1 & 0x00FF00FFu;
-        q[4] = (w1 >> 8) & 0x00FF00FFu;  q[5] = s12 & 0x00FF00FFu;  q[6] = (s12 >> 8) & 0x00FF00FFu;  q[7] = w2 & 0x00FF00FFu;
-        q[8] = (w2 >> 8) & 0x00FF00FFu;  q[9] = s23 & 0x00FF00FFu;  q[10] = (s23 >> 8) & 0x00FF00FFu; q[11] = w3 & 0x00FF00FFu;
-        uint32_t o[4];
 #pragma unroll
-        for (int p = 0; p < 4; p++) {
-            const int i0 = (p & 1) + 4 * (p >> 1);   // output columns (i0, i0+2): 0,1,4,5
-            o[p] = 18u * (q[i0] + q[i0 + 6]) + 34u * (q[i0 + 1] + q[i0 + 5]) + 48u * (q[i0 + 2] + q[i0 + 4]) + 56u * q[i0 + 3];
+        for (int k = 0; k < PER; k++) {
+            const int it = threadIdx.x + 256 * k;
+            if (it < NW) reinterpret_cast<uint32_t *>(s_in)[it] = v[k];
         }
-        *reinterpret_cast<uint4 *>(s_h + r * (BT / 2) + 4 * g) = make_uint4(o[0], o[1], o[2], o[3]);
     }
     __syncthreads();
-    // vertical: item = (4-pixel column group, 4-row segment); words (2cg, 2cg+1) hold columns (0,2),(1,3) of the group
-    {
+    // horizontal: item = (row pair p, group g of 8 output columns); 31 x 8 = 248 items
+    if (threadIdx.x < (BROWS / 2) * 8) {
+        const int p = threadIdx.x >> 3, g = threadIdx.x & 7;
+        constexpr uint32_t KA = 18u | (34u << 8) | (48u << 16) | (56u << 24), KB = 48u | (34u << 8) | (18u << 16);
+        uint32_t hs[2][8];
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++) {
+            const uint2 a = *reinterpret_cast<const uint2 *>(s_in + (2 * p + rr) * BIN_PITCH + 8 * g);
+            const uint2 b = *reinterpret_cast<const uint2 *>(s_in + (2 * p + rr) * BIN_PITCH + 8 * g + 8);
+            const uint32_t W[4] = {a.x, a.y, b.x, b.y};
+            // U[o] = staged bytes 8g+o .. 8g+o+3; output column 8g+i reads bytes i+1 .. i+7 = U[i+1] (4 taps) + U[i+5] (3 taps)
+            uint32_t U[13];
+#pragma unroll
+            for (int o = 1; o <= 12; o++) U[o] = (o & 3) ? __funnelshift_r(W[o >> 2], W[(o >> 2) + 1], 8 * (o & 3)) : W[o >> 2];
+#pragma unroll
+            for (int i = 0; i < 8; i++) hs[rr][i] = __dp4a(U[i + 5], KB, __dp4a(U[i + 1], KA, 0u));
+        }
+        uint32_t o[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) o[i] = hs[0][i] | (hs[1][i] << 16);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_h + p * BTW + 8 * g);
+        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+    __syncthreads();
+    // vertical: item = (4-column group cg, segment of 4 output rows); 16 x 14 = 224 items.  Output row y reads staged rows
+    // y .. y+6: for even y the pairs y/2 .. y/2+3 with taps (18,34)(48,56)(48,34)(18,0), for odd y the pairs
+    // (y-1)/2 .. (y-1)/2+3 with taps (0,18)(34,48)(56,48)(34,18).
+    if (threadIdx.x < 16 * (BTH / 4)) {
         const int cg = threadIdx.x & 15, seg = threadIdx.x >> 4;
         const int gx = x0 + 4 * cg;
-        if (gx < L.w) {
-            uint32_t lo[10], hi[10];
+        if (gx < w) {
+            constexpr uint32_t EA = 18u | (34u << 8) | (48u << 16) | (56u << 24), EB = 48u | (34u << 8) | (18u << 16);
+            constexpr uint32_t OA = (18u << 8) | (34u << 16) | (48u << 24), OB = 56u | (48u << 8) | (34u << 16) | (18u << 24);
+            uint32_t P[5][4];
 #pragma unroll
-            for (int r = 0; r < 10; r++) {
-                const uint2 v = *reinterpret_cast<const uint2 *>(s_h + (4 * seg + r) * (BT / 2) + 2 * cg);
-                lo[r] = v.x; hi[r] = v.y;
+            for (int k = 0; k < 5; k++) {
+                const uint4 q = *reinterpret_cast<const uint4 *>(s_h + (2 * seg + k) * BTW + 4 * cg);
+                P[k][0] = q.x; P[k][1] = q.y; P[k][2] = q.z; P[k][3] = q.w;
             }
-            uint8_t *__restrict__ dst = L.blur + (size_t)f * L.blur_fstride;
+            uint8_t *__restrict__ dst = L.blur + (size_t)f * L.blur_fstride + gx;
+            const int bp = L.blur_pitch;
 #pragma unroll
             for (int r = 0; r < 4; r++) {
                 const int gy = y0 + 4 * seg + r;
-                if (gy >= L.h) break;
-                uint32_t px[4];
+                const int pb = r >> 1;
+                const uint32_t ka = (r & 1) ? OA : EA, kb = (r & 1) ? OB : EB;
+                uint32_t px = 0;
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
-                    // column c of the group: c=0 -> lo lane0, c=1 -> hi lane0, c=2 -> lo lane1, c=3 -> hi lane1
-                    uint32_t acc = 32768u;
-#pragma unroll
-                    for (int k = 0; k < 7; k++) {
-                        const uint32_t wv = (c & 1) ? hi[r + k] : lo[r + k];
-                        const uint32_t e = (c & 2) ? (wv >> 16) : (wv & 0xFFFFu);
-                        const uint32_t kk = (k == 0 || k == 6) ? 18u : (k == 1 || k == 5) ? 34u : (k == 2 || k == 4) ? 48u : 56u;
-                        acc += kk * e;
-                    }
-                    px[c] = acc >> 16;
+                    uint32_t acc = __dp2a_lo(P[pb][c], ka, 32768u);
+                    acc = __dp2a_hi(P[pb + 1][c], ka, acc);
+                    acc = __dp2a_lo(P[pb + 2][c], kb, acc);
+                    acc = __dp2a_hi(P[pb + 3][c], kb, acc);
+                    px |= (acc >> 16) << (8 * c);
                 }
-                *reinterpret_cast<uint32_t *>(dst + (size_t)gy * L.blur_pitch + gx) = px[0] | (px[1] << 8) | (px[2] << 16) | (px[3] << 24);
+                if (gy < h) *reinterpret_cast<uint32_t *>(dst + (size_t)gy * bp) = px;
             }
         }
     }
