@@ -15,6 +15,7 @@
 #include "../../include/orbx.h"
 #include "orbx_dev.h"
 #include "orbx_plan.h"
+#include "orbx_tma.cuh"
 
 using namespace orbx;
 
@@ -74,6 +75,8 @@ struct orbx_handle {
     KeypointRec *d_kp = nullptr;    // [batch][kp_cap]
     uint8_t *d_desc = nullptr;      // [batch][kp_cap][32]
     int *d_n = nullptr, *d_mono = nullptr;
+    FastTma ftma{};                 // tensor maps of the level planes (TMA-staged FAST kernel)
+    int sm_count = 148;
     uint8_t *l0_own = nullptr;      // arena copy of level 0 (host-input path)
     size_t l0_own_fstride = 0;
     int l0_own_pitch = 0;
@@ -134,6 +137,38 @@ static cudaError_t dev_upload(orbx_handle *h, T **out, const std::vector<T> &v) 
     cudaError_t e = dev_alloc(h, out, v.size());
     if (e != cudaSuccess || v.empty()) return e;
     return cudaMemcpy(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+static_assert(sizeof(CUtensorMap) == 128, "FastTma stores tensor maps as 128-byte blobs");
+
+// (Re)encode the tensor map of one level plane; marks the level unusable when the plane misses the TMA alignment rules.
+static void encode_fast_map(orbx_handle *h, int l) {
+    const LevelDev &D = h->h_levels[l];
+    FastTma &T = h->ftma;
+    T.level_ok[l] = T.box_w[l] > 0 && tma_make_plane_map(reinterpret_cast<CUtensorMap *>(T.map[l]), D.img, D.w, D.h, h->batch_cap, (size_t)D.pitch,
+                                                       D.img_fstride, T.box_w[l], T.box_h[l]);
+    T.ok = !getenv("ORBX_NO_TMA");
+    for (int k = 0; k < h->plan.nlevels; k++) T.ok = T.ok && (T.level_ok[k] || h->plan.lv[k].ncells == 0);
+}
+
+// Box of a level = the largest ROI of its cells plus the 4-pixel-group / row-pair overhang the scoring items read.
+static void build_fast_maps(orbx_handle *h) {
+    FastTma &T = h->ftma;
+    std::memset(&T, 0, sizeof(T));
+    for (int l = 0; l < h->plan.nlevels; l++) {
+        const LevelPlan &LP = h->plan.lv[l];
+        int rw = 0, rh = 0;
+        for (int c = LP.first_cell; c < LP.first_cell + LP.ncells; c++) {
+            rw = std::max(rw, h->plan.cells[c].x1 - h->plan.cells[c].x0);
+            rh = std::max(rh, h->plan.cells[c].y1 - h->plan.cells[c].y0);
+        }
+        if (LP.ncells == 0) continue;
+        int bw = (15 + rw + 5 + 15) / 16 * 16;   // the box starts at x0 rounded down to 16 bytes (TMA rule)
+        if (bw % 64 == 0) bw += 16;          // rows two apart would fall on the same banks
+        T.box_w[l] = bw; T.box_h[l] = rh + 1;
+        if (bw > 96 || rh + 1 > 80) { T.box_w[l] = 0; }   // larger than the shared-memory stage: no TMA for this plan
+    }
+    for (int l = 0; l < h->plan.nlevels; l++) encode_fast_map(h, l);
 }
 
 // (Re)build the geometry plan and the workspace for w x h frames, `batch` frames per call.
@@ -199,6 +234,7 @@ static int ensure_plan(orbx_handle *h, int w, int ht, int batch) {
     h->ntiles = (int)tiles.size();
     CU_TRY(h, dev_upload(h, &h->d_tiles, tiles));
     CU_TRY(h, cudaMemcpy(h->d_levels, h->h_levels, sizeof(h->h_levels), cudaMemcpyHostToDevice));
+    build_fast_maps(h);
     // pinned staging
     h->h_in_bytes = (size_t)B * pl.lv[0].plane_bytes;
     CU_TRY(h, cudaMallocHost((void **)&h->h_in, h->h_in_bytes));
@@ -215,6 +251,7 @@ static int set_level0(orbx_handle *h, const uint8_t *img, int pitch, size_t fstr
     LevelDev &D = h->h_levels[0];
     if (D.img == img && D.pitch == pitch && D.img_fstride == fstride) return ORBX_OK;
     D.img = const_cast<uint8_t *>(img); D.pitch = pitch; D.img_fstride = fstride;
+    encode_fast_map(h, 0);
     CU_TRY(h, cudaMemcpyAsync(h->d_levels, &h->h_levels[0], sizeof(LevelDev), cudaMemcpyHostToDevice, h->stream));
     return ORBX_OK;
 }
@@ -258,31 +295,41 @@ static int run_pipeline(orbx_handle *h, int f0, int batch, int lap0, int lap1, K
     const int nl = pl.nlevels;
     const bool prof = h->profiling && stream == h->stream;
     const bool fork = !prof && side != nullptr;
-#define STAGE_MARK(i) do { if (prof) CU_TRY(h, cudaEventRecord(h->ev[i], stream)); } while (0)
+    static const bool dbg_sync = getenv("ORBX_DEBUG_SYNC") != nullptr;   // localise a faulting kernel: sync after every stage
+#define STAGE_MARK(i)                                                                                             \
+    do {                                                                                                          \
+        if (prof) CU_TRY(h, cudaEventRecord(h->ev[i], stream));                                                   \
+        if (dbg_sync) {                                                                                           \
+            cudaError_t e__ = cudaStreamSynchronize(stream);                                                      \
+            if (e__ != cudaSuccess) { h->err = std::string("stage ") + #i + ": " + cudaGetErrorString(e__); return ORBX_E_CUDA; } \
+        }                                                                                                         \
+    } while (0)
     STAGE_MARK(0);
     for (int l = 1; l < nl; l++) h->launches += launch_resize(h->d_levels, h->h_levels, l, f0, batch, stream);
     STAGE_MARK(1);
     // The blurred planes are only needed by the descriptor stage, and the quadtree kernel (one CTA per frame x level,
-    // latency-bound) cannot fill the machine: outside profiling mode the Gaussian pass runs on a side stream next to
-    // quadtree + slot assignment.  It is forked after FAST because two machine-filling kernels gain nothing from
-    // running side by side.
+    // latency-bound) cannot fill the machine: outside profiling mode quadtree + slot assignment run on the side stream,
+    // which has the highest priority so that its few CTAs are placed first, while the Gaussian pass fills the rest of
+    // the machine from the main stream.  The fork comes after FAST because two machine-filling kernels gain nothing
+    // from running side by side.
     if (!fork) h->launches += launch_blur(h->d_levels, h->d_tiles, h->ntiles, f0, batch, stream);
     STAGE_MARK(2);
-    h->launches += launch_fast(h->d_levels, h->d_cells, (int)pl.cells.size(), f0, batch, h->P.ini_th, h->P.min_th, h->d_overflow, stream);
+    h->launches += launch_fast(h->d_levels, h->h_levels, h->d_cells, (int)pl.cells.size(), f0, batch, h->P.ini_th, h->P.min_th, h->d_overflow, stream, &h->ftma, h->sm_count);
     STAGE_MARK(3);
+    cudaStream_t qs = fork ? side : stream;
     if (fork) {
         CU_TRY(h, cudaEventRecord(ev_fork, stream));
         CU_TRY(h, cudaStreamWaitEvent(side, ev_fork, 0));
     }
-    h->launches += launch_octree(h->d_levels, h->h_levels, nl, f0, batch, h->d_overflow, stream);
-    if (fork) {
-        h->launches += launch_blur(h->d_levels, h->d_tiles, h->ntiles, f0, batch, side);
-        CU_TRY(h, cudaEventRecord(ev_join, side));
-    }
+    h->launches += launch_octree(h->d_levels, h->h_levels, nl, f0, batch, h->d_overflow, qs);
     STAGE_MARK(4);
-    h->launches += launch_finalize(h->d_levels, nl, f0, batch, pl.total_out_cap, lap0, lap1, d_kp, cap, h->d_slot, d_n, d_mono, h->d_overflow, stream);
+    h->launches += launch_finalize(h->d_levels, nl, f0, batch, pl.total_out_cap, lap0, lap1, d_kp, cap, h->d_slot, d_n, d_mono, h->d_overflow, qs);
     STAGE_MARK(5);
-    if (fork) CU_TRY(h, cudaStreamWaitEvent(stream, ev_join, 0));
+    if (fork) {
+        CU_TRY(h, cudaEventRecord(ev_join, side));
+        h->launches += launch_blur(h->d_levels, h->d_tiles, h->ntiles, f0, batch, stream);
+        CU_TRY(h, cudaStreamWaitEvent(stream, ev_join, 0));
+    }
     h->launches += launch_describe(h->d_levels, nl, f0, batch, pl.total_out_cap, h->d_slot, d_kp, d_desc, cap, stream);
     STAGE_MARK(6);
 #undef STAGE_MARK
@@ -322,12 +369,16 @@ int orbx_create(const orbx_config *cfg, orbx_handle **out) {
     }
     if (cfg->device < 0 || cfg->device >= ndev) { delete h; return fail(nullptr, ORBX_E_INVALID, "device ordinal out of range"); }
     h->device = cfg->device;
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device);
+    if (h->sm_count < 1) h->sm_count = 148;
     if ((e = cudaSetDevice(h->device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
         g_create_error = std::string("cuda init: ") + cudaGetErrorString(e);
         delete h; return ORBX_E_CUDA;
     }
     h->own_stream = h->stream;
-    if ((e = cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if ((e = cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming)) != cudaSuccess) {
         g_create_error = std::string("cuda init: ") + cudaGetErrorString(e);

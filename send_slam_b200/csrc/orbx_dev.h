@@ -44,8 +44,16 @@ struct KeypointRec {           // == orbx_keypoint == cv::KeyPoint
 // They process frames [f0, f0 + batch) of the workspace.
 int launch_resize(const LevelDev *d_levels, const LevelDev *h_levels, int level, int f0, int batch, cudaStream_t stream);
 int launch_blur(const LevelDev *d_levels, const BlurTile *d_tiles, int ntiles, int f0, int batch, cudaStream_t stream);
-int launch_fast(const LevelDev *d_levels, const CellRect *d_cells, int ncells, int f0, int batch, int ini_th, int min_th,
-                int *d_overflow, cudaStream_t stream);
+// Tensor maps of the level planes for the TMA-staged FAST kernel (host side: orbx_api.cu builds them; 128 bytes each,
+// stored opaquely so that this header does not need <cuda.h>).
+struct FastTma {
+    alignas(64) unsigned char map[kMaxLevels][128];
+    int box_w[kMaxLevels], box_h[kMaxLevels];
+    bool level_ok[kMaxLevels];
+    bool ok;                    // every level has a valid map
+};
+int launch_fast(const LevelDev *d_levels, const LevelDev *h_levels, const CellRect *d_cells, int ncells, int f0, int batch,
+                int ini_th, int min_th, int *d_overflow, cudaStream_t stream, const FastTma *tma, int sm_count);
 int launch_octree(const LevelDev *d_levels, const LevelDev *h_levels, int nlevels, int f0, int batch, int *d_overflow,
                   cudaStream_t stream);
 int launch_finalize(const LevelDev *d_levels, int nlevels, int f0, int batch, int total_out_cap, int lap0, int lap1,

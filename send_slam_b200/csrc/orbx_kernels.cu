@@ -13,8 +13,10 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstring>
 
 #include "orbx_dev.h"
+#include "orbx_tma.cuh"
 
 namespace orbx {
 
@@ -317,11 +319,12 @@ __device__ __forceinline__ uint32_t fast_score_lanes(const uint32_t (&r)[16], ui
     return umax3(dark, bright, 0x01000100u) & 0x00FF00FFu;
 }
 
-// rows[7][3]: staged words of ROI rows y-3..y+3, bytes 4g..4g+11 (pixels of interest at bytes 3..6).
-__device__ __forceinline__ uint32_t fast_score4(const uint32_t (&w)[7][3]) {
-    // 4-byte slices at byte offset o of a row: o=0 w0, o=4 w1, else funnel shifts
-#define SL(row, o) ((o) == 0 ? w[row][0] : (o) == 4 ? w[row][1] : (o) < 4 ? __funnelshift_r(w[row][0], w[row][1], 8 * (o)) \
-                                                                   : __funnelshift_r(w[row][1], w[row][2], 8 * ((o)-4)))
+// w[7][4]: staged words of rows y-3..y+3, 16 bytes each; the four pixels of interest sit at bytes M+3 .. M+6 (M = 0..3 is
+// the misalignment of the ROI inside its 16-byte aligned TMA box; the fallback kernel stages aligned ROIs, M = 0).
+template <int M>
+__device__ __forceinline__ uint32_t fast_score4(const uint32_t (&w)[7][4]) {
+    // 4-byte slices at byte offset o of a row
+#define SL(row, o) ((((o) + M) & 3) == 0 ? w[row][((o) + M) >> 2] : __funnelshift_r(w[row][((o) + M) >> 2], w[row][(((o) + M) >> 2) + 1], 8 * (((o) + M) & 3)))
     uint32_t r[16];
     r[0] = SL(6, 3);  r[1] = SL(6, 4);  r[2] = SL(5, 5);  r[3] = SL(4, 6);
     r[4] = SL(3, 6);  r[5] = SL(2, 6);  r[6] = SL(1, 5);  r[7] = SL(0, 4);
@@ -335,6 +338,24 @@ __device__ __forceinline__ uint32_t fast_score4(const uint32_t (&w)[7][3]) {
     for (int k = 0; k < 16; k++) re[k] = r[k] << 8;
     const uint32_t even = fast_score_lanes(re, c << 8);   // pixels 0, 2
     return even | (odd << 8);
+}
+
+// scores of a 4-pixel x 2-row item: p = first staged word of row 2s of the item, pitch in bytes
+template <int M>
+__device__ __forceinline__ void fast_item(const uint8_t *p, int pitch, uint32_t &sa, uint32_t &sb) {
+    uint32_t w[8][4];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(p + r * pitch);
+        w[r][0] = q[0]; w[r][1] = q[1]; w[r][2] = q[2];
+        w[r][3] = M >= 2 ? q[3] : 0u;   // a window of 12 bytes is enough for M < 2
+    }
+    uint32_t wa[7][4], wb[7][4];
+#pragma unroll
+    for (int r = 0; r < 7; r++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) { wa[r][k] = w[r][k]; wb[r][k] = w[r + 1][k]; }
+    sa = fast_score4<M>(wa); sb = fast_score4<M>(wb);
 }
 
 __global__ void __launch_bounds__(192) k_fast_cells(const LevelDev *__restrict__ lv, const CellRect *__restrict__ cells,
@@ -392,18 +413,8 @@ __global__ void __launch_bounds__(192) k_fast_cells(const LevelDev *__restrict__
     const int ng = (iw + 3) >> 2, ns = (ih + 1) >> 1;
     for (int it = threadIdx.x; it < ng * ns; it += blockDim.x) {
         const int s = (int)(((uint32_t)it * (65536u / (uint32_t)ng + 1u)) >> 16), g = it - s * ng;
-        uint32_t w[8][3];
-#pragma unroll
-        for (int r = 0; r < 8; r++) {
-            const uint32_t *p = reinterpret_cast<const uint32_t *>(s_roi + (2 * s + r) * FT_PITCH + 4 * g);
-            w[r][0] = p[0]; w[r][1] = p[1]; w[r][2] = p[2];
-        }
-        uint32_t wa[7][3], wb[7][3];
-#pragma unroll
-        for (int r = 0; r < 7; r++)
-#pragma unroll
-            for (int k = 0; k < 3; k++) { wa[r][k] = w[r][k]; wb[r][k] = w[r + 1][k]; }
-        uint32_t sa = fast_score4(wa), sb = fast_score4(wb);
+        uint32_t sa, sb;
+        fast_item<0>(s_roi + (2 * s) * FT_PITCH + 4 * g, FT_PITCH, sa, sb);
         // mask pixels beyond the interior (group / row-pair overhang)
         const int valid = iw - 4 * g;
         if (valid < 4) { const uint32_t m = 0xFFFFFFFFu >> (8 * (4 - valid)); sa &= m; sb &= m; }
@@ -475,9 +486,216 @@ __global__ void __launch_bounds__(192) k_fast_cells(const LevelDev *__restrict__
     }
 }
 
-int launch_fast(const LevelDev *d_levels, const CellRect *d_cells, int ncells, int f0, int batch, int ini_th, int min_th,
-                int *d_overflow, cudaStream_t stream) {
+// TMA-staged, persistent, warp-specialised variant (the one the pipeline runs; k_fast_cells above stays as the fallback
+// for level-0 planes that do not meet the TMA alignment rules).  Each CTA walks (cell, frame) items with stride
+// gridDim.x.  Warps 0..5 only ever touch shared memory: they score and suppress.  Warp 6 is the helper: it keeps the
+// ROIs of the next FT_STAGES items in flight (cp.async.bulk.tensor, completion on an mbarrier) and appends the finished
+// candidate list of the previous item to the level's global list, so that neither the global-load latency of the
+// staging nor the round trip of the global atomic is on the path of the compute warps.
+//   * A TMA box must start on a 16-byte boundary of the innermost dimension (measured: an unaligned start coordinate
+//     raises "illegal instruction"), so the box starts at x0 & ~15 and the 4-pixel groups are laid out on absolute
+//     multiples of 4 (window = pixel - 3): every shared-memory read stays an aligned word, at the price of up to 3
+//     masked pixels in the first group of a row.
+//   * Score tile and candidate list are double-buffered by item parity; a cell costs the compute warps two named
+//     barriers (scores complete, list complete).  Hand-offs with the helper go through mbarriers:
+//     full[s] (TMA bytes landed), empty[s] (stage read), ready[p] (list complete), free[p] (list appended).
+//   * Candidates above iniThFAST fill the list from the front, the rest from the back: the per-cell threshold
+//     fallback is then a choice of sub-array.
+// Scores, NMS rule and emitted candidate sets are identical to k_fast_cells (candidate order is free by design).
+constexpr int FT_STAGES = 3;
+constexpr int FT_LIST = 36 * 36 + 8;
+constexpr int FT_CTHREADS = 192, FT_THREADS = FT_CTHREADS + 32;
+constexpr int FT_SC_BYTES = (FT_ROWS - 4) * FS_PITCH;
+
+struct FastTmaParams {
+    CUtensorMap map[kMaxLevels];        // level plane [frames][h][w], box = box_w x box_h x 1
+    int box_w[kMaxLevels], box_h[kMaxLevels];
+    uint32_t *cand[kMaxLevels];         // [frames][cand_cap]
+    int *cand_count[kMaxLevels];        // [frames]
+    int cand_cap[kMaxLevels];
+    int stage_bytes;                    // shared-memory bytes per ROI stage (multiple of 128)
+};
+
+struct FastItem { int x0, y0, iw, ih, level, f, pad0, pad1; };
+
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tma_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, %0;" ::"n"(FT_CTHREADS) : "memory"); }
+
+__global__ void __launch_bounds__(FT_THREADS, 4) k_fast_tma(const __grid_constant__ FastTmaParams P, const CellRect *__restrict__ cells,
+                                                            int ncells, int total, int ini_th, int min_th, int f0,
+                                                            int *__restrict__ overflow) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t *s_roi_base = smem;                                                          // FT_STAGES x stage_bytes
+    uint8_t *s_sc_base = smem + FT_STAGES * P.stage_bytes;                               // 2 x FT_SC_BYTES (16-byte aligned)
+    uint32_t *s_list_base = reinterpret_cast<uint32_t *>(s_sc_base + 2 * FT_SC_BYTES);   // 2 x FT_LIST
+    FastItem *s_item = reinterpret_cast<FastItem *>(s_list_base + 2 * FT_LIST);          // FT_STAGES
+    uint64_t *s_full = reinterpret_cast<uint64_t *>(s_item + FT_STAGES);                 // FT_STAGES
+    uint64_t *s_empty = s_full + FT_STAGES;                                              // FT_STAGES
+    uint64_t *s_ready = s_empty + FT_STAGES, *s_free = s_ready + 2;                      // 2 + 2
+    int *s_cnt = reinterpret_cast<int *>(s_free + 2);                                    // [parity][above iniTh, rest]
+
+    for (int i = threadIdx.x; i < 2 * FT_SC_BYTES / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(s_sc_base)[i] = 0;
+    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < FT_STAGES; i++) { tma_mbar_init(&s_full[i], 1); tma_mbar_init(&s_empty[i], 1); }
+        for (int i = 0; i < 2; i++) { tma_mbar_init(&s_ready[i], 1); tma_mbar_init(&s_free[i], 1); }
+        tma_mbar_fence_init();
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int first = blockIdx.x, stride = gridDim.x;
+    const int nmine = first < total ? (total - first + stride - 1) / stride : 0;
+
+    if (threadIdx.x >= FT_CTHREADS) {
+        // ================= helper warp =================
+        auto issue = [&](int q) {           // lane 0: describe item q in shared memory and start its TMA
+            const int item = first + q * stride, st = q % FT_STAGES;
+            const int fi = item / ncells;
+            const CellRect c = cells[item - fi * ncells];
+            FastItem d;
+            d.x0 = c.x0; d.y0 = c.y0; d.iw = c.x1 - c.x0 - 6; d.ih = c.y1 - c.y0 - 6; d.level = c.level; d.f = f0 + fi; d.pad0 = d.pad1 = 0;
+            s_item[st] = d;
+            tma_mbar_expect_tx(&s_full[st], (uint32_t)(P.box_w[c.level] * P.box_h[c.level]));
+            tma_load_3d(s_roi_base + st * P.stage_bytes, &P.map[c.level], c.x0 & ~15, c.y0, f0 + fi, &s_full[st]);
+        };
+        if (lane == 0) for (int q = 0; q < FT_STAGES && q < nmine; q++) issue(q);
+        for (int q = 0; q < nmine; q++) {
+            const int par = q & 1, st = q % FT_STAGES;
+            tma_mbar_wait(&s_ready[par], (uint32_t)(q >> 1) & 1u);
+            // per-cell fallback: if any corner passes iniThFAST keep only those, else keep everything above minThFAST
+            const FastItem d = s_item[st];
+            const int n_ini = s_cnt[2 * par], n_low = s_cnt[2 * par + 1];
+            const int n = n_ini > 0 ? n_ini : n_low;
+            const uint32_t *src = s_list_base + par * FT_LIST + (n_ini > 0 ? 0 : FT_LIST - n_low);
+            if (n > 0) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(P.cand_count[d.level] + d.f, n);
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                const int cap = P.cand_cap[d.level];
+                uint32_t *__restrict__ out = P.cand[d.level] + (size_t)d.f * cap;
+                for (int i = lane; i < n; i += 32) {
+                    if (base + i < cap) out[base + i] = src[i]; else *overflow = 1;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                s_cnt[2 * par] = 0; s_cnt[2 * par + 1] = 0;
+                mbar_arrive_cta(&s_free[par]);
+                if (q + FT_STAGES < nmine) {
+                    tma_mbar_wait(&s_empty[st], (uint32_t)(q / FT_STAGES) & 1u);   // scoring of item q has left the stage
+                    issue(q + FT_STAGES);
+                }
+            }
+            __syncwarp();
+        }
+        return;
+    }
+
+    // ================= compute warps =================
+    for (int q = 0; q < nmine; q++) {
+        const int par = q & 1, st = q % FT_STAGES;
+        tma_mbar_wait(&s_full[st], (uint32_t)(q / FT_STAGES) & 1u);
+        const FastItem d = s_item[st];
+        const int rp = P.box_w[d.level];                                    // staged row pitch in bytes
+        const uint8_t *__restrict__ s_roi = s_roi_base + st * P.stage_bytes;
+        uint8_t *__restrict__ s_sc = s_sc_base + par * FT_SC_BYTES;
+        uint32_t *__restrict__ s_list = s_list_base + par * FT_LIST;
+        const int iw = d.iw, ih = d.ih;                                     // tested pixels
+        // groups of 4 pixels on absolute multiples of 4: window = bytes X-3 .. X+8 of the first pixel X of a group
+        const int xi = d.x0 + 3;                                            // first tested column
+        const int lead_px = d.x0 & 3;                                       // it sits at lane lead_px of group 0
+        const int wbase = (d.x0 & ~3) - (d.x0 & ~15);                       // byte offset of group 0's window in the box
+        const int ng = (lead_px + iw + 3) >> 2, ns = (ih + 1) >> 1;
+        const uint32_t inv_ng = 65536u / (uint32_t)ng + 1u;
+        // scores: work item = (group g, row pair s)
+        for (int wi = threadIdx.x; wi < ng * ns; wi += FT_CTHREADS) {
+            const int s = (int)(((uint32_t)wi * inv_ng) >> 16), g = wi - s * ng;
+            uint32_t sa, sb;
+            fast_item<0>(s_roi + (2 * s) * rp + wbase + 4 * g, rp, sa, sb);
+            // mask pixels outside the tested columns (leading lanes of group 0, trailing lanes of the last group)
+            const int lo = lead_px - 4 * g, hi = lead_px + iw - 4 * g;       // valid lanes: lo <= k < hi
+            uint32_t m = 0xFFFFFFFFu;
+            if (lo > 0) m &= 0xFFFFFFFFu << (8 * lo);
+            if (hi < 4) m &= 0xFFFFFFFFu >> (8 * (4 - hi));
+            sa &= m; sb &= m;
+            // score tile: lane k of group g on tested row y at [(y+1)*FS_PITCH + 4 + 4g + k]  (word 0 and row 0 are the zero ring)
+            *reinterpret_cast<uint32_t *>(s_sc + (2 * s + 1) * FS_PITCH + 4 + 4 * g) = sa;
+            if (2 * s + 1 < ih) *reinterpret_cast<uint32_t *>(s_sc + (2 * s + 2) * FS_PITCH + 4 + 4 * g) = sb;
+        }
+        bar_compute();
+        if (threadIdx.x == 0) mbar_arrive_cta(&s_empty[st]);
+        if (q >= 2) tma_mbar_wait(&s_free[par], (uint32_t)((q >> 1) - 1) & 1u);   // list of item q-2 has been appended
+        // NMS (strict 8-neighbour maximum inside the cell, neighbours outside count 0): see k_fast_cells
+        {
+            const uint32_t thr = ((uint32_t)min_th << 8) | ((uint32_t)min_th << 24);
+            for (int wi = threadIdx.x; wi < ng * ih; wi += FT_CTHREADS) {
+                const int y = (int)(((uint32_t)wi * inv_ng) >> 16), g = wi - y * ng;
+                const uint32_t *ru = reinterpret_cast<const uint32_t *>(s_sc + y * FS_PITCH) + g;
+                const uint32_t *rm = ru + FS_PITCH / 4, *rd = rm + FS_PITCH / 4;
+                const uint32_t c_m = rm[1];
+                if (c_m == 0) continue;
+                const uint32_t u0 = ru[0], u1 = ru[1], u2 = ru[2], m0 = rm[0], m2 = rm[2], d0 = rd[0], d1 = rd[1], d2 = rd[2];
+                const uint32_t lu = __funnelshift_r(u0, u1, 24), lm = __funnelshift_r(m0, c_m, 24), ld = __funnelshift_r(d0, d1, 24);
+                const uint32_t ruu = __funnelshift_r(u1, u2, 8), rmm = __funnelshift_r(c_m, m2, 8), rdd = __funnelshift_r(d1, d2, 8);
+                uint32_t mo = umax3(umax3(lu, ld, lm), umax3(ruu, rdd, rmm), umax3(u1, d1, thr));
+                uint32_t me = umax3(umax3(lu << 8, ld << 8, lm << 8), umax3(ruu << 8, rdd << 8, rmm << 8), umax3(u1 << 8, d1 << 8, thr));
+                const uint32_t so = c_m & 0xFF00FF00u, se = (c_m << 8) & 0xFF00FF00u;
+                mo |= 0x00FF00FFu; me |= 0x00FF00FFu;
+                const uint32_t fo = umax2(so, mo) ^ mo, fe = umax2(se, me) ^ me;
+                uint32_t mask = ((fe & 0xFFFFu) ? 1u : 0u) | ((fo & 0xFFFFu) ? 2u : 0u) | ((fe >> 16) ? 4u : 0u) | ((fo >> 16) ? 8u : 0u);
+                while (mask) {
+                    const int k = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const int m = (c_m >> (8 * k)) & 0xFF, x = 4 * g + k - lead_px;
+                    // relative coordinates (x - 16, y - 16) of the reference's vToDistributeKeys entries
+                    const uint32_t xr = (uint32_t)(xi + x - kMinBorder), yr = (uint32_t)(d.y0 + 3 + y - kMinBorder);
+                    const uint32_t e = (yr << 20) | (xr << 8) | (uint32_t)(m - 1);
+                    if (m > ini_th) s_list[atomicAdd(&s_cnt[2 * par], 1)] = e;
+                    else s_list[FT_LIST - 1 - atomicAdd(&s_cnt[2 * par + 1], 1)] = e;
+                }
+            }
+            // the other parity's score tile was last read two barriers ago: clear it for the next item
+            uint32_t *z = reinterpret_cast<uint32_t *>(s_sc_base + (par ^ 1) * FT_SC_BYTES);
+            for (int i = threadIdx.x; i < FT_SC_BYTES / 4; i += FT_CTHREADS) z[i] = 0;
+        }
+        bar_compute();
+        if (threadIdx.x == 0) mbar_arrive_cta(&s_ready[par]);
+    }
+}
+
+static size_t fast_tma_smem(int stage_bytes) {
+    return (size_t)FT_STAGES * stage_bytes + 2 * FT_SC_BYTES + 2 * FT_LIST * 4 + FT_STAGES * sizeof(FastItem) + (2 * FT_STAGES + 4) * 8 + 16;
+}
+
+int launch_fast(const LevelDev *d_levels, const LevelDev *h_levels, const CellRect *d_cells, int ncells, int f0, int batch,
+                int ini_th, int min_th, int *d_overflow, cudaStream_t stream, const FastTma *tma, int sm_count) {
     if (ncells <= 0) return 0;
+    if (tma && tma->ok) {
+        static_assert(sizeof(FastTma::map) == sizeof(FastTmaParams::map), "tensor map storage mismatch");
+        FastTmaParams P;
+        memcpy(P.map, tma->map, sizeof(P.map));
+        int stage = 128;
+        for (int l = 0; l < kMaxLevels; l++) {
+            P.box_w[l] = tma->box_w[l]; P.box_h[l] = tma->box_h[l];
+            P.cand[l] = h_levels[l].cand; P.cand_count[l] = h_levels[l].cand_count; P.cand_cap[l] = h_levels[l].cand_cap;
+            stage = max(stage, (tma->box_w[l] * tma->box_h[l] + 8 + 127) / 128 * 128);   // + 8: the last window may read past its row
+        }
+        P.stage_bytes = stage;
+        const size_t smem = fast_tma_smem(stage);
+        static size_t configured = 0;
+        static int per_sm = 0;   // resident CTAs per SM: the persistent grid is exactly one wave
+        if (smem > configured) {
+            cudaFuncSetAttribute(k_fast_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            configured = smem;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fast_tma, FT_THREADS, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        }
+        const int total = ncells * batch;
+        const int grid = total < sm_count * per_sm ? total : sm_count * per_sm;
+        k_fast_tma<<<grid, FT_THREADS, smem, stream>>>(P, d_cells, ncells, total, ini_th, min_th, f0, d_overflow);
+        return 1;
+    }
     dim3 grid(ncells, batch);
     k_fast_cells<<<grid, 192, 0, stream>>>(d_levels, d_cells, ini_th, min_th, f0, d_overflow);
     return 1;
