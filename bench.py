@@ -220,12 +220,14 @@ def main():
     nkp = float(d_n.float().mean().item())
 
     # ---- e2e through the C ABI with host buffers: inputs and result arrays live in page-locked host memory
-    e2e_steps = max(3, min(args.steps, 20))
+    e2e_steps = max(RING, min(args.steps, 40))
     pinned_in = [torch.from_numpy(b).pin_memory() for b in host_batches]
     pin_kp = torch.empty((BATCH, cap, 7), dtype=torch.float32).pin_memory()
     pin_desc = torch.empty((BATCH, cap, 32), dtype=torch.uint8).pin_memory()
     out_arrays = (pin_kp.numpy().view(orbx.KP_DTYPE).reshape(BATCH, cap), pin_desc.numpy())
-    for i in range(2):
+    # two passes over the ring: the library captures a CUDA graph per (input buffer, output buffer) pair on its second
+    # sighting, so the timed region below measures the steady state of a streaming caller that reuses its buffers
+    for i in range(2 * RING + 1):
         ex.extract_batch(pinned_in[i % RING].numpy(), out=out_arrays)
     barrier()
     t0 = time.perf_counter()

@@ -1137,7 +1137,7 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     return a;
 }
 
-__device__ __forceinline__ float warp_ic_angle(const uint8_t *__restrict__ center, int pitch, int lane) {
+__device__ __forceinline__ void warp_ic_moments(const uint8_t *__restrict__ center, int pitch, int lane, int &m01_out, int &m10_out) {
     // lane <-> column u = lane - 15; all 31 row loads of a lane are independent (fully unrolled, predicated by the
     // circular patch mask umax[|v|] = 15,15,15,15,14,14,14,13,13,12,11,10,9,8,6,3)
     constexpr int UM[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
@@ -1153,14 +1153,25 @@ __device__ __forceinline__ float warp_ic_angle(const uint8_t *__restrict__ cente
     int m10 = u * sum;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xFFFFFFFFu, m10, o); m01 += __shfl_xor_sync(0xFFFFFFFFu, m01, o); }
+    m01_out = m01; m10_out = m10;
+}
+
+__device__ __forceinline__ float warp_ic_angle(const uint8_t *__restrict__ center, int pitch, int lane) {
+    int m01, m10;
+    warp_ic_moments(center, pitch, lane, m01, m10);
     return fast_atan2_deg((float)m01, (float)m10);
 }
 
-__device__ __forceinline__ uint8_t warp_brief_byte(const uint8_t *__restrict__ center, int pitch, float angle_deg, int lane) {
+// cosf / sinf of the reference are modelled as the correctly rounded fp32 value of the fp64 result (DESIGN.md "trig rule")
+__device__ __forceinline__ void steer_trig(float angle_deg, float &a, float &b) {
     const float factor = 0.017453292519943295f;   // (float)(CV_PI / 180.f)
     const float ang = __fmul_rn(angle_deg, factor);
-    // cosf / sinf of the reference are modelled as the correctly rounded fp32 value (DESIGN.md "trig rule")
-    const float a = __double2float_rn(cos((double)ang)), b = __double2float_rn(sin((double)ang));
+    double sd, cd;
+    sincos((double)ang, &sd, &cd);
+    a = __double2float_rn(cd); b = __double2float_rn(sd);
+}
+
+__device__ __forceinline__ uint8_t warp_brief_byte(const uint8_t *__restrict__ center, int pitch, float a, float b, int lane) {
     const char4 *pat = reinterpret_cast<const char4 *>(g_pattern) + lane * 8;
     uint32_t val = 0;
 #pragma unroll
@@ -1177,31 +1188,55 @@ __device__ __forceinline__ uint8_t warp_brief_byte(const uint8_t *__restrict__ c
     return (uint8_t)val;
 }
 
+// One warp handles DG consecutive keypoint slots: the moments of keypoint j end up in lane j, so that fastAtan2 and
+// the fp64 sincos of the steering angle are evaluated once per keypoint in separate lanes (the fp64 pipe is narrow;
+// evaluating them warp-wide per keypoint made this kernel DP-bound) and then broadcast for the 256 tests.
+constexpr int DG = 1;   // measured: 8 slots per warp is slower (87 -> 107 us): the kernel is bound by the scattered BRIEF gathers, not by fp64
 __global__ void __launch_bounds__(256) k_describe(const LevelDev *__restrict__ lv, int nlevels, int total_out_cap,
                                                   const int *__restrict__ slot, KeypointRec *__restrict__ kp,
                                                   uint8_t *__restrict__ desc, int cap, int f0) {
     const int f = f0 + blockIdx.y, lane = threadIdx.x & 31;
-    const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (item >= total_out_cap) return;
+    const int item0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * DG;
+    if (item0 >= total_out_cap) return;
+    int lvl[DG], px[DG], py[DG];
+    int my01 = 0, my10 = 0;
     int l = 0;
-    while (l + 1 < nlevels && item >= lv[l + 1].out_base) l++;
-    const LevelDev &L = lv[l];
-    const int idx = item - L.out_base;
-    if (idx >= L.sel_count[f]) return;
-    const uint32_t c = L.sel[(size_t)f * L.out_cap + idx];
-    const int x = (c >> 8) & 0xFFF, y = c >> 20;
-    const uint8_t *img = L.img + (size_t)f * L.img_fstride + (size_t)y * L.pitch + x;
-    const float angle = warp_ic_angle(img, L.pitch, lane);
-    const uint8_t *bl = L.blur + (size_t)f * L.blur_fstride + (size_t)y * L.blur_pitch + x;
-    const uint8_t byte = warp_brief_byte(bl, L.blur_pitch, angle, lane);
-    const int sl = slot[(size_t)f * total_out_cap + item];
-    desc[((size_t)f * cap + sl) * 32 + lane] = byte;
-    if (lane == 0) kp[(size_t)f * cap + sl].angle = angle;
+#pragma unroll
+    for (int j = 0; j < DG; j++) {
+        const int item = item0 + j;
+        lvl[j] = -1; px[j] = py[j] = 0;
+        if (item >= total_out_cap) continue;
+        while (l + 1 < nlevels && item >= lv[l + 1].out_base) l++;
+        const LevelDev &L = lv[l];
+        const int idx = item - L.out_base;
+        if (idx >= L.sel_count[f]) continue;
+        const uint32_t c = L.sel[(size_t)f * L.out_cap + idx];
+        lvl[j] = l; px[j] = (c >> 8) & 0xFFF; py[j] = c >> 20;
+        int m01, m10;
+        warp_ic_moments(L.img + (size_t)f * L.img_fstride + (size_t)py[j] * L.pitch + px[j], L.pitch, lane, m01, m10);
+        if (lane == j) { my01 = m01; my10 = m10; }
+    }
+    float angle = 0.f, a = 1.f, b = 0.f;
+    if (lane < DG) {
+        angle = fast_atan2_deg((float)my01, (float)my10);
+        steer_trig(angle, a, b);
+    }
+#pragma unroll
+    for (int j = 0; j < DG; j++) {
+        const float aj = __shfl_sync(0xFFFFFFFFu, a, j), bj = __shfl_sync(0xFFFFFFFFu, b, j), angj = __shfl_sync(0xFFFFFFFFu, angle, j);
+        if (lvl[j] < 0) continue;
+        const LevelDev &L = lv[lvl[j]];
+        const uint8_t *bl = L.blur + (size_t)f * L.blur_fstride + (size_t)py[j] * L.blur_pitch + px[j];
+        const uint8_t byte = warp_brief_byte(bl, L.blur_pitch, aj, bj, lane);
+        const int sl = slot[(size_t)f * total_out_cap + item0 + j];
+        desc[((size_t)f * cap + sl) * 32 + lane] = byte;
+        if (lane == 0) kp[(size_t)f * cap + sl].angle = angj;
+    }
 }
 
 int launch_describe(const LevelDev *d_levels, int nlevels, int f0, int batch, int total_out_cap, const int *d_slot,
                     KeypointRec *d_kp, uint8_t *d_desc, int cap, cudaStream_t stream) {
-    dim3 grid((total_out_cap + 7) / 8, batch);
+    dim3 grid((total_out_cap + 8 * DG - 1) / (8 * DG), batch);
     k_describe<<<grid, 256, 0, stream>>>(d_levels, nlevels, total_out_cap, d_slot, d_kp, d_desc, cap, f0);
     return 1;
 }
@@ -1217,7 +1252,11 @@ __global__ void __launch_bounds__(256) k_describe_points(const uint8_t *__restri
     if (angle_in) angle = angle_in[i];
     else angle = warp_ic_angle(img + (size_t)y * pitch + x, pitch, lane);
     if (angle_out && lane == 0) angle_out[i] = angle;
-    if (desc && blur) desc[(size_t)i * 32 + lane] = warp_brief_byte(blur + (size_t)y * pitch + x, pitch, angle, lane);
+    if (desc && blur) {
+        float a, b;
+        steer_trig(angle, a, b);
+        desc[(size_t)i * 32 + lane] = warp_brief_byte(blur + (size_t)y * pitch + x, pitch, a, b, lane);
+    }
 }
 
 int launch_describe_points(const uint8_t *d_img, const uint8_t *d_blur, int pitch, const float *d_xy, int n,
