@@ -164,8 +164,8 @@ static void build_fast_maps(orbx_handle *h) {
         }
         if (LP.ncells == 0) continue;
         int bw = (15 + rw + 5 + 15) / 16 * 16;   // the box starts at x0 rounded down to 16 bytes (TMA rule)
-        if (bw % 64 == 0) bw += 16;          // rows two apart would fall on the same banks
         T.box_w[l] = bw; T.box_h[l] = rh + 1;
+        T.max_iw = std::max(T.max_iw, rw - 6); T.max_ih = std::max(T.max_ih, rh - 6);
         if (bw > 96 || rh + 1 > 80) { T.box_w[l] = 0; }   // larger than the shared-memory stage: no TMA for this plan
     }
     for (int l = 0; l < h->plan.nlevels; l++) encode_fast_map(h, l);

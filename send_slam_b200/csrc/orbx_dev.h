@@ -49,6 +49,7 @@ int launch_blur(const LevelDev *d_levels, const BlurTile *d_tiles, int ntiles, i
 struct FastTma {
     alignas(64) unsigned char map[kMaxLevels][128];
     int box_w[kMaxLevels], box_h[kMaxLevels];
+    int max_iw, max_ih;         // largest tested-pixel extent of any cell (sizes the per-warp score tile and list)
     bool level_ok[kMaxLevels];
     bool ok;                    // every level has a valid map
 };

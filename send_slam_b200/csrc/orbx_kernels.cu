@@ -486,26 +486,20 @@ __global__ void __launch_bounds__(192) k_fast_cells(const LevelDev *__restrict__
     }
 }
 
-// TMA-staged, persistent, warp-specialised variant (the one the pipeline runs; k_fast_cells above stays as the fallback
-// for level-0 planes that do not meet the TMA alignment rules).  Each CTA walks (cell, frame) items with stride
-// gridDim.x.  Warps 0..5 only ever touch shared memory: they score and suppress.  Warp 6 is the helper: it keeps the
-// ROIs of the next FT_STAGES items in flight (cp.async.bulk.tensor, completion on an mbarrier) and appends the finished
-// candidate list of the previous item to the level's global list, so that neither the global-load latency of the
-// staging nor the round trip of the global atomic is on the path of the compute warps.
+// TMA-staged, persistent, warp-tiled variant (the one the pipeline runs; k_fast_cells above stays as the fallback for
+// level-0 planes that do not meet the TMA alignment rules).  One WARP owns one cell at a time: it walks (cell, frame)
+// items with a grid-wide stride, keeps the ROI of its next item in flight (cp.async.bulk.tensor into its second
+// shared-memory stage, completion on its own mbarrier) and needs nothing but __syncwarp between scoring, NMS and
+// the hand-over of the candidates - no CTA barrier anywhere, which is what bounded the CTA-per-cell kernels
+// (ncu: 27 % of the samples sat on the two barriers per cell).
 //   * A TMA box must start on a 16-byte boundary of the innermost dimension (measured: an unaligned start coordinate
 //     raises "illegal instruction"), so the box starts at x0 & ~15 and the 4-pixel groups are laid out on absolute
 //     multiples of 4 (window = pixel - 3): every shared-memory read stays an aligned word, at the price of up to 3
 //     masked pixels in the first group of a row.
-//   * Score tile and candidate list are double-buffered by item parity; a cell costs the compute warps two named
-//     barriers (scores complete, list complete).  Hand-offs with the helper go through mbarriers:
-//     full[s] (TMA bytes landed), empty[s] (stage read), ready[p] (list complete), free[p] (list appended).
-//   * Candidates above iniThFAST fill the list from the front, the rest from the back: the per-cell threshold
-//     fallback is then a choice of sub-array.
+//   * Candidates above iniThFAST fill the warp's list from the front, the rest from the back: the per-cell threshold
+//     fallback is then a choice of sub-array, appended to the level's global list with one atomic per cell.
 // Scores, NMS rule and emitted candidate sets are identical to k_fast_cells (candidate order is free by design).
-constexpr int FT_STAGES = 3;
-constexpr int FT_LIST = 36 * 36 + 8;
-constexpr int FT_CTHREADS = 192, FT_THREADS = FT_CTHREADS + 32;
-constexpr int FT_SC_BYTES = (FT_ROWS - 4) * FS_PITCH;
+constexpr int FW_WARPS = 4;             // warps per CTA (all independent); 6 CTAs/SM at 85 registers
 
 struct FastTmaParams {
     CUtensorMap map[kMaxLevels];        // level plane [frames][h][w], box = box_w x box_h x 1
@@ -513,104 +507,75 @@ struct FastTmaParams {
     uint32_t *cand[kMaxLevels];         // [frames][cand_cap]
     int *cand_count[kMaxLevels];        // [frames]
     int cand_cap[kMaxLevels];
-    int stage_bytes;                    // shared-memory bytes per ROI stage (multiple of 128)
+    int stage_bytes;                    // per-warp shared memory: 2 ROI stages (multiple of 128 each) ...
+    int sc_pitch, sc_bytes;             // ... score tile (row pitch, size) ...
+    int list_cap;                       // ... candidate list (entries) ...
+    int warp_bytes;                     // ... total per warp (multiple of 128)
 };
 
-struct FastItem { int x0, y0, iw, ih, level, f, pad0, pad1; };
-
-__device__ __forceinline__ void mbar_arrive_cta(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tma_smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, %0;" ::"n"(FT_CTHREADS) : "memory"); }
-
-__global__ void __launch_bounds__(FT_THREADS, 4) k_fast_tma(const __grid_constant__ FastTmaParams P, const CellRect *__restrict__ cells,
+__global__ void __launch_bounds__(FW_WARPS * 32, 6) k_fast_tma(const __grid_constant__ FastTmaParams P, const CellRect *__restrict__ cells,
                                                             int ncells, int total, int ini_th, int min_th, int f0,
                                                             int *__restrict__ overflow) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t *s_roi_base = smem;                                                          // FT_STAGES x stage_bytes
-    uint8_t *s_sc_base = smem + FT_STAGES * P.stage_bytes;                               // 2 x FT_SC_BYTES (16-byte aligned)
-    uint32_t *s_list_base = reinterpret_cast<uint32_t *>(s_sc_base + 2 * FT_SC_BYTES);   // 2 x FT_LIST
-    FastItem *s_item = reinterpret_cast<FastItem *>(s_list_base + 2 * FT_LIST);          // FT_STAGES
-    uint64_t *s_full = reinterpret_cast<uint64_t *>(s_item + FT_STAGES);                 // FT_STAGES
-    uint64_t *s_empty = s_full + FT_STAGES;                                              // FT_STAGES
-    uint64_t *s_ready = s_empty + FT_STAGES, *s_free = s_ready + 2;                      // 2 + 2
-    int *s_cnt = reinterpret_cast<int *>(s_free + 2);                                    // [parity][above iniTh, rest]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t *wsm = smem + (size_t)warp * P.warp_bytes;
+    uint8_t *s_roi2 = wsm;                                                        // 2 x stage_bytes
+    uint8_t *s_sc = wsm + 2 * P.stage_bytes;                                      // sc_bytes
+    uint32_t *s_list = reinterpret_cast<uint32_t *>(s_sc + P.sc_bytes);           // list_cap
+    uint64_t *s_full = reinterpret_cast<uint64_t *>(s_list + P.list_cap);         // 2 mbarriers
+    int *s_cnt = reinterpret_cast<int *>(s_full + 2);                             // [above iniTh, rest]
+    const int scp = P.sc_pitch, lcap = P.list_cap;
 
-    for (int i = threadIdx.x; i < 2 * FT_SC_BYTES / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(s_sc_base)[i] = 0;
-    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < FT_STAGES; i++) { tma_mbar_init(&s_full[i], 1); tma_mbar_init(&s_empty[i], 1); }
-        for (int i = 0; i < 2; i++) { tma_mbar_init(&s_ready[i], 1); tma_mbar_init(&s_free[i], 1); }
+    if (lane == 0) {
+        tma_mbar_init(&s_full[0], 1); tma_mbar_init(&s_full[1], 1);
         tma_mbar_fence_init();
+        s_cnt[0] = 0; s_cnt[1] = 0;
     }
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int first = blockIdx.x, stride = gridDim.x;
-    const int nmine = first < total ? (total - first + stride - 1) / stride : 0;
-
-    if (threadIdx.x >= FT_CTHREADS) {
-        // ================= helper warp =================
-        auto issue = [&](int q) {           // lane 0: describe item q in shared memory and start its TMA
-            const int item = first + q * stride, st = q % FT_STAGES;
-            const int fi = item / ncells;
-            const CellRect c = cells[item - fi * ncells];
-            FastItem d;
-            d.x0 = c.x0; d.y0 = c.y0; d.iw = c.x1 - c.x0 - 6; d.ih = c.y1 - c.y0 - 6; d.level = c.level; d.f = f0 + fi; d.pad0 = d.pad1 = 0;
-            s_item[st] = d;
-            tma_mbar_expect_tx(&s_full[st], (uint32_t)(P.box_w[c.level] * P.box_h[c.level]));
-            tma_load_3d(s_roi_base + st * P.stage_bytes, &P.map[c.level], c.x0 & ~15, c.y0, f0 + fi, &s_full[st]);
-        };
-        if (lane == 0) for (int q = 0; q < FT_STAGES && q < nmine; q++) issue(q);
-        for (int q = 0; q < nmine; q++) {
-            const int par = q & 1, st = q % FT_STAGES;
-            tma_mbar_wait(&s_ready[par], (uint32_t)(q >> 1) & 1u);
-            // per-cell fallback: if any corner passes iniThFAST keep only those, else keep everything above minThFAST
-            const FastItem d = s_item[st];
-            const int n_ini = s_cnt[2 * par], n_low = s_cnt[2 * par + 1];
-            const int n = n_ini > 0 ? n_ini : n_low;
-            const uint32_t *src = s_list_base + par * FT_LIST + (n_ini > 0 ? 0 : FT_LIST - n_low);
-            if (n > 0) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(P.cand_count[d.level] + d.f, n);
-                base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                const int cap = P.cand_cap[d.level];
-                uint32_t *__restrict__ out = P.cand[d.level] + (size_t)d.f * cap;
-                for (int i = lane; i < n; i += 32) {
-                    if (base + i < cap) out[base + i] = src[i]; else *overflow = 1;
-                }
-            }
-            __syncwarp();
-            if (lane == 0) {
-                s_cnt[2 * par] = 0; s_cnt[2 * par + 1] = 0;
-                mbar_arrive_cta(&s_free[par]);
-                if (q + FT_STAGES < nmine) {
-                    tma_mbar_wait(&s_empty[st], (uint32_t)(q / FT_STAGES) & 1u);   // scoring of item q has left the stage
-                    issue(q + FT_STAGES);
-                }
-            }
-            __syncwarp();
-        }
-        return;
-    }
-
-    // ================= compute warps =================
-    for (int q = 0; q < nmine; q++) {
-        const int par = q & 1, st = q % FT_STAGES;
-        tma_mbar_wait(&s_full[st], (uint32_t)(q / FT_STAGES) & 1u);
-        const FastItem d = s_item[st];
-        const int rp = P.box_w[d.level];                                    // staged row pitch in bytes
-        const uint8_t *__restrict__ s_roi = s_roi_base + st * P.stage_bytes;
-        uint8_t *__restrict__ s_sc = s_sc_base + par * FT_SC_BYTES;
-        uint32_t *__restrict__ s_list = s_list_base + par * FT_LIST;
-        const int iw = d.iw, ih = d.ih;                                     // tested pixels
+    for (int i = lane; i < P.sc_bytes / 4; i += 32) reinterpret_cast<uint32_t *>(s_sc)[i] = 0;
+    __syncwarp();
+    const int stride = gridDim.x * FW_WARPS;
+    int item = blockIdx.x * FW_WARPS + warp;
+    if (item >= total) return;
+    auto load_cell = [&](int it, int &fi) -> CellRect {
+        CellRect c; c.level = -1; c.x0 = c.y0 = c.x1 = c.y1 = 0; fi = 0;
+        if (it < total) { fi = it / ncells; c = cells[it - fi * ncells]; }
+        return c;
+    };
+    auto issue = [&](const CellRect &c, int fi, int stage) {      // lane 0 only
+        tma_mbar_expect_tx(&s_full[stage], (uint32_t)(P.box_w[c.level] * P.box_h[c.level]));
+        tma_load_3d(s_roi2 + stage * P.stage_bytes, &P.map[c.level], c.x0 & ~15, c.y0, f0 + fi, &s_full[stage]);
+    };
+    int fi_cur, fi_nxt;
+    CellRect cur = load_cell(item, fi_cur), nxt = load_cell(item + stride, fi_nxt);
+    if (lane == 0) issue(cur, fi_cur, 0);
+    for (int q = 0; item < total; item += stride, q++) {
+        const int st = q & 1;
+        // the other stage was last read while scoring item q-1 (program order of this warp): refill it
+        if (lane == 0 && nxt.level >= 0) issue(nxt, fi_nxt, st ^ 1);
+        int fi_nn;
+        const CellRect nn = load_cell(item + 2 * stride, fi_nn);            // descriptor prefetch, consumed next iteration
+        const int f = f0 + fi_cur, level = cur.level;
+        const int rp = P.box_w[level];                                      // staged row pitch in bytes
+        const uint8_t *__restrict__ s_roi = s_roi2 + st * P.stage_bytes;
+        const int iw = cur.x1 - cur.x0 - 6, ih = cur.y1 - cur.y0 - 6;       // tested pixels
         // groups of 4 pixels on absolute multiples of 4: window = bytes X-3 .. X+8 of the first pixel X of a group
-        const int xi = d.x0 + 3;                                            // first tested column
-        const int lead_px = d.x0 & 3;                                       // it sits at lane lead_px of group 0
-        const int wbase = (d.x0 & ~3) - (d.x0 & ~15);                       // byte offset of group 0's window in the box
+        const int xi = cur.x0 + 3;                                          // first tested column
+        const int lead_px = cur.x0 & 3;                                     // it sits at lane lead_px of group 0
+        const int wbase = (cur.x0 & ~3) - (cur.x0 & ~15);                   // byte offset of group 0's window in the box
         const int ng = (lead_px + iw + 3) >> 2, ns = (ih + 1) >> 1;
         const uint32_t inv_ng = 65536u / (uint32_t)ng + 1u;
+        // zero ring of the score tile for this geometry: rows 0 and ih+1, words 0 and ng+1 of the rows between
+        for (int i = lane; i < ng + 2; i += 32) {
+            reinterpret_cast<uint32_t *>(s_sc)[i] = 0;
+            reinterpret_cast<uint32_t *>(s_sc + (ih + 1) * scp)[i] = 0;
+        }
+        for (int y = 1 + lane; y <= ih; y += 32) {
+            reinterpret_cast<uint32_t *>(s_sc + y * scp)[0] = 0;
+            reinterpret_cast<uint32_t *>(s_sc + y * scp)[ng + 1] = 0;
+        }
+        tma_mbar_wait(&s_full[st], (uint32_t)(q >> 1) & 1u);
         // scores: work item = (group g, row pair s)
-        for (int wi = threadIdx.x; wi < ng * ns; wi += FT_CTHREADS) {
+        for (int wi = lane; wi < ng * ns; wi += 32) {
             const int s = (int)(((uint32_t)wi * inv_ng) >> 16), g = wi - s * ng;
             uint32_t sa, sb;
             fast_item<0>(s_roi + (2 * s) * rp + wbase + 4 * g, rp, sa, sb);
@@ -620,20 +585,19 @@ __global__ void __launch_bounds__(FT_THREADS, 4) k_fast_tma(const __grid_constan
             if (lo > 0) m &= 0xFFFFFFFFu << (8 * lo);
             if (hi < 4) m &= 0xFFFFFFFFu >> (8 * (4 - hi));
             sa &= m; sb &= m;
-            // score tile: lane k of group g on tested row y at [(y+1)*FS_PITCH + 4 + 4g + k]  (word 0 and row 0 are the zero ring)
-            *reinterpret_cast<uint32_t *>(s_sc + (2 * s + 1) * FS_PITCH + 4 + 4 * g) = sa;
-            if (2 * s + 1 < ih) *reinterpret_cast<uint32_t *>(s_sc + (2 * s + 2) * FS_PITCH + 4 + 4 * g) = sb;
+            // score tile: lane k of group g on tested row y at [(y+1)*scp + 4 + 4g + k]  (word 0 and row 0 are the zero ring)
+            *reinterpret_cast<uint32_t *>(s_sc + (2 * s + 1) * scp + 4 + 4 * g) = sa;
+            if (2 * s + 1 < ih) *reinterpret_cast<uint32_t *>(s_sc + (2 * s + 2) * scp + 4 + 4 * g) = sb;
         }
-        bar_compute();
-        if (threadIdx.x == 0) mbar_arrive_cta(&s_empty[st]);
-        if (q >= 2) tma_mbar_wait(&s_free[par], (uint32_t)((q >> 1) - 1) & 1u);   // list of item q-2 has been appended
+        __syncwarp();
         // NMS (strict 8-neighbour maximum inside the cell, neighbours outside count 0): see k_fast_cells
         {
             const uint32_t thr = ((uint32_t)min_th << 8) | ((uint32_t)min_th << 24);
-            for (int wi = threadIdx.x; wi < ng * ih; wi += FT_CTHREADS) {
+            for (int wi = lane; wi < ng * ih; wi += 32) {
                 const int y = (int)(((uint32_t)wi * inv_ng) >> 16), g = wi - y * ng;
-                const uint32_t *ru = reinterpret_cast<const uint32_t *>(s_sc + y * FS_PITCH) + g;
-                const uint32_t *rm = ru + FS_PITCH / 4, *rd = rm + FS_PITCH / 4;
+                const uint32_t *ru = reinterpret_cast<const uint32_t *>(s_sc + y * scp) + g;
+                const uint32_t *rm = reinterpret_cast<const uint32_t *>(s_sc + (y + 1) * scp) + g;
+                const uint32_t *rd = reinterpret_cast<const uint32_t *>(s_sc + (y + 2) * scp) + g;
                 const uint32_t c_m = rm[1];
                 if (c_m == 0) continue;
                 const uint32_t u0 = ru[0], u1 = ru[1], u2 = ru[2], m0 = rm[0], m2 = rm[2], d0 = rd[0], d1 = rd[1], d2 = rd[2];
@@ -650,23 +614,35 @@ __global__ void __launch_bounds__(FT_THREADS, 4) k_fast_tma(const __grid_constan
                     mask &= mask - 1;
                     const int m = (c_m >> (8 * k)) & 0xFF, x = 4 * g + k - lead_px;
                     // relative coordinates (x - 16, y - 16) of the reference's vToDistributeKeys entries
-                    const uint32_t xr = (uint32_t)(xi + x - kMinBorder), yr = (uint32_t)(d.y0 + 3 + y - kMinBorder);
+                    const uint32_t xr = (uint32_t)(xi + x - kMinBorder), yr = (uint32_t)(cur.y0 + 3 + y - kMinBorder);
                     const uint32_t e = (yr << 20) | (xr << 8) | (uint32_t)(m - 1);
-                    if (m > ini_th) s_list[atomicAdd(&s_cnt[2 * par], 1)] = e;
-                    else s_list[FT_LIST - 1 - atomicAdd(&s_cnt[2 * par + 1], 1)] = e;
+                    if (m > ini_th) s_list[atomicAdd(&s_cnt[0], 1)] = e;
+                    else s_list[lcap - 1 - atomicAdd(&s_cnt[1], 1)] = e;
                 }
             }
-            // the other parity's score tile was last read two barriers ago: clear it for the next item
-            uint32_t *z = reinterpret_cast<uint32_t *>(s_sc_base + (par ^ 1) * FT_SC_BYTES);
-            for (int i = threadIdx.x; i < FT_SC_BYTES / 4; i += FT_CTHREADS) z[i] = 0;
         }
-        bar_compute();
-        if (threadIdx.x == 0) mbar_arrive_cta(&s_ready[par]);
+        __syncwarp();
+        // per-cell fallback: if any corner passes iniThFAST keep only those, else keep everything above minThFAST
+        {
+            const int n_ini = s_cnt[0], n_low = s_cnt[1];
+            const int n = n_ini > 0 ? n_ini : n_low;
+            const uint32_t *src = s_list + (n_ini > 0 ? 0 : lcap - n_low);
+            if (n > 0) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(P.cand_count[level] + f, n);
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                const int cap = P.cand_cap[level];
+                uint32_t *__restrict__ out = P.cand[level] + (size_t)f * cap;
+                for (int i = lane; i < n; i += 32) {
+                    if (base + i < cap) out[base + i] = src[i]; else *overflow = 1;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
+            __syncwarp();
+        }
+        cur = nxt; fi_cur = fi_nxt; nxt = nn; fi_nxt = fi_nn;
     }
-}
-
-static size_t fast_tma_smem(int stage_bytes) {
-    return (size_t)FT_STAGES * stage_bytes + 2 * FT_SC_BYTES + 2 * FT_LIST * 4 + FT_STAGES * sizeof(FastItem) + (2 * FT_STAGES + 4) * 8 + 16;
 }
 
 int launch_fast(const LevelDev *d_levels, const LevelDev *h_levels, const CellRect *d_cells, int ncells, int f0, int batch,
@@ -683,17 +659,25 @@ int launch_fast(const LevelDev *d_levels, const LevelDev *h_levels, const CellRe
             stage = max(stage, (tma->box_w[l] * tma->box_h[l] + 8 + 127) / 128 * 128);   // + 8: the last window may read past its row
         }
         P.stage_bytes = stage;
-        const size_t smem = fast_tma_smem(stage);
-        static size_t configured = 0;
+        P.sc_pitch = 4 * ((tma->max_iw + 3 + 3) / 4 + 2);
+        P.sc_bytes = (P.sc_pitch * (tma->max_ih + 2) + 8 + 15) / 16 * 16;
+        P.list_cap = (((tma->max_iw + 1) / 2) * ((tma->max_ih + 1) / 2) + 8 + 3) / 4 * 4;
+        P.warp_bytes = (2 * stage + P.sc_bytes + P.list_cap * 4 + 2 * 8 + 2 * 4 + 127) / 128 * 128;
+        const size_t smem = (size_t)FW_WARPS * P.warp_bytes;
+        static size_t configured = 0, last = 0;
         static int per_sm = 0;   // resident CTAs per SM: the persistent grid is exactly one wave
         if (smem > configured) {
             cudaFuncSetAttribute(k_fast_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             configured = smem;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fast_tma, FT_THREADS, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        }
+        if (smem != last) {
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fast_tma, FW_WARPS * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+            last = smem;
         }
         const int total = ncells * batch;
-        const int grid = total < sm_count * per_sm ? total : sm_count * per_sm;
-        k_fast_tma<<<grid, FT_THREADS, smem, stream>>>(P, d_cells, ncells, total, ini_th, min_th, f0, d_overflow);
+        const int want = (total + FW_WARPS - 1) / FW_WARPS;
+        const int grid = want < sm_count * per_sm ? want : sm_count * per_sm;
+        k_fast_tma<<<grid, FW_WARPS * 32, smem, stream>>>(P, d_cells, ncells, total, ini_th, min_th, f0, d_overflow);
         return 1;
     }
     dim3 grid(ncells, batch);
