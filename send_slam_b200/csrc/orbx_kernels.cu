@@ -507,31 +507,30 @@ struct FastTmaParams {
     uint32_t *cand[kMaxLevels];         // [frames][cand_cap]
     int *cand_count[kMaxLevels];        // [frames]
     int cand_cap[kMaxLevels];
-    int stage_bytes;                    // per-warp shared memory: 2 ROI stages (multiple of 128 each) ...
+    int stage_bytes;                    // per-warp shared memory: ROI stage (multiple of 128) ...
     int sc_pitch, sc_bytes;             // ... score tile (row pitch, size) ...
-    int list_cap;                       // ... candidate list (entries) ...
+    int list_cap;                       // ... candidate list (u16 entries) ...
     int warp_bytes;                     // ... total per warp (multiple of 128)
 };
 
 __global__ void __launch_bounds__(FW_WARPS * 32, 6) k_fast_tma(const __grid_constant__ FastTmaParams P, const CellRect *__restrict__ cells,
-                                                            int ncells, int total, int ini_th, int min_th, int f0,
-                                                            int *__restrict__ overflow) {
+                                                               int ncells, int total, int ini_th, int min_th, int f0,
+                                                               int *__restrict__ overflow) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t *wsm = smem + (size_t)warp * P.warp_bytes;
-    uint8_t *s_roi2 = wsm;                                                        // 2 x stage_bytes
-    uint8_t *s_sc = wsm + 2 * P.stage_bytes;                                      // sc_bytes
-    uint32_t *s_list = reinterpret_cast<uint32_t *>(s_sc + P.sc_bytes);           // list_cap
-    uint64_t *s_full = reinterpret_cast<uint64_t *>(s_list + P.list_cap);         // 2 mbarriers
-    int *s_cnt = reinterpret_cast<int *>(s_full + 2);                             // [above iniTh, rest]
+    uint8_t *s_roi = wsm;                                                         // stage_bytes
+    uint8_t *s_sc = wsm + P.stage_bytes;                                          // sc_bytes
+    uint16_t *s_list = reinterpret_cast<uint16_t *>(s_sc + P.sc_bytes);           // list_cap entries: tile row << 8 | tile byte column
+    uint64_t *s_full = reinterpret_cast<uint64_t *>(s_list + P.list_cap);         // 1 mbarrier
+    int *s_cnt = reinterpret_cast<int *>(s_full + 1);                             // [above iniTh, rest]
     const int scp = P.sc_pitch, lcap = P.list_cap;
 
     if (lane == 0) {
-        tma_mbar_init(&s_full[0], 1); tma_mbar_init(&s_full[1], 1);
+        tma_mbar_init(s_full, 1);
         tma_mbar_fence_init();
         s_cnt[0] = 0; s_cnt[1] = 0;
     }
-    for (int i = lane; i < P.sc_bytes / 4; i += 32) reinterpret_cast<uint32_t *>(s_sc)[i] = 0;
     __syncwarp();
     const int stride = gridDim.x * FW_WARPS;
     int item = blockIdx.x * FW_WARPS + warp;
@@ -541,81 +540,87 @@ __global__ void __launch_bounds__(FW_WARPS * 32, 6) k_fast_tma(const __grid_cons
         if (it < total) { fi = it / ncells; c = cells[it - fi * ncells]; }
         return c;
     };
-    auto issue = [&](const CellRect &c, int fi, int stage) {      // lane 0 only
-        tma_mbar_expect_tx(&s_full[stage], (uint32_t)(P.box_w[c.level] * P.box_h[c.level]));
-        tma_load_3d(s_roi2 + stage * P.stage_bytes, &P.map[c.level], c.x0 & ~15, c.y0, f0 + fi, &s_full[stage]);
+    auto issue = [&](const CellRect &c, int fi) {      // lane 0 only
+        tma_mbar_expect_tx(s_full, (uint32_t)(P.box_w[c.level] * P.box_h[c.level]));
+        tma_load_3d(s_roi, &P.map[c.level], c.x0 & ~15, c.y0, f0 + fi, s_full);
     };
     int fi_cur, fi_nxt;
     CellRect cur = load_cell(item, fi_cur), nxt = load_cell(item + stride, fi_nxt);
-    if (lane == 0) issue(cur, fi_cur, 0);
+    if (lane == 0) issue(cur, fi_cur);
+    const uint32_t thr = ((uint32_t)min_th << 8) | ((uint32_t)min_th << 24);
     for (int q = 0; item < total; item += stride, q++) {
-        const int st = q & 1;
-        // the other stage was last read while scoring item q-1 (program order of this warp): refill it
-        if (lane == 0 && nxt.level >= 0) issue(nxt, fi_nxt, st ^ 1);
         int fi_nn;
         const CellRect nn = load_cell(item + 2 * stride, fi_nn);            // descriptor prefetch, consumed next iteration
         const int f = f0 + fi_cur, level = cur.level;
         const int rp = P.box_w[level];                                      // staged row pitch in bytes
-        const uint8_t *__restrict__ s_roi = s_roi2 + st * P.stage_bytes;
         const int iw = cur.x1 - cur.x0 - 6, ih = cur.y1 - cur.y0 - 6;       // tested pixels
         // groups of 4 pixels on absolute multiples of 4: window = bytes X-3 .. X+8 of the first pixel X of a group
-        const int xi = cur.x0 + 3;                                          // first tested column
-        const int lead_px = cur.x0 & 3;                                     // it sits at lane lead_px of group 0
+        const int lead_px = cur.x0 & 3;                                     // first tested column sits at lane lead_px of group 0
         const int wbase = (cur.x0 & ~3) - (cur.x0 & ~15);                   // byte offset of group 0's window in the box
         const int ng = (lead_px + iw + 3) >> 2, ns = (ih + 1) >> 1;
         const uint32_t inv_ng = 65536u / (uint32_t)ng + 1u;
-        // zero ring of the score tile for this geometry: rows 0 and ih+1, words 0 and ng+1 of the rows between
+        // zero ring of the score tile for this geometry: rows 0, ih+1 (and ih+2 for the row-pair overhang), words 0 and
+        // ng+1 of the rows between
         for (int i = lane; i < ng + 2; i += 32) {
             reinterpret_cast<uint32_t *>(s_sc)[i] = 0;
             reinterpret_cast<uint32_t *>(s_sc + (ih + 1) * scp)[i] = 0;
+            reinterpret_cast<uint32_t *>(s_sc + (ih + 2) * scp)[i] = 0;
         }
         for (int y = 1 + lane; y <= ih; y += 32) {
             reinterpret_cast<uint32_t *>(s_sc + y * scp)[0] = 0;
             reinterpret_cast<uint32_t *>(s_sc + y * scp)[ng + 1] = 0;
         }
-        tma_mbar_wait(&s_full[st], (uint32_t)(q >> 1) & 1u);
+        tma_mbar_wait(s_full, (uint32_t)q & 1u);
         // scores: work item = (group g, row pair s)
         for (int wi = lane; wi < ng * ns; wi += 32) {
-            const int s = (int)(((uint32_t)wi * inv_ng) >> 16), g = wi - s * ng;
+            const int s2 = (int)(((uint32_t)wi * inv_ng) >> 16), g = wi - s2 * ng;
             uint32_t sa, sb;
-            fast_item<0>(s_roi + (2 * s) * rp + wbase + 4 * g, rp, sa, sb);
+            fast_item<0>(s_roi + (2 * s2) * rp + wbase + 4 * g, rp, sa, sb);
             // mask pixels outside the tested columns (leading lanes of group 0, trailing lanes of the last group)
             const int lo = lead_px - 4 * g, hi = lead_px + iw - 4 * g;       // valid lanes: lo <= k < hi
             uint32_t m = 0xFFFFFFFFu;
             if (lo > 0) m &= 0xFFFFFFFFu << (8 * lo);
             if (hi < 4) m &= 0xFFFFFFFFu >> (8 * (4 - hi));
             sa &= m; sb &= m;
+            if (2 * s2 + 1 >= ih) sb = 0;
             // score tile: lane k of group g on tested row y at [(y+1)*scp + 4 + 4g + k]  (word 0 and row 0 are the zero ring)
-            *reinterpret_cast<uint32_t *>(s_sc + (2 * s + 1) * scp + 4 + 4 * g) = sa;
-            if (2 * s + 1 < ih) *reinterpret_cast<uint32_t *>(s_sc + (2 * s + 2) * scp + 4 + 4 * g) = sb;
+            *reinterpret_cast<uint32_t *>(s_sc + (2 * s2 + 1) * scp + 4 + 4 * g) = sa;
+            *reinterpret_cast<uint32_t *>(s_sc + (2 * s2 + 2) * scp + 4 + 4 * g) = sb;
         }
         __syncwarp();
-        // NMS (strict 8-neighbour maximum inside the cell, neighbours outside count 0): see k_fast_cells
-        {
-            const uint32_t thr = ((uint32_t)min_th << 8) | ((uint32_t)min_th << 24);
-            for (int wi = lane; wi < ng * ih; wi += 32) {
-                const int y = (int)(((uint32_t)wi * inv_ng) >> 16), g = wi - y * ng;
-                const uint32_t *ru = reinterpret_cast<const uint32_t *>(s_sc + y * scp) + g;
-                const uint32_t *rm = reinterpret_cast<const uint32_t *>(s_sc + (y + 1) * scp) + g;
-                const uint32_t *rd = reinterpret_cast<const uint32_t *>(s_sc + (y + 2) * scp) + g;
-                const uint32_t c_m = rm[1];
+        // the ROI stage is free again: start the next item's TMA now; it lands while this item is suppressed and emitted
+        if (lane == 0 && nxt.level >= 0) issue(nxt, fi_nxt);
+        // NMS (strict 8-neighbour maximum inside the cell, neighbours outside count 0), same (group, row pair) items:
+        // per tile row the 3-wide horizontal maximum H and the left/right maximum LR (with minTh folded in) are formed
+        // once in u16 lanes (odd pixels as they are, even pixels shifted up a byte); ring(y) = max3(H(y-1), H(y+1), LR(y)).
+        for (int wi = lane; wi < ng * ns; wi += 32) {
+            const int s2 = (int)(((uint32_t)wi * inv_ng) >> 16), g = wi - s2 * ng;
+            const uint8_t *t0 = s_sc + (2 * s2) * scp + 4 * g;               // tile rows 2s .. 2s+3 = tested rows 2s-1 .. 2s+2
+            uint32_t mid[4], Ho[4], He[4], LRo[4], LRe[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const uint32_t *p = reinterpret_cast<const uint32_t *>(t0 + r * scp);
+                const uint32_t w0 = p[0], w1 = p[1], w2 = p[2];
+                const uint32_t l = __funnelshift_r(w0, w1, 24), rr = __funnelshift_r(w1, w2, 8);
+                mid[r] = w1;
+                Ho[r] = umax3(l, w1, rr); LRo[r] = umax3(l, rr, thr);
+                const uint32_t le = l << 8, me = w1 << 8, re = rr << 8;
+                He[r] = umax3(le, me, re); LRe[r] = umax3(le, re, thr);
+            }
+#pragma unroll
+            for (int c = 1; c <= 2; c++) {
+                const uint32_t c_m = mid[c];
                 if (c_m == 0) continue;
-                const uint32_t u0 = ru[0], u1 = ru[1], u2 = ru[2], m0 = rm[0], m2 = rm[2], d0 = rd[0], d1 = rd[1], d2 = rd[2];
-                const uint32_t lu = __funnelshift_r(u0, u1, 24), lm = __funnelshift_r(m0, c_m, 24), ld = __funnelshift_r(d0, d1, 24);
-                const uint32_t ruu = __funnelshift_r(u1, u2, 8), rmm = __funnelshift_r(c_m, m2, 8), rdd = __funnelshift_r(d1, d2, 8);
-                uint32_t mo = umax3(umax3(lu, ld, lm), umax3(ruu, rdd, rmm), umax3(u1, d1, thr));
-                uint32_t me = umax3(umax3(lu << 8, ld << 8, lm << 8), umax3(ruu << 8, rdd << 8, rmm << 8), umax3(u1 << 8, d1 << 8, thr));
+                const uint32_t mo = umax3(Ho[c - 1], Ho[c + 1], LRo[c]) | 0x00FF00FFu;
+                const uint32_t me = umax3(He[c - 1], He[c + 1], LRe[c]) | 0x00FF00FFu;
                 const uint32_t so = c_m & 0xFF00FF00u, se = (c_m << 8) & 0xFF00FF00u;
-                mo |= 0x00FF00FFu; me |= 0x00FF00FFu;
-                const uint32_t fo = umax2(so, mo) ^ mo, fe = umax2(se, me) ^ me;
+                const uint32_t fo = umax2(so, mo) ^ mo, fe = umax2(se, me) ^ me;   // non-zero lane <=> strict maximum above minTh
                 uint32_t mask = ((fe & 0xFFFFu) ? 1u : 0u) | ((fo & 0xFFFFu) ? 2u : 0u) | ((fe >> 16) ? 4u : 0u) | ((fo >> 16) ? 8u : 0u);
                 while (mask) {
                     const int k = __ffs(mask) - 1;
                     mask &= mask - 1;
-                    const int m = (c_m >> (8 * k)) & 0xFF, x = 4 * g + k - lead_px;
-                    // relative coordinates (x - 16, y - 16) of the reference's vToDistributeKeys entries
-                    const uint32_t xr = (uint32_t)(xi + x - kMinBorder), yr = (uint32_t)(cur.y0 + 3 + y - kMinBorder);
-                    const uint32_t e = (yr << 20) | (xr << 8) | (uint32_t)(m - 1);
+                    const int m = (c_m >> (8 * k)) & 0xFF;
+                    const uint16_t e = (uint16_t)(((2 * s2 + c) << 8) | (4 + 4 * g + k));   // tile row, tile byte column
                     if (m > ini_th) s_list[atomicAdd(&s_cnt[0], 1)] = e;
                     else s_list[lcap - 1 - atomicAdd(&s_cnt[1], 1)] = e;
                 }
@@ -626,15 +631,20 @@ __global__ void __launch_bounds__(FW_WARPS * 32, 6) k_fast_tma(const __grid_cons
         {
             const int n_ini = s_cnt[0], n_low = s_cnt[1];
             const int n = n_ini > 0 ? n_ini : n_low;
-            const uint32_t *src = s_list + (n_ini > 0 ? 0 : lcap - n_low);
+            const uint16_t *src = s_list + (n_ini > 0 ? 0 : lcap - n_low);
             if (n > 0) {
                 int base = 0;
                 if (lane == 0) base = atomicAdd(P.cand_count[level] + f, n);
                 base = __shfl_sync(0xFFFFFFFFu, base, 0);
                 const int cap = P.cand_cap[level];
                 uint32_t *__restrict__ out = P.cand[level] + (size_t)f * cap;
+                // relative coordinates (x - 16, y - 16) of the reference's vToDistributeKeys entries
+                const int xrel = cur.x0 + 3 - lead_px - 4 - kMinBorder, yrel = cur.y0 + 3 - 1 - kMinBorder;
                 for (int i = lane; i < n; i += 32) {
-                    if (base + i < cap) out[base + i] = src[i]; else *overflow = 1;
+                    const uint32_t e = src[i], ty = e >> 8, tx = e & 0xFF;
+                    const uint32_t score = s_sc[ty * scp + tx];
+                    const uint32_t v = ((uint32_t)(yrel + (int)ty) << 20) | ((uint32_t)(xrel + (int)tx) << 8) | (score - 1u);
+                    if (base + i < cap) out[base + i] = v; else *overflow = 1;
                 }
             }
             __syncwarp();
@@ -660,9 +670,9 @@ int launch_fast(const LevelDev *d_levels, const LevelDev *h_levels, const CellRe
         }
         P.stage_bytes = stage;
         P.sc_pitch = 4 * ((tma->max_iw + 3 + 3) / 4 + 2);
-        P.sc_bytes = (P.sc_pitch * (tma->max_ih + 2) + 8 + 15) / 16 * 16;
+        P.sc_bytes = (P.sc_pitch * (tma->max_ih + 4) + 8 + 15) / 16 * 16;
         P.list_cap = (((tma->max_iw + 1) / 2) * ((tma->max_ih + 1) / 2) + 8 + 3) / 4 * 4;
-        P.warp_bytes = (2 * stage + P.sc_bytes + P.list_cap * 4 + 2 * 8 + 2 * 4 + 127) / 128 * 128;
+        P.warp_bytes = (stage + P.sc_bytes + P.list_cap * 2 + 8 + 2 * 4 + 127) / 128 * 128;
         const size_t smem = (size_t)FW_WARPS * P.warp_bytes;
         static size_t configured = 0, last = 0;
         static int per_sm = 0;   // resident CTAs per SM: the persistent grid is exactly one wave
