@@ -98,7 +98,8 @@ int orbx_extract_batch_device(orbx_handle *h, const uint8_t *d_frames, size_t fr
                               uint8_t *d_desc_out, int cap, int *d_n_out, int *d_mono_out);
 int orbx_sync(orbx_handle *h);
 /* Issue all further work of this handle on the caller's CUDA stream (cudaStream_t; NULL = back to the handle's own
- * stream), e.g. torch's current stream so that the caller's events bracket the kernels. */
+ * stream), e.g. a torch stream so that the caller's events bracket the kernels.  The legacy default stream has the
+ * handle NULL as well: name it as cudaStreamLegacy ((cudaStream_t)0x1) to order this handle's work with it. */
 int orbx_set_stream(orbx_handle *h, void *cuda_stream);
 /* Number of kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 long long orbx_launch_count(const orbx_handle *h);

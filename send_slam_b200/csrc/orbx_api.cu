@@ -450,9 +450,11 @@ long long orbx_launch_count(const orbx_handle *h) { return h ? h->launches : 0; 
 
 int orbx_set_stream(orbx_handle *h, void *cuda_stream) {
     if (!h) return ORBX_E_INVALID;
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    if (s == h->stream) return ORBX_OK;
     CU_TRY(h, cudaSetDevice(h->device));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
-    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    h->stream = s;
     return ORBX_OK;
 }
 

@@ -288,9 +288,11 @@ void orbx_knn2_destroy_db(orbx_db *db) {
 
 int orbx_knn2_set_stream(orbx_db *db, void *cuda_stream) {
     if (!db) return ORBX_E_INVALID;
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : db->own_stream;
+    if (s == db->stream) return ORBX_OK;
     DB_TRY(db, cudaSetDevice(db->device));
     DB_TRY(db, cudaStreamSynchronize(db->stream));
-    db->stream = cuda_stream ? (cudaStream_t)cuda_stream : db->own_stream;
+    db->stream = s;
     return ORBX_OK;
 }
 

@@ -250,7 +250,8 @@ class ORBextractor:
         self._check(self._L.orbx_sync(self._h))
 
     def set_stream(self, cuda_stream: int):
-        """cuda_stream: raw cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); 0 = the handle's own stream."""
+        """cuda_stream: raw cudaStream_t (e.g. torch.cuda.Stream().cuda_stream); 0 = the handle's own stream.  torch's
+        default stream also has handle 0: pass 1 (cudaStreamLegacy) to order the work with it."""
         self._check(self._L.orbx_set_stream(self._h, C.c_void_p(cuda_stream)))
 
     def launch_count(self):

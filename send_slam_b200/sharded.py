@@ -47,8 +47,11 @@ def knn2_sharded(index, d_queries, group=None, stream: Optional[int] = None):
     import torch
     nq = d_queries.shape[0]
     dev = d_queries.device
-    cur = torch.cuda.current_stream(dev)
-    index.set_stream(cur.cuda_stream if stream is None else stream)
+    if stream is None:
+        # torch's default stream has handle 0, which the C ABI reads as "the handle's own stream": name the legacy default
+        # stream explicitly (cudaStreamLegacy = 1) so that the query, the NCCL all-gather and the merge stay ordered
+        stream = torch.cuda.current_stream(dev).cuda_stream or 1
+    index.set_stream(stream)
     local = torch.empty((nq, 2), dtype=torch.int64, device=dev)
     index.query_device(d_queries.data_ptr(), nq, local.data_ptr())
 
