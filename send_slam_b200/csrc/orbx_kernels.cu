@@ -288,14 +288,24 @@ __device__ __forceinline__ uint32_t umin2(uint32_t a, uint32_t b) { return __vmi
 __device__ __forceinline__ uint32_t umax3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_u16x2(a, b, c); }
 __device__ __forceinline__ uint32_t umin3(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u16x2(a, b, c); }
 
+// a + b - min(a, b) on the FMA pipe: two IMADs with multiplier 1 (an asm block keeps ptxas from folding them back into one
+// ALU-pipe IADD3)
+__constant__ uint32_t c_one = 1u;   // a multiplier ptxas cannot fold: keeps the two adds of pair_max as IMADs (FMA pipe)
+__device__ __forceinline__ uint32_t pair_max(uint32_t a, uint32_t b, uint32_t mn) {
+    const uint32_t one = c_one;
+    return (a + b * one) - mn * one;
+}
+
 // r[0..15] ring lanes, v centre lanes (pixel value in the high byte of each u16 lane).  Returns the two scores as
 // clean u16 lanes.
 __device__ __forceinline__ uint32_t fast_score_lanes(const uint32_t (&r)[16], uint32_t v) {
     uint32_t qx[8], qn[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-        qx[j] = umax2(r[2 * j + 1], r[(2 * j + 2) & 15]);
+        // max = a + b - min holds for the whole word (exact integer identity per lane, carries cancel): the additions
+        // can issue on the FMA pipe (IMAD.IADD) while the ALU pipe, which bounds this kernel, does the min/max
         qn[j] = umin2(r[2 * j + 1], r[(2 * j + 2) & 15]);
+        qx[j] = pair_max(r[2 * j + 1], r[(2 * j + 2) & 15], qn[j]);
     }
     uint32_t q2x[8], q2n[8];
 #pragma unroll
@@ -307,8 +317,9 @@ __device__ __forceinline__ uint32_t fast_score_lanes(const uint32_t (&r)[16], ui
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         const uint32_t a = r[2 * i], b = r[(2 * i + 9) & 15];
-        fx[i] = umax3(q2x[i], q2x[(i + 2) & 7], umin2(a, b));   // max over arc, smaller of the two arcs sharing 8 pixels
-        fn[i] = umin3(q2n[i], q2n[(i + 2) & 7], umax2(a, b));
+        const uint32_t mn = umin2(a, b);
+        fx[i] = umax3(q2x[i], q2x[(i + 2) & 7], mn);   // max over arc, smaller of the two arcs sharing 8 pixels
+        fn[i] = umin3(q2n[i], q2n[(i + 2) & 7], pair_max(a, b, mn));
     }
     uint32_t min_arc_max = umin3(umin3(fx[0], fx[1], fx[2]), umin3(fx[3], fx[4], fx[5]), umin2(fx[6], fx[7]));
     uint32_t max_arc_min = umax3(umax3(fn[0], fn[1], fn[2]), umax3(fn[3], fn[4], fn[5]), umax2(fn[6], fn[7]));
