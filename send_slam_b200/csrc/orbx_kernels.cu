@@ -825,13 +825,28 @@ __global__ void __launch_bounds__(OT_THREADS) k_octree(const LevelDev *__restric
     for (int i = tid; i < L.nbins; i += OT_THREADS) { bin_start[i] = 0; best[i] = 0; }
     if (tid == 0) { bin_start[L.nbins] = 0; S.len = 0; S.phase = 0; S.finish = 0; S.need_sorted = 0; S.sorted_done = 0; }
     __syncthreads();
-    // pass A: histogram + per-bin winner
-    for (int k = tid; k < n; k += OT_THREADS) {
-        const uint32_t c = cand[k];
-        const uint32_t xr = (c >> 8) & 0xFFF, yr = c >> 20;
-        const uint32_t b = L.xbin[xr] | L.ybin[yr];
-        atomicAdd(&bin_start[b], 1);
-        atomicMax(&best[b], ((c & 0xFFu) << 24) | (0xFFFFFFu - (L.xord[xr] + L.yord[yr])));
+    // pass A: histogram + per-bin winner.  Four candidates per thread are in flight (candidate word, then its four LUT
+    // entries) before the shared-memory atomics of any of them: the loop is bound by the dependent global loads.
+    {
+        const uint32_t *__restrict__ xbin = L.xbin, *__restrict__ ybin = L.ybin, *__restrict__ xord = L.xord, *__restrict__ yord = L.yord;
+        for (int k0 = tid; k0 < n; k0 += 4 * OT_THREADS) {
+            uint32_t c[4], bb[4], oo[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) { const int k = k0 + u * OT_THREADS; c[u] = k < n ? __ldg(cand + k) : 0u; }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t xr = (c[u] >> 8) & 0xFFF, yr = c[u] >> 20;
+                bb[u] = __ldg(xbin + xr) | __ldg(ybin + yr);
+                oo[u] = __ldg(xord + xr) + __ldg(yord + yr);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (k0 + u * OT_THREADS < n) {
+                    atomicAdd(&bin_start[bb[u]], 1);
+                    atomicMax(&best[bb[u]], ((c[u] & 0xFFu) << 24) | (0xFFFFFFu - oo[u]));
+                }
+            }
+        }
     }
     __syncthreads();
     block_excl_scan(bin_start, L.nbins + 1, s_warp);   // bin_start[b] = first key of bin b, bin_start[nbins] = n
