@@ -317,9 +317,19 @@ def main():
         hbm = float(peaks["hbm_gbs"])
         ach = stage_bytes[dom] * BATCH / (acc[dom] * 1e-3) / 1e9
         total_bytes = plan["algorithmic_bytes"]
-        roofline = {"bound": "hbm", "kernel": {"pyramid": "k_resize (7 launches)", "blur": "k_blur", "fast": "k_fast_cells",
-                                                 "describe": "k_describe"}[dom],
-                    "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+        kname = {"pyramid": "k_resize", "blur": "k_blur", "fast": "k_fast_tma", "describe": "k_describe"}[dom]
+        traffic = None      # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel (profiles/)
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))
+            if kname in tj and dom != "pyramid":      # the pyramid is 7 launches; its capture is one level only
+                traffic = tj[kname]["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        roofline = {"bound": "hbm", "kernel": kname + (" (7 launches)" if dom == "pyramid" else ""),
+                    "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": traffic,
+                    "note": "the contract's bound for byte work is HBM; ncu shows this kernel bound by the integer ALU pipe "
+                            "(sm__pipe_alu_cycles_active, profiles/k_fast_tma_r01_summary.txt): FAST scoring costs ~40 min/max ops "
+                            "per pixel and 59 % of the synthetic frames' pixels are corners" if dom == "fast" else None,
                     "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": stage_bytes[dom] * BATCH,
                     "launch_ms": acc[dom],
