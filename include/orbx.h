@@ -97,6 +97,25 @@ int orbx_extract_batch_device(orbx_handle *h, const uint8_t *d_frames, size_t fr
                               int height, int stride, int lap0, int lap1, orbx_keypoint *d_kp_out,
                               uint8_t *d_desc_out, int cap, int *d_n_out, int *d_mono_out);
 int orbx_sync(orbx_handle *h);
+
+/* Pixel format of the frames handed to orbx_extract / orbx_extract_batch / orbx_extract_batch_device.
+ * Replaces the cv::cvtColor(RGB2GRAY / BGR2GRAY / RGBA2GRAY / BGRA2GRAY) that UPSTREAM Tracking::GrabImageMonocular runs
+ * on the CPU between cv::imdecode (orbslam3_mono_networked.cc:546) and the Frame constructor; which of RGB / BGR applies
+ * is the caller's Camera.RGB flag (`rgb: 1`, send_slam/lib/send_slam/slam_handler.ex:222).  With a colour format `stride`
+ * is the BYTE stride of a colour row and the conversion runs on the device straight into the level-0 plane.
+ * gray_shift selects OpenCV's 8U fixed-point form: ORBX_GRAY_Q15 = (R*9798 + G*19235 + B*3735 + 2^14) >> 15 (bit-exact
+ * against cv2 4.13, the pin of this repository), ORBX_GRAY_Q14 = (R*4899 + G*9617 + B*1868 + 2^13) >> 14 (older builds). */
+#define ORBX_FMT_GRAY8 0
+#define ORBX_FMT_RGB8 1
+#define ORBX_FMT_BGR8 2
+#define ORBX_FMT_RGBA8 3
+#define ORBX_FMT_BGRA8 4
+#define ORBX_GRAY_Q15 15
+#define ORBX_GRAY_Q14 14
+int orbx_set_input_format(orbx_handle *h, int format, int gray_shift);
+/* The conversion alone (parity tests): src = colour image (format != GRAY8), dst = gray plane. */
+int orbx_debug_gray(orbx_handle *h, const uint8_t *src, int width, int height, int stride, int format, int gray_shift,
+                    uint8_t *dst, int dst_stride);
 /* Issue all further work of this handle on the caller's CUDA stream (cudaStream_t; NULL = back to the handle's own
  * stream), e.g. a torch stream so that the caller's events bracket the kernels.  The legacy default stream has the
  * handle NULL as well: name it as cudaStreamLegacy ((cudaStream_t)0x1) to order this handle's work with it. */

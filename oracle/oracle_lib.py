@@ -42,6 +42,7 @@ def lib():
         L.orb_oracle_level_size.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, i32p, i32p]
         L.orb_oracle_resize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.orb_oracle_blur7.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.orb_oracle_gray.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.orb_oracle_fast.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.orb_oracle_fast_cells.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.orb_oracle_octree.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
@@ -148,6 +149,15 @@ def resize(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
     src = np.ascontiguousarray(src, np.uint8)
     dst = np.zeros((dh, dw), np.uint8)
     lib().orb_oracle_resize(_p(src), src.shape[1], src.shape[0], src.shape[1], _p(dst), dw, dh, dw)
+    return dst
+
+
+def gray(src: np.ndarray, fmt: int, shift: int = 15) -> np.ndarray:
+    """cv::cvtColor(*2GRAY) restatement; fmt 1 RGB, 2 BGR, 3 RGBA, 4 BGRA."""
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.zeros(src.shape[:2], np.uint8)
+    rc = lib().orb_oracle_gray(_p(src), src.shape[1], src.shape[0], src.strides[0], int(fmt), int(shift), _p(dst), dst.shape[1])
+    assert rc == 0
     return dst
 
 

@@ -155,6 +155,24 @@ static void resize_axis(int dst, int src, int is_x, int *ofs, short *c0, short *
     }
 }
 
+/* cv::cvtColor(src, COLOR_RGB2GRAY / BGR2GRAY / RGBA2GRAY / BGRA2GRAY), 8U: what UPSTREAM Tracking::GrabImageMonocular applies to a
+ * colour frame before the Frame constructor (reached from slam_backends/orb_slam_3/orbslam3_mono_networked.cc:594; RGB vs BGR
+ * = Camera.RGB, `rgb: 1` in send_slam/lib/send_slam/slam_handler.ex:222).  format: 1 RGB, 2 BGR, 3 RGBA, 4 BGRA.
+ * shift 15: (R*9798 + G*19235 + B*3735 + 2^14) >> 15 -- bit-identical to cv2 4.13 (tests/test_oracle_golden.py);
+ * shift 14: (R*4899 + G*9617 + B*1868 + 2^13) >> 14 -- the fixed-point form of older OpenCV builds. */
+int orb_oracle_gray(const u8 *src, int w, int h, int stride, int format, int shift, u8 *dst, int dstride) {
+    if (!src || !dst || w < 1 || h < 1 || format < 1 || format > 4 || (shift != 15 && shift != 14)) return -1;
+    const int ch = format >= 3 ? 4 : 3, rgb = (format == 1 || format == 3);
+    const unsigned r = shift == 15 ? 9798u : 4899u, g = shift == 15 ? 19235u : 9617u, b = shift == 15 ? 3735u : 1868u;
+    const unsigned c0 = rgb ? r : b, c2 = rgb ? b : r, half = 1u << (shift - 1);
+    for (int y = 0; y < h; y++) {
+        const u8 *p = src + (size_t)y * stride;
+        u8 *q = dst + (size_t)y * dstride;
+        for (int x = 0; x < w; x++, p += ch) q[x] = (u8)((p[0] * c0 + p[1] * g + p[2] * c2 + half) >> shift);
+    }
+    return 0;
+}
+
 int orb_oracle_resize(const u8 *src, int sw, int sh, int sstride, u8 *dst, int dw, int dh, int dstride) {
     int *xo = (int *)malloc(sizeof(int) * dw), *yo = (int *)malloc(sizeof(int) * dh);
     short *xa = (short *)malloc(sizeof(short) * dw * 2), *ya = (short *)malloc(sizeof(short) * dh * 2);

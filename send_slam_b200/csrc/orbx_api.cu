@@ -27,10 +27,10 @@ static thread_local std::string g_create_error;
 struct GraphKey {
     const void *in, *kp, *desc;
     cudaStream_t stream;
-    int batch, width, height, stride, lap0, lap1, cap, chunk;
+    int batch, width, height, stride, lap0, lap1, cap, chunk, fmt;
     bool operator==(const GraphKey &o) const {
         return in == o.in && kp == o.kp && desc == o.desc && stream == o.stream && batch == o.batch && width == o.width &&
-               height == o.height && stride == o.stride && lap0 == o.lap0 && lap1 == o.lap1 && cap == o.cap && chunk == o.chunk;
+               height == o.height && stride == o.stride && lap0 == o.lap0 && lap1 == o.lap1 && cap == o.cap && chunk == o.chunk && fmt == o.fmt;
     }
 };
 struct GraphEntry { GraphKey key; cudaGraphExec_t exec; long long launches; };
@@ -77,6 +77,11 @@ struct orbx_handle {
     int *d_n = nullptr, *d_mono = nullptr;
     FastTma ftma{};                 // tensor maps of the level planes (TMA-staged FAST kernel)
     int sm_count = 148;
+    // colour input (orbx_set_input_format): frames are uploaded to d_color and converted into the level-0 planes on the device
+    int in_fmt = ORBX_FMT_GRAY8, gray_shift = ORBX_GRAY_Q15;
+    uint8_t *d_color = nullptr, *h_color = nullptr;
+    int color_pitch = 0, color_fmt = 0;
+    size_t color_fstride = 0;
     uint8_t *l0_own = nullptr;      // arena copy of level 0 (host-input path)
     size_t l0_own_fstride = 0;
     int l0_own_pitch = 0;
@@ -120,6 +125,8 @@ static void free_plan(orbx_handle *h) {
     if (h->h_kp) cudaFreeHost(h->h_kp);
     if (h->h_desc) cudaFreeHost(h->h_desc);
     if (h->h_n) cudaFreeHost(h->h_n);
+    if (h->h_color) cudaFreeHost(h->h_color);
+    h->h_color = nullptr; h->d_color = nullptr; h->color_fmt = 0;
     h->h_in = nullptr; h->h_kp = nullptr; h->h_desc = nullptr; h->h_n = nullptr; h->h_mono = nullptr; h->h_overflow = nullptr;
     h->planned = false;
 }
@@ -242,6 +249,7 @@ static int ensure_plan(orbx_handle *h, int w, int ht, int batch) {
     CU_TRY(h, cudaMallocHost((void **)&h->h_desc, (size_t)B * h->kp_cap * 32));
     CU_TRY(h, cudaMallocHost((void **)&h->h_n, (size_t)(2 * B + 1) * sizeof(int)));
     h->h_mono = h->h_n + B; h->h_overflow = h->h_n + 2 * B;
+    CU_TRY(h, cudaStreamSynchronize(cudaStreamLegacy));   // table uploads above are blocking copies on the legacy stream
     h->planned = true;
     return ORBX_OK;
 }
@@ -282,6 +290,22 @@ static int ensure_pipeline(orbx_handle *h) {
     return ORBX_OK;
 }
 
+// Device + pinned staging for colour frames of the current plan (3 or 4 bytes per pixel).
+static int ensure_color(orbx_handle *h) {
+    const int bpp = h->in_fmt >= ORBX_FMT_RGBA8 ? 4 : 3;
+    if (h->d_color && h->color_fmt == bpp) return ORBX_OK;
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    for (auto &g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    h->graphs.clear();
+    if (h->h_color) { cudaFreeHost(h->h_color); h->h_color = nullptr; }
+    h->color_pitch = (h->plan.width * bpp + 15) / 16 * 16;
+    h->color_fstride = (size_t)h->color_pitch * h->plan.height;
+    CU_TRY(h, dev_alloc(h, &h->d_color, h->color_fstride * h->batch_cap + 64));   // freed with the plan
+    CU_TRY(h, cudaMallocHost((void **)&h->h_color, h->color_fstride * h->batch_cap));
+    h->color_fmt = bpp;
+    return ORBX_OK;
+}
+
 // Clears the per-frame counters of the whole workspace (must precede the kernels of every frame range of a call).
 static int reset_counters(orbx_handle *h, cudaStream_t stream) {
     CU_TRY(h, cudaMemsetAsync(h->d_counts, 0, sizeof(int) * 2 * h->plan.nlevels * h->batch_cap, stream));
@@ -291,8 +315,11 @@ static int reset_counters(orbx_handle *h, cudaStream_t stream) {
 
 // The kernel pipeline for frames [f0, f0 + batch) of the workspace, whose level 0 is already in place.  Everything is
 // issued on `stream`; with a `side` stream the Gaussian pass is forked onto it (ev_fork / ev_join order it).
+struct ColorSrc { const uint8_t *ptr; int pitch; size_t fstride; };   // device memory holding colour frames; ptr == nullptr: gray input
+
 static int run_pipeline(orbx_handle *h, int f0, int batch, int lap0, int lap1, KeypointRec *d_kp, uint8_t *d_desc, int cap,
-                        int *d_n, int *d_mono, cudaStream_t stream, cudaStream_t side, cudaEvent_t ev_fork, cudaEvent_t ev_join) {
+                        int *d_n, int *d_mono, cudaStream_t stream, cudaStream_t side, cudaEvent_t ev_fork, cudaEvent_t ev_join,
+                        ColorSrc color = ColorSrc{nullptr, 0, 0}) {
     const Plan &pl = h->plan;
     const int nl = pl.nlevels;
     const bool prof = h->profiling && stream == h->stream;
@@ -306,6 +333,9 @@ static int run_pipeline(orbx_handle *h, int f0, int batch, int lap0, int lap1, K
             if (e__ != cudaSuccess) { h->err = std::string("stage ") + #i + ": " + cudaGetErrorString(e__); return ORBX_E_CUDA; } \
         }                                                                                                         \
     } while (0)
+    if (color.ptr)   // cv::cvtColor of Tracking::GrabImageMonocular, on the device, into the level-0 planes
+        h->launches += launch_gray(color.ptr, color.fstride, color.pitch, h->in_fmt, h->gray_shift, h->l0_own, h->l0_own_fstride, h->l0_own_pitch,
+                                   pl.width, pl.height, f0, batch, stream);
     STAGE_MARK(0);
     for (int l = 1; l < nl; l++) h->launches += launch_resize(h->d_levels, h->h_levels, l, f0, batch, stream);
     STAGE_MARK(1);
@@ -478,6 +508,34 @@ int orbx_get_stage_times(orbx_handle *h, float *ms6) {
     return ORBX_OK;
 }
 
+int orbx_set_input_format(orbx_handle *h, int format, int gray_shift) {
+    if (!h) return ORBX_E_INVALID;
+    if (format < ORBX_FMT_GRAY8 || format > ORBX_FMT_BGRA8 || (gray_shift != ORBX_GRAY_Q15 && gray_shift != ORBX_GRAY_Q14))
+        return fail(h, ORBX_E_INVALID, "format must be ORBX_FMT_*, gray_shift ORBX_GRAY_Q15 or ORBX_GRAY_Q14");
+    h->in_fmt = format; h->gray_shift = gray_shift;
+    return ORBX_OK;
+}
+
+int orbx_debug_gray(orbx_handle *h, const uint8_t *src, int w, int ht, int stride, int format, int gray_shift, uint8_t *dst, int dstride) {
+    if (!h || !src || !dst || w < 1 || ht < 1 || format < ORBX_FMT_RGB8 || format > ORBX_FMT_BGRA8 || dstride < w ||
+        (gray_shift != ORBX_GRAY_Q15 && gray_shift != ORBX_GRAY_Q14))
+        return ORBX_E_INVALID;
+    const int bpp = format >= ORBX_FMT_RGBA8 ? 4 : 3;
+    if (stride < w * bpp) return ORBX_E_INVALID;
+    CU_TRY(h, cudaSetDevice(h->device));
+    Scratch S;
+    const int sp = (w * bpp + 15) / 16 * 16, dp = (w + 31) / 32 * 32;
+    uint8_t *d_src = S.get<uint8_t>((size_t)sp * ht + 64), *d_dst = S.get<uint8_t>((size_t)dp * ht + 64);
+    if (!d_src || !d_dst) return fail(h, ORBX_E_CUDA, "cudaMalloc failed");
+    CU_TRY(h, cudaMemcpy2D(d_src, sp, src, stride, (size_t)w * bpp, ht, cudaMemcpyHostToDevice));
+    CU_TRY(h, cudaStreamSynchronize(cudaStreamLegacy));   // blocking pageable uploads may still be in DMA; h->stream is non-blocking
+    h->launches += launch_gray(d_src, (size_t)sp * ht, sp, format, gray_shift, d_dst, (size_t)dp * ht, dp, w, ht, 0, 1, h->stream);
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    CU_TRY(h, cudaMemcpy2D(dst, dstride, d_dst, dp, w, ht, cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+}
+
 int orbx_sync(orbx_handle *h) {
     if (!h) return ORBX_E_INVALID;
     CU_TRY(h, cudaSetDevice(h->device));
@@ -499,16 +557,23 @@ int orbx_extract_batch_device(orbx_handle *h, const uint8_t *d_frames, size_t fr
     if (!h) return ORBX_E_INVALID;
     if (!d_frames || !d_kp_out || !d_desc_out || !d_n_out || !d_mono_out) return fail(h, ORBX_E_INVALID, "null argument");
     if (width < 1 || height < 1) return fail(h, ORBX_E_EMPTY, "empty image");
-    if (batch < 1 || stride < width || frame_stride_bytes < (size_t)stride * (height - 1) + width) return fail(h, ORBX_E_INVALID, "bad batch / stride");
+    const int bpp = h->in_fmt == ORBX_FMT_GRAY8 ? 1 : h->in_fmt >= ORBX_FMT_RGBA8 ? 4 : 3, rowb = width * bpp;
+    if (batch < 1 || stride < rowb || frame_stride_bytes < (size_t)stride * (height - 1) + rowb) return fail(h, ORBX_E_INVALID, "bad batch / stride");
     CU_TRY(h, cudaSetDevice(h->device));
     int rc = ensure_plan(h, width, height, batch);
     if (rc) return rc;
     if (cap < h->plan.total_out_cap) return fail(h, ORBX_E_CAPACITY, "cap smaller than orbx_keypoint_capacity for this frame size");
-    if ((rc = set_level0(h, d_frames, stride, frame_stride_bytes))) return rc;
+    ColorSrc color{nullptr, 0, 0};
+    if (bpp == 1) {
+        if ((rc = set_level0(h, d_frames, stride, frame_stride_bytes))) return rc;
+    } else {
+        color = ColorSrc{d_frames, stride, frame_stride_bytes};      // converted straight out of the caller's memory
+        if ((rc = set_level0(h, h->l0_own, h->l0_own_pitch, h->l0_own_fstride))) return rc;
+    }
     if ((rc = reset_counters(h, h->stream))) return rc;
     h->last_batch = batch;
     return run_pipeline(h, 0, batch, lap0, lap1, reinterpret_cast<KeypointRec *>(d_kp_out), d_desc_out, cap, d_n_out, d_mono_out,
-                        h->stream, h->side_stream, h->ev_fork, h->ev_join);
+                        h->stream, h->side_stream, h->ev_fork, h->ev_join, color);
 }
 
 int orbx_extract_batch(orbx_handle *h, const uint8_t *const *frames, int batch, int width, int height, int stride, int lap0,
@@ -519,19 +584,26 @@ int orbx_extract_batch(orbx_handle *h, const uint8_t *const *frames, int batch, 
         for (int i = 0; i < batch; i++) { n_out[i] = 0; mono_index_out[i] = -1; }
         return fail(h, ORBX_E_EMPTY, "empty image");
     }
-    if (batch < 1 || stride < width) return fail(h, ORBX_E_INVALID, "bad batch / stride");
+    const int bpp = h->in_fmt == ORBX_FMT_GRAY8 ? 1 : h->in_fmt >= ORBX_FMT_RGBA8 ? 4 : 3, rowb = width * bpp;
+    if (batch < 1 || stride < rowb) return fail(h, ORBX_E_INVALID, "bad batch / stride");
     for (int i = 0; i < batch; i++) if (!frames[i]) return fail(h, ORBX_E_INVALID, "null frame pointer");
     CU_TRY(h, cudaSetDevice(h->device));
     int rc = ensure_plan(h, width, height, batch);
     if (rc) return rc;
+    if (bpp > 1 && (rc = ensure_color(h))) return rc;
     const int kc = h->kp_cap;
-    const int pitch0 = h->l0_own_pitch;
-    const size_t fstride0 = h->l0_own_fstride;
+    // upload target: the level-0 planes themselves for gray frames, the colour staging planes otherwise
+    uint8_t *const up_dev = bpp == 1 ? h->l0_own : h->d_color;
+    uint8_t *const up_host = bpp == 1 ? h->h_in : h->h_color;
+    const int pitch0 = bpp == 1 ? h->l0_own_pitch : h->color_pitch;
+    const size_t fstride0 = bpp == 1 ? h->l0_own_fstride : h->color_fstride;
+    const ColorSrc color = bpp == 1 ? ColorSrc{nullptr, 0, 0} : ColorSrc{h->d_color, h->color_pitch, h->color_fstride};
     // Input: page-locked caller memory is DMA'd straight into the level-0 planes (one strided 2D copy per frame, or a
     // single one per frame range when the frames are evenly spaced); pageable memory is first repacked into the
     // handle's pinned staging.  Output: page-locked caller buffers of the internal record capacity receive the
     // result blocks directly.
     const bool in_pinned = is_pinned_host(frames[0]) && is_pinned_host(frames[batch - 1] + (size_t)stride * (height - 1));
+    const int width_b = rowb;   // bytes per row to move
     const bool out_direct = cap >= kc && is_pinned_host(kp_out) && is_pinned_host(desc_out);
     bool even = in_pinned && fstride0 == (size_t)pitch0 * height;
     for (int i = 1; i < batch && even; i++) even = (frames[i] - frames[i - 1]) == (ptrdiff_t)stride * height;
@@ -539,20 +611,20 @@ int orbx_extract_batch(orbx_handle *h, const uint8_t *const *frames, int batch, 
     auto stage_in = [&](int f0, int n) {
         if (in_pinned) return;
         for (int i = f0; i < f0 + n; i++) {
-            uint8_t *dst = h->h_in + (size_t)i * fstride0;
+            uint8_t *dst = up_host + (size_t)i * fstride0;
             const uint8_t *src = frames[i];
-            if (stride == pitch0) std::memcpy(dst, src, (size_t)stride * (height - 1) + width);
-            else for (int y = 0; y < height; y++) std::memcpy(dst + (size_t)y * pitch0, src + (size_t)y * stride, (size_t)width);
+            if (stride == pitch0) std::memcpy(dst, src, (size_t)stride * (height - 1) + width_b);
+            else for (int y = 0; y < height; y++) std::memcpy(dst + (size_t)y * pitch0, src + (size_t)y * stride, (size_t)width_b);
         }
     };
     auto copy_in = [&](int f0, int n, cudaStream_t st) -> int {
         if (!in_pinned) {
-            CU_TRY(h, cudaMemcpyAsync(h->l0_own + (size_t)f0 * fstride0, h->h_in + (size_t)f0 * fstride0, (size_t)n * fstride0, cudaMemcpyHostToDevice, st));
+            CU_TRY(h, cudaMemcpyAsync(up_dev + (size_t)f0 * fstride0, up_host + (size_t)f0 * fstride0, (size_t)n * fstride0, cudaMemcpyHostToDevice, st));
         } else if (even) {
-            CU_TRY(h, cudaMemcpy2DAsync(h->l0_own + (size_t)f0 * fstride0, pitch0, frames[f0], stride, width, (size_t)height * n, cudaMemcpyHostToDevice, st));
+            CU_TRY(h, cudaMemcpy2DAsync(up_dev + (size_t)f0 * fstride0, pitch0, frames[f0], stride, width_b, (size_t)height * n, cudaMemcpyHostToDevice, st));
         } else {
             for (int i = f0; i < f0 + n; i++)
-                CU_TRY(h, cudaMemcpy2DAsync(h->l0_own + (size_t)i * fstride0, pitch0, frames[i], stride, width, height, cudaMemcpyHostToDevice, st));
+                CU_TRY(h, cudaMemcpy2DAsync(up_dev + (size_t)i * fstride0, pitch0, frames[i], stride, width_b, height, cudaMemcpyHostToDevice, st));
         }
         return ORBX_OK;
     };
@@ -568,7 +640,7 @@ int orbx_extract_batch(orbx_handle *h, const uint8_t *const *frames, int batch, 
         return ORBX_OK;
     };
     h->last_batch = batch;
-    if ((rc = set_level0(h, h->l0_own, pitch0, fstride0))) return rc;
+    if ((rc = set_level0(h, h->l0_own, h->l0_own_pitch, h->l0_own_fstride))) return rc;
     const int chunk = h->profiling ? batch : pipeline_chunk(batch);
     if (chunk < batch && (rc = ensure_pipeline(h))) return rc;
     // Everything the device does for this call, issued relative to the handle's stream.  `cpu_stage` = do the pageable
@@ -580,7 +652,7 @@ int orbx_extract_batch(orbx_handle *h, const uint8_t *const *frames, int batch, 
             // one frame range: copy in, compute, copy out, all on the handle's stream (+ its side stream)
             if (cpu_stage) stage_in(0, batch);
             if ((rc2 = copy_in(0, batch, h->stream))) return rc2;
-            if ((rc2 = run_pipeline(h, 0, batch, lap0, lap1, h->d_kp, h->d_desc, kc, h->d_n, h->d_mono, h->stream, h->side_stream, h->ev_fork, h->ev_join))) return rc2;
+            if ((rc2 = run_pipeline(h, 0, batch, lap0, lap1, h->d_kp, h->d_desc, kc, h->d_n, h->d_mono, h->stream, h->side_stream, h->ev_fork, h->ev_join, color))) return rc2;
             if ((rc2 = download(0, batch, h->stream))) return rc2;
         } else {
             // Software pipeline over frame ranges: the copy engines stream range k+1 in and range k-1 out while the SMs
@@ -598,7 +670,7 @@ int orbx_extract_batch(orbx_handle *h, const uint8_t *const *frames, int batch, 
                 if ((rc2 = copy_in(f0, n, h->h2d_stream))) return rc2;
                 CU_TRY(h, cudaEventRecord(h->ev_in[k], h->h2d_stream));
                 CU_TRY(h, cudaStreamWaitEvent(cs, h->ev_in[k], 0));
-                if ((rc2 = run_pipeline(h, f0, n, lap0, lap1, h->d_kp, h->d_desc, kc, h->d_n, h->d_mono, cs, nullptr, nullptr, nullptr))) return rc2;
+                if ((rc2 = run_pipeline(h, f0, n, lap0, lap1, h->d_kp, h->d_desc, kc, h->d_n, h->d_mono, cs, nullptr, nullptr, nullptr, color))) return rc2;
                 CU_TRY(h, cudaEventRecord(h->ev_done[k], cs));
                 CU_TRY(h, cudaStreamWaitEvent(h->d2h_stream, h->ev_done[k], 0));
                 if ((rc2 = download(f0, n, h->d2h_stream))) return rc2;
@@ -619,7 +691,7 @@ int orbx_extract_batch(orbx_handle *h, const uint8_t *const *frames, int batch, 
         if ((rc = enqueue(true))) return rc;
     } else {
         GraphKey key{in_pinned ? frames[0] : nullptr, out_direct ? (const void *)kp_out : nullptr, out_direct ? (const void *)desc_out : nullptr,
-                     h->stream, batch, width, height, stride, lap0, lap1, out_direct ? cap : 0, chunk};
+                     h->stream, batch, width, height, stride, lap0, lap1, out_direct ? cap : 0, chunk, h->in_fmt * 100 + h->gray_shift};
         GraphEntry *e = nullptr;
         for (auto &g : h->graphs) if (g.key == key) { e = &g; break; }
         if (!e) {
@@ -768,6 +840,7 @@ int orbx_debug_resize(orbx_handle *h, const uint8_t *src, int sw, int sh, int ss
     CU_TRY(h, cudaMemcpy(d_xt, xt.data(), sizeof(ResizeTap) * dw, cudaMemcpyHostToDevice));
     CU_TRY(h, cudaMemcpy(d_yt, yt.data(), sizeof(ResizeTap) * dh, cudaMemcpyHostToDevice));
     CU_TRY(h, cudaMemcpy(d_lv, lv, sizeof(lv), cudaMemcpyHostToDevice));
+    CU_TRY(h, cudaStreamSynchronize(cudaStreamLegacy));   // blocking pageable uploads may still be in DMA; h->stream is non-blocking
     h->launches += launch_resize(d_lv, lv, 1, 0, 1, h->stream);
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaStreamSynchronize(h->stream));
@@ -791,6 +864,7 @@ int orbx_debug_blur(orbx_handle *h, const uint8_t *src, int w, int ht, int sstri
     CU_TRY(h, cudaMemcpy2D(d_src, p, src, sstride, w, ht, cudaMemcpyHostToDevice));
     CU_TRY(h, cudaMemcpy(d_t, tiles.data(), sizeof(BlurTile) * tiles.size(), cudaMemcpyHostToDevice));
     CU_TRY(h, cudaMemcpy(d_lv, &lv, sizeof(lv), cudaMemcpyHostToDevice));
+    CU_TRY(h, cudaStreamSynchronize(cudaStreamLegacy));   // blocking pageable uploads may still be in DMA; h->stream is non-blocking
     h->launches += launch_blur(d_lv, d_t, (int)tiles.size(), 0, 1, h->stream);
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaStreamSynchronize(h->stream));
@@ -817,6 +891,7 @@ int orbx_debug_describe(orbx_handle *h, const uint8_t *img, const uint8_t *blurr
     if (blurred) CU_TRY(h, cudaMemcpy2D(d_bl, p, blurred, stride, w, ht, cudaMemcpyHostToDevice));
     CU_TRY(h, cudaMemcpy(d_xy, xy, sizeof(float) * 2 * n, cudaMemcpyHostToDevice));
     if (angle_in) CU_TRY(h, cudaMemcpy(d_ai, angle_in, sizeof(float) * n, cudaMemcpyHostToDevice));
+    CU_TRY(h, cudaStreamSynchronize(cudaStreamLegacy));   // blocking pageable uploads may still be in DMA; h->stream is non-blocking
     h->launches += launch_describe_points(d_img, d_bl, p, d_xy, n, d_ai, d_ao, d_desc, h->stream);
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaStreamSynchronize(h->stream));
@@ -871,6 +946,7 @@ int orbx_debug_octree(orbx_handle *h, const float *keys, int n, int minX, int ma
     D.ord_cell_area = LP.ord_cell_area; D.ord_ncols = LP.ord_ncols; D.wcell = LP.wcell; D.hcell = LP.hcell;
     D.cand = d_cand; D.sorted = d_sorted; D.bin_cursor = d_cur; D.cand_cap = ccap; D.cand_count = d_cnt; D.sel = d_sel; D.sel_count = d_cnt + 1;
     CU_TRY(h, cudaMemcpy(d_lv, &D, sizeof(D), cudaMemcpyHostToDevice));
+    CU_TRY(h, cudaStreamSynchronize(cudaStreamLegacy));   // blocking pageable uploads may still be in DMA; h->stream is non-blocking
     h->launches += launch_octree(d_lv, &D, 1, 0, 1, d_cnt + 2, h->stream);
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaStreamSynchronize(h->stream));

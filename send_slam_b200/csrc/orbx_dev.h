@@ -42,6 +42,8 @@ struct KeypointRec {           // == orbx_keypoint == cv::KeyPoint
 
 // launch wrappers (orbx_kernels.cu); all asynchronous on `stream`, return the number of kernel launches issued.
 // They process frames [f0, f0 + batch) of the workspace.
+int launch_gray(const uint8_t *d_src, size_t src_fstride, int src_pitch, int format, int shift, uint8_t *d_dst, size_t dst_fstride,
+                int dst_pitch, int w, int h, int f0, int batch, cudaStream_t stream);
 int launch_resize(const LevelDev *d_levels, const LevelDev *h_levels, int level, int f0, int batch, cudaStream_t stream);
 int launch_blur(const LevelDev *d_levels, const BlurTile *d_tiles, int ntiles, int f0, int batch, cudaStream_t stream);
 // Tensor maps of the level planes for the TMA-staged FAST kernel (host side: orbx_api.cu builds them; 128 bytes each,

@@ -35,6 +35,57 @@ void upload_constants() {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// K0  colour -> gray (cv::cvtColor RGB2GRAY / BGR2GRAY / RGBA2GRAY / BGRA2GRAY, 8U fixed point): what UPSTREAM
+//     Tracking::GrabImageMonocular does on the CPU before the Frame is built.  gray = (c0*ch0 + c1*ch1 + c2*ch2 + half) >> shift
+//     with (R, G, B) weights (9798, 19235, 3735) >> 15 (cv2 4.13, bit-exact) or (4899, 9617, 1868) >> 14 (older builds).
+//     4 pixels per thread: 3 or 4 aligned words in, one word out (level-0 plane of the workspace).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_gray(const uint8_t *__restrict__ src, size_t src_fstride, int src_pitch, int channels,
+                                              uint32_t c0, uint32_t c1, uint32_t c2, uint32_t half, int shift,
+                                              uint8_t *__restrict__ dst, size_t dst_fstride, int dst_pitch, int w, int f0) {
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (x0 >= w) return;
+    const int y = blockIdx.y, f = f0 + blockIdx.z;
+    const uint8_t *row = src + (size_t)f * src_fstride + (size_t)y * src_pitch + (size_t)x0 * channels;
+    uint32_t px[4][3];
+    const bool words = ((reinterpret_cast<uintptr_t>(row) & 3) == 0) && x0 + 3 < w;
+    if (words && channels == 3) {
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(row);
+        const uint32_t a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);      // bytes 0..11 = 4 x (ch0, ch1, ch2)
+        px[0][0] = a & 0xFF;         px[0][1] = (a >> 8) & 0xFF;  px[0][2] = (a >> 16) & 0xFF;
+        px[1][0] = a >> 24;          px[1][1] = b & 0xFF;         px[1][2] = (b >> 8) & 0xFF;
+        px[2][0] = (b >> 16) & 0xFF; px[2][1] = b >> 24;          px[2][2] = c & 0xFF;
+        px[3][0] = (c >> 8) & 0xFF;  px[3][1] = (c >> 16) & 0xFF; px[3][2] = c >> 24;
+    } else if (words) {
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(row);
+#pragma unroll
+        for (int i = 0; i < 4; i++) { const uint32_t a = __ldg(q + i); px[i][0] = a & 0xFF; px[i][1] = (a >> 8) & 0xFF; px[i][2] = (a >> 16) & 0xFF; }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int xi = min(x0 + i, w - 1) - x0;
+            px[i][0] = row[xi * channels]; px[i][1] = row[xi * channels + 1]; px[i][2] = row[xi * channels + 2];
+        }
+    }
+    uint32_t out = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) out |= ((px[i][0] * c0 + px[i][1] * c1 + px[i][2] * c2 + half) >> shift) << (8 * i);
+    *reinterpret_cast<uint32_t *>(dst + (size_t)f * dst_fstride + (size_t)y * dst_pitch + x0) = out;
+}
+
+// format: 1 RGB, 2 BGR, 3 RGBA, 4 BGRA (ORBX_FMT_*); shift 15 or 14.  dst rows must be 4-byte aligned with a padded pitch.
+int launch_gray(const uint8_t *d_src, size_t src_fstride, int src_pitch, int format, int shift, uint8_t *d_dst, size_t dst_fstride,
+                int dst_pitch, int w, int h, int f0, int batch, cudaStream_t stream) {
+    const int channels = format >= 3 ? 4 : 3;
+    const bool rgb = format == 1 || format == 3;
+    const uint32_t r = shift == 15 ? 9798u : 4899u, g = shift == 15 ? 19235u : 9617u, b = shift == 15 ? 3735u : 1868u;
+    dim3 grid((w + 4 * 128 - 1) / (4 * 128), h, batch);
+    k_gray<<<grid, 128, 0, stream>>>(d_src, src_fstride, src_pitch, channels, rgb ? r : b, g, rgb ? b : r, 1u << (shift - 1), shift, d_dst,
+                                     dst_fstride, dst_pitch, w, f0);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // K1  pyramid resize (cv::resize INTER_LINEAR, 8UC1).  Taps are tabulated on the host (orbx_plan.cpp).
 //     k_resize: 4 destination pixels x 2 destination rows per thread.  The <= 8 source bytes a 4-pixel group needs are
 //     fetched as three aligned words per source row and realigned once; each pixel then costs one PRMT (its two
@@ -117,11 +168,13 @@ __global__ void __launch_bounds__(128) k_resize(const LevelDev *__restrict__ lv,
 #pragma unroll
             for (int i = 0; i < 4; i++) r[k][i] = __dp2a_lo(coef[i], __byte_perm(a, b, sel[i]), 0u);
         }
+        // (c * x) >> 16 as the high word of (c << 16) * x: one IMAD.HI on the FMA pipe instead of IMAD + shift (c >= 0 here)
+        const uint32_t c0s = (uint32_t)ty[rr].c0 << 16, c1s = (uint32_t)ty[rr].c1 << 16;
         uint32_t packed = 0;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            const int v = ((((int)ty[rr].c0 * (int)(r[0][i] >> 4)) >> 16) + (((int)ty[rr].c1 * (int)(r[1][i] >> 4)) >> 16) + 2) >> 2;
-            packed |= (uint32_t)min(v, 255) << (8 * i);
+            const uint32_t v = (__umulhi(c0s, r[0][i] >> 4) + __umulhi(c1s, r[1][i] >> 4) + 2u) >> 2;
+            packed |= min(v, 255u) << (8 * i);
         }
         if (dy0 + rr < dh) *reinterpret_cast<uint32_t *>(drow + (size_t)rr * D.pitch) = packed;
     }
@@ -1192,6 +1245,7 @@ __device__ __forceinline__ void steer_trig(float angle_deg, float &a, float &b) 
 }
 
 __device__ __forceinline__ uint8_t warp_brief_byte(const uint8_t *__restrict__ center, int pitch, float a, float b, int lane) {
+    // (measured: a float4 pattern table and a running row pointer for the moments both made this kernel slower, 81 -> 119 us)
     const char4 *pat = reinterpret_cast<const char4 *>(g_pattern) + lane * 8;
     uint32_t val = 0;
 #pragma unroll

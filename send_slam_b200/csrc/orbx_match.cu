@@ -252,6 +252,7 @@ int orbx_knn2_create_db(int device, const uint8_t *rows, long long nrows, long l
     uint8_t *d = nullptr;
     cudaError_t e = cudaMalloc((void **)&d, std::max<size_t>((size_t)nrows * 32, 256));
     if (e == cudaSuccess && nrows > 0) e = cudaMemcpy(d, rows, (size_t)nrows * 32, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);   // the tail of a pageable upload may still be in DMA; queries run on a non-blocking stream
     if (e != cudaSuccess) {
         g_db_error = std::string("db upload: ") + cudaGetErrorString(e);
         if (d) cudaFree(d);

@@ -20,6 +20,8 @@ KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4
                      ("octave", "<i4"), ("class_id", "<i4")])  # == cv::KeyPoint == orbx_keypoint
 
 ORBX_OK, ORBX_E_INVALID, ORBX_E_CUDA, ORBX_E_CAPACITY, ORBX_E_EMPTY, ORBX_E_OVERFLOW = 0, -1, -2, -3, -4, -5
+FMT_GRAY8, FMT_RGB8, FMT_BGR8, FMT_RGBA8, FMT_BGRA8 = 0, 1, 2, 3, 4     # ORBX_FMT_*
+GRAY_Q15, GRAY_Q14 = 15, 14                                              # ORBX_GRAY_*
 
 
 class OrbxError(RuntimeError):
@@ -43,7 +45,7 @@ EXPORTS = [
     "orbx_knn2_create_db", "orbx_knn2_create_db_device", "orbx_knn2_destroy_db", "orbx_knn2_last_error", "orbx_knn2_query",
     "orbx_knn2_query_device", "orbx_knn2_merge_device", "orbx_knn2_sync", "orbx_knn2_launch_count", "orbx_plan_probe",
     "orbx_version", "orbx_set_profiling", "orbx_get_stage_times", "orbx_set_stream",
-    "orbx_knn2_set_stream", "orbx_knn2_set_backend",
+    "orbx_knn2_set_stream", "orbx_knn2_set_backend", "orbx_set_input_format", "orbx_debug_gray",
 ]
 
 _lib = None
@@ -80,6 +82,8 @@ def lib():
     L.orbx_debug_get_level_keypoints.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, ip]
     L.orbx_debug_resize.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int]
     L.orbx_debug_blur.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int]
+    L.orbx_set_input_format.argtypes = [vp, C.c_int, C.c_int]
+    L.orbx_debug_gray.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int]
     L.orbx_debug_octree.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, ip]
     L.orbx_debug_describe.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp]
     L.orbx_distance_batch.argtypes = [vp, vp, vp, C.c_int, vp]
@@ -137,6 +141,7 @@ class ORBextractor:
                  max_height=1080, max_batch=1):
         self._L = lib()
         self._h = C.c_void_p()
+        self._fmt = FMT_GRAY8
         cfg = _Config(int(nfeatures), float(scaleFactor), int(nlevels), int(iniThFAST), int(minThFAST), int(device),
                       int(max_width), int(max_height), int(max_batch))
         rc = self._L.orbx_create(C.byref(cfg), C.byref(self._h))
@@ -201,11 +206,13 @@ class ORBextractor:
         """Returns (monoIndex, keypoints, descriptors).  Empty image: (-1, empty, empty) like the reference."""
         if image is None or image.size == 0:
             return -1, np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8)
-        if image.dtype != np.uint8 or image.ndim != 2:
-            raise OrbxError(ORBX_E_INVALID, "image must be CV_8UC1 (the reference asserts image.type() == CV_8UC1)")
-        if image.strides[1] != 1:
+        bpp = {FMT_GRAY8: 1, FMT_RGB8: 3, FMT_BGR8: 3, FMT_RGBA8: 4, FMT_BGRA8: 4}[self._fmt]
+        if image.dtype != np.uint8 or (bpp == 1 and image.ndim != 2) or (bpp > 1 and (image.ndim != 3 or image.shape[2] != bpp)):
+            raise OrbxError(ORBX_E_INVALID, "image must be CV_8UC1 (the reference asserts image.type() == CV_8UC1), or "
+                                            "[H,W,3|4] after set_input_format")
+        if image.strides[1] != bpp or (bpp > 1 and image.strides[2] != 1):
             image = np.ascontiguousarray(image)
-        h, w = image.shape
+        h, w = image.shape[:2]
         kps = np.zeros(self.capacity, KP_DTYPE)
         desc = np.zeros((self.capacity, 32), np.uint8)
         n, mono = C.c_int(), C.c_int()
@@ -218,11 +225,12 @@ class ORBextractor:
         """frames: uint8 [B,H,W] (C-contiguous rows).  Returns (mono[B], n[B], kps[B,cap], desc[B,cap,32]).
         out = (kps, desc) lets the caller supply (e.g. page-locked) result arrays of shape [B,cap] / [B,cap,32]."""
         frames = np.asarray(frames)
-        if frames.dtype != np.uint8 or frames.ndim != 3:
-            raise OrbxError(ORBX_E_INVALID, "frames must be uint8 [B,H,W]")
-        if frames.strides[2] != 1:
+        bpp = {FMT_GRAY8: 1, FMT_RGB8: 3, FMT_BGR8: 3, FMT_RGBA8: 4, FMT_BGRA8: 4}[self._fmt]
+        if frames.dtype != np.uint8 or frames.ndim != (3 if bpp == 1 else 4) or (bpp > 1 and frames.shape[3] != bpp):
+            raise OrbxError(ORBX_E_INVALID, "frames must be uint8 [B,H,W] (or [B,H,W,3|4] after set_input_format)")
+        if frames.strides[2] != bpp or (bpp > 1 and frames.strides[3] != 1):
             frames = np.ascontiguousarray(frames)
-        B, h, w = frames.shape
+        B, h, w = frames.shape[:3]
         base, step = frames.ctypes.data, frames.strides[0]
         ptrs = (C.c_void_p * B)(*range(base, base + B * step, step)) if step > 0 else (C.c_void_p * B)(*[base] * B)
         if out is None:
@@ -248,6 +256,19 @@ class ORBextractor:
 
     def sync(self):
         self._check(self._L.orbx_sync(self._h))
+
+    def set_input_format(self, fmt: int, gray_shift: int = 15):
+        """FMT_GRAY8 (default) or FMT_RGB8 / FMT_BGR8 / FMT_RGBA8 / FMT_BGRA8: colour frames are converted on the device
+        (cv::cvtColor *2GRAY of UPSTREAM Tracking::GrabImageMonocular); gray_shift 15 = cv2 4.13 fixed point, 14 = older."""
+        self._check(self._L.orbx_set_input_format(self._h, int(fmt), int(gray_shift)))
+        self._fmt = int(fmt)
+
+    def debug_gray(self, src, fmt, gray_shift=15):
+        src = np.ascontiguousarray(src, np.uint8)
+        dst = np.zeros(src.shape[:2], np.uint8)
+        self._check(self._L.orbx_debug_gray(self._h, _p(src), src.shape[1], src.shape[0], src.strides[0], int(fmt), int(gray_shift),
+                                            _p(dst), dst.shape[1]))
+        return dst
 
     def set_stream(self, cuda_stream: int):
         """cuda_stream: raw cudaStream_t (e.g. torch.cuda.Stream().cuda_stream); 0 = the handle's own stream.  torch's

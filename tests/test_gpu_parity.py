@@ -311,6 +311,57 @@ def test_pinned_batch_graph_replay(oracle):
     e.close()
 
 
+def test_colour_input(ex, oracle):
+    """cvtColor(*2GRAY) on the device.  Conversion alone and colour frames through every entry point
+    must equal the oracle's gray conversion followed by the gray path."""
+    import torch
+    rng = np.random.default_rng(11)
+    for (w, h) in [(131, 97), (640, 480), (5, 3), (1021, 7)]:
+        c3 = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        c4 = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        for fmt in (orbx.FMT_RGB8, orbx.FMT_BGR8, orbx.FMT_RGBA8, orbx.FMT_BGRA8):
+            src = c3 if fmt < orbx.FMT_RGBA8 else c4
+            for shift in (15, 14):
+                assert np.array_equal(ex.debug_gray(src, fmt, shift), oracle.gray(src, fmt, shift)), (w, h, fmt, shift)
+    # colour frames: a textured luminance pattern with per-channel offsets so that channel order matters
+    B, w, h, nf = 36, 640, 480, 1000
+    lum = np.stack([synth.textured_frame(400 + s, w, h) for s in range(B)]).astype(np.int16)
+    col = np.stack([np.clip(lum + 17, 0, 255), np.clip(lum - 9, 0, 255), np.clip(lum // 2 + 60, 0, 255)], axis=-1).astype(np.uint8)
+    e = orbx.ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=B)
+    o = oracle.Oracle(nf)
+    for fmt in (orbx.FMT_RGB8, orbx.FMT_BGR8):
+        e.set_input_format(fmt, 15)
+        gray = np.stack([oracle.gray(col[i], fmt, 15) for i in range(B)])
+        mono, n, kps, desc = e.extract_batch(col)                          # pageable, pipelined ranges
+        for i in (0, 17, 35):
+            k_o, d_o, m_o = o.extract(gray[i])
+            assert n[i] == len(k_o) and mono[i] == m_o and np.array_equal(desc[i, :n[i]], d_o), (fmt, i)
+            assert np.array_equal(kps[i, :n[i]]["angle"], k_o["angle"])
+        assert_same_extraction(e(col[3]), o.extract(gray[3]), "single colour frame")
+        # page-locked buffers (graph replay on the third call) and device-resident colour frames
+        pin = torch.from_numpy(col).pin_memory()
+        for rep in range(3):
+            mono2, n2, kps2, desc2 = e.extract_batch(pin.numpy())
+            assert np.array_equal(n2, n) and np.array_equal(desc2, desc), (fmt, rep)
+        cap = e.capacity
+        d_in = torch.from_numpy(col).cuda()
+        d_kp = torch.zeros((B, cap, 7), dtype=torch.float32, device="cuda")
+        d_desc = torch.zeros((B, cap, 32), dtype=torch.uint8, device="cuda")
+        d_n = torch.zeros(B, dtype=torch.int32, device="cuda")
+        d_mono = torch.zeros(B, dtype=torch.int32, device="cuda")
+        e.extract_batch_device(d_in.data_ptr(), w * h * 3, B, w, h, w * 3, d_kp.data_ptr(), d_desc.data_ptr(), cap, d_n.data_ptr(), d_mono.data_ptr())
+        e.sync()
+        dn = d_n.cpu().numpy()
+        assert np.array_equal(dn, n)
+        dd = d_desc.cpu().numpy()
+        for i in range(B):
+            assert np.array_equal(dd[i, :n[i]], desc[i, :n[i]]), (fmt, i)
+    # back to gray on the same handle
+    e.set_input_format(orbx.FMT_GRAY8)
+    assert_same_extraction(e(gray[0]), o.extract(gray[0]), "gray after colour")
+    e.close()
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # matching
 # ---------------------------------------------------------------------------------------------------------------------

@@ -143,3 +143,27 @@ def test_brief_against_cv2_orb(oracle):
     mine = np.stack([oracle.brief(bl, k.pt[0], k.pt[1], k.angle) for k in kps2])
     diff = int(np.unpackbits(mine ^ desc).sum())
     assert diff <= 1e-3 * desc.size * 8, diff
+
+
+def test_oracle_gray_matches_cv2_and_pins(oracle):
+    """cv::cvtColor(*2GRAY) restatement (SURVEY.md §8f-1): bit-identical to cv2 where it is importable; SHA pins (made in the
+    build container from the cv2-verified output) travel to machines without it."""
+    rng = np.random.default_rng(2024)
+    img = rng.integers(0, 256, (97, 131, 3), dtype=np.uint8)
+    img4 = rng.integers(0, 256, (97, 131, 4), dtype=np.uint8)
+    pins = {1: ("e7335b921ef03000", "b352c2ddaf675db7"), 2: ("da27676cd09f3c3f", "0ed6f66dacaa68de"),
+            3: ("0d491f1097b7e592", "b41cea11e9741c38"), 4: ("02a4fe3fc4cd48dc", "1c4bd514d10ed9f9")}
+    try:
+        import cv2
+        codes = {1: cv2.COLOR_RGB2GRAY, 2: cv2.COLOR_BGR2GRAY, 3: cv2.COLOR_RGBA2GRAY, 4: cv2.COLOR_BGRA2GRAY}
+    except ImportError:
+        cv2, codes = None, {}
+    for fmt in (1, 2, 3, 4):
+        src = img if fmt < 3 else img4
+        g15, g14 = oracle.gray(src, fmt, 15), oracle.gray(src, fmt, 14)
+        assert sha(g15)[:16] == pins[fmt][0] and sha(g14)[:16] == pins[fmt][1], fmt
+        if cv2 is not None:
+            assert np.array_equal(g15, cv2.cvtColor(src, codes[fmt])), fmt
+    # the two fixed-point forms differ on a fraction of a percent of the pixels (SURVEY.md §8f-1)
+    frac = float((oracle.gray(img, 1, 15) != oracle.gray(img, 1, 14)).mean())
+    assert 0 < frac < 0.01
