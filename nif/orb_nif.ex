@@ -19,6 +19,9 @@ defmodule SendSlam.OrbNif do
 
   def extract(_handle, _gray_binary, _width, _height), do: :erlang.nif_error(:nif_not_loaded)
 
+  @doc "format: 1 = RGB, 2 = BGR (an `Evision.Mat` from `Evision.VideoCapture.read/1`), 3 = RGBA, 4 = BGRA; gray conversion on the GPU"
+  def extract_color(_handle, _pixels_binary, _width, _height, _format), do: :erlang.nif_error(:nif_not_loaded)
+
   def match_windowed(_handle, _q_desc, _q_uvr, _q_levels, _t_kp, _t_desc, _bounds),
     do: :erlang.nif_error(:nif_not_loaded)
 end

@@ -87,6 +87,34 @@ static ERL_NIF_TERM nif_extract(ErlNifEnv *env, int argc, const ERL_NIF_TERM arg
                             enif_make_sub_binary(env, desc_term, 0, (size_t)n * ORBX_DESC_BYTES));
 }
 
+/* extract_color(handle, pixels_binary, width, height, format) with format = 1 RGB | 2 BGR | 3 RGBA | 4 BGRA (ORBX_FMT_*): the
+ * Evision.Mat of camera_producer.ex (BGR) goes in as it is; cvtColor runs on the device (include/orbx.h, orbx_set_input_format).
+ * Same result tuple as extract/4. */
+static ERL_NIF_TERM nif_extract_color(ErlNifEnv *env, int argc, const ERL_NIF_TERM argv[]) {
+    nif_handle *nh;
+    ErlNifBinary img;
+    int w, h, fmt;
+    if (argc != 5 || !enif_get_resource(env, argv[0], g_handle_type, (void **)&nh) || !enif_inspect_binary(env, argv[1], &img) ||
+        !enif_get_int(env, argv[2], &w) || !enif_get_int(env, argv[3], &h) || !enif_get_int(env, argv[4], &fmt))
+        return enif_make_badarg(env);
+    if (!nh->h) return mk_error(env, "closed");
+    if (fmt < ORBX_FMT_RGB8 || fmt > ORBX_FMT_BGRA8) return enif_make_badarg(env);
+    const int bpp = fmt >= ORBX_FMT_RGBA8 ? 4 : 3;
+    if (w < 1 || h < 1 || (size_t)w * (size_t)h * (size_t)bpp != img.size) return mk_error(env, "size_mismatch");
+    ERL_NIF_TERM kp_term, desc_term;
+    unsigned char *kp = enif_make_new_binary(env, (size_t)nh->cap * sizeof(orbx_keypoint), &kp_term);
+    unsigned char *desc = enif_make_new_binary(env, (size_t)nh->cap * ORBX_DESC_BYTES, &desc_term);
+    if (!kp || !desc) return mk_error(env, "enomem");
+    int n = 0, mono = -1;
+    int rc = orbx_set_input_format(nh->h, fmt, ORBX_GRAY_Q15);
+    if (rc == ORBX_OK) rc = orbx_extract(nh->h, img.data, w, h, w * bpp, 0, 1000, (orbx_keypoint *)kp, desc, nh->cap, &n, &mono);
+    orbx_set_input_format(nh->h, ORBX_FMT_GRAY8, ORBX_GRAY_Q15);
+    if (rc != ORBX_OK) return mk_error(env, code_atom(rc));
+    return enif_make_tuple5(env, enif_make_atom(env, "ok"), enif_make_int(env, n), enif_make_int(env, mono),
+                            enif_make_sub_binary(env, kp_term, 0, (size_t)n * sizeof(orbx_keypoint)),
+                            enif_make_sub_binary(env, desc_term, 0, (size_t)n * ORBX_DESC_BYTES));
+}
+
 /* match_windowed(handle, q_desc, q_uvr, q_levels, t_kp, t_desc, {minx, miny, maxx, maxy}) -> {:ok, best_idx, best_dist, second_idx, second_dist} (int32 binaries) */
 static ERL_NIF_TERM nif_match_windowed(ErlNifEnv *env, int argc, const ERL_NIF_TERM argv[]) {
     nif_handle *nh;
@@ -122,6 +150,7 @@ static int on_load(ErlNifEnv *env, void **priv, ERL_NIF_TERM info) {
 static ErlNifFunc nif_funcs[] = {
     {"create", 8, nif_create, ERL_NIF_DIRTY_JOB_IO_BOUND},
     {"extract", 4, nif_extract, ERL_NIF_DIRTY_JOB_IO_BOUND},
+    {"extract_color", 5, nif_extract_color, ERL_NIF_DIRTY_JOB_IO_BOUND},
     {"match_windowed", 7, nif_match_windowed, ERL_NIF_DIRTY_JOB_IO_BOUND},
 };
 

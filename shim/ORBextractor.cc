@@ -34,11 +34,20 @@ ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int
 
 ORBextractor::~ORBextractor() { orbx_destroy(mHandle); }
 
+bool ORBextractor::SetInputFormat(int orbx_fmt, int gray_shift) {
+    if (!mHandle || orbx_set_input_format(mHandle, orbx_fmt, gray_shift) != ORBX_OK) return false;
+    mInputFormat = orbx_fmt;
+    return true;
+}
+
 int ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*_mask*/, std::vector<cv::KeyPoint> &_keypoints,
                              cv::OutputArray _descriptors, std::vector<int> &vLappingArea) {
     if (_image.empty() || !mHandle) return -1;
     cv::Mat image = _image.getMat();
-    if (image.type() != CV_8UC1) return -1;             // upstream: assert(image.type() == CV_8UC1)
+    // upstream: assert(image.type() == CV_8UC1).  Extension: after SetInputFormat(ORBX_FMT_RGB8 ...) the colour
+    // Mat that Tracking::GrabImageMonocular would have run through cv::cvtColor is accepted as it is.
+    const int want = mInputFormat == ORBX_FMT_GRAY8 ? CV_8UC1 : mInputFormat >= ORBX_FMT_RGBA8 ? CV_8UC4 : CV_8UC3;
+    if (image.type() != want) return -1;
     const int lap0 = vLappingArea.size() > 0 ? vLappingArea[0] : 0, lap1 = vLappingArea.size() > 1 ? vLappingArea[1] : 0;
     _keypoints.resize((size_t)mCap);
     int n = 0, mono = -1;

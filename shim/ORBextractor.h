@@ -32,6 +32,9 @@ public:
     int operator()(cv::InputArray _image, cv::InputArray _mask, std::vector<cv::KeyPoint> &_keypoints,
                    cv::OutputArray _descriptors, std::vector<int> &vLappingArea);
 
+    // not in upstream: colour frames converted on the device (cv::cvtColor *2GRAY of Tracking::GrabImageMonocular)
+    bool SetInputFormat(int orbx_fmt, int gray_shift = ORBX_GRAY_Q15);
+
     int inline GetLevels() { return nlevels; }
     float inline GetScaleFactor() { return (float)scaleFactor; }
     std::vector<float> inline GetScaleFactors() { return mvScaleFactor; }
@@ -53,6 +56,7 @@ protected:
     std::vector<float> mvScaleFactor, mvInvScaleFactor, mvLevelSigma2, mvInvLevelSigma2;
 
 private:
+    int mInputFormat = ORBX_FMT_GRAY8;
     orbx_handle *mHandle = nullptr;      // one CUDA stream + workspace; single-flight like the reference's call pattern
     std::vector<unsigned char> mDesc;    // staging for descriptors (cap x 32)
     int mCap = 0;

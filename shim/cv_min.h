@@ -7,6 +7,8 @@
 #include <vector>
 #define CV_8U 0
 #define CV_8UC1 0
+#define CV_8UC3 16
+#define CV_8UC4 24
 namespace cv {
 struct Point2f { float x, y; };
 struct KeyPoint { Point2f pt; float size, angle, response; int octave, class_id; };
