@@ -33,7 +33,7 @@ public:
                    cv::OutputArray _descriptors, std::vector<int> &vLappingArea);
 
     // not in upstream: colour frames converted on the device (cv::cvtColor *2GRAY of Tracking::GrabImageMonocular)
-    bool SetInputFormat(int orbx_fmt, int gray_shift = ORBX_GRAY_Q15);
+    bool SetInputFormat(int orbx_fmt, int gray_shift = 15 /* ORBX_GRAY_Q15 */);
 
     int inline GetLevels() { return nlevels; }
     float inline GetScaleFactor() { return (float)scaleFactor; }
@@ -56,7 +56,7 @@ protected:
     std::vector<float> mvScaleFactor, mvInvScaleFactor, mvLevelSigma2, mvInvLevelSigma2;
 
 private:
-    int mInputFormat = ORBX_FMT_GRAY8;
+    int mInputFormat = 0;                // ORBX_FMT_GRAY8
     orbx_handle *mHandle = nullptr;      // one CUDA stream + workspace; single-flight like the reference's call pattern
     std::vector<unsigned char> mDesc;    // staging for descriptors (cap x 32)
     int mCap = 0;
