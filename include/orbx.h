@@ -179,6 +179,32 @@ int orbx_knn2_query_device(orbx_db *db, const uint8_t *d_queries, int nq, unsign
  * orbx_knn2_query_device output) into d_packed_out[nq*2]; all pointers in HBM on the db's device. */
 int orbx_knn2_merge_device(orbx_db *db, const unsigned long long *d_partials, int nparts, int nq,
                            unsigned long long *d_packed_out);
+/* ---- Frame post-extraction steps ---------------------------------------------------------------------------
+ * What UPSTREAM ORB-SLAM3 src/Frame.cc runs between ORBextractor::operator() and the matchers, on the device:
+ *   Frame::UndistortKeyPoints   = cv::undistortPoints(pts, pts, K, mDistCoef, cv::Mat(), K)  (5 iterations, double precision)
+ *   Frame::ComputeImageBounds   = the same for the four image corners
+ *   Frame::AssignFeaturesToGrid = Frame::PosInGrid on the FRAME_GRID_COLS x FRAME_GRID_ROWS = 64 x 48 grid
+ * Camera = pinhole + radial-tangential, the values of the calibration message (orbslam3_mono_networked.cc:173-176:
+ * Camera1.fx fy cx cy k1 k2 p1 p2 [k3]).  k1 == 0 means "no distortion" exactly as upstream tests mDistCoef.at<float>(0). */
+typedef struct orbx_camera { float fx, fy, cx, cy, k1, k2, p1, p2, k3; } orbx_camera;
+#define ORBX_GRID_COLS 64
+#define ORBX_GRID_ROWS 48
+#define ORBX_GRID_CELLS (ORBX_GRID_COLS * ORBX_GRID_ROWS)
+/* cv::undistortPoints on n (x, y) pairs (host buffers). */
+int orbx_undistort_points(orbx_handle *h, const float *xy, int n, const orbx_camera *cam, float *xy_out);
+/* bounds4_out = mnMinX, mnMinY, mnMaxX, mnMaxY of Frame::ComputeImageBounds for a width x height image. */
+int orbx_image_bounds(orbx_handle *h, const orbx_camera *cam, int width, int height, float *bounds4_out);
+/* One frame, host buffers: kp_un_out[n] = keypoints with undistorted pt (mvKeysUn); cell_start_out[ORBX_GRID_CELLS + 1] and
+ * cell_items_out[n] = mGrid as CSR, cell = posX * ORBX_GRID_ROWS + posY, items of a cell in push_back (index) order;
+ * cell_start_out[ORBX_GRID_CELLS] = number of keypoints inside the grid. */
+int orbx_frame_grid(orbx_handle *h, const orbx_keypoint *kp, int n, const orbx_camera *cam, const float *bounds4,
+                    orbx_keypoint *kp_un_out, int32_t *cell_start_out, int32_t *cell_items_out);
+/* The same for the device-resident results of orbx_extract_batch_device: d_kp [batch][cap], d_n [batch] ->
+ * d_kp_un [batch][cap], d_cell_start [batch][ORBX_GRID_CELLS + 1], d_cell_items [batch][cap].  Asynchronous on the handle's stream. */
+int orbx_frame_grid_batch_device(orbx_handle *h, const orbx_keypoint *d_kp, const int *d_n, int batch, int cap,
+                                 const orbx_camera *cam, const float *bounds4, orbx_keypoint *d_kp_un, int32_t *d_cell_start,
+                                 int32_t *d_cell_items);
+
 /* Distance backend of a shard: ORBX_KNN_TENSOR (default) = descriptors expanded to {-1,+1} int8, q.d = 256 - 2H on
  * tcgen05.mma kind::i8 with the top-2 taken from TMEM; ORBX_KNN_POPC = XOR + POPC on the CUDA cores.  Identical results. */
 #define ORBX_KNN_POPC 0

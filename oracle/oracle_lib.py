@@ -65,6 +65,9 @@ def lib():
         L.orb_oracle_knn2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_int]
         L.orb_oracle_match_windowed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                                 C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orb_oracle_undistort_points.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.orb_oracle_image_bounds.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.orb_oracle_frame_grid.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -255,3 +258,36 @@ def match_windowed(qdesc, quvr, qlevels, tkp, tdesc, bounds):
     lib().orb_oracle_match_windowed(_p(qdesc), _p(quvr), _p(qlevels), nq, _p(tkp), _p(tdesc), len(tkp), _p(bounds),
                                     _p(out[0]), _p(out[1]), _p(out[2]), _p(out[3]))
     return tuple(out)  # best_idx, best_dist, second_idx, second_dist
+
+
+def _cam(cam) -> np.ndarray:
+    c = np.zeros(9, np.float32)
+    c[:len(cam)] = np.asarray(cam, np.float32)
+    return c
+
+
+def undistort_points(xy: np.ndarray, cam) -> np.ndarray:
+    """cv::undistortPoints(xy, K, D, P=K) restatement; cam = (fx, fy, cx, cy, k1, k2, p1, p2[, k3])."""
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    out = np.zeros_like(xy)
+    c = _cam(cam)
+    lib().orb_oracle_undistort_points(_p(xy), len(xy), _p(c), _p(out))
+    return out
+
+
+def image_bounds(cam, w: int, h: int) -> np.ndarray:
+    b = np.zeros(4, np.float32)
+    c = _cam(cam)
+    lib().orb_oracle_image_bounds(_p(c), int(w), int(h), _p(b))
+    return b
+
+
+def frame_grid(kps: np.ndarray, cam, bounds):
+    """Frame::UndistortKeyPoints + AssignFeaturesToGrid.  Returns (kps_un, cell_start[3073], cell_items[inside])."""
+    kps = np.ascontiguousarray(kps)
+    un = np.zeros_like(kps)
+    start = np.zeros(64 * 48 + 1, np.int32)
+    items = np.zeros(max(len(kps), 1), np.int32)
+    c, b = _cam(cam), np.ascontiguousarray(bounds, np.float32)
+    lib().orb_oracle_frame_grid(_p(kps), len(kps), _p(c), _p(b), _p(un), _p(start), _p(items))
+    return un, start, items[:start[-1]]

@@ -820,6 +820,70 @@ int orb_oracle_knn2(const u8 *q, int nq, const u8 *db, long ndb, int32_t *idx, i
     return 0;
 }
 
+/* ---- Frame post-extraction steps (UPSTREAM ORB-SLAM3 src/Frame.cc, not under /root/reference) ------------------
+ * cv::undistortPoints(src, dst, K, D, noArray(), K) as Frame::UndistortKeyPoints calls it: cvUndistortPointsInternal with
+ * criteria = (MAX_ITER, 5), no tilt, R = I, P = K; all arithmetic in double, results stored as float.  cam = fx fy cx cy k1 k2 p1
+ * p2 k3 (the calibration values of slam_backends/orb_slam_3/orbslam3_mono_networked.cc:173-176).  Pinned against
+ * cv2.undistortPoints in tests/test_oracle_golden.py (agreement to float rounding; OpenCV's own build may contract FMAs). */
+static void undistort_point(float u_in, float v_in, const float *cam, float *xo, float *yo) {
+    const double fx = cam[0], fy = cam[1], cx = cam[2], cy = cam[3];
+    const double k0 = cam[4], k1 = cam[5], k2 = cam[6], k3 = cam[7], k4 = cam[8];
+    const double ifx = 1.0 / fx, ify = 1.0 / fy;
+    const double u = u_in, v = v_in;
+    double x = (u - cx) * ifx, y = (v - cy) * ify;
+    const double x0 = x, y0 = y;
+    for (int j = 0; j < 5; j++) {
+        const double r2 = x * x + y * y;
+        const double icdist = (1 + ((0.0 * r2 + 0.0) * r2 + 0.0) * r2) / (1 + ((k4 * r2 + k1) * r2 + k0) * r2);
+        if (icdist < 0) { x = (u - cx) * ifx; y = (v - cy) * ify; break; }
+        const double deltaX = 2 * k2 * x * y + k3 * (r2 + 2 * x * x) + 0.0 * r2 + 0.0 * r2 * r2;
+        const double deltaY = k2 * (r2 + 2 * y * y) + 2 * k3 * x * y + 0.0 * r2 + 0.0 * r2 * r2;
+        x = (x0 - deltaX) * icdist;
+        y = (y0 - deltaY) * icdist;
+    }
+    const double xx = fx * x + 0.0 * y + cx, yy = 0.0 * x + fy * y + cy, ww = 1.0 / (0.0 * x + 0.0 * y + 1.0);
+    *xo = (float)(xx * ww); *yo = (float)(yy * ww);
+}
+
+int orb_oracle_undistort_points(const float *xy, int n, const float *cam, float *out) {
+    for (int i = 0; i < n; i++) undistort_point(xy[2 * i], xy[2 * i + 1], cam, &out[2 * i], &out[2 * i + 1]);
+    return 0;
+}
+
+/* Frame::ComputeImageBounds: mnMinX, mnMinY, mnMaxX, mnMaxY */
+int orb_oracle_image_bounds(const float *cam, int w, int h, float *b) {
+    if (cam[4] == 0.f) { b[0] = 0.f; b[1] = 0.f; b[2] = (float)w; b[3] = (float)h; return 0; }
+    const float c[8] = {0.f, 0.f, (float)w, 0.f, 0.f, (float)h, (float)w, (float)h};
+    float un[8];
+    orb_oracle_undistort_points(c, 4, cam, un);
+    b[0] = un[0] < un[4] ? un[0] : un[4]; b[2] = un[2] > un[6] ? un[2] : un[6];
+    b[1] = un[1] < un[3] ? un[1] : un[3]; b[3] = un[5] > un[7] ? un[5] : un[7];
+    return 0;
+}
+
+/* Frame::UndistortKeyPoints + Frame::AssignFeaturesToGrid (PosInGrid, 64 x 48): kp_un = keypoints with undistorted pt,
+ * mGrid as CSR: cell = posX * 48 + posY, cell_start[3073], items in push_back order. */
+int orb_oracle_frame_grid(const oracle_kp *kp, int n, const float *cam, const float *bounds, oracle_kp *kp_un,
+                          int32_t *cell_start, int32_t *cell_items) {
+    const float minX = bounds[0], minY = bounds[1], maxX = bounds[2], maxY = bounds[3];
+    const float invW = 64.f / (maxX - minX), invH = 48.f / (maxY - minY);
+    int *cell_of = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+    memset(cell_start, 0, sizeof(int32_t) * (64 * 48 + 1));
+    for (int i = 0; i < n; i++) {
+        kp_un[i] = kp[i];
+        if (cam[4] != 0.f) undistort_point(kp[i].x, kp[i].y, cam, &kp_un[i].x, &kp_un[i].y);
+        const int px = (int)roundf((kp_un[i].x - minX) * invW), py = (int)roundf((kp_un[i].y - minY) * invH);
+        if (px < 0 || px >= 64 || py < 0 || py >= 48) { cell_of[i] = -1; continue; }
+        cell_of[i] = px * 48 + py; cell_start[cell_of[i] + 1]++;
+    }
+    for (int c = 0; c < 64 * 48; c++) cell_start[c + 1] += cell_start[c];
+    int *fill = (int *)malloc(sizeof(int) * 64 * 48);
+    for (int c = 0; c < 64 * 48; c++) fill[c] = cell_start[c];
+    for (int i = 0; i < n; i++) if (cell_of[i] >= 0) cell_items[fill[cell_of[i]]++] = i;
+    free(cell_of); free(fill);
+    return 0;
+}
+
 /* Frame::PosInGrid + Frame::GetFeaturesInArea + best / second-best DescriptorDistance.
  * train keypoints: oracle_kp records (x, y, octave used).  query q: desc + (u, v, r, minLevel, maxLevel).
  * bounds = {minX, minY, maxX, maxY} of the (undistorted) image.  Candidate visiting order = grid cell

@@ -983,6 +983,79 @@ int orbx_match_windowed(orbx_handle *h, const uint8_t *q_desc, const float *q_uv
                           second_idx, second_dist, h->err, h->launches);
 }
 
+// ---- Frame post-extraction steps (kernels in orbx_frame.cu) -----------------------------------------------------------------
+static_assert(sizeof(orbx_camera) == sizeof(CameraDev), "orbx_camera layout");
+static CameraDev to_dev(const orbx_camera *c) { CameraDev d; std::memcpy(&d, c, sizeof(d)); return d; }
+static bool camera_ok(const orbx_camera *c) { return c && c->fx != 0.f && c->fy != 0.f; }
+
+int orbx_undistort_points(orbx_handle *h, const float *xy, int n, const orbx_camera *cam, float *xy_out) {
+    if (!h) return ORBX_E_INVALID;
+    if (!xy || !xy_out || n < 0 || !camera_ok(cam)) return fail(h, ORBX_E_INVALID, "null argument / bad camera");
+    if (n == 0) return ORBX_OK;
+    CU_TRY(h, cudaSetDevice(h->device));
+    Scratch S;
+    float *d_in = S.get<float>((size_t)2 * n), *d_out = S.get<float>((size_t)2 * n);
+    if (!d_in || !d_out) return fail(h, ORBX_E_CUDA, "cudaMalloc failed");
+    CU_TRY(h, cudaMemcpyAsync(d_in, xy, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, h->stream));
+    h->launches += launch_undistort_xy(d_in, n, to_dev(cam), d_out, h->stream);
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaMemcpyAsync(xy_out, d_out, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return ORBX_OK;
+}
+
+int orbx_image_bounds(orbx_handle *h, const orbx_camera *cam, int width, int height, float *bounds4_out) {
+    if (!h) return ORBX_E_INVALID;
+    if (!bounds4_out || width < 1 || height < 1 || !camera_ok(cam)) return fail(h, ORBX_E_INVALID, "null argument / bad camera");
+    if (cam->k1 == 0.f) {   // Frame::ComputeImageBounds: mDistCoef.at<float>(0) == 0.0
+        bounds4_out[0] = 0.f; bounds4_out[1] = 0.f; bounds4_out[2] = (float)width; bounds4_out[3] = (float)height;
+        return ORBX_OK;
+    }
+    const float corners[8] = {0.f, 0.f, (float)width, 0.f, 0.f, (float)height, (float)width, (float)height};
+    float un[8];
+    const int rc = orbx_undistort_points(h, corners, 4, cam, un);
+    if (rc) return rc;
+    bounds4_out[0] = std::min(un[0], un[4]); bounds4_out[2] = std::max(un[2], un[6]);     // mnMinX, mnMaxX
+    bounds4_out[1] = std::min(un[1], un[3]); bounds4_out[3] = std::max(un[5], un[7]);     // mnMinY, mnMaxY
+    return ORBX_OK;
+}
+
+int orbx_frame_grid_batch_device(orbx_handle *h, const orbx_keypoint *d_kp, const int *d_n, int batch, int cap, const orbx_camera *cam,
+                                 const float *bounds4, orbx_keypoint *d_kp_un, int32_t *d_cell_start, int32_t *d_cell_items) {
+    if (!h) return ORBX_E_INVALID;
+    if (!d_kp || !d_n || !bounds4 || !d_kp_un || !d_cell_start || !d_cell_items || batch < 1 || cap < 1 || !camera_ok(cam))
+        return fail(h, ORBX_E_INVALID, "null argument / bad camera");
+    if (!(bounds4[2] > bounds4[0]) || !(bounds4[3] > bounds4[1])) return fail(h, ORBX_E_INVALID, "empty image bounds");
+    CU_TRY(h, cudaSetDevice(h->device));
+    h->launches += launch_frame_grid(reinterpret_cast<const KeypointRec *>(d_kp), d_n, 0, batch, cap, to_dev(cam), bounds4,
+                                     reinterpret_cast<KeypointRec *>(d_kp_un), d_cell_start, d_cell_items, h->stream);
+    CU_TRY(h, cudaGetLastError());
+    return ORBX_OK;
+}
+
+int orbx_frame_grid(orbx_handle *h, const orbx_keypoint *kp, int n, const orbx_camera *cam, const float *bounds4, orbx_keypoint *kp_un_out,
+                    int32_t *cell_start_out, int32_t *cell_items_out) {
+    if (!h) return ORBX_E_INVALID;
+    if ((!kp && n > 0) || n < 0 || !bounds4 || (!kp_un_out && n > 0) || !cell_start_out || (!cell_items_out && n > 0) || !camera_ok(cam))
+        return fail(h, ORBX_E_INVALID, "null argument / bad camera");
+    if (!(bounds4[2] > bounds4[0]) || !(bounds4[3] > bounds4[1])) return fail(h, ORBX_E_INVALID, "empty image bounds");
+    CU_TRY(h, cudaSetDevice(h->device));
+    Scratch S;
+    const int cap = std::max(n, 1);
+    KeypointRec *d_kp = S.get<KeypointRec>(cap), *d_un = S.get<KeypointRec>(cap);
+    int32_t *d_start = S.get<int32_t>(ORBX_GRID_CELLS + 1), *d_items = S.get<int32_t>(cap);
+    if (!d_kp || !d_un || !d_start || !d_items) return fail(h, ORBX_E_CUDA, "cudaMalloc failed");
+    if (n > 0) CU_TRY(h, cudaMemcpyAsync(d_kp, kp, sizeof(KeypointRec) * n, cudaMemcpyHostToDevice, h->stream));
+    h->launches += launch_frame_grid(d_kp, nullptr, n, 1, cap, to_dev(cam), bounds4, d_un, d_start, d_items, h->stream);
+    CU_TRY(h, cudaGetLastError());
+    if (n > 0) CU_TRY(h, cudaMemcpyAsync(kp_un_out, d_un, sizeof(KeypointRec) * n, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(cell_start_out, d_start, sizeof(int32_t) * (ORBX_GRID_CELLS + 1), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    const int inside = cell_start_out[ORBX_GRID_CELLS];
+    if (inside > 0) CU_TRY(h, cudaMemcpy(cell_items_out, d_items, sizeof(int32_t) * inside, cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+}
+
 // ---- plan inspection without a GPU (used by the CPU-only tests) --------------------------------------------------
 // Fills level sizes, cell counts, quotas and candidate capacities of the plan for (params, w, h); returns nlevels or < 0.
 int orbx_plan_probe(int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th, int width, int height,

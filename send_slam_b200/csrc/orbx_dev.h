@@ -63,6 +63,12 @@ int launch_finalize(const LevelDev *d_levels, int nlevels, int f0, int batch, in
                     KeypointRec *d_kp, int cap, int *d_slot, int *d_n, int *d_mono, int *d_overflow, cudaStream_t stream);
 int launch_describe(const LevelDev *d_levels, int nlevels, int f0, int batch, int total_out_cap, const int *d_slot,
                     KeypointRec *d_kp, uint8_t *d_desc, int cap, cudaStream_t stream);
+// Frame post-extraction steps (orbx_frame.cu): cv::undistortPoints of Frame::UndistortKeyPoints and the 64 x 48 feature grid
+constexpr int kGridCols = 64, kGridRows = 48;
+struct CameraDev { float fx, fy, cx, cy, k1, k2, p1, p2, k3; };   // == orbx_camera
+int launch_undistort_xy(const float *d_xy, int n, const CameraDev &cam, float *d_out, cudaStream_t stream);
+int launch_frame_grid(const KeypointRec *d_kp, const int *d_n, int n_one, int batch, int cap, const CameraDev &cam, const float *bounds4,
+                      KeypointRec *d_kp_un, int32_t *d_cell_start, int32_t *d_cell_items, cudaStream_t stream);
 // stand-alone stage launchers for the debug / parity entry points
 int launch_describe_points(const uint8_t *d_img, const uint8_t *d_blur, int pitch, const float *d_xy, int n,
                            const float *d_angle_in, float *d_angle_out, uint8_t *d_desc, cudaStream_t stream);

@@ -46,6 +46,7 @@ EXPORTS = [
     "orbx_knn2_query_device", "orbx_knn2_merge_device", "orbx_knn2_sync", "orbx_knn2_launch_count", "orbx_plan_probe",
     "orbx_version", "orbx_set_profiling", "orbx_get_stage_times", "orbx_set_stream",
     "orbx_knn2_set_stream", "orbx_knn2_set_backend", "orbx_set_input_format", "orbx_debug_gray",
+    "orbx_undistort_points", "orbx_image_bounds", "orbx_frame_grid", "orbx_frame_grid_batch_device",
 ]
 
 _lib = None
@@ -83,6 +84,10 @@ def lib():
     L.orbx_debug_resize.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int]
     L.orbx_debug_blur.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int]
     L.orbx_set_input_format.argtypes = [vp, C.c_int, C.c_int]
+    L.orbx_undistort_points.argtypes = [vp, vp, C.c_int, vp, vp]
+    L.orbx_image_bounds.argtypes = [vp, vp, C.c_int, C.c_int, vp]
+    L.orbx_frame_grid.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp]
+    L.orbx_frame_grid_batch_device.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp]
     L.orbx_debug_gray.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int]
     L.orbx_debug_octree.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, ip]
     L.orbx_debug_describe.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp]
@@ -262,6 +267,45 @@ class ORBextractor:
         (cv::cvtColor *2GRAY of UPSTREAM Tracking::GrabImageMonocular); gray_shift 15 = cv2 4.13 fixed point, 14 = older."""
         self._check(self._L.orbx_set_input_format(self._h, int(fmt), int(gray_shift)))
         self._fmt = int(fmt)
+
+    # -- Frame post-extraction steps (Frame::UndistortKeyPoints / ComputeImageBounds / AssignFeaturesToGrid)
+    GRID_COLS, GRID_ROWS = 64, 48
+
+    @staticmethod
+    def _camera(cam):
+        """(fx, fy, cx, cy, k1, k2, p1, p2[, k3]) -> orbx_camera"""
+        c = np.zeros(9, np.float32)
+        c[:len(cam)] = np.asarray(cam, np.float32)
+        return c
+
+    def undistort_points(self, xy, cam):
+        xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+        out = np.zeros_like(xy)
+        c = self._camera(cam)
+        self._check(self._L.orbx_undistort_points(self._h, _p(xy), len(xy), _p(c), _p(out)))
+        return out
+
+    def image_bounds(self, cam, width, height):
+        b = np.zeros(4, np.float32)
+        c = self._camera(cam)
+        self._check(self._L.orbx_image_bounds(self._h, _p(c), int(width), int(height), _p(b)))
+        return b
+
+    def frame_grid(self, kps, cam, bounds):
+        """Returns (mvKeysUn, cell_start[3073], cell_items): the feature grid as CSR, cell = posX * 48 + posY."""
+        kps = np.ascontiguousarray(kps, KP_DTYPE)
+        un = np.zeros_like(kps)
+        start = np.zeros(self.GRID_COLS * self.GRID_ROWS + 1, np.int32)
+        items = np.zeros(max(len(kps), 1), np.int32)
+        c, b = self._camera(cam), np.ascontiguousarray(bounds, np.float32)
+        self._check(self._L.orbx_frame_grid(self._h, _p(kps), len(kps), _p(c), _p(b), _p(un), _p(start), _p(items)))
+        return un, start, items[:start[-1]]
+
+    def frame_grid_batch_device(self, d_kp_ptr, d_n_ptr, batch, cap, cam, bounds, d_kp_un_ptr, d_cell_start_ptr, d_cell_items_ptr):
+        c, b = self._camera(cam), np.ascontiguousarray(bounds, np.float32)
+        self._check(self._L.orbx_frame_grid_batch_device(self._h, C.c_void_p(d_kp_ptr), C.c_void_p(d_n_ptr), int(batch), int(cap), _p(c),
+                                                         _p(b), C.c_void_p(d_kp_un_ptr), C.c_void_p(d_cell_start_ptr),
+                                                         C.c_void_p(d_cell_items_ptr)))
 
     def debug_gray(self, src, fmt, gray_shift=15):
         src = np.ascontiguousarray(src, np.uint8)

@@ -362,6 +362,54 @@ def test_colour_input(ex, oracle):
     e.close()
 
 
+def test_frame_undistort_and_grid(ex, oracle):
+    """SURVEY.md §8f-2: Frame::UndistortKeyPoints / ComputeImageBounds / AssignFeaturesToGrid on the device, bit-exact against
+    the oracle (which equals cv2.undistortPoints bit for bit, tests/test_oracle_golden.py)."""
+    import torch
+    cams = [((458.654, 457.296, 367.215, 248.375, -0.28340811, 0.07395907, 0.00019359, 1.76187114e-05, 0.0), (752, 480)),
+            ((520.9, 521.0, 325.1, 249.7, 0.2624, -0.9531, -0.0054, 0.0026, 1.1633), (640, 480)),
+            ((500.0, 500.0, 320.0, 240.0, 0.0, 0.0, 0.0, 0.0, 0.0), (640, 480))]          # no distortion: copy
+    rng = np.random.default_rng(6)
+    for cam, (w, h) in cams:
+        xy = np.stack([rng.uniform(-5, w + 5, 7001), rng.uniform(-5, h + 5, 7001)], 1).astype(np.float32)
+        assert np.array_equal(ex.undistort_points(xy, cam), oracle.undistort_points(xy, cam)), cam
+        b = ex.image_bounds(cam, w, h)
+        assert np.array_equal(b, oracle.image_bounds(cam, w, h)), cam
+        nf = 1200
+        o = oracle.Oracle(nf)
+        frames = np.stack([synth.textured_frame(600 + s, w, h, "textured" if s != 2 else "sparse") for s in range(4)])
+        e = orbx.ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=4)
+        for i in range(4):
+            mono, kps, desc = e(frames[i])
+            un, start, items = e.frame_grid(kps, cam, b)
+            un_o, start_o, items_o = oracle.frame_grid(kps, cam, b)
+            assert np.array_equal(un.view(np.int32), un_o.view(np.int32)), (cam, i)
+            assert np.array_equal(start, start_o) and np.array_equal(items, items_o), (cam, i)
+        un0, start0, items0 = e.frame_grid(kps[:0], cam, b)                                # empty frame
+        assert len(un0) == 0 and not start0.any() and len(items0) == 0
+        # device-resident batch: extraction results stay in HBM and feed the grid kernel directly
+        cap = e.capacity
+        d_in = torch.from_numpy(frames).cuda()
+        d_kp = torch.zeros((4, cap, 7), dtype=torch.float32, device="cuda")
+        d_desc = torch.zeros((4, cap, 32), dtype=torch.uint8, device="cuda")
+        d_n = torch.zeros(4, dtype=torch.int32, device="cuda")
+        d_mono = torch.zeros(4, dtype=torch.int32, device="cuda")
+        d_un = torch.zeros_like(d_kp)
+        d_start = torch.zeros((4, 64 * 48 + 1), dtype=torch.int32, device="cuda")
+        d_items = torch.zeros((4, cap), dtype=torch.int32, device="cuda")
+        e.extract_batch_device(d_in.data_ptr(), w * h, 4, w, h, w, d_kp.data_ptr(), d_desc.data_ptr(), cap, d_n.data_ptr(), d_mono.data_ptr())
+        e.frame_grid_batch_device(d_kp.data_ptr(), d_n.data_ptr(), 4, cap, cam, b, d_un.data_ptr(), d_start.data_ptr(), d_items.data_ptr())
+        e.sync()
+        n = d_n.cpu().numpy()
+        for i in range(4):
+            kps_i = d_kp[i, :n[i]].cpu().numpy().view(orbx.KP_DTYPE).reshape(-1)
+            un_o, start_o, items_o = oracle.frame_grid(kps_i, cam, b)
+            assert np.array_equal(d_un[i, :n[i]].cpu().numpy().view(np.int32).reshape(-1), un_o.view(np.int32).reshape(-1)), (cam, i)
+            assert np.array_equal(d_start[i].cpu().numpy(), start_o), (cam, i)
+            assert np.array_equal(d_items[i, :start_o[-1]].cpu().numpy(), items_o), (cam, i)
+        e.close()
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # matching
 # ---------------------------------------------------------------------------------------------------------------------

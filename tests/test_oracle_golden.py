@@ -167,3 +167,49 @@ def test_oracle_gray_matches_cv2_and_pins(oracle):
     # the two fixed-point forms differ on a fraction of a percent of the pixels
     frac = float((oracle.gray(img, 1, 15) != oracle.gray(img, 1, 14)).mean())
     assert 0 < frac < 0.01
+
+
+UNDISTORT_PINS = ['b72560e635450f41', '2df5dc6e0f1f241a', '0a789e7802a91ad2']
+CAMERAS = [((458.654, 457.296, 367.215, 248.375, -0.28340811, 0.07395907, 0.00019359, 1.76187114e-05, 0.0), (752, 480)),   # EuRoC cam0
+           ((520.9, 521.0, 325.1, 249.7, 0.2624, -0.9531, -0.0054, 0.0026, 1.1633), (640, 480)),                           # TUM fr1-like, k3 != 0
+           ((900.0, 905.0, 640.0, 360.0, -0.12, 0.05, 0.001, -0.0007, 0.0), (1280, 720))]
+
+
+def test_oracle_undistort_matches_cv2_and_pins(oracle):
+    """Frame::UndistortKeyPoints = cv::undistortPoints(K, D, P=K) (SURVEY.md §8f-2): the restatement equals cv2 bit for bit
+    where cv2 is importable; SHA pins of the verified output travel."""
+    try:
+        import cv2
+    except ImportError:
+        cv2 = None
+    rng = np.random.default_rng(5)
+    shas = []
+    for cam, (w, h) in CAMERAS:
+        xy = np.stack([rng.uniform(0, w, 5000), rng.uniform(0, h, 5000)], 1).astype(np.float32)
+        got = oracle.undistort_points(xy, cam)
+        shas.append(sha(got)[:16])
+        if cv2 is not None:
+            K = np.array([[cam[0], 0, cam[2]], [0, cam[1], cam[3]], [0, 0, 1]], np.float32)
+            ref = cv2.undistortPoints(xy.reshape(-1, 1, 2), K, np.array(cam[4:9], np.float32), None, K).reshape(-1, 2)
+            assert np.array_equal(got, ref), cam
+        b = oracle.image_bounds(cam, w, h)
+        assert b[0] < b[2] and b[1] < b[3]
+    assert shas == UNDISTORT_PINS, shas
+    # no distortion: bounds are the image, keypoints are copied
+    assert np.array_equal(oracle.image_bounds((500, 500, 320, 240, 0, 0, 0, 0), 640, 480), np.array([0, 0, 640, 480], np.float32))
+
+
+def test_oracle_frame_grid_properties(oracle):
+    cam, (w, h) = CAMERAS[0]
+    o = oracle.Oracle(1200)
+    kps, desc, mono = o.extract(synth.textured_frame(3, w, h))
+    b = oracle.image_bounds(cam, w, h)
+    un, start, items = oracle.frame_grid(kps, cam, b)
+    assert len(un) == len(kps) and start[0] == 0 and start[-1] == len(items) <= len(kps)
+    assert np.array_equal(un["x"], oracle.undistort_points(np.stack([kps["x"], kps["y"]], 1), cam)[:, 0])
+    invw, invh = np.float32(64) / (b[2] - b[0]), np.float32(48) / (b[3] - b[1])
+    for c in np.nonzero(np.diff(start))[0][:200]:
+        seg = items[start[c]:start[c + 1]]
+        assert np.all(np.diff(seg) > 0)                                          # push_back order
+        px = np.floor((un["x"][seg] - b[0]) * invw + np.float32(0.5)).astype(int)  # round() for non-negative arguments
+        assert np.all(px == c // 48)
