@@ -680,20 +680,29 @@ int orbx_extract_batch(orbx_handle *h, const uint8_t *const *frames, int batch, 
             // of one range overlaps the machine-filling kernels of the next.
             CU_TRY(h, cudaEventRecord(h->ev_start, h->stream));
             CU_TRY(h, cudaStreamWaitEvent(h->h2d_stream, h->ev_start, 0));
-            const int nchunks = (batch + chunk - 1) / chunk, ncs = std::min(h->ncs, nchunks);
+            // each uploaded range is computed as `sub` sub-ranges on different streams (same reason as in the device-resident path)
+            static const int sub_env = [] { const char *e = getenv("ORBX_SUB"); return e ? atoi(e) : 0; }();
+            const int nchunks = (batch + chunk - 1) / chunk;
+            int sub = sub_env > 0 ? sub_env : 1;   // measured: 2 or 4 sub-ranges do not help here (0.86 -> 0.91 / 0.96 ms), the upload paces the flow
+            while (sub > 1 && (chunk / sub < 8 || nchunks * sub > orbx_handle::kMaxChunks)) sub--;
+            const int ncs = std::min(h->ncs, nchunks * sub);
             for (int i = 0; i < ncs; i++) CU_TRY(h, cudaStreamWaitEvent(h->cs[i], h->ev_start, 0));
-            int k = 0;
+            int k = 0, r = 0;
             for (int f0 = 0; f0 < batch; f0 += chunk, k++) {
                 const int n = std::min(chunk, batch - f0);
-                cudaStream_t cs = h->cs[k % ncs];
                 if (cpu_stage) stage_in(f0, n);
                 if ((rc2 = copy_in(f0, n, h->h2d_stream))) return rc2;
                 CU_TRY(h, cudaEventRecord(h->ev_in[k], h->h2d_stream));
-                CU_TRY(h, cudaStreamWaitEvent(cs, h->ev_in[k], 0));
-                if ((rc2 = run_pipeline(h, f0, n, lap0, lap1, h->d_kp, h->d_desc, kc, h->d_n, h->d_mono, cs, nullptr, nullptr, nullptr, color))) return rc2;
-                CU_TRY(h, cudaEventRecord(h->ev_done[k], cs));
-                CU_TRY(h, cudaStreamWaitEvent(h->d2h_stream, h->ev_done[k], 0));
-                if ((rc2 = download(f0, n, h->d2h_stream))) return rc2;
+                const int per = (n + sub - 1) / sub;
+                for (int g0 = f0; g0 < f0 + n; g0 += per, r++) {
+                    const int m = std::min(per, f0 + n - g0);
+                    cudaStream_t cs = h->cs[r % ncs];
+                    CU_TRY(h, cudaStreamWaitEvent(cs, h->ev_in[k], 0));
+                    if ((rc2 = run_pipeline(h, g0, m, lap0, lap1, h->d_kp, h->d_desc, kc, h->d_n, h->d_mono, cs, nullptr, nullptr, nullptr, color))) return rc2;
+                    CU_TRY(h, cudaEventRecord(h->ev_done[r], cs));
+                    CU_TRY(h, cudaStreamWaitEvent(h->d2h_stream, h->ev_done[r], 0));
+                    if ((rc2 = download(g0, m, h->d2h_stream))) return rc2;
+                }
             }
             CU_TRY(h, cudaEventRecord(h->ev_end, h->d2h_stream));
             CU_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_end, 0));
