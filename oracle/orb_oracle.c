@@ -15,7 +15,9 @@
  * PIN STATUS: the reference holds no golden vector, known-answer test or fixture for this path
  * (send_slam/test/send_slam_test.exs:5-7 is its only test).  What pins this file instead:
  *   - resize / FAST+NMS / GaussianBlur / fastAtan2 / BFMatcher: bit-compared with the real OpenCV code via cv2
- *     4.13 (oracle/orb_cv2.py; tests/test_oracle_vs_cv2.py; fixtures under tests/golden/).
+ *     4.13 (oracle/orb_cv2.py; tests/test_oracle_golden.py; fixtures under tests/golden/ made by tests/golden/make_golden.py).
+ *   - cvtColor *2GRAY and cv::undistortPoints (the SURVEY.md 8f rows): bit-compared with cv2 4.13 in
+ *     tests/test_oracle_golden.py, SHA pins of the verified outputs committed there.
  *   - steered BRIEF: bit-compared with cv2.ORB_create().compute() on the same keypoints/angles.
  *   - cell grid, DistributeOctTree, output ordering: "parity unpinned" -- restated from the published
  *     ORB-SLAM3 v1.0 algorithm; cross-checked only against the independent Python
