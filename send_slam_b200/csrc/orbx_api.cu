@@ -344,7 +344,7 @@ static int run_pipeline(orbx_handle *h, int f0, int batch, int lap0, int lap1, K
     // which has the highest priority so that its few CTAs are placed first, while the Gaussian pass fills the rest of
     // the machine from the main stream.  The fork comes after FAST because two machine-filling kernels gain nothing
     // from running side by side.
-    if (!fork) h->launches += launch_blur(h->d_levels, h->d_tiles, h->ntiles, f0, batch, stream);
+    if (!fork) h->launches += launch_blur(h->h_levels, h->d_tiles, h->ntiles, f0, batch, stream);
     STAGE_MARK(2);
     h->launches += launch_fast(h->d_levels, h->h_levels, h->d_cells, (int)pl.cells.size(), f0, batch, h->P.ini_th, h->P.min_th, h->d_overflow, stream, &h->ftma, h->sm_count);
     STAGE_MARK(3);
@@ -355,14 +355,14 @@ static int run_pipeline(orbx_handle *h, int f0, int batch, int lap0, int lap1, K
     }
     h->launches += launch_octree(h->d_levels, h->h_levels, nl, f0, batch, h->d_overflow, qs);
     STAGE_MARK(4);
-    h->launches += launch_finalize(h->d_levels, nl, f0, batch, pl.total_out_cap, lap0, lap1, d_kp, cap, h->d_slot, d_n, d_mono, h->d_overflow, qs);
+    h->launches += launch_finalize(h->h_levels, nl, f0, batch, pl.total_out_cap, lap0, lap1, d_kp, cap, h->d_slot, d_n, d_mono, h->d_overflow, qs);
     STAGE_MARK(5);
     if (fork) {
         CU_TRY(h, cudaEventRecord(ev_join, side));
-        h->launches += launch_blur(h->d_levels, h->d_tiles, h->ntiles, f0, batch, stream);
+        h->launches += launch_blur(h->h_levels, h->d_tiles, h->ntiles, f0, batch, stream);
         CU_TRY(h, cudaStreamWaitEvent(stream, ev_join, 0));
     }
-    h->launches += launch_describe(h->d_levels, nl, f0, batch, pl.total_out_cap, h->d_slot, d_kp, d_desc, cap, stream);
+    h->launches += launch_describe(h->h_levels, nl, f0, batch, pl.total_out_cap, h->d_slot, d_kp, d_desc, cap, stream);
     STAGE_MARK(6);
 #undef STAGE_MARK
     if (stream == h->stream) h->ev_valid = prof;
@@ -843,7 +843,7 @@ int orbx_debug_resize(orbx_handle *h, const uint8_t *src, int sw, int sh, int ss
     build_resize_taps(dw, sw, true, xt);
     build_resize_taps(dh, sh, false, yt);
     ResizeTap *d_xt = S.get<ResizeTap>(dw), *d_yt = S.get<ResizeTap>(dh);
-    LevelDev lv[2]; std::memset(lv, 0, sizeof(lv));
+    LevelDev lv[kMaxLevels]; std::memset(lv, 0, sizeof(lv));
     LevelDev *d_lv = S.get<LevelDev>(2);
     if (!d_src || !d_dst || !d_xt || !d_yt || !d_lv) return fail(h, ORBX_E_CUDA, "cudaMalloc failed");
     lv[0].img = d_src; lv[0].w = sw; lv[0].h = sh; lv[0].pitch = sp; lv[0].img_fstride = (size_t)sp * sh;
@@ -868,7 +868,7 @@ int orbx_debug_resize(orbx_handle *h, const uint8_t *src, int sw, int sh, int ss
     CU_TRY(h, cudaMemcpy2D(d_src, sp, src, sstride, sw, sh, cudaMemcpyHostToDevice));
     CU_TRY(h, cudaMemcpy(d_xt, xt.data(), sizeof(ResizeTap) * dw, cudaMemcpyHostToDevice));
     CU_TRY(h, cudaMemcpy(d_yt, yt.data(), sizeof(ResizeTap) * dh, cudaMemcpyHostToDevice));
-    CU_TRY(h, cudaMemcpy(d_lv, lv, sizeof(lv), cudaMemcpyHostToDevice));
+    CU_TRY(h, cudaMemcpy(d_lv, lv, 2 * sizeof(LevelDev), cudaMemcpyHostToDevice));
     CU_TRY(h, cudaStreamSynchronize(cudaStreamLegacy));   // blocking pageable uploads may still be in DMA; h->stream is non-blocking
     h->launches += launch_resize(d_lv, lv, 1, 0, 1, h->stream);
     CU_TRY(h, cudaGetLastError());
@@ -886,7 +886,8 @@ int orbx_debug_blur(orbx_handle *h, const uint8_t *src, int w, int ht, int sstri
     std::vector<BlurTile> tiles;
     for (int ty = 0; ty * kBlurTileH < ht; ty++) for (int tx = 0; tx * kBlurTileW < w; tx++) tiles.push_back(BlurTile{0, (int16_t)tx, (int16_t)ty, 0});
     BlurTile *d_t = S.get<BlurTile>(tiles.size());
-    LevelDev lv; std::memset(&lv, 0, sizeof(lv));
+    LevelDev lvs[kMaxLevels]; std::memset(lvs, 0, sizeof(lvs));
+    LevelDev &lv = lvs[0];
     LevelDev *d_lv = S.get<LevelDev>(1);
     if (!d_src || !d_dst || !d_t || !d_lv) return fail(h, ORBX_E_CUDA, "cudaMalloc failed");
     lv.img = d_src; lv.blur = d_dst; lv.w = w; lv.h = ht; lv.pitch = p; lv.blur_pitch = p; lv.img_fstride = lv.blur_fstride = (size_t)p * ht;
@@ -894,7 +895,7 @@ int orbx_debug_blur(orbx_handle *h, const uint8_t *src, int w, int ht, int sstri
     CU_TRY(h, cudaMemcpy(d_t, tiles.data(), sizeof(BlurTile) * tiles.size(), cudaMemcpyHostToDevice));
     CU_TRY(h, cudaMemcpy(d_lv, &lv, sizeof(lv), cudaMemcpyHostToDevice));
     CU_TRY(h, cudaStreamSynchronize(cudaStreamLegacy));   // blocking pageable uploads may still be in DMA; h->stream is non-blocking
-    h->launches += launch_blur(d_lv, d_t, (int)tiles.size(), 0, 1, h->stream);
+    h->launches += launch_blur(lvs, d_t, (int)tiles.size(), 0, 1, h->stream);
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     CU_TRY(h, cudaMemcpy2D(dst, dstride, d_dst, p, w, ht, cudaMemcpyDeviceToHost));
@@ -943,7 +944,8 @@ int orbx_debug_octree(orbx_handle *h, const float *keys, int n, int minX, int ma
     const LevelPlan &LP = pl.lv[0];
     if (LP.ncols <= 0 || LP.nrows <= 0) { *n_out = 0; return ORBX_OK; }
     Scratch S;
-    LevelDev D; std::memset(&D, 0, sizeof(D));
+    LevelDev Ds[kMaxLevels]; std::memset(Ds, 0, sizeof(Ds));
+    LevelDev &D = Ds[0];
     uint32_t *t0 = S.get<uint32_t>(LP.xbin.size()), *t1 = S.get<uint32_t>(LP.ybin.size()), *t2 = S.get<uint32_t>(LP.xord.size()), *t3 = S.get<uint32_t>(LP.yord.size());
     const int ccap = std::max(n, 1);
     uint32_t *d_cand = S.get<uint32_t>(ccap), *d_sorted = S.get<uint32_t>(ccap), *d_cur = S.get<uint32_t>(std::max(LP.nbins, 1)), *d_sel = S.get<uint32_t>(LP.out_cap);
@@ -976,7 +978,7 @@ int orbx_debug_octree(orbx_handle *h, const float *keys, int n, int minX, int ma
     D.cand = d_cand; D.sorted = d_sorted; D.bin_cursor = d_cur; D.cand_cap = ccap; D.cand_count = d_cnt; D.sel = d_sel; D.sel_count = d_cnt + 1;
     CU_TRY(h, cudaMemcpy(d_lv, &D, sizeof(D), cudaMemcpyHostToDevice));
     CU_TRY(h, cudaStreamSynchronize(cudaStreamLegacy));   // blocking pageable uploads may still be in DMA; h->stream is non-blocking
-    h->launches += launch_octree(d_lv, &D, 1, 0, 1, d_cnt + 2, h->stream);
+    h->launches += launch_octree(d_lv, Ds, 1, 0, 1, d_cnt + 2, h->stream);
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     CU_TRY(h, cudaMemcpy(counts, d_cnt, sizeof(counts), cudaMemcpyDeviceToHost));

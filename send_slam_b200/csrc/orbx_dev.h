@@ -41,11 +41,12 @@ struct KeypointRec {           // == orbx_keypoint == cv::KeyPoint
 };
 
 // launch wrappers (orbx_kernels.cu); all asynchronous on `stream`, return the number of kernel launches issued.
-// They process frames [f0, f0 + batch) of the workspace.
+// They process frames [f0, f0 + batch) of the workspace.  h_levels = HOST copy of the level table (kMaxLevels entries): it is
+// passed to the kernels by value in the parameter bank; d_levels (device copy) is kept for the signatures that predate that.
 int launch_gray(const uint8_t *d_src, size_t src_fstride, int src_pitch, int format, int shift, uint8_t *d_dst, size_t dst_fstride,
                 int dst_pitch, int w, int h, int f0, int batch, cudaStream_t stream);
 int launch_resize(const LevelDev *d_levels, const LevelDev *h_levels, int level, int f0, int batch, cudaStream_t stream);
-int launch_blur(const LevelDev *d_levels, const BlurTile *d_tiles, int ntiles, int f0, int batch, cudaStream_t stream);
+int launch_blur(const LevelDev *h_levels, const BlurTile *d_tiles, int ntiles, int f0, int batch, cudaStream_t stream);
 // Tensor maps of the level planes for the TMA-staged FAST kernel (host side: orbx_api.cu builds them; 128 bytes each,
 // stored opaquely so that this header does not need <cuda.h>).
 struct FastTma {
@@ -59,9 +60,9 @@ int launch_fast(const LevelDev *d_levels, const LevelDev *h_levels, const CellRe
                 int ini_th, int min_th, int *d_overflow, cudaStream_t stream, const FastTma *tma, int sm_count);
 int launch_octree(const LevelDev *d_levels, const LevelDev *h_levels, int nlevels, int f0, int batch, int *d_overflow,
                   cudaStream_t stream);
-int launch_finalize(const LevelDev *d_levels, int nlevels, int f0, int batch, int total_out_cap, int lap0, int lap1,
+int launch_finalize(const LevelDev *h_levels, int nlevels, int f0, int batch, int total_out_cap, int lap0, int lap1,
                     KeypointRec *d_kp, int cap, int *d_slot, int *d_n, int *d_mono, int *d_overflow, cudaStream_t stream);
-int launch_describe(const LevelDev *d_levels, int nlevels, int f0, int batch, int total_out_cap, const int *d_slot,
+int launch_describe(const LevelDev *h_levels, int nlevels, int f0, int batch, int total_out_cap, const int *d_slot,
                     KeypointRec *d_kp, uint8_t *d_desc, int cap, cudaStream_t stream);
 // Frame post-extraction steps (orbx_frame.cu): cv::undistortPoints of Frame::UndistortKeyPoints and the 64 x 48 feature grid
 constexpr int kGridCols = 64, kGridRows = 48;

@@ -20,6 +20,14 @@
 
 namespace orbx {
 
+// The level table travels in the kernel parameter bank (constant memory), so that no kernel starts with dependent global loads.
+struct LevelTable { LevelDev lv[kMaxLevels]; };
+static LevelTable make_table(const LevelDev *h_levels) {
+    LevelTable t;
+    memcpy(t.lv, h_levels, sizeof(t.lv));
+    return t;
+}
+
 __device__ int8_t g_pattern[1024];
 __constant__ int c_umax[16];
 
@@ -92,7 +100,8 @@ int launch_gray(const uint8_t *d_src, size_t src_fstride, int src_pitch, int for
 //     neighbouring source bytes) and one IDP.2A (s0*c0 + s1*c1) per source row.
 //     k_resize_generic: byte-wise fallback for source planes that are not 4-byte aligned (caller-owned level 0).
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_resize_generic(const LevelDev *__restrict__ lv, int level, int f0) {
+__global__ void __launch_bounds__(128) k_resize_generic(const __grid_constant__ LevelTable T, int level, int f0) {
+    const LevelDev *lv = T.lv;   // level table in the kernel parameter (constant) bank: no dependent global loads
     const LevelDev &D = lv[level];
     const LevelDev &S = lv[level - 1];
     const int dx0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -122,7 +131,8 @@ __global__ void __launch_bounds__(128) k_resize_generic(const LevelDev *__restri
 // the narrow upper levels too; all 6*RR source words of an item are requested before the first one is used (the kernel
 // is latency-bound otherwise: a level is a few MB).
 constexpr int RR = 4;
-__global__ void __launch_bounds__(128) k_resize(const LevelDev *__restrict__ lv, int level, int f0, int ngx, int nitems) {
+__global__ void __launch_bounds__(128) k_resize(const __grid_constant__ LevelTable T, int level, int f0, int ngx, int nitems) {
+    const LevelDev *lv = T.lv;   // level table in the kernel parameter (constant) bank: no dependent global loads
     const LevelDev &D = lv[level];
     const LevelDev &S = lv[level - 1];
     const int item = blockIdx.x * blockDim.x + threadIdx.x;
@@ -187,10 +197,10 @@ int launch_resize(const LevelDev *d_levels, const LevelDev *h_levels, int level,
     if (aligned) {
         const int ngx = (D.w + 3) / 4, nitems = ngx * ((D.h + RR - 1) / RR);
         dim3 grid((nitems + 127) / 128, batch);
-        k_resize<<<grid, 128, 0, stream>>>(d_levels, level, f0, ngx, nitems);
+        k_resize<<<grid, 128, 0, stream>>>(make_table(h_levels), level, f0, ngx, nitems);
     } else {
         dim3 grid((D.w + 4 * 128 - 1) / (4 * 128), D.h, batch);
-        k_resize_generic<<<grid, 128, 0, stream>>>(d_levels, level, f0);
+        k_resize_generic<<<grid, 128, 0, stream>>>(make_table(h_levels), level, f0);
     }
     return 1;
 }
@@ -216,7 +226,8 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return i >= n ? p - i : i;
 }
 
-__global__ void __launch_bounds__(256) k_blur(const LevelDev *__restrict__ lv, const BlurTile *__restrict__ tiles, int f0) {
+__global__ void __launch_bounds__(256) k_blur(const __grid_constant__ LevelTable T, const BlurTile *__restrict__ tiles, int f0) {
+    const LevelDev *lv = T.lv;   // level table in the kernel parameter (constant) bank: no dependent global loads
     __shared__ __align__(16) uint8_t s_in[BROWS * BIN_PITCH];
     __shared__ __align__(16) uint32_t s_h[(BROWS / 2) * BTW];   // [row pair][column]: H(2p, c) | H(2p+1, c) << 16
     const BlurTile t = tiles[blockIdx.x];
@@ -315,10 +326,10 @@ __global__ void __launch_bounds__(256) k_blur(const LevelDev *__restrict__ lv, c
     }
 }
 
-int launch_blur(const LevelDev *d_levels, const BlurTile *d_tiles, int ntiles, int f0, int batch, cudaStream_t stream) {
+int launch_blur(const LevelDev *h_levels, const BlurTile *d_tiles, int ntiles, int f0, int batch, cudaStream_t stream) {
     if (ntiles <= 0) return 0;
     dim3 grid(ntiles, batch);
-    k_blur<<<grid, 256, 0, stream>>>(d_levels, d_tiles, f0);
+    k_blur<<<grid, 256, 0, stream>>>(make_table(h_levels), d_tiles, f0);
     return 1;
 }
 
@@ -422,8 +433,9 @@ __device__ __forceinline__ void fast_item(const uint8_t *p, int pitch, uint32_t 
     sa = fast_score4<M>(wa); sb = fast_score4<M>(wb);
 }
 
-__global__ void __launch_bounds__(192) k_fast_cells(const LevelDev *__restrict__ lv, const CellRect *__restrict__ cells,
+__global__ void __launch_bounds__(192) k_fast_cells(const __grid_constant__ LevelTable T, const CellRect *__restrict__ cells,
                                                     int ini_th, int min_th, int f0, int *__restrict__ overflow) {
+    const LevelDev *lv = T.lv;   // level table in the kernel parameter (constant) bank: no dependent global loads
     __shared__ __align__(16) uint8_t s_roi[FT_ROWS * FT_PITCH];
     __shared__ __align__(16) uint8_t s_sc[(FT_ROWS - 4) * FS_PITCH];   // interior scores with a 1-px zero ring
     __shared__ uint32_t s_list[36 * 36 + 8];
@@ -755,7 +767,7 @@ int launch_fast(const LevelDev *d_levels, const LevelDev *h_levels, const CellRe
         return 1;
     }
     dim3 grid(ncells, batch);
-    k_fast_cells<<<grid, 192, 0, stream>>>(d_levels, d_cells, ini_th, min_th, f0, d_overflow);
+    k_fast_cells<<<grid, 192, 0, stream>>>(make_table(h_levels), d_cells, ini_th, min_th, f0, d_overflow);
     return 1;
 }
 
@@ -850,8 +862,9 @@ __device__ void split_node(const LevelDev &L, const QNode &p, const int *bin_sta
     }
 }
 
-__global__ void __launch_bounds__(OT_THREADS) k_octree(const LevelDev *__restrict__ lv, int nlevels, int cap_nodes,
+__global__ void __launch_bounds__(OT_THREADS) k_octree(const __grid_constant__ LevelTable T, int nlevels, int cap_nodes,
                                                        int f0, int *__restrict__ overflow) {
+    const LevelDev *lv = T.lv;   // level table in the kernel parameter (constant) bank: no dependent global loads
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int level = blockIdx.x, f = f0 + blockIdx.y;
     const LevelDev &L = lv[level];
@@ -1119,7 +1132,7 @@ int launch_octree(const LevelDev *d_levels, const LevelDev *h_levels, int nlevel
         configured = smem;
     }
     dim3 grid(nlevels, batch);
-    k_octree<<<grid, OT_THREADS, smem, stream>>>(d_levels, nlevels, cap, f0, d_overflow);
+    k_octree<<<grid, OT_THREADS, smem, stream>>>(make_table(h_levels), nlevels, cap, f0, d_overflow);
     return 1;
 }
 
@@ -1127,9 +1140,10 @@ int launch_octree(const LevelDev *d_levels, const LevelDev *h_levels, int nlevel
 // K7  output slots.  One CTA per frame: walks levels 0..L-1 in list order, scales to image coordinates and assigns
 //     the reference's slot (lapping-area keypoints fill from the back, the rest from the front).
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_finalize(const LevelDev *__restrict__ lv, int nlevels, int total_out_cap, int lap0,
+__global__ void __launch_bounds__(256) k_finalize(const __grid_constant__ LevelTable T, int nlevels, int total_out_cap, int lap0,
                                                   int lap1, KeypointRec *__restrict__ kp, int cap, int *__restrict__ slot,
                                                   int *__restrict__ n_out, int *__restrict__ mono_out, int f0, int *__restrict__ overflow) {
+    const LevelDev *lv = T.lv;   // level table in the kernel parameter (constant) bank: no dependent global loads
     const int f = f0 + blockIdx.x, tid = threadIdx.x;
     __shared__ int s_cnt[kMaxLevels + 1];
     __shared__ int s_warp[8];
@@ -1179,9 +1193,9 @@ __global__ void __launch_bounds__(256) k_finalize(const LevelDev *__restrict__ l
     if (tid == 0) { n_out[f] = ntot; mono_out[f] = ntot - s_run; }
 }
 
-int launch_finalize(const LevelDev *d_levels, int nlevels, int f0, int batch, int total_out_cap, int lap0, int lap1,
+int launch_finalize(const LevelDev *h_levels, int nlevels, int f0, int batch, int total_out_cap, int lap0, int lap1,
                     KeypointRec *d_kp, int cap, int *d_slot, int *d_n, int *d_mono, int *d_overflow, cudaStream_t stream) {
-    k_finalize<<<batch, 256, 0, stream>>>(d_levels, nlevels, total_out_cap, lap0, lap1, d_kp, cap, d_slot, d_n, d_mono, f0, d_overflow);
+    k_finalize<<<batch, 256, 0, stream>>>(make_table(h_levels), nlevels, total_out_cap, lap0, lap1, d_kp, cap, d_slot, d_n, d_mono, f0, d_overflow);
     return 1;
 }
 
@@ -1266,9 +1280,10 @@ __device__ __forceinline__ uint8_t warp_brief_byte(const uint8_t *__restrict__ c
 // the fp64 sincos of the steering angle are evaluated once per keypoint in separate lanes (the fp64 pipe is narrow;
 // evaluating them warp-wide per keypoint made this kernel DP-bound) and then broadcast for the 256 tests.
 constexpr int DG = 1;   // measured: 8 slots per warp is slower (87 -> 107 us): the kernel is bound by the scattered BRIEF gathers, not by fp64
-__global__ void __launch_bounds__(256) k_describe(const LevelDev *__restrict__ lv, int nlevels, int total_out_cap,
+__global__ void __launch_bounds__(256) k_describe(const __grid_constant__ LevelTable T, int nlevels, int total_out_cap,
                                                   const int *__restrict__ slot, KeypointRec *__restrict__ kp,
                                                   uint8_t *__restrict__ desc, int cap, int f0) {
+    const LevelDev *lv = T.lv;   // level table in the kernel parameter (constant) bank: no dependent global loads
     const int f = f0 + blockIdx.y, lane = threadIdx.x & 31;
     const int item0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * DG;
     if (item0 >= total_out_cap) return;
@@ -1308,10 +1323,10 @@ __global__ void __launch_bounds__(256) k_describe(const LevelDev *__restrict__ l
     }
 }
 
-int launch_describe(const LevelDev *d_levels, int nlevels, int f0, int batch, int total_out_cap, const int *d_slot,
+int launch_describe(const LevelDev *h_levels, int nlevels, int f0, int batch, int total_out_cap, const int *d_slot,
                     KeypointRec *d_kp, uint8_t *d_desc, int cap, cudaStream_t stream) {
     dim3 grid((total_out_cap + 8 * DG - 1) / (8 * DG), batch);
-    k_describe<<<grid, 256, 0, stream>>>(d_levels, nlevels, total_out_cap, d_slot, d_kp, d_desc, cap, f0);
+    k_describe<<<grid, 256, 0, stream>>>(make_table(h_levels), nlevels, total_out_cap, d_slot, d_kp, d_desc, cap, f0);
     return 1;
 }
 
