@@ -239,6 +239,7 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ LevelTable
     // stage rows y0-3 .. y0+58, columns x0-4 .. x0+75 (20 words per row): aligned word loads where the word lies inside
     // the image, per-byte BORDER_REFLECT_101 elsewhere.  1240 words, 5 per thread, all requested before the first store.
     const bool word_ok = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)pitch) & 3) == 0;
+    const bool big = w >= 96 && h >= 96;   // staged indices reach < 80 past an edge (partial last tiles)
     {
         constexpr int NW = BROWS * (BIN_PITCH / 4), PER = (NW + 255) / 256;
         uint32_t v[PER];
@@ -250,6 +251,18 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ LevelTable
                 const int gy = y0 - 3 + r, gx = x0 - 4 + 4 * wc;
                 if (word_ok && gx >= 0 && gx + 3 < w && gy >= 0 && gy < h) {
                     v[k] = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)gy * pitch + gx));
+                } else if (big) {
+                    // one reflection keeps every staged index in range for images >= 96 px (border tiles
+                    // execute this for a few words per warp; the general path costs an integer division per byte)
+                    const int ry = gy < 0 ? -gy : (gy >= h ? 2 * h - 2 - gy : gy);
+                    const uint8_t *row = src + (size_t)ry * pitch;
+                    uint32_t acc = 0;
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const int x = gx + b, rx = x < 0 ? -x : (x >= w ? 2 * w - 2 - x : x);
+                        acc |= (uint32_t)row[rx] << (8 * b);
+                    }
+                    v[k] = acc;
                 } else {
                     const uint8_t *row = src + (size_t)reflect101(gy, h) * pitch;
                     v[k] = (uint32_t)row[reflect101(gx, w)] | ((uint32_t)row[reflect101(gx + 1, w)] << 8) |
