@@ -206,7 +206,7 @@ static int ensure_plan(orbx_handle *h, int w, int ht, int batch) {
     for (int l = 0; l < nl; l++) {
         const LevelPlan &LP = pl.lv[l];
         LevelDev &D = h->h_levels[l];
-        D.w = LP.w; D.h = LP.h; D.pitch = LP.pitch; D.blur_pitch = LP.pitch;
+        D.w = LP.w; D.h = LP.h; D.pitch = LP.pitch; D.blur_pitch = LP.pitch; D.padded = 1;
         D.img_fstride = LP.plane_bytes; D.blur_fstride = LP.plane_bytes;
         CU_TRY(h, dev_alloc(h, &D.img, LP.plane_bytes * B + 64));
         CU_TRY(h, dev_alloc(h, &D.blur, LP.plane_bytes * B + 64));
@@ -259,6 +259,7 @@ static int set_level0(orbx_handle *h, const uint8_t *img, int pitch, size_t fstr
     LevelDev &D = h->h_levels[0];
     if (D.img == img && D.pitch == pitch && D.img_fstride == fstride) return ORBX_OK;
     D.img = const_cast<uint8_t *>(img); D.pitch = pitch; D.img_fstride = fstride;
+    D.padded = img == h->l0_own ? 1 : 0;
     encode_fast_map(h, 0);
     CU_TRY(h, cudaMemcpyAsync(h->d_levels, &h->h_levels[0], sizeof(LevelDev), cudaMemcpyHostToDevice, h->stream));
     return ORBX_OK;

@@ -14,6 +14,7 @@ struct LevelDev {
     size_t img_fstride;        // bytes between consecutive frames in img
     size_t blur_fstride;
     int w, h, pitch, blur_pitch;
+    int padded;                // img is a workspace plane with slack behind its rows (0 when level 0 aliases caller memory)
     const ResizeTap *xtap, *ytap;                   // taps from level l-1
     const uint32_t *xpack;                          // x taps as ofs << 16 | c1 (c0 = 2048 - c1), padded to 4; may be null
     const uint32_t *xbin, *ybin, *xord, *yord;      // quadtree / order LUTs, indexed by (x-16), (y-16)

@@ -131,6 +131,9 @@ __global__ void __launch_bounds__(128) k_resize_generic(const __grid_constant__ 
 // the narrow upper levels too; all 6*RR source words of an item are requested before the first one is used (the kernel
 // is latency-bound otherwise: a level is a few MB).
 constexpr int RR = 4;
+// PADDED: the source plane is one of the workspace's own (>= 16 bytes of slack behind every row it can be asked for), so the three
+// words of a row are read at constant offsets from one address; otherwise (level 0 aliasing caller memory) word offsets are clamped.
+template <bool PADDED>
 __global__ void __launch_bounds__(128) k_resize(const __grid_constant__ LevelTable T, int level, int f0, int ngx, int nitems) {
     const LevelDev *lv = T.lv;   // level table in the kernel parameter (constant) bank: no dependent global loads
     const LevelDev &D = lv[level];
@@ -156,9 +159,14 @@ __global__ void __launch_bounds__(128) k_resize(const __grid_constant__ LevelTab
 #pragma unroll
         for (int k = 0; k < 2; k++) {
             const uint8_t *row = sbase + (size_t)(k ? ty[rr].ofs1 : ty[rr].ofs) * spitch;
-            w[rr][k][0] = __ldg(reinterpret_cast<const uint32_t *>(row + o0));
-            w[rr][k][1] = __ldg(reinterpret_cast<const uint32_t *>(row + o1));
-            w[rr][k][2] = __ldg(reinterpret_cast<const uint32_t *>(row + o2));
+            if (PADDED) {
+                const uint32_t *q = reinterpret_cast<const uint32_t *>(row + o0);
+                w[rr][k][0] = __ldg(q); w[rr][k][1] = __ldg(q + 1); w[rr][k][2] = __ldg(q + 2);
+            } else {
+                w[rr][k][0] = __ldg(reinterpret_cast<const uint32_t *>(row + o0));
+                w[rr][k][1] = __ldg(reinterpret_cast<const uint32_t *>(row + o1));
+                w[rr][k][2] = __ldg(reinterpret_cast<const uint32_t *>(row + o2));
+            }
         }
     uint32_t sel[4], coef[4];
 #pragma unroll
@@ -197,7 +205,8 @@ int launch_resize(const LevelDev *d_levels, const LevelDev *h_levels, int level,
     if (aligned) {
         const int ngx = (D.w + 3) / 4, nitems = ngx * ((D.h + RR - 1) / RR);
         dim3 grid((nitems + 127) / 128, batch);
-        k_resize<<<grid, 128, 0, stream>>>(make_table(h_levels), level, f0, ngx, nitems);
+        if (S.padded) k_resize<true><<<grid, 128, 0, stream>>>(make_table(h_levels), level, f0, ngx, nitems);
+        else k_resize<false><<<grid, 128, 0, stream>>>(make_table(h_levels), level, f0, ngx, nitems);
     } else {
         dim3 grid((D.w + 4 * 128 - 1) / (4 * 128), D.h, batch);
         k_resize_generic<<<grid, 128, 0, stream>>>(make_table(h_levels), level, f0);
