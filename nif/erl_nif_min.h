@@ -29,6 +29,8 @@ ERL_NIF_TERM enif_make_tuple(ErlNifEnv *, unsigned, ...);
 unsigned char *enif_make_new_binary(ErlNifEnv *, size_t, ERL_NIF_TERM *);
 ERL_NIF_TERM enif_make_sub_binary(ErlNifEnv *, ERL_NIF_TERM, size_t, size_t);
 ErlNifResourceType *enif_open_resource_type(ErlNifEnv *, const char *, const char *, ErlNifResourceDtor *, ErlNifResourceFlags, ErlNifResourceFlags *);
+/* the function table ends with a {NULL} sentinel in mock mode so that nif/mock_host.c can walk it */
 #define ERL_NIF_INIT(MOD, FUNCS, LOAD, RELOAD, UPGRADE, UNLOAD) \
-    const ErlNifFunc *orbx_nif_funcs_for_check(void) { (void)LOAD; return FUNCS; }
+    const ErlNifFunc *orbx_nif_funcs_for_check(void) { return FUNCS; } \
+    int orbx_nif_mock_load(void) { return LOAD(NULL, NULL, 0); }
 #endif

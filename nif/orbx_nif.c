@@ -152,6 +152,9 @@ static ErlNifFunc nif_funcs[] = {
     {"extract", 4, nif_extract, ERL_NIF_DIRTY_JOB_IO_BOUND},
     {"extract_color", 5, nif_extract_color, ERL_NIF_DIRTY_JOB_IO_BOUND},
     {"match_windowed", 7, nif_match_windowed, ERL_NIF_DIRTY_JOB_IO_BOUND},
+#ifdef ORBX_NIF_MIN
+    {NULL, 0, NULL, 0},   /* sentinel for the mock host (nif/mock_host.c); the real ERL_NIF_INIT takes the array size */
+#endif
 };
 
 ERL_NIF_INIT(Elixir.SendSlam.OrbNif, nif_funcs, on_load, NULL, NULL, NULL)

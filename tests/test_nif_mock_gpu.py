@@ -1,0 +1,165 @@
+"""GPU: the erl_nif wrapper (nif/orbx_nif.c) loaded and CALLED through the mock BEAM host (nif/mock_host.c) -- SURVEY.md §8b
+seam b3 and the shape of BASELINE config 5: 8 concurrent 1280x720 camera streams, nFeatures 1250 (the reference's YAML value,
+orbslam3_mono_networked.cc:193), extraction + previous-frame windowed matching, each stream on its own NIF resource from its
+own thread (a dirty-scheduler call per frame in the BEAM; here ctypes drops the GIL for the duration of the call)."""
+import ctypes as C
+import os
+import shutil
+import subprocess
+import threading
+
+import numpy as np
+import pytest
+
+from send_slam_b200 import orbx, synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+T_INT, T_ATOM, T_BIN, T_TUPLE, T_RES, T_BADARG = 1, 3, 4, 5, 6, 7
+
+
+@pytest.fixture(scope="module")
+def nif(tmp_path_factory):
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    so = str(tmp_path_factory.mktemp("nif") / "orbx_nif_mock.so")
+    libdir = os.path.join(ROOT, "send_slam_b200")
+    subprocess.check_call(["gcc", "-std=c11", "-O1", "-Wall", "-Werror", "-DORBX_NIF_MIN", "-I", os.path.join(ROOT, "include"), "-I",
+                           os.path.join(ROOT, "nif"), "-shared", "-fPIC", os.path.join(ROOT, "nif", "orbx_nif.c"),
+                           os.path.join(ROOT, "nif", "mock_host.c"), "-L", libdir, "-lorbx", "-Wl,-rpath," + libdir, "-o", so])
+    L = C.CDLL(so)
+    ul = C.c_ulong
+    L.mock_int.restype = ul; L.mock_int.argtypes = [C.c_int]
+    L.mock_double.restype = ul; L.mock_double.argtypes = [C.c_double]
+    L.mock_binary.restype = ul; L.mock_binary.argtypes = [C.c_void_p, C.c_size_t]
+    L.mock_tuple4.restype = ul; L.mock_tuple4.argtypes = [ul, ul, ul, ul]
+    L.mock_resource_keep.restype = C.c_void_p; L.mock_resource_keep.argtypes = [ul]
+    L.mock_resource_term.restype = ul; L.mock_resource_term.argtypes = [C.c_void_p]
+    L.mock_resource_drop.argtypes = [C.c_void_p]
+    L.mock_call.restype = ul; L.mock_call.argtypes = [C.c_char_p, C.c_int, C.POINTER(ul)]
+    L.mock_kind.argtypes = [ul]; L.mock_get_int.restype = C.c_long; L.mock_get_int.argtypes = [ul]
+    L.mock_get_atom.restype = C.c_char_p; L.mock_get_atom.argtypes = [ul]
+    L.mock_tuple_arity.argtypes = [ul]; L.mock_tuple_elem.restype = ul; L.mock_tuple_elem.argtypes = [ul, C.c_int]
+    L.mock_bin_size.restype = C.c_size_t; L.mock_bin_size.argtypes = [ul]
+    L.mock_bin_data.restype = C.c_void_p; L.mock_bin_data.argtypes = [ul]
+    assert L.orbx_nif_mock_load() == 0
+    return L
+
+
+def call(L, name, *terms):
+    arr = (C.c_ulong * len(terms))(*terms)
+    return L.mock_call(name.encode(), len(terms), arr)
+
+
+def decode(L, t):
+    k = L.mock_kind(t)
+    if k == T_INT:
+        return int(L.mock_get_int(t))
+    if k == T_ATOM:
+        return L.mock_get_atom(t).decode()
+    if k == T_BIN:
+        return C.string_at(L.mock_bin_data(t), L.mock_bin_size(t))
+    if k == T_TUPLE:
+        return tuple(decode(L, L.mock_tuple_elem(t, i)) for i in range(L.mock_tuple_arity(t)))
+    if k == T_BADARG:
+        return "badarg"
+    return ("term", k)
+
+
+def nif_create(L, nfeatures, w, h):
+    r = call(L, "create", L.mock_int(nfeatures), L.mock_double(1.2), L.mock_int(8), L.mock_int(20), L.mock_int(7), L.mock_int(0),
+             L.mock_int(w), L.mock_int(h))
+    assert L.mock_kind(r) == T_TUPLE and decode(L, L.mock_tuple_elem(r, 0)) == "ok", decode(L, r)
+    res = L.mock_resource_keep(L.mock_tuple_elem(r, 1))      # the "process" keeps the handle term alive across calls
+    L.mock_reset()
+    return res
+
+
+def nif_extract(L, res, frame, fmt=None):
+    h, w = frame.shape[:2]
+    buf = np.ascontiguousarray(frame)
+    args = [L.mock_resource_term(res), L.mock_binary(buf.ctypes.data, buf.nbytes), L.mock_int(w), L.mock_int(h)]
+    r = decode(L, call(L, "extract", *args) if fmt is None else call(L, "extract_color", *args, L.mock_int(fmt)))
+    L.mock_reset()
+    assert r[0] == "ok", r
+    _, n, mono, kp, desc = r
+    return mono, np.frombuffer(kp, orbx.KP_DTYPE).copy(), np.frombuffer(desc, np.uint8).reshape(n, 32).copy()
+
+
+def test_nif_errors_and_single_stream(nif, oracle):
+    L = nif
+    w, h, nf = 1280, 720, 1250
+    res = nif_create(L, nf, w, h)
+    f = synth.textured_frame(700, w, h)
+    mono, kps, desc = nif_extract(L, res, f)
+    k_o, d_o, m_o = oracle.Oracle(nf).extract(f)
+    assert mono == m_o and np.array_equal(desc, d_o) and np.array_equal(kps.view(np.int32), k_o.view(np.int32))
+    # colour binary (BGR, what Evision hands over): gray conversion on the device
+    bgr = np.stack([f, f, f], -1)
+    mono2, kps2, desc2 = nif_extract(L, res, bgr, fmt=orbx.FMT_BGR8)
+    g = oracle.gray(bgr, orbx.FMT_BGR8, 15)
+    k_g, d_g, m_g = oracle.Oracle(nf).extract(g)
+    assert mono2 == m_g and np.array_equal(desc2, d_g)
+    # error tuples, never exceptions: size mismatch, frame larger than the handle was created for, bad arguments
+    r = decode(L, call(L, "extract", L.mock_resource_term(res), L.mock_binary(f.ctypes.data, 100), L.mock_int(w), L.mock_int(h)))
+    L.mock_reset()
+    assert r == ("error", "size_mismatch")
+    big = np.zeros((800, 1400), np.uint8)
+    r = decode(L, call(L, "extract", L.mock_resource_term(res), L.mock_binary(big.ctypes.data, big.nbytes), L.mock_int(1400), L.mock_int(800)))
+    L.mock_reset()
+    assert r == ("error", "capacity")
+    assert decode(L, call(L, "extract", L.mock_int(3), L.mock_int(4), L.mock_int(5), L.mock_int(6))) == "badarg"
+    L.mock_reset()
+    L.mock_resource_drop(res)                                  # last reference: the resource destructor destroys the handle
+
+
+def test_eight_concurrent_streams(nif, oracle):
+    """BASELINE config 5 on one GPU: 8 streams x 1280x720, each frame extracted and matched against the stream's previous frame."""
+    L = nif
+    w, h, nf, nstreams, nframes = 1280, 720, 1250, 8, 3
+    frames = [[synth.shifted_frame(synth.textured_frame(800 + s, w, h), 3 * t, -2 * t, seed=s) for t in range(nframes)] for s in range(nstreams)]
+    out = [None] * nstreams
+    errs = []
+
+    def stream(s):
+        try:
+            res = nif_create(L, nf, w, h)
+            got, prev = [], None
+            for t in range(nframes):
+                mono, kps, desc = nif_extract(L, res, frames[s][t])
+                m = None
+                if prev is not None:
+                    pk, pd = prev
+                    quvr = np.stack([pk["x"] + 3, pk["y"] - 2, 15.0 * np.float32(1.2) ** pk["octave"]], 1).astype(np.float32)
+                    qlev = np.stack([pk["octave"] - 1, pk["octave"] + 1], 1).astype(np.int32)
+                    b = L.mock_tuple4(L.mock_double(0.0), L.mock_double(0.0), L.mock_double(float(w)), L.mock_double(float(h)))
+                    r = decode(L, call(L, "match_windowed", L.mock_resource_term(res), L.mock_binary(pd.ctypes.data, pd.nbytes),
+                                       L.mock_binary(quvr.ctypes.data, quvr.nbytes), L.mock_binary(qlev.ctypes.data, qlev.nbytes),
+                                       L.mock_binary(kps.ctypes.data, kps.nbytes), L.mock_binary(desc.ctypes.data, desc.nbytes), b))
+                    L.mock_reset()
+                    assert r[0] == "ok", r
+                    m = (tuple(np.frombuffer(x, np.int32).copy() for x in r[1:]), quvr, qlev)
+                got.append((mono, kps, desc, m))
+                prev = (kps, desc)
+            L.mock_resource_drop(res)
+            out[s] = got
+        except Exception as e:                                  # surface failures of worker threads
+            errs.append((s, repr(e)))
+
+    th = [threading.Thread(target=stream, args=(s,)) for s in range(nstreams)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    o = oracle.Oracle(nf)
+    for s in range(nstreams):
+        for t in range(nframes):
+            mono, kps, desc, m = out[s][t]
+            if s in (0, 5) or t == 0:                            # full oracle comparison on a subset keeps the test short
+                k_o, d_o, m_o = o.extract(frames[s][t])
+                assert mono == m_o and np.array_equal(desc, d_o) and np.array_equal(kps.view(np.int32), k_o.view(np.int32)), (s, t)
+            if m is not None and s in (0, 5):
+                (bi, bd, si, sd), quvr, qlev = m
+                pk, pd = out[s][t - 1][1], out[s][t - 1][2]
+                want = oracle.match_windowed(pd, quvr, qlev, kps, desc, np.array([0, 0, w, h], np.float32))
+                assert np.array_equal(bi, want[0]) and np.array_equal(bd, want[1]) and np.array_equal(si, want[2]) and np.array_equal(sd, want[3])
+                assert ((bi >= 0) & (bd <= 100)).mean() > 0.4
