@@ -65,7 +65,6 @@ struct orbx_handle {
     int kp_cap = 0;                 // keypoints per frame the internal result buffers hold
     std::vector<void *> dev_allocs; // everything freed on re-plan / destroy
     LevelDev h_levels[kMaxLevels];
-    LevelDev *d_levels = nullptr;
     CellRect *d_cells = nullptr;
     BlurTile *d_tiles = nullptr;
     int ntiles = 0;
@@ -191,7 +190,6 @@ static int ensure_plan(orbx_handle *h, int w, int ht, int batch) {
     const int B = h->cfg.max_batch, nl = pl.nlevels;
     h->batch_cap = B;
     h->kp_cap = pl.total_out_cap;
-    CU_TRY(h, dev_alloc(h, &h->d_levels, (size_t)kMaxLevels));
     CU_TRY(h, dev_upload(h, &h->d_cells, pl.cells));
     CU_TRY(h, dev_alloc(h, &h->d_counts, (size_t)2 * nl * B));
     CU_TRY(h, dev_alloc(h, &h->d_overflow, (size_t)1));
@@ -240,7 +238,6 @@ static int ensure_plan(orbx_handle *h, int w, int ht, int batch) {
     }
     h->ntiles = (int)tiles.size();
     CU_TRY(h, dev_upload(h, &h->d_tiles, tiles));
-    CU_TRY(h, cudaMemcpy(h->d_levels, h->h_levels, sizeof(h->h_levels), cudaMemcpyHostToDevice));
     build_fast_maps(h);
     // pinned staging
     h->h_in_bytes = (size_t)B * pl.lv[0].plane_bytes;
@@ -261,7 +258,6 @@ static int set_level0(orbx_handle *h, const uint8_t *img, int pitch, size_t fstr
     D.img = const_cast<uint8_t *>(img); D.pitch = pitch; D.img_fstride = fstride;
     D.padded = img == h->l0_own ? 1 : 0;
     encode_fast_map(h, 0);
-    CU_TRY(h, cudaMemcpyAsync(h->d_levels, &h->h_levels[0], sizeof(LevelDev), cudaMemcpyHostToDevice, h->stream));
     return ORBX_OK;
 }
 
@@ -338,7 +334,7 @@ static int run_pipeline(orbx_handle *h, int f0, int batch, int lap0, int lap1, K
         h->launches += launch_gray(color.ptr, color.fstride, color.pitch, h->in_fmt, h->gray_shift, h->l0_own, h->l0_own_fstride, h->l0_own_pitch,
                                    pl.width, pl.height, f0, batch, stream);
     STAGE_MARK(0);
-    for (int l = 1; l < nl; l++) h->launches += launch_resize(h->d_levels, h->h_levels, l, f0, batch, stream);
+    for (int l = 1; l < nl; l++) h->launches += launch_resize(h->h_levels, l, f0, batch, stream);
     STAGE_MARK(1);
     // The blurred planes are only needed by the descriptor stage, and the quadtree kernel (one CTA per frame x level,
     // latency-bound) cannot fill the machine: outside profiling mode quadtree + slot assignment run on the side stream,
@@ -347,14 +343,14 @@ static int run_pipeline(orbx_handle *h, int f0, int batch, int lap0, int lap1, K
     // from running side by side.
     if (!fork) h->launches += launch_blur(h->h_levels, h->d_tiles, h->ntiles, f0, batch, stream);
     STAGE_MARK(2);
-    h->launches += launch_fast(h->d_levels, h->h_levels, h->d_cells, (int)pl.cells.size(), f0, batch, h->P.ini_th, h->P.min_th, h->d_overflow, stream, &h->ftma, h->sm_count);
+    h->launches += launch_fast(h->h_levels, h->d_cells, (int)pl.cells.size(), f0, batch, h->P.ini_th, h->P.min_th, h->d_overflow, stream, &h->ftma, h->sm_count);
     STAGE_MARK(3);
     cudaStream_t qs = fork ? side : stream;
     if (fork) {
         CU_TRY(h, cudaEventRecord(ev_fork, stream));
         CU_TRY(h, cudaStreamWaitEvent(side, ev_fork, 0));
     }
-    h->launches += launch_octree(h->d_levels, h->h_levels, nl, f0, batch, h->d_overflow, qs);
+    h->launches += launch_octree(h->h_levels, nl, f0, batch, h->d_overflow, qs);
     STAGE_MARK(4);
     h->launches += launch_finalize(h->h_levels, nl, f0, batch, pl.total_out_cap, lap0, lap1, d_kp, cap, h->d_slot, d_n, d_mono, h->d_overflow, qs);
     STAGE_MARK(5);
@@ -845,8 +841,7 @@ int orbx_debug_resize(orbx_handle *h, const uint8_t *src, int sw, int sh, int ss
     build_resize_taps(dh, sh, false, yt);
     ResizeTap *d_xt = S.get<ResizeTap>(dw), *d_yt = S.get<ResizeTap>(dh);
     LevelDev lv[kMaxLevels]; std::memset(lv, 0, sizeof(lv));
-    LevelDev *d_lv = S.get<LevelDev>(2);
-    if (!d_src || !d_dst || !d_xt || !d_yt || !d_lv) return fail(h, ORBX_E_CUDA, "cudaMalloc failed");
+    if (!d_src || !d_dst || !d_xt || !d_yt) return fail(h, ORBX_E_CUDA, "cudaMalloc failed");
     lv[0].img = d_src; lv[0].w = sw; lv[0].h = sh; lv[0].pitch = sp; lv[0].img_fstride = (size_t)sp * sh;
     lv[1].img = d_dst; lv[1].w = dw; lv[1].h = dh; lv[1].pitch = dp; lv[1].img_fstride = (size_t)dp * dh; lv[1].xtap = d_xt; lv[1].ytap = d_yt;
     {   // compact taps when they fit (same rule as build_plan)
@@ -869,9 +864,8 @@ int orbx_debug_resize(orbx_handle *h, const uint8_t *src, int sw, int sh, int ss
     CU_TRY(h, cudaMemcpy2D(d_src, sp, src, sstride, sw, sh, cudaMemcpyHostToDevice));
     CU_TRY(h, cudaMemcpy(d_xt, xt.data(), sizeof(ResizeTap) * dw, cudaMemcpyHostToDevice));
     CU_TRY(h, cudaMemcpy(d_yt, yt.data(), sizeof(ResizeTap) * dh, cudaMemcpyHostToDevice));
-    CU_TRY(h, cudaMemcpy(d_lv, lv, 2 * sizeof(LevelDev), cudaMemcpyHostToDevice));
     CU_TRY(h, cudaStreamSynchronize(cudaStreamLegacy));   // blocking pageable uploads may still be in DMA; h->stream is non-blocking
-    h->launches += launch_resize(d_lv, lv, 1, 0, 1, h->stream);
+    h->launches += launch_resize(lv, 1, 0, 1, h->stream);
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     CU_TRY(h, cudaMemcpy2D(dst, dstride, d_dst, dp, dw, dh, cudaMemcpyDeviceToHost));
@@ -889,12 +883,10 @@ int orbx_debug_blur(orbx_handle *h, const uint8_t *src, int w, int ht, int sstri
     BlurTile *d_t = S.get<BlurTile>(tiles.size());
     LevelDev lvs[kMaxLevels]; std::memset(lvs, 0, sizeof(lvs));
     LevelDev &lv = lvs[0];
-    LevelDev *d_lv = S.get<LevelDev>(1);
-    if (!d_src || !d_dst || !d_t || !d_lv) return fail(h, ORBX_E_CUDA, "cudaMalloc failed");
+    if (!d_src || !d_dst || !d_t) return fail(h, ORBX_E_CUDA, "cudaMalloc failed");
     lv.img = d_src; lv.blur = d_dst; lv.w = w; lv.h = ht; lv.pitch = p; lv.blur_pitch = p; lv.img_fstride = lv.blur_fstride = (size_t)p * ht;
     CU_TRY(h, cudaMemcpy2D(d_src, p, src, sstride, w, ht, cudaMemcpyHostToDevice));
     CU_TRY(h, cudaMemcpy(d_t, tiles.data(), sizeof(BlurTile) * tiles.size(), cudaMemcpyHostToDevice));
-    CU_TRY(h, cudaMemcpy(d_lv, &lv, sizeof(lv), cudaMemcpyHostToDevice));
     CU_TRY(h, cudaStreamSynchronize(cudaStreamLegacy));   // blocking pageable uploads may still be in DMA; h->stream is non-blocking
     h->launches += launch_blur(lvs, d_t, (int)tiles.size(), 0, 1, h->stream);
     CU_TRY(h, cudaGetLastError());
@@ -951,8 +943,7 @@ int orbx_debug_octree(orbx_handle *h, const float *keys, int n, int minX, int ma
     const int ccap = std::max(n, 1);
     uint32_t *d_cand = S.get<uint32_t>(ccap), *d_sorted = S.get<uint32_t>(ccap), *d_cur = S.get<uint32_t>(std::max(LP.nbins, 1)), *d_sel = S.get<uint32_t>(LP.out_cap);
     int *d_cnt = S.get<int>(4);
-    LevelDev *d_lv = S.get<LevelDev>(1);
-    if (!t0 || !t1 || !t2 || !t3 || !d_cand || !d_sorted || !d_cur || !d_sel || !d_cnt || !d_lv) return fail(h, ORBX_E_CUDA, "cudaMalloc failed");
+    if (!t0 || !t1 || !t2 || !t3 || !d_cand || !d_sorted || !d_cur || !d_sel || !d_cnt) return fail(h, ORBX_E_CUDA, "cudaMalloc failed");
     CU_TRY(h, cudaMemcpy(t0, LP.xbin.data(), LP.xbin.size() * 4, cudaMemcpyHostToDevice));
     CU_TRY(h, cudaMemcpy(t1, LP.ybin.data(), LP.ybin.size() * 4, cudaMemcpyHostToDevice));
     CU_TRY(h, cudaMemcpy(t2, LP.xord.data(), LP.xord.size() * 4, cudaMemcpyHostToDevice));
@@ -977,9 +968,8 @@ int orbx_debug_octree(orbx_handle *h, const float *keys, int n, int minX, int ma
     for (int r = 0; r < kMaxRoots; r++) { D.root_ulx[r] = LP.root_ulx[r]; D.root_brx[r] = LP.root_brx[r]; }
     D.ord_cell_area = LP.ord_cell_area; D.ord_ncols = LP.ord_ncols; D.wcell = LP.wcell; D.hcell = LP.hcell;
     D.cand = d_cand; D.sorted = d_sorted; D.bin_cursor = d_cur; D.cand_cap = ccap; D.cand_count = d_cnt; D.sel = d_sel; D.sel_count = d_cnt + 1;
-    CU_TRY(h, cudaMemcpy(d_lv, &D, sizeof(D), cudaMemcpyHostToDevice));
     CU_TRY(h, cudaStreamSynchronize(cudaStreamLegacy));   // blocking pageable uploads may still be in DMA; h->stream is non-blocking
-    h->launches += launch_octree(d_lv, Ds, 1, 0, 1, d_cnt + 2, h->stream);
+    h->launches += launch_octree(Ds, 1, 0, 1, d_cnt + 2, h->stream);
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     CU_TRY(h, cudaMemcpy(counts, d_cnt, sizeof(counts), cudaMemcpyDeviceToHost));

@@ -43,10 +43,10 @@ struct KeypointRec {           // == orbx_keypoint == cv::KeyPoint
 
 // launch wrappers (orbx_kernels.cu); all asynchronous on `stream`, return the number of kernel launches issued.
 // They process frames [f0, f0 + batch) of the workspace.  h_levels = HOST copy of the level table (kMaxLevels entries): it is
-// passed to the kernels by value in the parameter bank; d_levels (device copy) is kept for the signatures that predate that.
+// passed to the kernels by value in the parameter bank (no device copy exists).
 int launch_gray(const uint8_t *d_src, size_t src_fstride, int src_pitch, int format, int shift, uint8_t *d_dst, size_t dst_fstride,
                 int dst_pitch, int w, int h, int f0, int batch, cudaStream_t stream);
-int launch_resize(const LevelDev *d_levels, const LevelDev *h_levels, int level, int f0, int batch, cudaStream_t stream);
+int launch_resize(const LevelDev *h_levels, int level, int f0, int batch, cudaStream_t stream);
 int launch_blur(const LevelDev *h_levels, const BlurTile *d_tiles, int ntiles, int f0, int batch, cudaStream_t stream);
 // Tensor maps of the level planes for the TMA-staged FAST kernel (host side: orbx_api.cu builds them; 128 bytes each,
 // stored opaquely so that this header does not need <cuda.h>).
@@ -57,9 +57,9 @@ struct FastTma {
     bool level_ok[kMaxLevels];
     bool ok;                    // every level has a valid map
 };
-int launch_fast(const LevelDev *d_levels, const LevelDev *h_levels, const CellRect *d_cells, int ncells, int f0, int batch,
+int launch_fast(const LevelDev *h_levels, const CellRect *d_cells, int ncells, int f0, int batch,
                 int ini_th, int min_th, int *d_overflow, cudaStream_t stream, const FastTma *tma, int sm_count);
-int launch_octree(const LevelDev *d_levels, const LevelDev *h_levels, int nlevels, int f0, int batch, int *d_overflow,
+int launch_octree(const LevelDev *h_levels, int nlevels, int f0, int batch, int *d_overflow,
                   cudaStream_t stream);
 int launch_finalize(const LevelDev *h_levels, int nlevels, int f0, int batch, int total_out_cap, int lap0, int lap1,
                     KeypointRec *d_kp, int cap, int *d_slot, int *d_n, int *d_mono, int *d_overflow, cudaStream_t stream);
@@ -74,7 +74,7 @@ int launch_frame_grid(const KeypointRec *d_kp, const int *d_n, int n_one, int ba
 // stand-alone stage launchers for the debug / parity entry points
 int launch_describe_points(const uint8_t *d_img, const uint8_t *d_blur, int pitch, const float *d_xy, int n,
                            const float *d_angle_in, float *d_angle_out, uint8_t *d_desc, cudaStream_t stream);
-void upload_constants();
+void upload_constants();   // pattern + umax to __constant__/__device__ memory (once per process per device)
 }  // namespace orbx
 
 #include <string>
@@ -98,6 +98,6 @@ int match_distance_batch(int device, cudaStream_t stream, const uint8_t *a, cons
                          std::string &err, long long &launches);
 int match_windowed(int device, cudaStream_t stream, const uint8_t *q_desc, const float *q_uvr, const int32_t *q_levels, int nq,
                    const orbx_keypoint *t_kp, const uint8_t *t_desc, int nt, const float *bounds4, int32_t *best_idx,
-                   int32_t *best_dist, int32_t *second_idx, int32_t *second_dist, std::string &err, long long &launches);       // pattern + umax to __constant__/__device__ memory (once per process per device)
+                   int32_t *best_dist, int32_t *second_idx, int32_t *second_dist, std::string &err, long long &launches);
 
 }  // namespace orbx

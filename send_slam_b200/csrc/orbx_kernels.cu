@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(128) k_resize(const __grid_constant__ LevelTab
     }
 }
 
-int launch_resize(const LevelDev *d_levels, const LevelDev *h_levels, int level, int f0, int batch, cudaStream_t stream) {
+int launch_resize(const LevelDev *h_levels, int level, int f0, int batch, cudaStream_t stream) {
     const LevelDev &D = h_levels[level];
     const LevelDev &S = h_levels[level - 1];
     const bool aligned = ((reinterpret_cast<uintptr_t>(S.img) | (uintptr_t)S.pitch | (uintptr_t)S.img_fstride) & 3) == 0 && D.xpack != nullptr;
@@ -753,7 +753,7 @@ __global__ void __launch_bounds__(FW_WARPS * 32, 6) k_fast_tma(const __grid_cons
     }
 }
 
-int launch_fast(const LevelDev *d_levels, const LevelDev *h_levels, const CellRect *d_cells, int ncells, int f0, int batch,
+int launch_fast(const LevelDev *h_levels, const CellRect *d_cells, int ncells, int f0, int batch,
                 int ini_th, int min_th, int *d_overflow, cudaStream_t stream, const FastTma *tma, int sm_count) {
     if (ncells <= 0) return 0;
     if (tma && tma->ok) {
@@ -1138,7 +1138,7 @@ static size_t octree_smem_bytes(int nbins, int cap) {
     return (size_t)2 * cap * sizeof(QNode) + (size_t)(2 * nbins + 1) * 4 + (size_t)7 * cap * 4 + 16;
 }
 
-int launch_octree(const LevelDev *d_levels, const LevelDev *h_levels, int nlevels, int f0, int batch, int *d_overflow,
+int launch_octree(const LevelDev *h_levels, int nlevels, int f0, int batch, int *d_overflow,
                   cudaStream_t stream) {
     // one launch for all levels: size the node arrays for the largest quota and the bins for the finest table
     int cap = 0, nbins = 0;
