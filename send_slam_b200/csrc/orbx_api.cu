@@ -75,6 +75,7 @@ struct orbx_handle {
     uint8_t *d_desc = nullptr;      // [batch][kp_cap][32]
     int *d_n = nullptr, *d_mono = nullptr;
     FastTma ftma{};                 // tensor maps of the level planes (TMA-staged FAST kernel)
+    DescTma dtma{};                 // ... and of the un-blurred / blurred planes for the descriptor kernel
     int sm_count = 148;
     // colour input (orbx_set_input_format): frames are uploaded to d_color and converted into the level-0 planes on the device
     int in_fmt = ORBX_FMT_GRAY8, gray_shift = ORBX_GRAY_Q15;
@@ -155,12 +156,19 @@ static void encode_fast_map(orbx_handle *h, int l) {
                                                        D.img_fstride, T.box_w[l], T.box_h[l]);
     T.ok = !getenv("ORBX_NO_TMA");
     for (int k = 0; k < h->plan.nlevels; k++) T.ok = T.ok && (T.level_ok[k] || h->plan.lv[k].ncells == 0);
+    // descriptor kernel: 64 x 31 box on the un-blurred plane, 64 x 39 box on the blurred plane
+    DescTma &Q = h->dtma;
+    Q.level_ok[l] = tma_make_plane_map(reinterpret_cast<CUtensorMap *>(Q.img[l]), D.img, D.w, D.h, h->batch_cap, (size_t)D.pitch, D.img_fstride, 64, 31) &&
+                    tma_make_plane_map(reinterpret_cast<CUtensorMap *>(Q.blur[l]), D.blur, D.w, D.h, h->batch_cap, (size_t)D.blur_pitch, D.blur_fstride, 64, 39);
+    Q.ok = !getenv("ORBX_NO_TMA");
+    for (int k = 0; k < h->plan.nlevels; k++) Q.ok = Q.ok && Q.level_ok[k];
 }
 
 // Box of a level = the largest ROI of its cells plus the 4-pixel-group / row-pair overhang the scoring items read.
 static void build_fast_maps(orbx_handle *h) {
     FastTma &T = h->ftma;
     std::memset(&T, 0, sizeof(T));
+    std::memset(&h->dtma, 0, sizeof(h->dtma));
     for (int l = 0; l < h->plan.nlevels; l++) {
         const LevelPlan &LP = h->plan.lv[l];
         int rw = 0, rh = 0;
@@ -359,7 +367,7 @@ static int run_pipeline(orbx_handle *h, int f0, int batch, int lap0, int lap1, K
         h->launches += launch_blur(h->h_levels, h->d_tiles, h->ntiles, f0, batch, stream);
         CU_TRY(h, cudaStreamWaitEvent(stream, ev_join, 0));
     }
-    h->launches += launch_describe(h->h_levels, nl, f0, batch, pl.total_out_cap, h->d_slot, d_kp, d_desc, cap, stream);
+    h->launches += launch_describe(h->h_levels, nl, f0, batch, pl.total_out_cap, h->d_slot, d_kp, d_desc, cap, stream, &h->dtma, h->sm_count);
     STAGE_MARK(6);
 #undef STAGE_MARK
     if (stream == h->stream) h->ev_valid = prof;

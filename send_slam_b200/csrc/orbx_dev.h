@@ -63,8 +63,15 @@ int launch_octree(const LevelDev *h_levels, int nlevels, int f0, int batch, int 
                   cudaStream_t stream);
 int launch_finalize(const LevelDev *h_levels, int nlevels, int f0, int batch, int total_out_cap, int lap0, int lap1,
                     KeypointRec *d_kp, int cap, int *d_slot, int *d_n, int *d_mono, int *d_overflow, cudaStream_t stream);
+// Tensor maps of the un-blurred and blurred level planes for the TMA-staged descriptor kernel (boxes 64 x 31 and 64 x 39).
+struct DescTma {
+    alignas(64) unsigned char img[kMaxLevels][128];
+    alignas(64) unsigned char blur[kMaxLevels][128];
+    bool level_ok[kMaxLevels];
+    bool ok;
+};
 int launch_describe(const LevelDev *h_levels, int nlevels, int f0, int batch, int total_out_cap, const int *d_slot,
-                    KeypointRec *d_kp, uint8_t *d_desc, int cap, cudaStream_t stream);
+                    KeypointRec *d_kp, uint8_t *d_desc, int cap, cudaStream_t stream, const DescTma *tma, int sm_count);
 // Frame post-extraction steps (orbx_frame.cu): cv::undistortPoints of Frame::UndistortKeyPoints and the 64 x 48 feature grid
 constexpr int kGridCols = 64, kGridRows = 48;
 struct CameraDev { float fx, fy, cx, cy, k1, k2, p1, p2, k3; };   // == orbx_camera

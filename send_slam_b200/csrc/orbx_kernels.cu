@@ -1345,8 +1345,143 @@ __global__ void __launch_bounds__(256) k_describe(const __grid_constant__ LevelT
     }
 }
 
+// explicit shared-space byte load: generic pointers into shared memory cost an address-space conversion per access
+__device__ __forceinline__ uint32_t lds_u8(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
+// warp_brief_byte on a patch in shared memory (center = shared-space address of the keypoint, rows 64 bytes apart)
+__device__ __forceinline__ uint8_t warp_brief_byte_smem(uint32_t center, float a, float b, int lane) {
+    const char4 *pat = reinterpret_cast<const char4 *>(g_pattern) + lane * 8;
+    uint32_t val = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const char4 p = pat[j];
+        const float x0 = (float)p.x, y0 = (float)p.y, x1 = (float)p.z, y1 = (float)p.w;
+        const int ix0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+        const int iy0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+        const int ix1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+        const int iy1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+        const uint32_t t0 = lds_u8(center + (uint32_t)(iy0 * 64 + ix0)), t1 = lds_u8(center + (uint32_t)(iy1 * 64 + ix1));
+        val |= (uint32_t)(t0 < t1) << j;
+    }
+    return (uint8_t)val;
+}
+
+// TMA-staged, persistent variant (the one the pipeline runs when every plane meets the TMA alignment rules).  One warp owns one
+// keypoint at a time and walks the (frame, slot) items with a grid stride.  The 31-row patch of the un-blurred level (IC_Angle)
+// and the 39-row patch of the blurred level (the rotated test points lie within radius 18.4 of the keypoint) are brought into
+// the warp's shared memory by cp.async.bulk.tensor, two keypoints deep, so the 31 moment loads and the 16 scattered BRIEF
+// gathers per lane become LDS with immediate / 32-bit offsets: k_describe spends half of its instructions on 64-bit address
+// arithmetic and is bound by the scattered gathers in L1.  Arithmetic and results are identical to k_describe.
+constexpr int DT_WARPS = 4;
+constexpr int DT_BOXW = 64, DT_IMG_ROWS = 31, DT_BLUR_ROWS = 39, DT_R = 19;
+constexpr int DT_IMG_BYTES = DT_BOXW * DT_IMG_ROWS, DT_BLUR_BYTES = DT_BOXW * DT_BLUR_ROWS;      // 1984 + 2496 bytes moved by TMA
+constexpr int DT_BLUR_OFS = 2048;                                                               // TMA destinations are 128-byte aligned
+constexpr int DT_STAGE = 4608;                                                                  // 2048 + 2496, rounded to 128
+constexpr int DT_WARP_BYTES = 2 * DT_STAGE + 128;                                               // + mbarriers
+
+struct DescTmaParams {
+    CUtensorMap img[kMaxLevels], blur[kMaxLevels];   // level planes [frames][h][w]; boxes 64 x 31 and 64 x 39
+};
+
+struct DescItem { int level, x, y, sl, f; };         // level < 0: nothing to do for this item
+
+__global__ void __launch_bounds__(DT_WARPS * 32, 6) k_describe_tma(const __grid_constant__ DescTmaParams P, const __grid_constant__ LevelTable T,
+                                                                   int nlevels, int total_out_cap, int nframes, const int *__restrict__ slot,
+                                                                   KeypointRec *__restrict__ kp, uint8_t *__restrict__ desc, int cap, int f0) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const LevelDev *lv = T.lv;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t *wsm = smem + (size_t)warp * DT_WARP_BYTES;
+    uint64_t *s_full = reinterpret_cast<uint64_t *>(wsm + 2 * DT_STAGE);
+    if (lane == 0) { tma_mbar_init(&s_full[0], 1); tma_mbar_init(&s_full[1], 1); tma_mbar_fence_init(); }
+    __syncwarp();
+    const int total = nframes * total_out_cap, stride = gridDim.x * DT_WARPS;
+    auto load_item = [&](int i) -> DescItem {
+        DescItem d; d.level = -1; d.x = d.y = d.sl = d.f = 0;
+        if (i >= total) return d;
+        const int fi = i / total_out_cap, item = i - fi * total_out_cap;
+        int l = 0;
+        while (l + 1 < nlevels && item >= lv[l + 1].out_base) l++;
+        const LevelDev &L = lv[l];
+        const int idx = item - L.out_base, f = f0 + fi;
+        if (idx >= L.sel_count[f]) return d;
+        const uint32_t c = L.sel[(size_t)f * L.out_cap + idx];
+        d.level = l; d.x = (c >> 8) & 0xFFF; d.y = c >> 20; d.f = f;
+        d.sl = slot[(size_t)f * total_out_cap + item];
+        return d;
+    };
+    auto issue = [&](const DescItem &d, int st) {        // lane 0 only
+        uint8_t *dst = wsm + st * DT_STAGE;
+        const int xa = (d.x - DT_R) & ~15;               // a TMA box starts on a 16-byte boundary
+        tma_mbar_expect_tx(&s_full[st], (uint32_t)(DT_IMG_BYTES + DT_BLUR_BYTES));
+        tma_load_3d(dst, &P.img[d.level], xa, d.y - kHalfPatch, d.f, &s_full[st]);
+        tma_load_3d(dst + DT_BLUR_OFS, &P.blur[d.level], xa, d.y - DT_R, d.f, &s_full[st]);
+    };
+    int i_cur = blockIdx.x * DT_WARPS + warp;
+    DescItem A = load_item(i_cur), B = load_item(i_cur + stride);
+    if (lane == 0) { if (A.level >= 0) issue(A, 0); if (B.level >= 0) issue(B, 1); }
+    uint32_t phase = 0;                                   // bit st = parity to wait for on stage st
+    constexpr int UM[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+    const int u = lane - kHalfPatch, au = u < 0 ? -u : u;
+    for (int q = 0; i_cur < total; q++, i_cur += stride) {
+        const int st = q & 1;
+        const DescItem Cn = load_item(i_cur + 2 * stride);                 // descriptor prefetch for the item after next
+        if (A.level >= 0) {
+            tma_mbar_wait(&s_full[st], (phase >> st) & 1u);
+            phase ^= 1u << st;
+            const uint8_t *ip = wsm + st * DT_STAGE, *bp = ip + DT_BLUR_OFS;
+            const int xo = A.x - ((A.x - DT_R) & ~15);                      // keypoint column inside the box: 19 .. 34
+            // IC_Angle moments: lane <-> column u, 31 rows at immediate offsets
+            int sum = 0, m01 = 0;
+            const uint32_t pc = tma_smem_u32(ip) + (uint32_t)(xo + u);
+#pragma unroll
+            for (int v = -kHalfPatch; v <= kHalfPatch; v++) {
+                const int d = UM[v < 0 ? -v : v];
+                const int val = (au <= d) ? (int)lds_u8(pc + (uint32_t)((v + kHalfPatch) * DT_BOXW)) : 0;
+                sum += val; m01 += v * val;
+            }
+            int m10 = u * sum;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xFFFFFFFFu, m10, o); m01 += __shfl_xor_sync(0xFFFFFFFFu, m01, o); }
+            float angle = 0.f, a = 1.f, b = 0.f;
+            if (lane == 0) {
+                angle = fast_atan2_deg((float)m01, (float)m10);
+                steer_trig(angle, a, b);
+            }
+            angle = __shfl_sync(0xFFFFFFFFu, angle, 0); a = __shfl_sync(0xFFFFFFFFu, a, 0); b = __shfl_sync(0xFFFFFFFFu, b, 0);
+            const uint8_t byte = warp_brief_byte_smem(tma_smem_u32(bp) + (uint32_t)(DT_R * DT_BOXW + xo), a, b, lane);
+            desc[((size_t)A.f * cap + A.sl) * 32 + lane] = byte;
+            if (lane == 0) kp[(size_t)A.f * cap + A.sl].angle = angle;
+        }
+        __syncwarp();
+        if (lane == 0 && Cn.level >= 0) issue(Cn, st);                     // the stage has been consumed: refill it
+        A = B; B = Cn;
+    }
+}
+
 int launch_describe(const LevelDev *h_levels, int nlevels, int f0, int batch, int total_out_cap, const int *d_slot,
-                    KeypointRec *d_kp, uint8_t *d_desc, int cap, cudaStream_t stream) {
+                    KeypointRec *d_kp, uint8_t *d_desc, int cap, cudaStream_t stream, const DescTma *tma, int sm_count) {
+    if (tma && tma->ok) {
+        static_assert(sizeof(DescTma::img) == sizeof(DescTmaParams::img), "tensor map storage mismatch");
+        DescTmaParams P;
+        memcpy(P.img, tma->img, sizeof(P.img));
+        memcpy(P.blur, tma->blur, sizeof(P.blur));
+        const size_t smem = (size_t)DT_WARPS * DT_WARP_BYTES;
+        static int per_sm = 0;
+        if (!per_sm) {
+            cudaFuncSetAttribute(k_describe_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_describe_tma, DT_WARPS * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        }
+        const int total = batch * total_out_cap;
+        const int want = (total + DT_WARPS - 1) / DT_WARPS;
+        const int grid = want < sm_count * per_sm ? want : sm_count * per_sm;
+        k_describe_tma<<<grid, DT_WARPS * 32, smem, stream>>>(P, make_table(h_levels), nlevels, total_out_cap, batch, d_slot, d_kp, d_desc, cap, f0);
+        return 1;
+    }
     dim3 grid((total_out_cap + 8 * DG - 1) / (8 * DG), batch);
     k_describe<<<grid, 256, 0, stream>>>(make_table(h_levels), nlevels, total_out_cap, d_slot, d_kp, d_desc, cap, f0);
     return 1;
