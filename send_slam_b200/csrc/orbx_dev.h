@@ -33,7 +33,7 @@ struct LevelDev {
     float scale, kp_size;
 };
 
-constexpr int kBlurTileW = 64, kBlurTileH = 56;
+constexpr int kBlurTileW = 64, kBlurTileH = 112;
 struct BlurTile { int16_t level, tx, ty, pad; };   // one kBlurTileW x kBlurTileH output tile of the Gaussian pass
 
 struct KeypointRec {           // == orbx_keypoint == cv::KeyPoint

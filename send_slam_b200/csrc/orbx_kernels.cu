@@ -216,14 +216,15 @@ int launch_resize(const LevelDev *h_levels, int level, int f0, int batch, cudaSt
 
 // ---------------------------------------------------------------------------------------------------------------
 // K5  7x7 Gaussian, fixed point [18,34,48,56,48,34,18]/256 per axis, exact 16.16 accumulation, REFLECT_101.
-//     Output tile 64 x 56 per CTA.  The halo tile (62 rows x 80 bytes) is staged with word loads; the horizontal pass is
+//     Output tile 64 x 112 per CTA (two rounds of items per thread amortise the per-thread set-up; 64 x 56 cost 20 % more
+//     instructions).  The halo tile (118 rows x 80 bytes) is staged with word loads; the horizontal pass is
 //     two IDP.4A per pixel on byte-aligned word slices (sums <= 65280 fit 16 bits) and leaves its sums packed as
 //     (row 2p, row 2p+1) pairs, so that the vertical pass is four IDP.2A per pixel (16-bit sums x 8-bit taps, 32-bit acc).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int BTW = kBlurTileW, BTH = kBlurTileH;   // 64 x 56
+constexpr int BTW = kBlurTileW, BTH = kBlurTileH;   // 64 x 112
 constexpr int BIN_PITCH = 80;          // bytes per staged input row: image columns x0-4 .. x0+75
-constexpr int BROWS = BTH + 6;         // 62 staged rows = 31 row pairs
-static_assert(BTW == 64 && BTH == 56, "k_blur's thread mapping is written for 64 x 56 tiles");
+constexpr int BROWS = BTH + 6;         // up to 118 staged rows = 59 row pairs
+static_assert(BTW == 64 && BTH % 4 == 0, "k_blur's item mapping needs 64-column tiles and 4-row segments");
 
 // BORDER_REFLECT_101 for any index (period 2(n-1)); n == 1 maps everything to 0
 __device__ __forceinline__ int reflect101(int i, int n) {
@@ -245,24 +246,26 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ LevelTable
     const int x0 = t.tx * BTW, y0 = t.ty * BTH;
     const int w = L.w, h = L.h, pitch = L.pitch;
     const uint8_t *__restrict__ src = L.img + (size_t)f * L.img_fstride;
-    // stage rows y0-3 .. y0+58, columns x0-4 .. x0+75 (20 words per row): aligned word loads where the word lies inside
-    // the image, per-byte BORDER_REFLECT_101 elsewhere.  1240 words, 5 per thread, all requested before the first store.
+    // rows of this tile (the last tile of a level is shorter): 4-row output segments, staged rows = 4 * nseg + 6
+    const int nseg = (min(BTH, h - y0) + 3) >> 2, srows = 4 * nseg + 6, npairs = srows >> 1;
+    // stage rows y0-3 .. y0-3+srows-1, columns x0-4 .. x0+75 (20 words per row): aligned word loads where the word lies
+    // inside the image, per-byte BORDER_REFLECT_101 elsewhere; five words per thread are requested before the first store.
     const bool word_ok = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)pitch) & 3) == 0;
-    const bool big = w >= 96 && h >= 96;   // staged indices reach < 80 past an edge (partial last tiles)
-    {
-        constexpr int NW = BROWS * (BIN_PITCH / 4), PER = (NW + 255) / 256;
-        uint32_t v[PER];
+    const bool big = w >= 96 && h >= 160;  // staged indices reach < 80 columns / < 120 rows past an edge (partial last tiles)
+    const int nw = srows * (BIN_PITCH / 4);
+    for (int it0 = threadIdx.x; it0 < nw; it0 += 256 * 5) {
+        uint32_t v[5];
 #pragma unroll
-        for (int k = 0; k < PER; k++) {
-            const int it = threadIdx.x + 256 * k;
-            if (it < NW) {
+        for (int k = 0; k < 5; k++) {
+            const int it = it0 + 256 * k;
+            if (it < nw) {
                 const int r = it / (BIN_PITCH / 4), wc = it - r * (BIN_PITCH / 4);
                 const int gy = y0 - 3 + r, gx = x0 - 4 + 4 * wc;
                 if (word_ok && gx >= 0 && gx + 3 < w && gy >= 0 && gy < h) {
                     v[k] = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)gy * pitch + gx));
                 } else if (big) {
-                    // one reflection keeps every staged index in range for images >= 96 px (border tiles
-                    // execute this for a few words per warp; the general path costs an integer division per byte)
+                    // one reflection keeps every staged index in range for large images (border tiles execute this for a
+                    // few words per warp; the general path costs an integer division per byte)
                     const int ry = gy < 0 ? -gy : (gy >= h ? 2 * h - 2 - gy : gy);
                     const uint8_t *row = src + (size_t)ry * pitch;
                     uint32_t acc = 0;
@@ -280,15 +283,15 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ LevelTable
             }
         }
 #pragma unroll
-        for (int k = 0; k < PER; k++) {
-            const int it = threadIdx.x + 256 * k;
-            if (it < NW) reinterpret_cast<uint32_t *>(s_in)[it] = v[k];
+        for (int k = 0; k < 5; k++) {
+            const int it = it0 + 256 * k;
+            if (it < nw) reinterpret_cast<uint32_t *>(s_in)[it] = v[k];
         }
     }
     __syncthreads();
-    // horizontal: item = (row pair p, group g of 8 output columns); 31 x 8 = 248 items
-    if (threadIdx.x < (BROWS / 2) * 8) {
-        const int p = threadIdx.x >> 3, g = threadIdx.x & 7;
+    // horizontal: item = (row pair p, group g of 8 output columns)
+    for (int it = threadIdx.x; it < npairs * 8; it += 256) {
+        const int p = it >> 3, g = it & 7;
         constexpr uint32_t KA = 18u | (34u << 8) | (48u << 16) | (56u << 24), KB = 48u | (34u << 8) | (18u << 16);
         uint32_t hs[2][8];
 #pragma unroll
@@ -311,11 +314,11 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ LevelTable
         dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
     }
     __syncthreads();
-    // vertical: item = (4-column group cg, segment of 4 output rows); 16 x 14 = 224 items.  Output row y reads staged rows
-    // y .. y+6: for even y the pairs y/2 .. y/2+3 with taps (18,34)(48,56)(48,34)(18,0), for odd y the pairs
-    // (y-1)/2 .. (y-1)/2+3 with taps (0,18)(34,48)(56,48)(34,18).
-    if (threadIdx.x < 16 * (BTH / 4)) {
-        const int cg = threadIdx.x & 15, seg = threadIdx.x >> 4;
+    // vertical: item = (4-column group cg, segment of 4 output rows).  Output row y reads staged rows y .. y+6: for even y the
+    // pairs y/2 .. y/2+3 with taps (18,34)(48,56)(48,34)(18,0), for odd y the pairs (y-1)/2 .. (y-1)/2+3 with taps
+    // (0,18)(34,48)(56,48)(34,18).
+    for (int it = threadIdx.x; it < 16 * nseg; it += 256) {
+        const int cg = it & 15, seg = it >> 4;
         const int gx = x0 + 4 * cg;
         if (gx < w) {
             constexpr uint32_t EA = 18u | (34u << 8) | (48u << 16) | (56u << 24), EB = 48u | (34u << 8) | (18u << 16);
