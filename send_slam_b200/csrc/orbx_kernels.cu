@@ -251,8 +251,45 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ LevelTable
     // stage rows y0-3 .. y0-3+srows-1, columns x0-4 .. x0+75 (20 words per row): aligned word loads where the word lies
     // inside the image, per-byte BORDER_REFLECT_101 elsewhere; five words per thread are requested before the first store.
     const bool word_ok = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)pitch) & 3) == 0;
-    const bool big = w >= 96 && h >= 160;  // staged indices reach < 80 columns / < 120 rows past an edge (partial last tiles)
+    const bool big = w >= 16 && h >= 16;   // one reflection per row index is enough (staged rows reach < 8 past an edge)
     const int nw = srows * (BIN_PITCH / 4);
+    if (big && word_ok && L.padded) {
+        // Fast staging (workspace planes of ordinary size): every word is an aligned load at a clamped column of the reflected
+        // row - no per-word edge branch, which made whole warps of every border tile (half of all tiles) run the per-byte
+        // path.  The three REFLECT_101 columns left of x = 0 and right of x = w - 1 are patched in shared memory afterwards.
+        const int lastw = (w - 1) & ~3;
+        for (int it0 = threadIdx.x; it0 < nw; it0 += 256 * 5) {
+            uint32_t v[5];
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                const int it = it0 + 256 * k;
+                if (it < nw) {
+                    const int r = it / (BIN_PITCH / 4), wc = it - r * (BIN_PITCH / 4);
+                    const int gy = y0 - 3 + r, gx = x0 - 4 + 4 * wc;
+                    const int ry = gy < 0 ? -gy : (gy >= h ? 2 * h - 2 - gy : gy);
+                    v[k] = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)ry * pitch + min(max(gx, 0), lastw)));
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                const int it = it0 + 256 * k;
+                if (it < nw) reinterpret_cast<uint32_t *>(s_in)[it] = v[k];
+            }
+        }
+        const bool left = x0 == 0, right = x0 + 76 > w;      // the staged columns x0-4 .. x0+75 leave the image
+        if (left || right) {
+            __syncthreads();
+            for (int r = threadIdx.x; r < srows; r += 256) {
+                uint8_t *row = s_in + r * BIN_PITCH;
+                if (left) { row[1] = row[7]; row[2] = row[6]; row[3] = row[5]; }      // x = -3, -2, -1 <- x = 3, 2, 1
+                if (right) {
+                    const int c = w - x0 + 4;                                           // staged column of image column w
+#pragma unroll
+                    for (int k = 0; k < 3; k++) if (c + k < BIN_PITCH) row[c + k] = row[c - 2 - k];   // x = w + k <- x = w - 2 - k
+                }
+            }
+        }
+    } else
     for (int it0 = threadIdx.x; it0 < nw; it0 += 256 * 5) {
         uint32_t v[5];
 #pragma unroll
@@ -263,18 +300,6 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ LevelTable
                 const int gy = y0 - 3 + r, gx = x0 - 4 + 4 * wc;
                 if (word_ok && gx >= 0 && gx + 3 < w && gy >= 0 && gy < h) {
                     v[k] = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)gy * pitch + gx));
-                } else if (big) {
-                    // one reflection keeps every staged index in range for large images (border tiles execute this for a
-                    // few words per warp; the general path costs an integer division per byte)
-                    const int ry = gy < 0 ? -gy : (gy >= h ? 2 * h - 2 - gy : gy);
-                    const uint8_t *row = src + (size_t)ry * pitch;
-                    uint32_t acc = 0;
-#pragma unroll
-                    for (int b = 0; b < 4; b++) {
-                        const int x = gx + b, rx = x < 0 ? -x : (x >= w ? 2 * w - 2 - x : x);
-                        acc |= (uint32_t)row[rx] << (8 * b);
-                    }
-                    v[k] = acc;
                 } else {
                     const uint8_t *row = src + (size_t)reflect101(gy, h) * pitch;
                     v[k] = (uint32_t)row[reflect101(gx, w)] | ((uint32_t)row[reflect101(gx + 1, w)] << 8) |
