@@ -258,22 +258,26 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ LevelTable
         // row - no per-word edge branch, which made whole warps of every border tile (half of all tiles) run the per-byte
         // path.  The three REFLECT_101 columns left of x = 0 and right of x = w - 1 are patched in shared memory afterwards.
         const int lastw = (w - 1) & ~3;
-        for (int it0 = threadIdx.x; it0 < nw; it0 += 256 * 5) {
-            uint32_t v[5];
+        // thread <-> (row tr of 12, word wc of 20): 240 threads stage 12 rows per step, five steps in flight
+        const int tr = threadIdx.x / (BIN_PITCH / 4), wc = threadIdx.x - tr * (BIN_PITCH / 4);
+        if (tr < 12) {
+            const int cx = min(max(x0 - 4 + 4 * wc, 0), lastw);
+            for (int r0 = tr; r0 < srows; r0 += 12 * 5) {
+                uint32_t v[5];
 #pragma unroll
-            for (int k = 0; k < 5; k++) {
-                const int it = it0 + 256 * k;
-                if (it < nw) {
-                    const int r = it / (BIN_PITCH / 4), wc = it - r * (BIN_PITCH / 4);
-                    const int gy = y0 - 3 + r, gx = x0 - 4 + 4 * wc;
-                    const int ry = gy < 0 ? -gy : (gy >= h ? 2 * h - 2 - gy : gy);
-                    v[k] = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)ry * pitch + min(max(gx, 0), lastw)));
+                for (int k = 0; k < 5; k++) {
+                    const int r = r0 + 12 * k;
+                    if (r < srows) {
+                        const int gy = y0 - 3 + r;
+                        const int ry = gy < 0 ? -gy : (gy >= h ? 2 * h - 2 - gy : gy);
+                        v[k] = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)ry * pitch + cx));
+                    }
                 }
-            }
 #pragma unroll
-            for (int k = 0; k < 5; k++) {
-                const int it = it0 + 256 * k;
-                if (it < nw) reinterpret_cast<uint32_t *>(s_in)[it] = v[k];
+                for (int k = 0; k < 5; k++) {
+                    const int r = r0 + 12 * k;
+                    if (r < srows) reinterpret_cast<uint32_t *>(s_in)[r * (BIN_PITCH / 4) + wc] = v[k];
+                }
             }
         }
         const bool left = x0 == 0, right = x0 + 76 > w;      // the staged columns x0-4 .. x0+75 leave the image
