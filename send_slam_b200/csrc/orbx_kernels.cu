@@ -153,7 +153,10 @@ __global__ void __launch_bounds__(128) k_resize(const __grid_constant__ LevelTab
     ResizeTap ty[RR];
     uint32_t w[RR][2][3];
 #pragma unroll
-    for (int rr = 0; rr < RR; rr++) ty[rr] = D.ytap[min(dy0 + rr, dh - 1)];
+    for (int rr = 0; rr < RR; rr++) {    // one 8-byte load per tap record
+        const uint2 q = __ldg(reinterpret_cast<const uint2 *>(D.ytap + min(dy0 + rr, dh - 1)));
+        ty[rr].ofs = (int16_t)(q.x & 0xFFFF); ty[rr].c0 = (int16_t)(q.x >> 16); ty[rr].c1 = (int16_t)(q.y & 0xFFFF); ty[rr].ofs1 = (int16_t)(q.y >> 16);
+    }
 #pragma unroll
     for (int rr = 0; rr < RR; rr++)
 #pragma unroll
@@ -191,8 +194,9 @@ __global__ void __launch_bounds__(128) k_resize(const __grid_constant__ LevelTab
         uint32_t packed = 0;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
+            // <= ((2048 * 32640) >> 16) + 2 >> 2 = 255 because c0 + c1 = 2048 and both are non-negative on this path: no clamp
             const uint32_t v = (__umulhi(c0s, r[0][i] >> 4) + __umulhi(c1s, r[1][i] >> 4) + 2u) >> 2;
-            packed |= min(v, 255u) << (8 * i);
+            packed |= v << (8 * i);
         }
         if (dy0 + rr < dh) *reinterpret_cast<uint32_t *>(drow + (size_t)rr * D.pitch) = packed;
     }
