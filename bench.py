@@ -138,7 +138,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-knn", action="store_true", help="skip the Hamming kNN leg")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "orbx" else args.warmup
+    # the library replays a CUDA graph per (input buffer, output buffers) pair from the third sighting on: the warm-up runs the
+    # ring of input batches twice (+1) so that the timed region is the steady state of a streaming caller; reported as done
+    args.warmup = max(args.warmup, 2 * RING + 1) if args.impl == "orbx" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -25,11 +25,11 @@ static thread_local std::string g_create_error;
 
 // Identity of a host-buffer batch call for CUDA-graph replay: buffers (null = the handle's own staging), geometry, stream.
 struct GraphKey {
-    const void *in, *kp, *desc;
+    const void *in, *kp, *desc, *aux0, *aux1;
     cudaStream_t stream;
     int batch, width, height, stride, lap0, lap1, cap, chunk, fmt;
     bool operator==(const GraphKey &o) const {
-        return in == o.in && kp == o.kp && desc == o.desc && stream == o.stream && batch == o.batch && width == o.width &&
+        return in == o.in && kp == o.kp && desc == o.desc && aux0 == o.aux0 && aux1 == o.aux1 && stream == o.stream && batch == o.batch && width == o.width &&
                height == o.height && stride == o.stride && lap0 == o.lap0 && lap1 == o.lap1 && cap == o.cap && chunk == o.chunk && fmt == o.fmt;
     }
 };
@@ -311,6 +311,38 @@ static int ensure_color(orbx_handle *h) {
     return ORBX_OK;
 }
 
+// CUDA-graph replay of a call shape: the first sighting of a key runs `enqueue` directly (which also performs every lazy
+// one-time initialisation outside a capture), the second captures it into a graph, later ones replay the graph.
+// enqueue(direct): direct = true when the work is issued for real, false while capturing.  before_launch runs before a replay.
+template <typename Enqueue, typename Before>
+static int run_graphed(orbx_handle *h, const GraphKey &key, Enqueue enqueue, Before before_launch) {
+    GraphEntry *e = nullptr;
+    for (auto &g : h->graphs) if (g.key == key) { e = &g; break; }
+    if (!e) {
+        if (h->graphs.size() >= 32) { if (h->graphs.front().exec) cudaGraphExecDestroy(h->graphs.front().exec); h->graphs.erase(h->graphs.begin()); }
+        h->graphs.push_back(GraphEntry{key, nullptr, 0});
+        return enqueue(true);
+    }
+    if (!e->exec) {
+        const long long l0 = h->launches;
+        CU_TRY(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue(false);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+        e->launches = h->launches - l0;
+        h->launches = l0;
+        if (rc) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
+        CU_TRY(h, ce);
+        const cudaError_t ie = cudaGraphInstantiate(&e->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        CU_TRY(h, ie);
+    }
+    before_launch();
+    CU_TRY(h, cudaGraphLaunch(e->exec, h->stream));
+    h->launches += e->launches;
+    return ORBX_OK;
+}
+
 // Clears the per-frame counters of the whole workspace (must precede the kernels of every frame range of a call).
 static int reset_counters(orbx_handle *h, cudaStream_t stream) {
     CU_TRY(h, cudaMemsetAsync(h->d_counts, 0, sizeof(int) * 2 * h->plan.nlevels * h->batch_cap, stream));
@@ -575,30 +607,40 @@ int orbx_extract_batch_device(orbx_handle *h, const uint8_t *d_frames, size_t fr
         color = ColorSrc{d_frames, stride, frame_stride_bytes};      // converted straight out of the caller's memory
         if ((rc = set_level0(h, h->l0_own, h->l0_own_pitch, h->l0_own_fstride))) return rc;
     }
-    if ((rc = reset_counters(h, h->stream))) return rc;
     h->last_batch = batch;
     // Large batches are issued as several frame ranges on concurrent streams: the latency-bound kernels of one range (pyramid
     // chain, quadtree, slot assignment) then overlap the machine-filling ones of another (ORBX_DEV_SPLIT overrides the count).
     static const int split_env = [] { const char *e = getenv("ORBX_DEV_SPLIT"); return e ? atoi(e) : 0; }();
     int parts = split_env > 0 ? split_env : 4;   // measured on 64 x 640x480: 1 -> 126.0 k, 2 -> 127.1 k, 3 -> 131.7 k, 4 -> 131.7 k frames/s
     parts = std::min(std::min(parts, orbx_handle::kComputeStreams), batch / 8);
-    if (parts <= 1 || h->profiling)
-        return run_pipeline(h, 0, batch, lap0, lap1, reinterpret_cast<KeypointRec *>(d_kp_out), d_desc_out, cap, d_n_out, d_mono_out,
-                            h->stream, h->side_stream, h->ev_fork, h->ev_join, color);
-    if ((rc = ensure_pipeline(h))) return rc;
-    CU_TRY(h, cudaEventRecord(h->ev_start, h->stream));
-    const int per = (batch + parts - 1) / parts;
-    int k = 0;
-    for (int f0 = 0; f0 < batch; f0 += per, k++) {
-        const int n = std::min(per, batch - f0);
-        CU_TRY(h, cudaStreamWaitEvent(h->cs[k], h->ev_start, 0));
-        if ((rc = run_pipeline(h, f0, n, lap0, lap1, reinterpret_cast<KeypointRec *>(d_kp_out), d_desc_out, cap, d_n_out, d_mono_out, h->cs[k],
-                               nullptr, nullptr, nullptr, color)))
-            return rc;
-        CU_TRY(h, cudaEventRecord(h->ev_done[k], h->cs[k]));
-        CU_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_done[k], 0));
-    }
-    return ORBX_OK;
+    if (h->profiling) parts = 1;
+    if (parts > 1 && (rc = ensure_pipeline(h))) return rc;
+    KeypointRec *d_kp = reinterpret_cast<KeypointRec *>(d_kp_out);
+    auto enqueue = [&](bool) -> int {
+        int rc2;
+        if ((rc2 = reset_counters(h, h->stream))) return rc2;
+        if (parts <= 1)
+            return run_pipeline(h, 0, batch, lap0, lap1, d_kp, d_desc_out, cap, d_n_out, d_mono_out, h->stream, h->side_stream, h->ev_fork,
+                                h->ev_join, color);
+        CU_TRY(h, cudaEventRecord(h->ev_start, h->stream));
+        const int per = (batch + parts - 1) / parts;
+        int k = 0;
+        for (int g0 = 0; g0 < batch; g0 += per, k++) {
+            const int n = std::min(per, batch - g0);
+            CU_TRY(h, cudaStreamWaitEvent(h->cs[k], h->ev_start, 0));
+            if ((rc2 = run_pipeline(h, g0, n, lap0, lap1, d_kp, d_desc_out, cap, d_n_out, d_mono_out, h->cs[k], nullptr, nullptr, nullptr, color)))
+                return rc2;
+            CU_TRY(h, cudaEventRecord(h->ev_done[k], h->cs[k]));
+            CU_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_done[k], 0));
+        }
+        return ORBX_OK;
+    };
+    // A streaming caller cycles through a few device buffers: a (buffers, geometry) key seen before is replayed as a CUDA graph,
+    // which takes the ~60 API calls of a call off the host (with several ranks per host the enqueue cost otherwise limits scaling).
+    if (!graphs_enabled() || h->profiling) return enqueue(true);
+    GraphKey key{d_frames, d_kp_out, d_desc_out, d_n_out, d_mono_out, h->stream, batch, width, height, stride, lap0, lap1, cap,
+                 0x1000 + parts, h->in_fmt * 100 + h->gray_shift + (int)(frame_stride_bytes % 1000003) * 1000};
+    return run_graphed(h, key, enqueue, [] {});
 }
 
 int orbx_extract_batch(orbx_handle *h, const uint8_t *const *frames, int batch, int width, int height, int stride, int lap0,
@@ -725,33 +767,9 @@ int orbx_extract_batch(orbx_handle *h, const uint8_t *const *frames, int batch, 
         if ((rc = enqueue(true))) return rc;
     } else {
         GraphKey key{in_pinned ? frames[0] : nullptr, out_direct ? (const void *)kp_out : nullptr, out_direct ? (const void *)desc_out : nullptr,
-                     h->stream, batch, width, height, stride, lap0, lap1, out_direct ? cap : 0, chunk, h->in_fmt * 100 + h->gray_shift};
-        GraphEntry *e = nullptr;
-        for (auto &g : h->graphs) if (g.key == key) { e = &g; break; }
-        if (!e) {
-            // first sighting: run directly (this also performs every lazy one-time initialisation outside a capture)
-            if (h->graphs.size() >= 16) { if (h->graphs.front().exec) cudaGraphExecDestroy(h->graphs.front().exec); h->graphs.erase(h->graphs.begin()); }
-            h->graphs.push_back(GraphEntry{key, nullptr, 0});
-            if ((rc = enqueue(true))) return rc;
-        } else {
-            if (!e->exec) {
-                const long long l0 = h->launches;
-                CU_TRY(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-                rc = enqueue(false);
-                cudaGraph_t graph = nullptr;
-                const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
-                e->launches = h->launches - l0;
-                h->launches = l0;
-                if (rc) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
-                CU_TRY(h, ce);
-                const cudaError_t ie = cudaGraphInstantiate(&e->exec, graph, 0);
-                cudaGraphDestroy(graph);
-                CU_TRY(h, ie);
-            }
-            stage_in(0, batch);
-            CU_TRY(h, cudaGraphLaunch(e->exec, h->stream));
-            h->launches += e->launches;
-        }
+                     nullptr, nullptr, h->stream, batch, width, height, stride, lap0, lap1, out_direct ? cap : 0, chunk,
+                     h->in_fmt * 100 + h->gray_shift};
+        if ((rc = run_graphed(h, key, enqueue, [&] { stage_in(0, batch); }))) return rc;
     }
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     if (*h->h_overflow) {
