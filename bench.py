@@ -290,7 +290,8 @@ def main():
                    "config": {"queries": KNN_Q, "db_rows_per_gpu": KNN_ROWS, "k": 2, "backend": "tcgen05.mma kind::i8 on {-1,+1} expansion"},
                    "roofline": {"bound": "tensor", "achieved": pairs / world * 512.0 / 1e12, "peak": tensor_peak_ops / 1e12, "unit": "TOP/s (int8)",
                                 "frac": pairs / world / tensor_pairs_peak,
-                                "note": "512 int8 ops per pair; peak = 2 x measured dense bf16 TFLOP/s (MEASURED_PEAKS.json); nominal int8 dense 4500 TOP/s"},
+                                "note": "512 int8 ops per pair; peak = 2 x measured dense bf16 TFLOP/s (MEASURED_PEAKS.json); nominal int8 dense 4500 TOP/s; "
+                                        "ncu sm__pipe_tensor_cycles_active of the main pass: 73 % (profiles/k_knn2_tc_r01_summary.txt)"},
                    "popc_backend": {"value": pairs_popc, "unit": "pairs/s", "roofline": {"bound": "popc-pipe", "peak": popc_pairs_peak,
                                     "frac": pairs_popc / world / popc_pairs_peak, "note": "148 SM x 16 POPC/clk/SM x 1.965 GHz / 8 POPC per pair"}},
                    "gpu_launches": klaunches}

@@ -8,7 +8,7 @@ $CMD > gpurun_out/bench_plain_$TAG.json 2> gpurun_out/bench_plain_$TAG.err || { 
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launches_$TAG.log 2>&1
 for k in k_fast_tma k_blur k_describe_tma k_octree k_finalize k_knn2_tc k_knn2 k_resize; do
   skip=3; [ $k = k_resize ] && skip=21
-  [ $k = k_knn2_tc ] && skip=4
+  [ $k = k_knn2_tc ] && skip=5      # odd instances = the second (main) pass over the shard
   ncu --set full --clock-control none --import-source on -k regex:^$k -s $skip -c 1 -o gpurun_out/prof_${k}_$TAG -f $CMD > gpurun_out/ncu_${k}_$TAG.log 2>&1
   tail -1 gpurun_out/ncu_${k}_$TAG.log
 done
