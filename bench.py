@@ -295,6 +295,17 @@ def main():
                    "popc_backend": {"value": pairs_popc, "unit": "pairs/s", "roofline": {"bound": "popc-pipe", "peak": popc_pairs_peak,
                                     "frac": pairs_popc / world / popc_pairs_peak, "note": "148 SM x 16 POPC/clk/SM x 1.965 GHz / 8 POPC per pair"}},
                    "gpu_launches": klaunches}
+        if rank == 0 and world == 1 and not args.no_cpu:
+            # CPU baseline of the matcher: the oracle's brute-force k = 2 search (XOR + popcount on 64-bit words,
+            # one thread per query range) on all host threads, the full 2000 x 1 M shard
+            from oracle import oracle_lib as ol
+            cores = os.cpu_count() or 1
+            ol.knn2(q[:64], db[:100000], nthreads=cores)
+            t0 = time.perf_counter()
+            ol.knn2(q, db, nthreads=cores)
+            dtc = time.perf_counter() - t0
+            hamming["cpu_baseline"] = {"value": KNN_Q * KNN_ROWS / dtc, "unit": "pairs/s", "cores": cores, "kind": "port",
+                                       "sample": f"{KNN_Q} queries x {KNN_ROWS} rows, oracle/orb_oracle.c orb_oracle_knn2"}
         index.close()
 
     # ---- cpu baseline (rank 0, N=1 only)
