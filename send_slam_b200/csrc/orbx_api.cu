@@ -200,12 +200,12 @@ static int ensure_plan(orbx_handle *h, int w, int ht, int batch) {
     h->kp_cap = pl.total_out_cap;
     CU_TRY(h, dev_upload(h, &h->d_cells, pl.cells));
     CU_TRY(h, dev_alloc(h, &h->d_counts, (size_t)2 * nl * B));
-    CU_TRY(h, dev_alloc(h, &h->d_overflow, (size_t)1));
     CU_TRY(h, dev_alloc(h, &h->d_slot, (size_t)B * pl.total_out_cap));
     CU_TRY(h, dev_alloc(h, &h->d_kp, (size_t)B * h->kp_cap));
     CU_TRY(h, dev_alloc(h, &h->d_desc, (size_t)B * h->kp_cap * 32));
-    CU_TRY(h, dev_alloc(h, &h->d_n, (size_t)B));
-    CU_TRY(h, dev_alloc(h, &h->d_mono, (size_t)B));
+    // counts, mono indices and the overflow flag share one block (same layout as the pinned h_n block): one D2H copy per call
+    CU_TRY(h, dev_alloc(h, &h->d_n, (size_t)2 * B + 1));
+    h->d_mono = h->d_n + B; h->d_overflow = h->d_n + 2 * B;
     std::vector<BlurTile> tiles;
     int out_base = 0;
     std::memset(h->h_levels, 0, sizeof(h->h_levels));
@@ -754,9 +754,7 @@ int orbx_extract_batch(orbx_handle *h, const uint8_t *const *frames, int batch, 
             CU_TRY(h, cudaEventRecord(h->ev_end, h->d2h_stream));
             CU_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_end, 0));
         }
-        CU_TRY(h, cudaMemcpyAsync(h->h_n, h->d_n, sizeof(int) * batch, cudaMemcpyDeviceToHost, h->stream));
-        CU_TRY(h, cudaMemcpyAsync(h->h_mono, h->d_mono, sizeof(int) * batch, cudaMemcpyDeviceToHost, h->stream));
-        CU_TRY(h, cudaMemcpyAsync(h->h_overflow, h->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(h, cudaMemcpyAsync(h->h_n, h->d_n, sizeof(int) * (2 * h->batch_cap + 1), cudaMemcpyDeviceToHost, h->stream));
         return ORBX_OK;
     };
     // CUDA-graph replay: a call shape seen before (same buffers, same geometry) is captured once and replayed, which
