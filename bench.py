@@ -317,7 +317,11 @@ def main():
         pool = np.concatenate(host_batches)
         sample_frames = pool[np.arange(nfr) % len(pool)]
         v = cpu_baseline(sample_frames, cores)
-        cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
+        t1 = time.perf_counter()
+        from oracle import oracle_lib as ol_
+        ol_.extract_batch(sample_frames[:24], NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, nthreads=1)
+        ms1 = 1e3 * (time.perf_counter() - t1) / 24
+        cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "single_thread_ms_per_frame": ms1,
                "sample": f"{nfr} of the benchmark's synthetic 640x480 frames, oracle/orb_oracle.c, one extractor per thread"}
 
     if rank == 0:
