@@ -7,6 +7,10 @@
 
 namespace orbx {
 
+// per-device bookkeeping of kernel attributes (cudaFuncSetAttribute is per device)
+constexpr int kMaxDevices = 64;
+int current_device_slot();
+
 // One pyramid level as the kernels see it.  Planes are [batch][h][pitch] u8; level 0 may alias caller memory.
 struct LevelDev {
     uint8_t *img;              // un-blurred plane (FAST, IC_Angle read this)

@@ -35,6 +35,12 @@ static const int8_t h_pattern[1024] = {
 #include "orb_pattern.inc"
 };
 
+int current_device_slot() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess) d = 0;
+    return d & (kMaxDevices - 1);
+}
+
 void upload_constants() {
     // umax for HALF_PATCH_SIZE 15 (ctor of ORBextractor; identical for every parameter set)
     static const int umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
@@ -808,8 +814,12 @@ int launch_fast(const LevelDev *h_levels, const CellRect *d_cells, int ncells, i
         P.list_cap = (((tma->max_iw + 1) / 2) * ((tma->max_ih + 1) / 2) + 8 + 3) / 4 * 4;
         P.warp_bytes = (stage + P.sc_bytes + P.list_cap * 2 + 8 + 2 * 4 + 127) / 128 * 128;
         const size_t smem = (size_t)FW_WARPS * P.warp_bytes;
-        static size_t configured = 0, last = 0;
-        static int per_sm = 0;   // resident CTAs per SM: the persistent grid is exactly one wave
+        // function attributes are per device: one slot per device ordinal (a process may hold handles on several GPUs)
+        static size_t configured_[kMaxDevices], last_[kMaxDevices];
+        static int per_sm_[kMaxDevices];   // resident CTAs per SM: the persistent grid is exactly one wave
+        const int dv = current_device_slot();
+        size_t &configured = configured_[dv], &last = last_[dv];
+        int &per_sm = per_sm_[dv];
         if (smem > configured) {
             cudaFuncSetAttribute(k_fast_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             configured = smem;
@@ -1184,7 +1194,8 @@ int launch_octree(const LevelDev *h_levels, int nlevels, int f0, int batch, int 
     }
     cap = (cap + 1) & ~1;
     const size_t smem = octree_smem_bytes(nbins, cap);
-    static size_t configured = 0;
+    static size_t configured_[kMaxDevices];
+    size_t &configured = configured_[current_device_slot()];
     if (smem > configured) {
         cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
@@ -1507,7 +1518,8 @@ int launch_describe(const LevelDev *h_levels, int nlevels, int f0, int batch, in
         memcpy(P.img, tma->img, sizeof(P.img));
         memcpy(P.blur, tma->blur, sizeof(P.blur));
         const size_t smem = (size_t)DT_WARPS * DT_WARP_BYTES;
-        static int per_sm = 0;
+        static int per_sm_[kMaxDevices];
+        int &per_sm = per_sm_[current_device_slot()];
         if (!per_sm) {
             cudaFuncSetAttribute(k_describe_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_describe_tma, DT_WARPS * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;

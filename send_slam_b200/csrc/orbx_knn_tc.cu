@@ -339,7 +339,8 @@ int launch_knn2_tc(const int8_t *d_qe, int nq, const int8_t *d_dbe, long long nr
     CUtensorMap mq, mdb;
     if (!make_map(&mq, d_qe, (long long)nqt * TC_QT, TC_QT, err)) return 0;
     if (!make_map(&mdb, d_dbe, ntiles_ll * TC_DT, TC_DT, err)) return 0;
-    static bool configured = false;
+    static bool configured_[kMaxDevices];
+    bool &configured = configured_[current_device_slot()];
     const size_t smem = knn_tc_smem_bytes();
     if (!configured) {
         if (cudaFuncSetAttribute(k_knn2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {

@@ -501,3 +501,25 @@ def test_windowed_matching(ex, oracle):
     z = e.match_windowed(d0[:5], quvr[:5], qlev[:5], k1[:0], d1[:0], bounds)
     assert np.all(z[0] == -1) and np.all(z[3] == 256)
     e.close()
+
+
+def test_two_devices_one_process(oracle):
+    """One process holding handles on two GPUs (kernel attributes and tensor maps are per device)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    w, h, nf = 640, 480, 1000
+    o = oracle.Oracle(nf)
+    frames = [synth.textured_frame(950 + i, w, h) for i in range(2)]
+    exs = [orbx.ORBextractor(nf, 1.2, 8, 20, 7, device=d, max_width=w, max_height=h, max_batch=2) for d in (0, 1)]
+    for rep in range(2):
+        for d in (0, 1):
+            assert_same_extraction(exs[d](frames[d]), o.extract(frames[d]), f"device {d}")
+    db = synth.descriptor_db(80000, seed=21)
+    q, _ = synth.queries_from_db(db, 100, seed=22)
+    want = oracle.knn2(q, db)
+    for d in (1, 0):
+        idx, dist = orbx.Knn2Index(db, device=d).knnMatch(q)
+        assert np.array_equal(idx, want[0]) and np.array_equal(dist, want[1]), d
+    for e in exs:
+        e.close()
