@@ -351,6 +351,12 @@ def main():
                             "(sm__pipe_alu_cycles_active, profiles/k_fast_tma_r01_summary.txt): FAST scoring costs ~40 min/max ops "
                             "per pixel and 59 % of the synthetic frames' pixels are corners" if dom == "fast" else None,
                     "peak_source": peak_src,
+                    # what actually binds the dominant kernel (FAST): the integer ALU pipe.  Algorithmic work = 57 u16x2 min/max per
+                    # pixel pair and pass on the ALU pipe (the 16 pair maxima per pass run as IMAD on the FMA pipe), 4 passes per 8
+                    # pixels; peak = VIMNMX.U16x2 rate measured by tools/ubench_pipes.cu (profiles/ubench_pipes_r01.jsonl)
+                    "alu_pipe": ({"achieved_Gops": S * BATCH * 28.5 / (acc["fast"] * 1e-3) / 1e9, "peak_Gops": 82.7 * 148 * 1.965,
+                                  "frac": S * BATCH * 28.5 / (acc["fast"] * 1e-3) / 1e9 / (82.7 * 148 * 1.965),
+                                  "ncu_pipe_alu_busy": 0.686, "source": "profiles/k_fast_tma_r01_summary.txt"} if dom == "fast" else None),
                     "algorithmic_bytes_per_launch": stage_bytes[dom] * BATCH,
                     "launch_ms": acc[dom],
                     "whole_step": {"algorithmic_bytes_per_frame": total_bytes,
