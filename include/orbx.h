@@ -205,6 +205,15 @@ int orbx_frame_grid_batch_device(orbx_handle *h, const orbx_keypoint *d_kp, cons
                                  const orbx_camera *cam, const float *bounds4, orbx_keypoint *d_kp_un, int32_t *d_cell_start,
                                  int32_t *d_cell_items);
 
+/* orbx_match_windowed on data that never left HBM: queries and the train frame's mvKeysUn / descriptors / feature grid (the outputs of
+ * orbx_extract_batch_device + orbx_frame_grid_batch_device for one frame) are device pointers; the candidate set of a query is read off
+ * the grid cells of its window (Frame::GetFeaturesInArea) instead of testing every train keypoint.  Same results, same tie order.
+ * Asynchronous on the handle's stream. */
+int orbx_match_windowed_grid_device(orbx_handle *h, const uint8_t *d_q_desc, const float *d_q_uvr, const int32_t *d_q_levels, int nq,
+                                    const orbx_keypoint *d_t_kp_un, const uint8_t *d_t_desc, const int32_t *d_cell_start,
+                                    const int32_t *d_cell_items, const float *bounds4, int32_t *d_best_idx, int32_t *d_best_dist,
+                                    int32_t *d_second_idx, int32_t *d_second_dist);
+
 /* Distance backend of a shard: ORBX_KNN_TENSOR (default) = descriptors expanded to {-1,+1} int8, q.d = 256 - 2H on
  * tcgen05.mma kind::i8 with the top-2 taken from TMEM; ORBX_KNN_POPC = XOR + POPC on the CUDA cores.  Identical results. */
 #define ORBX_KNN_POPC 0

@@ -102,6 +102,12 @@ int launch_knn2_tc(const int8_t *d_qe, int nq, const int8_t *d_dbe, long long nr
                    std::string &err);
 }  // namespace orbx
 
+namespace orbx {
+int match_windowed_grid_device(cudaStream_t stream, const uint8_t *d_q_desc, const float *d_q_uvr, const int32_t *d_q_levels, int nq,
+                               const KeypointRec *d_t_kp, const uint8_t *d_t_desc, const int32_t *d_cell_start, const int32_t *d_cell_items,
+                               const float *bounds4, int32_t *d_best_idx, int32_t *d_best_dist, int32_t *d_second_idx, int32_t *d_second_dist);
+}  // namespace orbx
+
 struct orbx_keypoint;
 namespace orbx {
 // matching launchers that run on an extractor handle's stream (orbx_match.cu)

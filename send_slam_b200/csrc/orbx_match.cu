@@ -86,6 +86,58 @@ __global__ void __launch_bounds__(256) k_match_windowed(const uint4 *__restrict_
     }
 }
 
+// The same search on the feature grid built by k_frame_grid (orbx_frame.cu): Frame::GetFeaturesInArea walks the cells
+// (ix outer, iy inner) of the query window; in the CSR layout (cell = ix * 48 + iy) the cells iy0..iy1 of one grid column are
+// one contiguous item range, so a warp strides over a few dozen candidates instead of every train keypoint.  The CSR position
+// is monotone in the reference's visiting order (grid column, grid row, train index), which makes it the tie-break key.
+__global__ void __launch_bounds__(256) k_match_windowed_grid(const uint4 *__restrict__ qdesc, const float *__restrict__ quvr,
+                                                             const int32_t *__restrict__ qlev, int nq,
+                                                             const KeypointRec *__restrict__ tkp, const uint4 *__restrict__ tdesc,
+                                                             const int32_t *__restrict__ cell_start, const int32_t *__restrict__ cell_items,
+                                                             float minX, float minY, float invW, float invH,
+                                                             int32_t *__restrict__ best_idx, int32_t *__restrict__ best_dist,
+                                                             int32_t *__restrict__ second_idx, int32_t *__restrict__ second_dist) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const uint4 q0 = qdesc[2 * q], q1 = qdesc[2 * q + 1];
+    const float x = quvr[3 * q], y = quvr[3 * q + 1], r = quvr[3 * q + 2];
+    const int minLevel = qlev[2 * q], maxLevel = qlev[2 * q + 1];
+    const bool check = (minLevel > 0) || (maxLevel >= 0);
+    const int cx0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, minX), r), invW)));
+    const int cx1 = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, minX), r), invW)));
+    const int cy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, minY), r), invH)));
+    const int cy1 = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, minY), r), invH)));
+    unsigned long long k1 = NONE64, k2 = NONE64;
+    if (cx0 < GRID_COLS && cx1 >= 0 && cy0 < GRID_ROWS && cy1 >= 0 && cy0 <= cy1) {
+        for (int ix = cx0; ix <= cx1; ix++) {
+            const int lo = cell_start[ix * GRID_ROWS + cy0], hi = cell_start[ix * GRID_ROWS + cy1 + 1];
+            for (int p = lo + lane; p < hi; p += 32) {
+                const int t = cell_items[p];
+                const KeypointRec kp = tkp[t];
+                if (check) {
+                    if (kp.octave < minLevel) continue;
+                    if (maxLevel >= 0 && kp.octave > maxLevel) continue;
+                }
+                if (!(fabsf(__fsub_rn(kp.x, x)) < r && fabsf(__fsub_rn(kp.y, y)) < r)) continue;
+                const int d = hamming256(q0, q1, tdesc[2 * t], tdesc[2 * t + 1]);
+                const unsigned long long key = ((unsigned long long)d << 40) | (unsigned long long)p;
+                if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
+            }
+        }
+    }
+    unsigned long long b = k1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(0xFFFFFFFFu, b, o); b = v < b ? v : b; }
+    unsigned long long s = (k1 == b) ? k2 : k1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(0xFFFFFFFFu, s, o); s = v < s ? v : s; }
+    if (lane == 0) {
+        best_idx[q] = b == NONE64 ? -1 : cell_items[(int)(b & 0xFFFFFFFFull)];  best_dist[q] = b == NONE64 ? 256 : (int32_t)(b >> 40);
+        second_idx[q] = s == NONE64 ? -1 : cell_items[(int)(s & 0xFFFFFFFFull)]; second_dist[q] = s == NONE64 ? 256 : (int32_t)(s >> 40);
+    }
+}
+
 // ---- brute-force kNN, k = 2 -----------------------------------------------------------------------------------
 constexpr int KQ_THREADS = 128;    // threads per CTA
 constexpr int KQ_QPT = 2;          // queries per thread (registers)
@@ -451,5 +503,19 @@ int match_windowed(int device, cudaStream_t stream, const uint8_t *q_desc, const
     cleanup();
 #undef M_TRY
     return ORBX_OK;
+}
+}  // namespace orbx
+
+namespace orbx {
+int match_windowed_grid_device(cudaStream_t stream, const uint8_t *d_q_desc, const float *d_q_uvr, const int32_t *d_q_levels, int nq,
+                               const KeypointRec *d_t_kp, const uint8_t *d_t_desc, const int32_t *d_cell_start, const int32_t *d_cell_items,
+                               const float *bounds4, int32_t *d_best_idx, int32_t *d_best_dist, int32_t *d_second_idx, int32_t *d_second_dist) {
+    if (nq <= 0) return 0;
+    const float minX = bounds4[0], minY = bounds4[1], maxX = bounds4[2], maxY = bounds4[3];
+    const float invW = (float)GRID_COLS / (maxX - minX), invH = (float)GRID_ROWS / (maxY - minY);
+    k_match_windowed_grid<<<(nq + 7) / 8, 256, 0, stream>>>(reinterpret_cast<const uint4 *>(d_q_desc), d_q_uvr, d_q_levels, nq, d_t_kp,
+                                                            reinterpret_cast<const uint4 *>(d_t_desc), d_cell_start, d_cell_items, minX, minY,
+                                                            invW, invH, d_best_idx, d_best_dist, d_second_idx, d_second_dist);
+    return 1;
 }
 }  // namespace orbx

@@ -47,6 +47,7 @@ EXPORTS = [
     "orbx_version", "orbx_set_profiling", "orbx_get_stage_times", "orbx_set_stream",
     "orbx_knn2_set_stream", "orbx_knn2_set_backend", "orbx_set_input_format", "orbx_debug_gray",
     "orbx_undistort_points", "orbx_image_bounds", "orbx_frame_grid", "orbx_frame_grid_batch_device",
+    "orbx_match_windowed_grid_device",
 ]
 
 _lib = None
@@ -88,6 +89,7 @@ def lib():
     L.orbx_image_bounds.argtypes = [vp, vp, C.c_int, C.c_int, vp]
     L.orbx_frame_grid.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp]
     L.orbx_frame_grid_batch_device.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp]
+    L.orbx_match_windowed_grid_device.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.orbx_debug_gray.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int]
     L.orbx_debug_octree.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, ip]
     L.orbx_debug_describe.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp]
@@ -306,6 +308,15 @@ class ORBextractor:
         self._check(self._L.orbx_frame_grid_batch_device(self._h, C.c_void_p(d_kp_ptr), C.c_void_p(d_n_ptr), int(batch), int(cap), _p(c),
                                                          _p(b), C.c_void_p(d_kp_un_ptr), C.c_void_p(d_cell_start_ptr),
                                                          C.c_void_p(d_cell_items_ptr)))
+
+    def match_windowed_grid_device(self, d_q_desc, d_q_uvr, d_q_levels, nq, d_t_kp_un, d_t_desc, d_cell_start, d_cell_items, bounds,
+                                   d_best_idx, d_best_dist, d_second_idx, d_second_dist):
+        """Windowed search on device-resident data through the feature grid (raw device pointers); asynchronous, see sync()."""
+        b = np.ascontiguousarray(bounds, np.float32)
+        p = [C.c_void_p(x) for x in (d_q_desc, d_q_uvr, d_q_levels)]
+        t = [C.c_void_p(x) for x in (d_t_kp_un, d_t_desc, d_cell_start, d_cell_items)]
+        o = [C.c_void_p(x) for x in (d_best_idx, d_best_dist, d_second_idx, d_second_dist)]
+        self._check(self._L.orbx_match_windowed_grid_device(self._h, p[0], p[1], p[2], int(nq), t[0], t[1], t[2], t[3], _p(b), *o))
 
     def debug_gray(self, src, fmt, gray_shift=15):
         src = np.ascontiguousarray(src, np.uint8)

@@ -523,3 +523,54 @@ def test_two_devices_one_process(oracle):
         assert np.array_equal(idx, want[0]) and np.array_equal(dist, want[1]), d
     for e in exs:
         e.close()
+
+
+def test_device_resident_frame_to_frame_matching(oracle):
+    """BASELINE config 3 without leaving HBM: two 1080p frames extracted device-resident, Frame::UndistortKeyPoints + feature grid on
+    the device, previous-frame windowed search through the grid -- compared with the oracle and with the brute-force kernel."""
+    import torch
+    w, h, nf = 1920, 1080, 2000
+    cam = (1400.0, 1400.0, 960.0, 540.0, -0.05, 0.01, 0.0005, -0.0003, 0.0)
+    f0 = synth.textured_frame(61, w, h)
+    frames = np.stack([f0, synth.shifted_frame(f0, 5, -4, seed=2)])
+    e = orbx.ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=2)
+    cap = e.capacity
+    dev = "cuda"
+    d_in = torch.from_numpy(frames).to(dev)
+    d_kp = torch.zeros((2, cap, 7), dtype=torch.float32, device=dev)
+    d_desc = torch.zeros((2, cap, 32), dtype=torch.uint8, device=dev)
+    d_n = torch.zeros(2, dtype=torch.int32, device=dev)
+    d_mono = torch.zeros(2, dtype=torch.int32, device=dev)
+    d_un = torch.zeros_like(d_kp)
+    d_start = torch.zeros((2, 64 * 48 + 1), dtype=torch.int32, device=dev)
+    d_items = torch.zeros((2, cap), dtype=torch.int32, device=dev)
+    bounds = e.image_bounds(cam, w, h)
+    e.extract_batch_device(d_in.data_ptr(), w * h, 2, w, h, w, d_kp.data_ptr(), d_desc.data_ptr(), cap, d_n.data_ptr(), d_mono.data_ptr())
+    e.frame_grid_batch_device(d_kp.data_ptr(), d_n.data_ptr(), 2, cap, cam, bounds, d_un.data_ptr(), d_start.data_ptr(), d_items.data_ptr())
+    e.sync()
+    n = d_n.cpu().numpy()
+    un = [d_un[i, :n[i]].cpu().numpy().view(orbx.KP_DTYPE).reshape(-1) for i in range(2)]
+    desc = [d_desc[i, :n[i]].cpu().numpy() for i in range(2)]
+    # queries: every keypoint of frame 0 searched around its (shifted) position in frame 1, radius 15 * scale[octave]
+    scale = e.GetScaleFactors()
+    k0 = un[0]
+    quvr = np.stack([k0["x"] + 5, k0["y"] - 4, 15.0 * scale[k0["octave"]]], 1).astype(np.float32)
+    qlev = np.stack([k0["octave"] - 1, k0["octave"] + 1], 1).astype(np.int32)
+    qlev[:40] = (-1, -1)
+    quvr[40:50, 2] = 300.0
+    nq = len(k0)
+    d_q = d_desc[0, :nq].contiguous()
+    d_quvr, d_qlev = torch.from_numpy(quvr).to(dev), torch.from_numpy(qlev).to(dev)
+    outs = [torch.zeros(nq, dtype=torch.int32, device=dev) for _ in range(4)]
+    t_kp, t_desc = d_un[1].contiguous(), d_desc[1].contiguous()
+    e.match_windowed_grid_device(d_q.data_ptr(), d_quvr.data_ptr(), d_qlev.data_ptr(), nq, t_kp.data_ptr(), t_desc.data_ptr(),
+                                 d_start[1].contiguous().data_ptr(), d_items[1].contiguous().data_ptr(), bounds, *[o.data_ptr() for o in outs])
+    e.sync()
+    got = [o.cpu().numpy() for o in outs]
+    want = oracle.match_windowed(desc[0], quvr, qlev, un[1], desc[1], bounds)
+    brute = e.match_windowed(desc[0], quvr, qlev, un[1], desc[1], bounds)
+    for g_, w_, b_, name in zip(got, want, brute, ["best_idx", "best_dist", "second_idx", "second_dist"]):
+        assert np.array_equal(g_, w_), name
+        assert np.array_equal(b_, w_), name
+    assert ((got[0] >= 0) & (got[1] <= orbx.ORBmatcher.TH_HIGH)).mean() > 0.5
+    e.close()
