@@ -51,7 +51,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -202,7 +202,6 @@ def main():
     barrier()
     dt = ev0.elapsed_time(ev1) * 1e-3
     launches = ex.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -242,6 +241,8 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dte = float(tt.item())
     e2e_fps = world * e2e_steps * BATCH / dte
+    # the clock sampler (nvidia-smi, 100 ms period) covers the device-timed region, the per-stage pass and the e2e region
+    clocks = sampler.stop() if rank == 0 else None
     h2d = BATCH * W * H
     d2h = BATCH * cap * (28 + 32) + BATCH * 8 + 4
 
