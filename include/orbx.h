@@ -214,6 +214,19 @@ int orbx_match_windowed_grid_device(orbx_handle *h, const uint8_t *d_q_desc, con
                                     const int32_t *d_cell_items, const float *bounds4, int32_t *d_best_idx, int32_t *d_best_dist,
                                     int32_t *d_second_idx, int32_t *d_second_dist);
 
+/* ---- Vocabulary-tree descent ------------------------------------------------------------------------------------
+ * DBoW2 TemplatedVocabulary<ORB>::transform as UPSTREAM Frame::ComputeBoW calls it (mpORBvocabulary->transform(desc, BowVec, FeatVec, 4)):
+ * per descriptor the word (leaf) reached by stepping to the child of smallest Hamming distance (first child wins ties), its weight, and
+ * the node `levelsup` levels above the leaf level (FeatureVector key; node 0 = root when levelsup >= depth).  The tree is handed over
+ * as arrays, node 0 = root, parents before children (the order of an ORBvoc.txt file): parent[n], desc[n][32], weight[n].  Word ids are
+ * the leaves in node order, as DBoW2::createWords assigns them.  BowVector accumulation / normalisation stays with the caller. */
+typedef struct orbx_vocab orbx_vocab;
+int orbx_vocab_create(int device, const int32_t *parent, const uint8_t *desc, const float *weight, int n_nodes, orbx_vocab **out);
+void orbx_vocab_destroy(orbx_vocab *v);
+const char *orbx_vocab_last_error(const orbx_vocab *v);
+int orbx_vocab_depth(const orbx_vocab *v);
+int orbx_vocab_transform(orbx_vocab *v, const uint8_t *desc, int n, int levelsup, int32_t *word_id, float *word_weight, int32_t *node_id);
+
 /* Distance backend of a shard: ORBX_KNN_TENSOR (default) = descriptors expanded to {-1,+1} int8, q.d = 256 - 2H on
  * tcgen05.mma kind::i8 with the top-2 taken from TMEM; ORBX_KNN_POPC = XOR + POPC on the CUDA cores.  Identical results. */
 #define ORBX_KNN_POPC 0

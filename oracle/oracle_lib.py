@@ -68,6 +68,7 @@ def lib():
         L.orb_oracle_undistort_points.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.orb_oracle_image_bounds.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.orb_oracle_frame_grid.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orb_oracle_bow_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -291,3 +292,13 @@ def frame_grid(kps: np.ndarray, cam, bounds):
     c, b = _cam(cam), np.ascontiguousarray(bounds, np.float32)
     lib().orb_oracle_frame_grid(_p(kps), len(kps), _p(c), _p(b), _p(un), _p(start), _p(items))
     return un, start, items[:start[-1]]
+
+
+def bow_transform(parent, ndesc, weight, feat, levelsup=4):
+    """DBoW2 transform restatement.  Returns (word_id, word_weight, node_id, depth)."""
+    parent = np.ascontiguousarray(parent, np.int32); ndesc = np.ascontiguousarray(ndesc, np.uint8)
+    weight = np.ascontiguousarray(weight, np.float32); feat = np.ascontiguousarray(feat, np.uint8)
+    n = len(feat)
+    w, wt, nid = np.zeros(n, np.int32), np.zeros(n, np.float32), np.zeros(n, np.int32)
+    depth = lib().orb_oracle_bow_transform(_p(parent), _p(ndesc), _p(weight), len(parent), _p(feat), n, int(levelsup), _p(w), _p(wt), _p(nid))
+    return w, wt, nid, depth

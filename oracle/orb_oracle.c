@@ -939,3 +939,39 @@ int orb_oracle_match_windowed(const u8 *qdesc, const float *quvr, const int32_t 
     free(cell_cnt); free(cell_of); free(fill); free(items);
     return 0;
 }
+
+/* ---- DBoW2 vocabulary-tree descent ----------------------------------------------------------------------------------
+ * TemplatedVocabulary<ORB>::transform(feature, word_id, weight, nid, levelsup) of the DBoW2 library the reference build links (third
+ * party, not under /root/reference; restated from the published source -- "parity unpinned").  Tree as arrays, node 0 = root, parents
+ * before children; children of a node in id order; word ids = leaves in id order; L = depth of the deepest node. */
+int orb_oracle_bow_transform(const int32_t *parent, const u8 *ndesc, const float *weight, int n_nodes, const u8 *feat, int n, int levelsup,
+                             int32_t *word_id, float *word_weight, int32_t *node_id) {
+    int *start = (int *)calloc((size_t)n_nodes + 1, sizeof(int)), *child = (int *)malloc(sizeof(int) * (size_t)n_nodes);
+    int *word = (int *)malloc(sizeof(int) * (size_t)n_nodes), *depth = (int *)calloc((size_t)n_nodes, sizeof(int));
+    int L = 0, nwords = 0;
+    for (int i = 1; i < n_nodes; i++) start[parent[i] + 1]++;
+    for (int i = 0; i < n_nodes; i++) start[i + 1] += start[i];
+    int *fill = (int *)malloc(sizeof(int) * (size_t)n_nodes);
+    memcpy(fill, start, sizeof(int) * (size_t)n_nodes);
+    for (int i = 1; i < n_nodes; i++) { child[fill[parent[i]]++] = i; depth[i] = depth[parent[i]] + 1; if (depth[i] > L) L = depth[i]; }
+    for (int i = 0; i < n_nodes; i++) word[i] = (start[i + 1] == start[i]) ? nwords++ : -1;
+    const int nid_level = L - levelsup;
+    for (int f = 0; f < n; f++) {
+        int final_id = 0, current_level = 0, nid = 0;
+        while (start[final_id + 1] > start[final_id]) {
+            ++current_level;
+            const int lo = start[final_id], hi = start[final_id + 1];
+            int best = child[lo], best_d = orb_oracle_distance(feat + (size_t)f * 32, ndesc + (size_t)child[lo] * 32);
+            for (int c = lo + 1; c < hi; c++) {
+                const int d = orb_oracle_distance(feat + (size_t)f * 32, ndesc + (size_t)child[c] * 32);
+                if (d < best_d) { best_d = d; best = child[c]; }
+            }
+            final_id = best;
+            if (current_level == nid_level) nid = final_id;
+        }
+        word_id[f] = word[final_id]; word_weight[f] = weight[final_id]; node_id[f] = nid;
+    }
+    free(start); free(child); free(word); free(depth); free(fill);
+    return L;
+}
+

@@ -48,6 +48,7 @@ EXPORTS = [
     "orbx_knn2_set_stream", "orbx_knn2_set_backend", "orbx_set_input_format", "orbx_debug_gray",
     "orbx_undistort_points", "orbx_image_bounds", "orbx_frame_grid", "orbx_frame_grid_batch_device",
     "orbx_match_windowed_grid_device",
+    "orbx_vocab_create", "orbx_vocab_destroy", "orbx_vocab_last_error", "orbx_vocab_depth", "orbx_vocab_transform",
 ]
 
 _lib = None
@@ -90,6 +91,12 @@ def lib():
     L.orbx_frame_grid.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp]
     L.orbx_frame_grid_batch_device.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp]
     L.orbx_match_windowed_grid_device.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.orbx_vocab_create.argtypes = [C.c_int, vp, vp, vp, C.c_int, C.POINTER(vp)]
+    L.orbx_vocab_destroy.argtypes = [vp]
+    L.orbx_vocab_last_error.restype = C.c_char_p
+    L.orbx_vocab_last_error.argtypes = [vp]
+    L.orbx_vocab_depth.argtypes = [vp]
+    L.orbx_vocab_transform.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, vp]
     L.orbx_debug_gray.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int]
     L.orbx_debug_octree.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, ip]
     L.orbx_debug_describe.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp]
@@ -509,3 +516,41 @@ def unpack_knn(packed: np.ndarray):
     idx[none] = -1
     dist[none] = -1
     return idx, dist
+
+
+class ORBVocabulary:
+    """DBoW2 vocabulary tree on one B200: transform() = the per-descriptor descent of TemplatedVocabulary::transform that UPSTREAM
+    Frame::ComputeBoW runs (word id, word weight, node id `levelsup` levels above the leaves).  The tree is given as arrays in node
+    order (node 0 = root, parents before children -- the order of an ORBvoc.txt file)."""
+
+    def __init__(self, parent, desc, weight, device=0):
+        self._L = lib()
+        self._v = C.c_void_p()
+        parent = np.ascontiguousarray(parent, np.int32); desc = np.ascontiguousarray(desc, np.uint8)
+        weight = np.ascontiguousarray(weight, np.float32)
+        if desc.shape != (len(parent), 32) or weight.shape != (len(parent),):
+            raise OrbxError(ORBX_E_INVALID, "desc must be [n,32] uint8 and weight [n] float32")
+        rc = self._L.orbx_vocab_create(int(device), _p(parent), _p(desc), _p(weight), len(parent), C.byref(self._v))
+        if rc != ORBX_OK:
+            raise OrbxError(rc, (self._L.orbx_vocab_last_error(None) or b"").decode())
+        self.depth = int(self._L.orbx_vocab_depth(self._v))
+
+    def transform(self, desc, levelsup=4):
+        desc = np.ascontiguousarray(desc, np.uint8)
+        n = len(desc)
+        w, wt, nid = np.zeros(n, np.int32), np.zeros(n, np.float32), np.zeros(n, np.int32)
+        rc = self._L.orbx_vocab_transform(self._v, _p(desc), n, int(levelsup), _p(w), _p(wt), _p(nid))
+        if rc != ORBX_OK:
+            raise OrbxError(rc, (self._L.orbx_vocab_last_error(self._v) or b"").decode())
+        return w, wt, nid
+
+    def close(self):
+        if self._v:
+            self._L.orbx_vocab_destroy(self._v)
+            self._v = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -574,3 +574,45 @@ def test_device_resident_frame_to_frame_matching(oracle):
         assert np.array_equal(b_, w_), name
     assert ((got[0] >= 0) & (got[1] <= orbx.ORBmatcher.TH_HIGH)).mean() > 0.5
     e.close()
+
+
+def _random_vocab(rng, k, L, ragged):
+    """Nodes in BFS order (parents before children); ragged: some inner nodes get fewer children, some become early leaves."""
+    parent = [-1]
+    frontier = [0]
+    for level in range(L):
+        nxt = []
+        for p in frontier:
+            if ragged and level > 0 and rng.random() < 0.1:
+                continue                                   # early leaf
+            nk = k if not ragged else int(rng.integers(1, k + 1))
+            for _ in range(nk):
+                parent.append(p); nxt.append(len(parent) - 1)
+        frontier = nxt
+    n = len(parent)
+    desc = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    # force distance ties between siblings so that the first-child rule is exercised
+    for i in range(2, n, 7):
+        if parent[i] == parent[i - 1]:
+            desc[i] = desc[i - 1]
+    weight = rng.random(n).astype(np.float32)
+    return np.array(parent, np.int32), desc, weight
+
+
+def test_bow_transform(oracle):
+    """DBoW2 vocabulary-tree descent on the device == the oracle's restatement (word, weight, FeatureVector node)."""
+    rng = np.random.default_rng(31)
+    for (k, L, ragged) in [(10, 4, False), (10, 5, True), (3, 7, True), (40, 2, False)]:
+        parent, nd, wt = _random_vocab(rng, k, L, ragged)
+        feats = rng.integers(0, 256, (3000, 32), dtype=np.uint8)
+        feats[:500] = nd[rng.integers(1, len(nd), 500)]       # exact node descriptors: distance 0 somewhere on the path
+        v = orbx.ORBVocabulary(parent, nd, wt)
+        for levelsup in (0, 2, 4, 9):
+            w_o, wt_o, nid_o, depth = oracle.bow_transform(parent, nd, wt, feats, levelsup)
+            assert v.depth == depth
+            w, wgt, nid = v.transform(feats, levelsup)
+            assert np.array_equal(w, w_o) and np.array_equal(wgt, wt_o) and np.array_equal(nid, nid_o), (k, L, ragged, levelsup)
+        assert len(v.transform(feats[:0])[0]) == 0
+        v.close()
+    with pytest.raises(orbx.OrbxError):
+        orbx.ORBVocabulary(np.array([0, 0], np.int32), np.zeros((2, 32), np.uint8), np.zeros(2, np.float32))   # node 0 must be the root
