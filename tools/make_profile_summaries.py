@@ -16,6 +16,7 @@ rows = [r for r in csv.reader(open(path, errors="replace")) if len(r) > 10 and r
 agg = collections.OrderedDict()
 for r in rows:
     name = re.sub(r"\(.*", "", r[4]).replace("orbx::", "").replace("(anonymous namespace)::", "")
+    name = re.sub(r"<.*", "", name.replace("void ", "")).strip()
     val = float(r[-1].replace(",", ""))
     unit = r[-2]
     us = val / 1000.0 if unit in ("ns", "nsecond") else val if unit in ("us", "usecond") else val * 1000.0
