@@ -33,7 +33,7 @@ struct GraphKey {
                height == o.height && stride == o.stride && lap0 == o.lap0 && lap1 == o.lap1 && cap == o.cap && chunk == o.chunk && fmt == o.fmt;
     }
 };
-struct GraphEntry { GraphKey key; cudaGraphExec_t exec; long long launches; };
+struct GraphEntry { GraphKey key; cudaGraphExec_t exec; long long launches; bool disabled; };
 
 static bool graphs_enabled() {
     static const bool on = [] { const char *e = getenv("ORBX_GRAPHS"); return !(e && e[0] == '0'); }();
@@ -320,22 +320,30 @@ static int run_graphed(orbx_handle *h, const GraphKey &key, Enqueue enqueue, Bef
     for (auto &g : h->graphs) if (g.key == key) { e = &g; break; }
     if (!e) {
         if (h->graphs.size() >= 32) { if (h->graphs.front().exec) cudaGraphExecDestroy(h->graphs.front().exec); h->graphs.erase(h->graphs.begin()); }
-        h->graphs.push_back(GraphEntry{key, nullptr, 0});
+        h->graphs.push_back(GraphEntry{key, nullptr, 0, h->stream == cudaStreamLegacy});   // the legacy stream cannot be captured
         return enqueue(true);
     }
+    if (e->disabled) return enqueue(true);
     if (!e->exec) {
+        // Any failure to capture or instantiate falls back to direct issue for this key (never an error for the caller).
         const long long l0 = h->launches;
-        CU_TRY(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();
+            e->disabled = true;
+            return enqueue(true);
+        }
         const int rc = enqueue(false);
         cudaGraph_t graph = nullptr;
         const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
         e->launches = h->launches - l0;
         h->launches = l0;
-        if (rc) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
-        CU_TRY(h, ce);
-        const cudaError_t ie = cudaGraphInstantiate(&e->exec, graph, 0);
+        if (rc != ORBX_OK || ce != cudaSuccess || !graph || cudaGraphInstantiate(&e->exec, graph, 0) != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            e->exec = nullptr; e->disabled = true;
+            return enqueue(true);
+        }
         cudaGraphDestroy(graph);
-        CU_TRY(h, ie);
     }
     before_launch();
     CU_TRY(h, cudaGraphLaunch(e->exec, h->stream));

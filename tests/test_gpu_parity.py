@@ -616,3 +616,29 @@ def test_bow_transform(oracle):
         v.close()
     with pytest.raises(orbx.OrbxError):
         orbx.ORBVocabulary(np.array([0, 0], np.int32), np.zeros((2, 32), np.uint8), np.zeros(2, np.float32))   # node 0 must be the root
+
+
+def test_legacy_default_stream_and_repeated_calls(oracle):
+    """Work ordered on the CUDA legacy default stream (torch's default stream; cannot be captured into a graph): repeated calls with
+    the same buffers must keep returning the same, correct result (graph replay silently falls back to direct issue)."""
+    import torch
+    B, w, h, nf = 9, 640, 480, 1000
+    frames = np.stack([synth.textured_frame(970 + s, w, h) for s in range(B)])
+    e = orbx.ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=B)
+    e.set_stream(1)                                   # cudaStreamLegacy
+    cap = e.capacity
+    d_in = torch.from_numpy(frames).cuda()
+    d_kp = torch.zeros((B, cap, 7), dtype=torch.float32, device="cuda")
+    d_desc = torch.zeros((B, cap, 32), dtype=torch.uint8, device="cuda")
+    d_n = torch.zeros(B, dtype=torch.int32, device="cuda")
+    d_mono = torch.zeros(B, dtype=torch.int32, device="cuda")
+    o = oracle.Oracle(nf)
+    ref = [o.extract(frames[i]) for i in range(B)]
+    for rep in range(4):
+        d_desc.zero_(); d_n.zero_()
+        e.extract_batch_device(d_in.data_ptr(), w * h, B, w, h, w, d_kp.data_ptr(), d_desc.data_ptr(), cap, d_n.data_ptr(), d_mono.data_ptr())
+        n = d_n.cpu().numpy()                         # torch's default stream is ordered after the legacy-stream work
+        dd = d_desc.cpu().numpy()
+        for i in range(B):
+            assert n[i] == len(ref[i][0]) and np.array_equal(dd[i, :n[i]], ref[i][1]), (rep, i)
+    e.close()
