@@ -14,6 +14,7 @@
 
 #include <cstdint>
 #include <cstring>
+#include <mutex>
 
 #include "orbx_dev.h"
 #include "orbx_tma.cuh"
@@ -34,6 +35,9 @@ __constant__ int c_umax[16];
 static const int8_t h_pattern[1024] = {
 #include "orb_pattern.inc"
 };
+
+// kernel attributes are set once per device; handles on several host threads may reach their first launch at the same time
+std::mutex g_attr_mutex;
 
 int current_device_slot() {
     int d = 0;
@@ -818,6 +822,7 @@ int launch_fast(const LevelDev *h_levels, const CellRect *d_cells, int ncells, i
         static size_t configured_[kMaxDevices], last_[kMaxDevices];
         static int per_sm_[kMaxDevices];   // resident CTAs per SM: the persistent grid is exactly one wave
         const int dv = current_device_slot();
+        std::lock_guard<std::mutex> lock(g_attr_mutex);
         size_t &configured = configured_[dv], &last = last_[dv];
         int &per_sm = per_sm_[dv];
         if (smem > configured) {
@@ -1196,9 +1201,12 @@ int launch_octree(const LevelDev *h_levels, int nlevels, int f0, int batch, int 
     const size_t smem = octree_smem_bytes(nbins, cap);
     static size_t configured_[kMaxDevices];
     size_t &configured = configured_[current_device_slot()];
-    if (smem > configured) {
-        cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
+    {
+        std::lock_guard<std::mutex> lock(g_attr_mutex);
+        if (smem > configured) {
+            cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            configured = smem;
+        }
     }
     dim3 grid(nlevels, batch);
     k_octree<<<grid, OT_THREADS, smem, stream>>>(make_table(h_levels), nlevels, cap, f0, d_overflow);
@@ -1520,6 +1528,7 @@ int launch_describe(const LevelDev *h_levels, int nlevels, int f0, int batch, in
         const size_t smem = (size_t)DT_WARPS * DT_WARP_BYTES;
         static int per_sm_[kMaxDevices];
         int &per_sm = per_sm_[current_device_slot()];
+        std::unique_lock<std::mutex> lock(g_attr_mutex);
         if (!per_sm) {
             cudaFuncSetAttribute(k_describe_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_describe_tma, DT_WARPS * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;

@@ -16,6 +16,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <mutex>
 #include <string>
 
 #include "orbx_dev.h"
@@ -340,6 +341,8 @@ int launch_knn2_tc(const int8_t *d_qe, int nq, const int8_t *d_dbe, long long nr
     if (!make_map(&mq, d_qe, (long long)nqt * TC_QT, TC_QT, err)) return 0;
     if (!make_map(&mdb, d_dbe, ntiles_ll * TC_DT, TC_DT, err)) return 0;
     static bool configured_[kMaxDevices];
+    static std::mutex attr_mutex;
+    std::lock_guard<std::mutex> attr_lock(attr_mutex);
     bool &configured = configured_[current_device_slot()];
     const size_t smem = knn_tc_smem_bytes();
     if (!configured) {
