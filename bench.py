@@ -88,6 +88,37 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Several ranks share one host: run this rank (and therefore first-touch its page-locked buffers) on the cores nvidia-smi lists
+    as local to its GPU, so that eight PCIe streams do not all cross the socket interconnect.  Best effort; returns the core list."""
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        hdr = None
+        for line in out.splitlines():
+            cols = line.split("\t")
+            cols = [c.strip() for c in cols]
+            if hdr is None and any(c.startswith("CPU Affinity") for c in cols):
+                hdr = [c for c in cols]
+                continue
+            if hdr and cols and cols[0] == f"GPU{gpu_index}":
+                # the header has one leading empty cell less than the rows in some driver versions: locate by name from the right
+                k = hdr.index(next(c for c in hdr if c.startswith("CPU Affinity")))   # rows and header align by position
+                spec = cols[k] if k < len(cols) else ""
+                cores = set()
+                for part in spec.split(","):
+                    if "-" in part:
+                        a, b = part.split("-")
+                        cores.update(range(int(a), int(b) + 1))
+                    elif part.strip().isdigit():
+                        cores.add(int(part))
+                if cores:
+                    os.sched_setaffinity(0, cores & os.sched_getaffinity(0) or os.sched_getaffinity(0))
+                    return sorted(cores)[:2] + ["..."] + sorted(cores)[-1:]
+    except Exception:
+        pass
+    return None
+
+
 def make_frames(n, seed0):
     from send_slam_b200 import synth
     return np.stack([synth.textured_frame(seed0 + i, W, H) for i in range(n)])
@@ -159,6 +190,7 @@ def main():
         print(json.dumps({"error": "no CUDA device: orbx has no CPU fallback"}), flush=True)
         return 2
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -452,7 +484,7 @@ def main():
                 "config": {"workload": f"ORB extraction, {BATCH} x {W}x{H} gray frames per GPU per step, nFeatures {NFEAT}, {NLEVELS} levels, "
                                        f"scale {SCALE}, iniTh {INI_TH}, minTh {MIN_TH} (BASELINE configs[0] shape, 64-frame batches of configs[1])",
                            "l2": f"inputs cycle through {RING} distinct batches = {RING * BATCH * W * H / 1e6:.0f} MB > 126 MB L2",
-                           "sharding": "frames sharded by rank, no collective", "keypoints_per_frame": nkp},
+                           "sharding": "frames sharded by rank, no collective", "numa_binding": numa, "keypoints_per_frame": nkp},
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps, "api": "orbx_extract_batch, pinned host frames in / pinned keypoint + descriptor arrays out",
