@@ -53,6 +53,27 @@ while time.time() - t0 < budget:
         n = d_n.cpu().numpy(); mono = d_mono.cpu().numpy()
         kp = d_kp.cpu().numpy().view(orbx.KP_DTYPE).reshape(B, cap); dd = d_desc.cpu().numpy()
         got = [(int(mono[i]), kp[i, :n[i]], dd[i, :n[i]]) for i in range(B)]
+    # every third case also goes through the colour path (gray conversion on the device) and the undistort + grid kernel
+    if ncase % 3 == 0:
+        fmt = int(rng.integers(1, 5))
+        ch = 4 if fmt >= 3 else 3
+        col = rng.integers(0, 256, (h, w, ch), dtype=np.uint8)
+        gray = ol.gray(col, fmt, 15)
+        e.set_input_format(fmt, 15)
+        mono_c, kps_c, desc_c = e(col)
+        e.set_input_format(orbx.FMT_GRAY8)
+        k_g, d_g, m_g = o.extract(gray)
+        if not (mono_c == m_g and np.array_equal(desc_c, d_g) and np.array_equal(kps_c.view(np.int32), k_g.view(np.int32))):
+            print("MISMATCH colour", tag, fmt); sys.exit(1)
+        cam = (0.9 * w, 0.92 * w, 0.5 * w + 3, 0.5 * h - 2, float(rng.uniform(-0.3, 0.3)), float(rng.uniform(-0.1, 0.1)), 1e-3, -5e-4, 0.0)
+        b = e.image_bounds(cam, w, h)
+        if np.array_equal(b, ol.image_bounds(cam, w, h)) and b[2] > b[0] and b[3] > b[1]:
+            un, st, it = e.frame_grid(kps_c, cam, b)
+            un_o, st_o, it_o = ol.frame_grid(kps_c, cam, b)
+            if not (np.array_equal(un.view(np.int32), un_o.view(np.int32)) and np.array_equal(st, st_o) and np.array_equal(it, it_o)):
+                print("MISMATCH grid", tag, cam); sys.exit(1)
+        elif not np.array_equal(b, ol.image_bounds(cam, w, h)):
+            print("MISMATCH bounds", tag, cam); sys.exit(1)
     for i in range(B):
         k_o, d_o, m_o = o.extract(frames[i])
         mono, kps, desc = got[i]
