@@ -90,6 +90,17 @@ int orbx_extract_batch(orbx_handle *h, const uint8_t *const *frames, int batch, 
                        int lap0, int lap1, orbx_keypoint *kp_out, uint8_t *desc_out, int cap, int *n_out,
                        int *mono_index_out);
 
+/* The same call in two halves for callers that stream batches (a camera group per handle): _submit queues the uploads,
+ * kernels and downloads of one batch and returns without waiting; _collect waits for that batch and fills n_out /
+ * mono_index_out (and, for pageable result buffers, kp_out / desc_out).  frames / kp_out / desc_out must stay valid and
+ * untouched until _collect returns.  One batch may be in flight per handle (a second _submit returns ORBX_E_INVALID);
+ * two handles used alternately from one thread overlap the upload of one batch with the kernels and download of the
+ * other.  orbx_extract_batch == _submit + _collect.  There is no counterpart in the reference: its operator() is
+ * synchronous (UPSTREAM Frame::ExtractORB), which is what orbx_extract keeps. */
+int orbx_extract_batch_submit(orbx_handle *h, const uint8_t *const *frames, int batch, int width, int height, int stride,
+                              int lap0, int lap1, orbx_keypoint *kp_out, uint8_t *desc_out, int cap);
+int orbx_extract_batch_collect(orbx_handle *h, int *n_out, int *mono_index_out);
+
 /* Device-resident variant: frames already in HBM at d_frames + i*frame_stride_bytes (row pitch `stride`), results
  * left in HBM (d_kp_out: batch*cap records, d_desc_out: batch*cap*32 B, d_n_out / d_mono_out: batch ints).
  * Asynchronous on the handle's stream; call orbx_sync before reading results from another stream. */

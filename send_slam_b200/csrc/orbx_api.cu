@@ -89,6 +89,9 @@ struct orbx_handle {
     uint8_t *h_in = nullptr; size_t h_in_bytes = 0;
     KeypointRec *h_kp = nullptr; uint8_t *h_desc = nullptr; int *h_n = nullptr, *h_mono = nullptr, *h_overflow = nullptr;
     int last_batch = 0;             // batch size of the most recent run (debug getters)
+    // a host-buffer batch queued by orbx_extract_batch_submit and not yet collected
+    struct Pending { bool active; int batch, cap; bool out_direct; orbx_keypoint *kp_out; uint8_t *desc_out; };
+    Pending pending{false, 0, 0, false, nullptr, nullptr};
     // optional per-stage timing (orbx_set_profiling): events around resize / blur / fast / octree / finalize / describe
     bool profiling = false;
     cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -651,14 +654,16 @@ int orbx_extract_batch_device(orbx_handle *h, const uint8_t *d_frames, size_t fr
     return run_graphed(h, key, enqueue, [] {});
 }
 
-int orbx_extract_batch(orbx_handle *h, const uint8_t *const *frames, int batch, int width, int height, int stride, int lap0,
-                       int lap1, orbx_keypoint *kp_out, uint8_t *desc_out, int cap, int *n_out, int *mono_index_out) {
+// Asynchronous half of the host-buffer batch call: everything up to (not including) the wait for the device.  The call
+// returns as soon as the copies and kernels are queued; orbx_extract_batch_collect waits and finishes the host side.
+// A caller that keeps two handles busy (submit A, submit B, collect A, submit A', collect B, ...) overlaps the upload
+// of one batch with the kernels and the download of the other from a single host thread.
+int orbx_extract_batch_submit(orbx_handle *h, const uint8_t *const *frames, int batch, int width, int height, int stride, int lap0,
+                              int lap1, orbx_keypoint *kp_out, uint8_t *desc_out, int cap) {
     if (!h) return ORBX_E_INVALID;
-    if (!frames || !kp_out || !desc_out || !n_out || !mono_index_out) return fail(h, ORBX_E_INVALID, "null argument");
-    if (width < 1 || height < 1) {
-        for (int i = 0; i < batch; i++) { n_out[i] = 0; mono_index_out[i] = -1; }
-        return fail(h, ORBX_E_EMPTY, "empty image");
-    }
+    if (h->pending.active) return fail(h, ORBX_E_INVALID, "a submitted batch has not been collected");
+    if (!frames || !kp_out || !desc_out) return fail(h, ORBX_E_INVALID, "null argument");
+    if (width < 1 || height < 1) return fail(h, ORBX_E_EMPTY, "empty image");
     const int bpp = h->in_fmt == ORBX_FMT_GRAY8 ? 1 : h->in_fmt >= ORBX_FMT_RGBA8 ? 4 : 3, rowb = width * bpp;
     if (batch < 1 || stride < rowb) return fail(h, ORBX_E_INVALID, "bad batch / stride");
     for (int i = 0; i < batch; i++) if (!frames[i]) return fail(h, ORBX_E_INVALID, "null frame pointer");
@@ -777,21 +782,45 @@ int orbx_extract_batch(orbx_handle *h, const uint8_t *const *frames, int batch, 
                      h->in_fmt * 100 + h->gray_shift};
         if ((rc = run_graphed(h, key, enqueue, [&] { stage_in(0, batch); }))) return rc;
     }
+    h->pending = orbx_handle::Pending{true, batch, cap, out_direct, kp_out, desc_out};
+    return ORBX_OK;
+}
+
+int orbx_extract_batch_collect(orbx_handle *h, int *n_out, int *mono_index_out) {
+    if (!h) return ORBX_E_INVALID;
+    if (!h->pending.active) return fail(h, ORBX_E_INVALID, "no submitted batch to collect");
+    if (!n_out || !mono_index_out) return fail(h, ORBX_E_INVALID, "null argument");
+    const orbx_handle::Pending p = h->pending;
+    h->pending.active = false;
+    CU_TRY(h, cudaSetDevice(h->device));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     if (*h->h_overflow) {
         char msg[96]; snprintf(msg, sizeof(msg), "internal buffer overflow (stage code %d)", *h->h_overflow);
         return fail(h, ORBX_E_OVERFLOW, msg);
     }
-    for (int i = 0; i < batch; i++) {
+    const int kc = h->kp_cap;
+    for (int i = 0; i < p.batch; i++) {
         const int n = h->h_n[i];
-        if (n > cap) return fail(h, ORBX_E_CAPACITY, "kp_out/desc_out capacity smaller than the number of keypoints");
+        if (n > p.cap) return fail(h, ORBX_E_CAPACITY, "kp_out/desc_out capacity smaller than the number of keypoints");
         n_out[i] = n; mono_index_out[i] = h->h_mono[i];
-        if (!out_direct) {
-            std::memcpy(kp_out + (size_t)i * cap, h->h_kp + (size_t)i * kc, (size_t)n * sizeof(KeypointRec));
-            std::memcpy(desc_out + (size_t)i * cap * 32, h->h_desc + (size_t)i * kc * 32, (size_t)n * 32);
+        if (!p.out_direct) {
+            std::memcpy(p.kp_out + (size_t)i * p.cap, h->h_kp + (size_t)i * kc, (size_t)n * sizeof(KeypointRec));
+            std::memcpy(p.desc_out + (size_t)i * p.cap * 32, h->h_desc + (size_t)i * kc * 32, (size_t)n * 32);
         }
     }
     return ORBX_OK;
+}
+
+int orbx_extract_batch(orbx_handle *h, const uint8_t *const *frames, int batch, int width, int height, int stride, int lap0,
+                       int lap1, orbx_keypoint *kp_out, uint8_t *desc_out, int cap, int *n_out, int *mono_index_out) {
+    if (!h) return ORBX_E_INVALID;
+    if (!frames || !kp_out || !desc_out || !n_out || !mono_index_out) return fail(h, ORBX_E_INVALID, "null argument");
+    if (width < 1 || height < 1) {
+        for (int i = 0; i < batch; i++) { n_out[i] = 0; mono_index_out[i] = -1; }
+        return fail(h, ORBX_E_EMPTY, "empty image");
+    }
+    const int rc = orbx_extract_batch_submit(h, frames, batch, width, height, stride, lap0, lap1, kp_out, desc_out, cap);
+    return rc ? rc : orbx_extract_batch_collect(h, n_out, mono_index_out);
 }
 
 int orbx_extract(orbx_handle *h, const uint8_t *gray, int width, int height, int stride, int lap0, int lap1,

@@ -39,7 +39,8 @@ class _Config(C.Structure):
 # every symbol include/orbx.h declares (tests check the library exports all of them)
 EXPORTS = [
     "orbx_create", "orbx_destroy", "orbx_last_error", "orbx_keypoint_capacity", "orbx_get_tables", "orbx_get_level_sizes",
-    "orbx_extract", "orbx_extract_batch", "orbx_extract_batch_device", "orbx_sync", "orbx_launch_count",
+    "orbx_extract", "orbx_extract_batch", "orbx_extract_batch_submit", "orbx_extract_batch_collect",
+    "orbx_extract_batch_device", "orbx_sync", "orbx_launch_count",
     "orbx_debug_get_level", "orbx_debug_get_candidates", "orbx_debug_get_level_keypoints", "orbx_debug_resize",
     "orbx_debug_blur", "orbx_debug_octree", "orbx_debug_describe", "orbx_distance_batch", "orbx_match_windowed",
     "orbx_knn2_create_db", "orbx_knn2_create_db_device", "orbx_knn2_destroy_db", "orbx_knn2_last_error", "orbx_knn2_query",
@@ -75,6 +76,9 @@ def lib():
     L.orbx_extract.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, ip, ip]
     L.orbx_extract_batch.argtypes = [vp, C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp,
                                      C.c_int, vp, vp]
+    L.orbx_extract_batch_submit.argtypes = [vp, C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp,
+                                            C.c_int]
+    L.orbx_extract_batch_collect.argtypes = [vp, vp, vp]
     L.orbx_extract_batch_device.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp,
                                             vp, C.c_int, vp, vp]
     L.orbx_sync.argtypes = [vp]
@@ -235,9 +239,7 @@ class ORBextractor:
         self._check(rc)
         return mono.value, kps[:n.value].copy(), desc[:n.value].copy()
 
-    def extract_batch(self, frames, vLappingArea=(0, 1000), out=None):
-        """frames: uint8 [B,H,W] (C-contiguous rows).  Returns (mono[B], n[B], kps[B,cap], desc[B,cap,32]).
-        out = (kps, desc) lets the caller supply (e.g. page-locked) result arrays of shape [B,cap] / [B,cap,32]."""
+    def _batch_args(self, frames, out):
         frames = np.asarray(frames)
         bpp = {FMT_GRAY8: 1, FMT_RGB8: 3, FMT_BGR8: 3, FMT_RGBA8: 4, FMT_BGRA8: 4}[self._fmt]
         if frames.dtype != np.uint8 or frames.ndim != (3 if bpp == 1 else 4) or (bpp > 1 and frames.shape[3] != bpp):
@@ -254,10 +256,35 @@ class ORBextractor:
             kps, desc = out
             if kps.shape != (B, self.capacity) or desc.shape != (B, self.capacity, 32) or kps.dtype != KP_DTYPE or desc.dtype != np.uint8:
                 raise OrbxError(ORBX_E_INVALID, "out arrays must be [B,cap] KP_DTYPE and [B,cap,32] uint8")
+        return frames, ptrs, B, w, h, kps, desc
+
+    def extract_batch(self, frames, vLappingArea=(0, 1000), out=None):
+        """frames: uint8 [B,H,W] (C-contiguous rows).  Returns (mono[B], n[B], kps[B,cap], desc[B,cap,32]).
+        out = (kps, desc) lets the caller supply (e.g. page-locked) result arrays of shape [B,cap] / [B,cap,32]."""
+        frames, ptrs, B, w, h, kps, desc = self._batch_args(frames, out)
         n, mono = np.zeros(B, np.int32), np.zeros(B, np.int32)
         rc = self._L.orbx_extract_batch(self._h, ptrs, B, w, h, frames.strides[1], int(vLappingArea[0]),
                                         int(vLappingArea[1]), _p(kps), _p(desc), self.capacity, _p(n), _p(mono))
         self._check(rc)
+        return mono, n, kps, desc
+
+    def extract_batch_submit(self, frames, vLappingArea=(0, 1000), out=None):
+        """Queue one batch (orbx_extract_batch_submit) and return without waiting; extract_batch_collect() returns the
+        results.  The frame and result arrays are kept alive by the extractor until then."""
+        frames, ptrs, B, w, h, kps, desc = self._batch_args(frames, out)
+        rc = self._L.orbx_extract_batch_submit(self._h, ptrs, B, w, h, frames.strides[1], int(vLappingArea[0]),
+                                               int(vLappingArea[1]), _p(kps), _p(desc), self.capacity)
+        self._check(rc)
+        self._inflight = (frames, ptrs, B, kps, desc)
+
+    def extract_batch_collect(self):
+        """Wait for the submitted batch: (mono[B], n[B], kps[B,cap], desc[B,cap,32])."""
+        if getattr(self, "_inflight", None) is None:
+            raise OrbxError(ORBX_E_INVALID, "no submitted batch to collect")
+        frames, ptrs, B, kps, desc = self._inflight
+        self._inflight = None
+        n, mono = np.zeros(B, np.int32), np.zeros(B, np.int32)
+        self._check(self._L.orbx_extract_batch_collect(self._h, _p(n), _p(mono)))
         return mono, n, kps, desc
 
     def extract_batch_device(self, d_frames_ptr, frame_stride, batch, width, height, stride, d_kp_ptr, d_desc_ptr, cap,

@@ -311,6 +311,57 @@ def test_pinned_batch_graph_replay(oracle):
     e.close()
 
 
+def test_submit_collect_streaming(oracle):
+    """orbx_extract_batch_submit / _collect: one host thread alternating two handles (batch i uploads while batch i-1
+    computes) returns, batch for batch, what the oracle returns; misuse is refused, not queued."""
+    import torch
+    B, w, h, nf, NB = 16, 640, 480, 1000, 6
+    batches = [np.stack([synth.textured_frame(900 + 16 * b + s, w, h, "textured" if (b + s) % 3 else "mixed") for s in range(B)])
+               for b in range(NB)]
+    lanes = []
+    for k in range(2):
+        e = orbx.ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=B)
+        cap = e.capacity
+        pk = torch.zeros((B, cap, 7), dtype=torch.float32).pin_memory()
+        pd = torch.zeros((B, cap, 32), dtype=torch.uint8).pin_memory()
+        lanes.append((e, (pk.numpy().view(orbx.KP_DTYPE).reshape(B, cap), pd.numpy()), (pk, pd)))
+    pins = [torch.from_numpy(b).pin_memory() for b in batches]
+    want = [oracle.extract_batch(b, nf, nthreads=os.cpu_count() or 1) for b in batches]
+
+    def check(b, got):
+        mono, n, kps, desc = got
+        kps_o, desc_o, n_o, mono_o = want[b]
+        assert np.array_equal(n, n_o) and np.array_equal(mono, mono_o), b
+        for i in range(B):
+            k = int(n[i])
+            assert np.array_equal(desc[i, :k], desc_o[i, :k]), (b, i)
+            for name in kps.dtype.names:
+                assert np.array_equal(kps[i, :k][name], kps_o[i, :k][name]), (b, i, name)
+
+    with pytest.raises(orbx.OrbxError):                                   # nothing submitted yet
+        lanes[0][0].extract_batch_collect()
+    for rep in range(3):                                                  # direct issue, graph capture, graph replay
+        inflight = [None, None]
+        for b in range(NB):
+            k = b & 1
+            e, out, _ = lanes[k]
+            if inflight[k] is not None:
+                check(inflight[k], e.extract_batch_collect())
+            e.extract_batch_submit(pins[b].numpy(), out=out)
+            inflight[k] = b
+            if b == 0:
+                with pytest.raises(orbx.OrbxError):                       # one batch in flight per handle
+                    e.extract_batch_submit(pins[b].numpy(), out=out)
+        for k in (0, 1):
+            check(inflight[k], lanes[k][0].extract_batch_collect())
+    # pageable frames and result arrays through the same pair (staged inside the handle)
+    e = lanes[0][0]
+    e.extract_batch_submit(batches[3])
+    check(3, e.extract_batch_collect())
+    for e, _, _ in lanes:
+        e.close()
+
+
 def test_colour_input(ex, oracle):
     """cvtColor(*2GRAY) on the device.  Conversion alone and colour frames through every entry point
     must equal the oracle's gray conversion followed by the gray path."""
