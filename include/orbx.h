@@ -101,6 +101,20 @@ int orbx_extract_batch_submit(orbx_handle *h, const uint8_t *const *frames, int 
                               int lap0, int lap1, orbx_keypoint *kp_out, uint8_t *desc_out, int cap);
 int orbx_extract_batch_collect(orbx_handle *h, int *n_out, int *mono_index_out);
 
+/* Frames as the reference puts them on the wire: SlamHandler encodes every frame with Evision.imencode(".ppm")
+ * (send_slam/lib/send_slam/slam_handler.ex:275-277, message field `encoding: "ppm"` :147) and the backend decodes it with
+ * cv::imdecode(packet.imageData, cv::IMREAD_UNCHANGED) (slam_backends/orb_slam_3/orbslam3_mono_networked.cc:546) before
+ * TrackMonocular converts it to gray.  orbx_pnm_header follows OpenCV's PxM header reader (white space and '#' comments
+ * before each number, exactly one byte consumed after each number); ORBX_E_EMPTY where imdecode returns an empty Mat (bad
+ * magic / header, truncated payload: the reference logs and skips the frame, :547-551), ORBX_E_INVALID for variants that
+ * decode but are not 8-bit binary (P1-P4, maxval > 255).  orbx_extract_pnm = imdecode + cvtColor + operator() with the
+ * payload uploaded as it lies: camera_rgb is the Camera.RGB flag (`rgb: 1`, slam_handler.ex:222) that selects RGB2GRAY vs
+ * BGR2GRAY on the decoded (BGR) Mat.  The frame size is returned through width_out / height_out (may be null). */
+int orbx_pnm_header(const uint8_t *data, size_t nbytes, int *width, int *height, int *channels, size_t *payload_offset);
+int orbx_extract_pnm(orbx_handle *h, const uint8_t *data, size_t nbytes, int camera_rgb, int lap0, int lap1,
+                     orbx_keypoint *kp_out, uint8_t *desc_out, int cap, int *n_out, int *mono_index_out, int *width_out,
+                     int *height_out);
+
 /* Device-resident variant: frames already in HBM at d_frames + i*frame_stride_bytes (row pitch `stride`), results
  * left in HBM (d_kp_out: batch*cap records, d_desc_out: batch*cap*32 B, d_n_out / d_mono_out: batch ints).
  * Asynchronous on the handle's stream; call orbx_sync before reading results from another stream. */

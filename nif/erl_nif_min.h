@@ -26,6 +26,7 @@ ERL_NIF_TERM enif_make_badarg(ErlNifEnv *);
 ERL_NIF_TERM enif_make_tuple(ErlNifEnv *, unsigned, ...);
 #define enif_make_tuple2(e, a, b) enif_make_tuple(e, 2, a, b)
 #define enif_make_tuple5(e, a, b, c, d, f) enif_make_tuple(e, 5, a, b, c, d, f)
+#define enif_make_tuple7(e, a, b, c, d, f, g, i) enif_make_tuple(e, 7, a, b, c, d, f, g, i)
 unsigned char *enif_make_new_binary(ErlNifEnv *, size_t, ERL_NIF_TERM *);
 ERL_NIF_TERM enif_make_sub_binary(ErlNifEnv *, ERL_NIF_TERM, size_t, size_t);
 ErlNifResourceType *enif_open_resource_type(ErlNifEnv *, const char *, const char *, ErlNifResourceDtor *, ErlNifResourceFlags, ErlNifResourceFlags *);

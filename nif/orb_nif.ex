@@ -22,6 +22,9 @@ defmodule SendSlam.OrbNif do
   @doc "format: 1 = RGB, 2 = BGR (an `Evision.Mat` from `Evision.VideoCapture.read/1`), 3 = RGBA, 4 = BGRA; gray conversion on the GPU"
   def extract_color(_handle, _pixels_binary, _width, _height, _format), do: :erlang.nif_error(:nif_not_loaded)
 
+  @doc "the wire's PPM binary (`Evision.imencode(\".ppm\", mat)`, slam_handler.ex:275-277) as it is; camera_rgb = 1 for `rgb: 1`"
+  def extract_ppm(_handle, _ppm_binary, _camera_rgb), do: :erlang.nif_error(:nif_not_loaded)
+
   def match_windowed(_handle, _q_desc, _q_uvr, _q_levels, _t_kp, _t_desc, _bounds),
     do: :erlang.nif_error(:nif_not_loaded)
 end

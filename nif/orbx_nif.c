@@ -115,6 +115,31 @@ static ERL_NIF_TERM nif_extract_color(ErlNifEnv *env, int argc, const ERL_NIF_TE
                             enif_make_sub_binary(env, desc_term, 0, (size_t)n * ORBX_DESC_BYTES));
 }
 
+/* extract_ppm(handle, ppm_binary, camera_rgb) -> {:ok, n, mono_index, keypoints_binary, descriptors_binary, width, height}: the binary
+ * SlamHandler already builds for the wire (`Evision.imencode(".ppm", mat)`, send_slam/lib/send_slam/slam_handler.ex:66,275-277) goes in
+ * unchanged; header parsing, the gray conversion the backend would do (imdecode + cvtColor by Camera.RGB, camera_rgb = 1 for the
+ * reference's `rgb: 1`, slam_handler.ex:222) and extraction happen in the library.  {:error, :empty_image} where the backend would log
+ * "Failed to decode frame image data" and skip the frame (orbslam3_mono_networked.cc:547-551). */
+static ERL_NIF_TERM nif_extract_ppm(ErlNifEnv *env, int argc, const ERL_NIF_TERM argv[]) {
+    nif_handle *nh;
+    ErlNifBinary ppm;
+    int camera_rgb;
+    if (argc != 3 || !enif_get_resource(env, argv[0], g_handle_type, (void **)&nh) || !enif_inspect_binary(env, argv[1], &ppm) ||
+        !enif_get_int(env, argv[2], &camera_rgb))
+        return enif_make_badarg(env);
+    if (!nh->h) return mk_error(env, "closed");
+    ERL_NIF_TERM kp_term, desc_term;
+    unsigned char *kp = enif_make_new_binary(env, (size_t)nh->cap * sizeof(orbx_keypoint), &kp_term);
+    unsigned char *desc = enif_make_new_binary(env, (size_t)nh->cap * ORBX_DESC_BYTES, &desc_term);
+    if (!kp || !desc) return mk_error(env, "enomem");
+    int n = 0, mono = -1, w = 0, h = 0;
+    int rc = orbx_extract_pnm(nh->h, ppm.data, ppm.size, camera_rgb != 0, 0, 1000, (orbx_keypoint *)kp, desc, nh->cap, &n, &mono, &w, &h);
+    if (rc != ORBX_OK) return mk_error(env, code_atom(rc));
+    return enif_make_tuple7(env, enif_make_atom(env, "ok"), enif_make_int(env, n), enif_make_int(env, mono),
+                            enif_make_sub_binary(env, kp_term, 0, (size_t)n * sizeof(orbx_keypoint)),
+                            enif_make_sub_binary(env, desc_term, 0, (size_t)n * ORBX_DESC_BYTES), enif_make_int(env, w), enif_make_int(env, h));
+}
+
 /* match_windowed(handle, q_desc, q_uvr, q_levels, t_kp, t_desc, {minx, miny, maxx, maxy}) -> {:ok, best_idx, best_dist, second_idx, second_dist} (int32 binaries) */
 static ERL_NIF_TERM nif_match_windowed(ErlNifEnv *env, int argc, const ERL_NIF_TERM argv[]) {
     nif_handle *nh;
@@ -151,6 +176,7 @@ static ErlNifFunc nif_funcs[] = {
     {"create", 8, nif_create, ERL_NIF_DIRTY_JOB_IO_BOUND},
     {"extract", 4, nif_extract, ERL_NIF_DIRTY_JOB_IO_BOUND},
     {"extract_color", 5, nif_extract_color, ERL_NIF_DIRTY_JOB_IO_BOUND},
+    {"extract_ppm", 3, nif_extract_ppm, ERL_NIF_DIRTY_JOB_IO_BOUND},
     {"match_windowed", 7, nif_match_windowed, ERL_NIF_DIRTY_JOB_IO_BOUND},
 #ifdef ORBX_NIF_MIN
     {NULL, 0, NULL, 0},   /* sentinel for the mock host (nif/mock_host.c); the real ERL_NIF_INIT takes the array size */

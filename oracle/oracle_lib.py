@@ -69,6 +69,8 @@ def lib():
         L.orb_oracle_image_bounds.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.orb_oracle_frame_grid.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orb_oracle_bow_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orb_oracle_pnm_header.argtypes = [C.c_void_p, C.c_size_t, i32p, i32p, i32p, C.POINTER(C.c_size_t)]
+        L.orb_oracle_pnm_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
         _lib = L
     return _lib
 
@@ -162,6 +164,21 @@ def gray(src: np.ndarray, fmt: int, shift: int = 15) -> np.ndarray:
     dst = np.zeros(src.shape[:2], np.uint8)
     rc = lib().orb_oracle_gray(_p(src), src.shape[1], src.shape[0], src.strides[0], int(fmt), int(shift), _p(dst), dst.shape[1])
     assert rc == 0
+    return dst
+
+
+def pnm_decode(data: bytes):
+    """cv::imdecode(data, IMREAD_UNCHANGED) for binary PNM: gray [H,W] (P5) or BGR [H,W,3] (P6); None where imdecode returns an
+    empty Mat; raises ValueError for variants the extractor cannot take (ASCII / bitmap / 16-bit)."""
+    buf = np.frombuffer(data, np.uint8)
+    w, h, ch, off = C.c_int32(), C.c_int32(), C.c_int32(), C.c_size_t()
+    rc = lib().orb_oracle_pnm_header(_p(buf), len(buf), C.byref(w), C.byref(h), C.byref(ch), C.byref(off)) if len(buf) else -1
+    if rc == -1:
+        return None
+    if rc == -2:
+        raise ValueError("PNM variant outside the CV_8U binary forms")
+    dst = np.zeros((h.value, w.value) if ch.value == 1 else (h.value, w.value, 3), np.uint8)
+    assert lib().orb_oracle_pnm_decode(_p(buf), len(buf), _p(dst)) == 0
     return dst
 
 

@@ -175,6 +175,70 @@ int orb_oracle_gray(const u8 *src, int w, int h, int stride, int format, int shi
     return 0;
 }
 
+/* cv::imdecode(buf, IMREAD_UNCHANGED) for the only encoding the reference puts on the wire: binary PNM
+ * (send_slam/lib/send_slam/slam_handler.ex:275-277 `Evision.imencode(".ppm", mat)`, field `encoding: "ppm"` :147; decoded at
+ * slam_backends/orb_slam_3/orbslam3_mono_networked.cc:546).  Restates OpenCV's PxM reader (modules/imgcodecs/src/grfmt_pxm.cpp,
+ * not in /root/reference; behaviour pinned against cv2 4.13 in tests/test_oracle_golden.py): 'P' + type digit, then width,
+ * height, maxval as decimal numbers, each preceded by any run of white space and '#' comments (to end of line) and each
+ * followed by exactly ONE consumed byte; binary samples are taken as they are (no rescaling for maxval < 255); a payload
+ * shorter than width*height*channels is a decode failure.  P5 -> 1 channel; P6 -> 3 channels, which imdecode stores as BGR
+ * (file order is RGB).  Returns 0 and (*w, *h, *ch, *offset = first payload byte), or -1 where cv::imdecode returns an empty
+ * Mat, or -2 for what it decodes but the extractor cannot take (ASCII / bitmap variants and 16-bit samples: CV_16U fails
+ * UPSTREAM's assert(image.type() == CV_8UC1)). */
+static int pnm_number(const u8 *d, size_t n, size_t *pos, long long *out) {
+    size_t p = *pos;
+    int c;
+#define PNM_GET() do { if (p >= n) return -1; c = d[p++]; } while (0)
+#define PNM_SPACE(c) ((c) == ' ' || ((c) >= 9 && (c) <= 13))
+    PNM_GET();
+    while (c < '0' || c > '9') {
+        if (c == '#') {
+            do PNM_GET(); while (c != '\n' && c != '\r');
+            PNM_GET();
+        } else if (PNM_SPACE(c)) {
+            while (PNM_SPACE(c)) PNM_GET();
+        } else return -1;
+    }
+    long long v = 0;
+    do {
+        v = v * 10 + (c - '0');
+        if (v > 2147483647LL) return -1;
+        PNM_GET();                       /* the byte after the last digit is consumed, whatever it is */
+    } while (c >= '0' && c <= '9');
+#undef PNM_GET
+#undef PNM_SPACE
+    *pos = p; *out = v;
+    return 0;
+}
+
+int orb_oracle_pnm_header(const u8 *data, size_t nbytes, int *w, int *h, int *ch, size_t *offset) {
+    if (!data || nbytes < 2 || data[0] != 'P' || data[1] < '1' || data[1] > '6') return -1;
+    const int type = data[1] - '0';
+    size_t pos = 2;
+    long long W, H, M = 1;
+    if (pnm_number(data, nbytes, &pos, &W) || pnm_number(data, nbytes, &pos, &H)) return -1;
+    if (type != 1 && type != 4 && pnm_number(data, nbytes, &pos, &M)) return -1;
+    if (W <= 0 || H <= 0 || M <= 0 || M > 65535) return -1;
+    if (type != 5 && type != 6) return -2;
+    if (M > 255) return -2;
+    const int c = type == 6 ? 3 : 1;
+    if ((unsigned long long)W * (unsigned long long)H * c > nbytes - pos) return -1;
+    *w = (int)W; *h = (int)H; *ch = c; *offset = pos;
+    return 0;
+}
+
+/* The Mat imdecode returns: gray for P5, BGR for P6 (dst: h rows of w*ch bytes). */
+int orb_oracle_pnm_decode(const u8 *data, size_t nbytes, u8 *dst) {
+    int w, h, ch; size_t off;
+    const int rc = orb_oracle_pnm_header(data, nbytes, &w, &h, &ch, &off);
+    if (rc) return rc;
+    const u8 *p = data + off;
+    const size_t npx = (size_t)w * h;
+    if (ch == 1) memcpy(dst, p, npx);
+    else for (size_t i = 0; i < npx; i++) { dst[3 * i] = p[3 * i + 2]; dst[3 * i + 1] = p[3 * i + 1]; dst[3 * i + 2] = p[3 * i]; }
+    return 0;
+}
+
 int orb_oracle_resize(const u8 *src, int sw, int sh, int sstride, u8 *dst, int dw, int dh, int dstride) {
     int *xo = (int *)malloc(sizeof(int) * dw), *yo = (int *)malloc(sizeof(int) * dh);
     short *xa = (short *)malloc(sizeof(short) * dw * 2), *ya = (short *)malloc(sizeof(short) * dh * 2);

@@ -40,7 +40,7 @@ class _Config(C.Structure):
 EXPORTS = [
     "orbx_create", "orbx_destroy", "orbx_last_error", "orbx_keypoint_capacity", "orbx_get_tables", "orbx_get_level_sizes",
     "orbx_extract", "orbx_extract_batch", "orbx_extract_batch_submit", "orbx_extract_batch_collect",
-    "orbx_extract_batch_device", "orbx_sync", "orbx_launch_count",
+    "orbx_extract_batch_device", "orbx_sync", "orbx_launch_count", "orbx_pnm_header", "orbx_extract_pnm",
     "orbx_debug_get_level", "orbx_debug_get_candidates", "orbx_debug_get_level_keypoints", "orbx_debug_resize",
     "orbx_debug_blur", "orbx_debug_octree", "orbx_debug_describe", "orbx_distance_batch", "orbx_match_windowed",
     "orbx_knn2_create_db", "orbx_knn2_create_db_device", "orbx_knn2_destroy_db", "orbx_knn2_last_error", "orbx_knn2_query",
@@ -53,6 +53,18 @@ EXPORTS = [
 ]
 
 _lib = None
+
+
+def pnm_header(data: bytes):
+    """(width, height, channels, payload_offset) of a binary PNM, None where cv::imdecode would return an empty Mat."""
+    buf = np.frombuffer(data, np.uint8)
+    w, h, ch, off = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
+    rc = lib().orbx_pnm_header(_p(buf) if len(buf) else None, len(buf), C.byref(w), C.byref(h), C.byref(ch), C.byref(off))
+    if rc == ORBX_E_EMPTY or (rc and not len(buf)):
+        return None
+    if rc:
+        raise OrbxError(rc, "PNM variant outside binary 8-bit P5 / P6")
+    return w.value, h.value, ch.value, off.value
 
 
 def lib():
@@ -79,6 +91,8 @@ def lib():
     L.orbx_extract_batch_submit.argtypes = [vp, C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp,
                                             C.c_int]
     L.orbx_extract_batch_collect.argtypes = [vp, vp, vp]
+    L.orbx_pnm_header.argtypes = [vp, C.c_size_t, ip, ip, ip, C.POINTER(C.c_size_t)]
+    L.orbx_extract_pnm.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, ip, ip, ip, ip]
     L.orbx_extract_batch_device.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp,
                                             vp, C.c_int, vp, vp]
     L.orbx_sync.argtypes = [vp]
@@ -238,6 +252,21 @@ class ORBextractor:
                                   _p(kps), _p(desc), self.capacity, C.byref(n), C.byref(mono))
         self._check(rc)
         return mono.value, kps[:n.value].copy(), desc[:n.value].copy()
+
+    def extract_pnm(self, data: bytes, camera_rgb: bool = True, vLappingArea=(0, 1000)):
+        """A frame as it arrives on the reference's wire (binary PPM / PGM): cv::imdecode + cvtColor + operator().
+        Returns (monoIndex, keypoints, descriptors, (width, height)); (-1, empty, empty, None) where imdecode fails."""
+        buf = np.frombuffer(data, np.uint8)
+        kps = np.zeros(self.capacity, KP_DTYPE)
+        desc = np.zeros((self.capacity, 32), np.uint8)
+        n, mono, w, h = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        rc = self._L.orbx_extract_pnm(self._h, _p(buf) if len(buf) else None, len(buf), int(bool(camera_rgb)), int(vLappingArea[0]),
+                                      int(vLappingArea[1]), _p(kps), _p(desc), self.capacity, C.byref(n), C.byref(mono),
+                                      C.byref(w), C.byref(h))
+        if rc == ORBX_E_EMPTY:
+            return -1, np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8), None
+        self._check(rc)
+        return mono.value, kps[:n.value].copy(), desc[:n.value].copy(), (w.value, h.value)
 
     def _batch_args(self, frames, out):
         frames = np.asarray(frames)

@@ -92,3 +92,30 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle_lib" not in txt and "orb_oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_pnm_header_host_logic(golden_dir):
+    """orbx_pnm_header is host code (no GPU): accept / reject verdict, frame geometry and payload offset equal what cv2's imdecode
+    did for the fixture's byte strings (tests/golden/make_golden_pnm.py) and what the oracle's restatement says."""
+    import numpy as np
+    from oracle import oracle_lib
+    from send_slam_b200 import orbx
+    g = np.load(os.path.join(golden_dir, "pnm_cases.npz"))
+    blob, pos = g["blob"].tobytes(), 0
+    for i, ln in enumerate(g["lengths"]):
+        data, verdict, shape = blob[pos:pos + ln], int(g["verdict"][i]), tuple(int(v) for v in g["shape"][i])
+        pos += ln
+        if verdict == 2:
+            with pytest.raises(orbx.OrbxError):
+                orbx.pnm_header(data)
+            continue
+        got = orbx.pnm_header(data)
+        if verdict == 0:
+            assert got is None, data[:16]
+            continue
+        w, h, ch, off = got
+        assert (h, w, ch) == shape, data[:16]
+        m = oracle_lib.pnm_decode(data)
+        pay = np.frombuffer(data, np.uint8)[off:off + w * h * ch].reshape(h, w, ch)
+        assert np.array_equal(pay[:, :, ::-1] if ch == 3 else pay[:, :, 0], m), data[:16]
+    assert orbx.pnm_header(b"") is None

@@ -151,7 +151,7 @@ def test_orientation_and_descriptor_standalone(ex, oracle):
 # ---------------------------------------------------------------------------------------------------------------------
 def test_golden_fixtures(golden_dir):
     for path in sorted(glob.glob(os.path.join(golden_dir, "*.npz"))):
-        if os.path.basename(path).startswith("knn2"):
+        if os.path.basename(path).startswith(("knn2", "pnm")):
             continue
         g = np.load(path)
         w, h, nf = int(g["width"]), int(g["height"]), int(g["nfeatures"])
@@ -411,6 +411,38 @@ def test_colour_input(ex, oracle):
     e.set_input_format(orbx.FMT_GRAY8)
     assert_same_extraction(e(gray[0]), o.extract(gray[0]), "gray after colour")
     e.close()
+
+
+def test_wire_ppm_frames(ex, oracle, golden_dir):
+    """Frames as the reference puts them on the wire (binary PPM, slam_handler.ex:275-277): orbx_extract_pnm == the reference's own
+    sequence imdecode -> cvtColor(RGB2GRAY | BGR2GRAY by Camera.RGB) -> operator(), each step taken from the oracle; the gray plane
+    the device built is also checked against the cv2 fixture."""
+    g = np.load(os.path.join(golden_dir, "pnm_cases.npz"))
+    w, h = (int(v) for v in g["wire_size"])
+    bgr = np.stack([synth.textured_frame(int(s), w, h) for s in g["wire_seeds"]], axis=2)
+    wire = g["wire_header"].tobytes() + bgr[:, :, ::-1].tobytes()
+    o = oracle.Oracle(1000)
+    import hashlib
+    for camera_rgb, pin in ((True, "gray_rgb1_sha"), (False, "gray_rgb0_sha")):
+        mat = oracle.pnm_decode(wire)                                # BGR, as cv::imdecode stores it
+        gray = oracle.gray(mat, 1 if camera_rgb else 2)              # RGB2GRAY on that memory when Camera.RGB = 1
+        assert hashlib.sha256(gray.tobytes()).hexdigest() == str(g[pin])
+        mono, kps, desc, size = ex.extract_pnm(wire, camera_rgb=camera_rgb)
+        assert size == (w, h)
+        lv = ex.debug_level(0, 0)
+        assert np.array_equal(lv, gray), "level 0 built on the device from the PPM payload"
+        assert_same_extraction((mono, kps, desc), o.extract(gray), "ppm rgb=%d" % camera_rgb)
+    # P5 (gray) frames, a header with a comment, and the input format of the handle left as it was
+    gw = b"P5\n# cam 0\n%d %d\n255\n" % (w, h) + bgr[:, :, 1].tobytes()
+    mono, kps, desc, size = ex.extract_pnm(gw)
+    assert_same_extraction((mono, kps, desc), o.extract(np.ascontiguousarray(bgr[:, :, 1])), "pgm")
+    assert_same_extraction(ex(np.ascontiguousarray(bgr[:, :, 1])), o.extract(np.ascontiguousarray(bgr[:, :, 1])), "gray call after pnm")
+    # what imdecode rejects comes back as the reference's 'skip this frame' (-1, no keypoints); other variants are refused
+    mono, kps, desc, size = ex.extract_pnm(wire[:-1])
+    assert mono == -1 and len(kps) == 0 and size is None
+    assert ex.extract_pnm(b"")[0] == -1 and ex.extract_pnm(b"JUNK" * 10)[0] == -1
+    with pytest.raises(orbx.OrbxError):
+        ex.extract_pnm(b"P6\n2 2\n65535\n" + bytes(24))
 
 
 def test_frame_undistort_and_grid(ex, oracle):

@@ -100,6 +100,21 @@ def test_nif_errors_and_single_stream(nif, oracle):
     g = oracle.gray(bgr, orbx.FMT_BGR8, 15)
     k_g, d_g, m_g = oracle.Oracle(nf).extract(g)
     assert mono2 == m_g and np.array_equal(desc2, d_g)
+    # the wire's PPM binary as SlamHandler builds it (Evision.imencode(".ppm"), slam_handler.ex:275-277): header parse + imdecode's
+    # BGR order + cvtColor by Camera.RGB all inside the library
+    col = np.stack([synth.textured_frame(701 + k, w, h) for k in range(3)], -1)             # the BGR Mat the camera produced
+    ppm = b"P6\n%d %d\n255\n" % (w, h) + col[:, :, ::-1].tobytes()                          # PPM stores RGB
+    for camera_rgb in (1, 0):
+        r = decode(L, call(L, "extract_ppm", L.mock_resource_term(res), L.mock_binary(ppm, len(ppm)), L.mock_int(camera_rgb)))
+        L.mock_reset()
+        assert r[0] == "ok" and r[5:] == (w, h), r[:3]
+        gp = oracle.gray(oracle.pnm_decode(ppm), 1 if camera_rgb else 2, 15)
+        k_p, d_p, m_p = oracle.Oracle(nf).extract(gp)
+        assert r[1] == len(k_p) and r[2] == m_p and np.array_equal(np.frombuffer(r[4], np.uint8).reshape(-1, 32), d_p)
+        assert np.array_equal(np.frombuffer(r[3], np.int32), k_p.view(np.int32).ravel())
+    r = decode(L, call(L, "extract_ppm", L.mock_resource_term(res), L.mock_binary(ppm, len(ppm) - 5), L.mock_int(1)))
+    L.mock_reset()
+    assert r == ("error", "empty_image")                        # truncated: the backend would skip this frame
     # error tuples, never exceptions: size mismatch, frame larger than the handle was created for, bad arguments
     r = decode(L, call(L, "extract", L.mock_resource_term(res), L.mock_binary(f.ctypes.data, 100), L.mock_int(w), L.mock_int(h)))
     L.mock_reset()

@@ -15,7 +15,7 @@ def sha(a):
 
 
 def golden_cases(golden_dir):
-    return sorted(p for p in glob.glob(os.path.join(golden_dir, "*.npz")) if not os.path.basename(p).startswith("knn2"))
+    return sorted(p for p in glob.glob(os.path.join(golden_dir, "*.npz")) if not os.path.basename(p).startswith(("knn2", "pnm")))
 
 
 def test_golden_files_present(golden_dir):
@@ -213,3 +213,47 @@ def test_oracle_frame_grid_properties(oracle):
         assert np.all(np.diff(seg) > 0)                                          # push_back order
         px = np.floor((un["x"][seg] - b[0]) * invw + np.float32(0.5)).astype(int)  # round() for non-negative arguments
         assert np.all(px == c // 48)
+
+
+def _pnm_cases(golden_dir):
+    g = np.load(os.path.join(golden_dir, "pnm_cases.npz"))
+    blob, out, pos = g["blob"].tobytes(), [], 0
+    for i, ln in enumerate(g["lengths"]):
+        out.append((blob[pos:pos + ln], int(g["verdict"][i]), tuple(int(v) for v in g["shape"][i]), str(g["digest"][i])))
+        pos += ln
+    return g, out
+
+
+def test_oracle_pnm_decode_matches_cv2_fixture(oracle, golden_dir):
+    """cv::imdecode of the wire's binary PNM (orbslam3_mono_networked.cc:546): the restatement returns, case by case, what cv2 4.13
+    returned when the fixture was made (tests/golden/make_golden_pnm.py) -- same accept / reject verdict, same Mat bytes."""
+    g, cases = _pnm_cases(golden_dir)
+    assert len(cases) == int(g["n"]) and sum(v == 1 for _, v, _, _ in cases) >= 10
+    for data, verdict, shape, digest in cases:
+        if verdict == 2:
+            with pytest.raises(ValueError):
+                oracle.pnm_decode(data)
+            continue
+        m = oracle.pnm_decode(data)
+        if verdict == 0:
+            assert m is None, data[:16]
+        else:
+            assert m is not None and (m.shape[0], m.shape[1], 1 if m.ndim == 2 else 3) == shape and sha(m) == digest, data[:16]
+    # the wire frame: imencode(".ppm") header form, decoded Mat and both gray conversions
+    w, h = (int(v) for v in g["wire_size"])
+    bgr = np.stack([synth.textured_frame(int(s), w, h) for s in g["wire_seeds"]], axis=2)
+    wire = g["wire_header"].tobytes() + bgr[:, :, ::-1].tobytes()
+    assert sha(np.frombuffer(wire, np.uint8)) == str(g["wire_sha"])
+    dec = oracle.pnm_decode(wire)
+    assert sha(dec) == str(g["decoded_sha"]) and np.array_equal(dec, bgr)
+    assert sha(oracle.gray(dec, 1)) == str(g["gray_rgb1_sha"]) and sha(oracle.gray(dec, 2)) == str(g["gray_rgb0_sha"])
+    try:
+        import cv2
+    except ImportError:
+        return
+    for data, verdict, shape, digest in cases:          # live cv2 where it exists
+        try:
+            ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_UNCHANGED) if data else None
+        except cv2.error:
+            ref = None
+        assert (ref is None) == (verdict == 0), data[:16]
