@@ -255,7 +255,7 @@ def main():
     nkp = float(d_n.float().mean().item())
 
     # ---- e2e through the C ABI with host buffers: inputs and result arrays live in page-locked host memory
-    e2e_steps = max(RING, min(args.steps, 40))
+    e2e_steps = max(RING, min(2 * args.steps, 40))
     pinned_in = [torch.from_numpy(b).pin_memory() for b in host_batches]
     pin_kp = torch.empty((BATCH, cap, 7), dtype=torch.float32).pin_memory()
     pin_desc = torch.empty((BATCH, cap, 32), dtype=torch.uint8).pin_memory()

@@ -743,7 +743,9 @@ int orbx_extract_batch_submit(orbx_handle *h, const uint8_t *const *frames, int 
             // each uploaded range is computed as `sub` sub-ranges on different streams (same reason as in the device-resident path)
             static const int sub_env = [] { const char *e = getenv("ORBX_SUB"); return e ? atoi(e) : 0; }();
             const int nchunks = (batch + chunk - 1) / chunk;
-            int sub = sub_env > 0 ? sub_env : 1;   // measured: 2 or 4 sub-ranges do not help here (0.86 -> 0.91 / 0.96 ms), the upload paces the flow
+            // measured (frames/s, 64 x 640x480, blocking call | two handles alternated with submit / collect): 1 sub-range 81 k | 134-139 k,
+            // 2 sub-ranges 82-87 k | 137-143 k, 4 (one 64-frame range) 58 k | 129 k
+            int sub = sub_env > 0 ? sub_env : 2;
             while (sub > 1 && (chunk / sub < 8 || nchunks * sub > orbx_handle::kMaxChunks)) sub--;
             const int ncs = std::min(h->ncs, nchunks * sub);
             for (int i = 0; i < ncs; i++) CU_TRY(h, cudaStreamWaitEvent(h->cs[i], h->ev_start, 0));
