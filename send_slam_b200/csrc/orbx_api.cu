@@ -15,6 +15,7 @@
 #include "../../include/orbx.h"
 #include "orbx_dev.h"
 #include "orbx_plan.h"
+#include "../../include/orbx_wire.h"
 #include "orbx_tma.cuh"
 
 using namespace orbx;
@@ -902,6 +903,24 @@ int orbx_extract_pnm(orbx_handle *h, const uint8_t *data, size_t nbytes, int cam
     const int rc = orbx_extract(h, data + off, w, ht, w * ch, lap0, lap1, kp_out, desc_out, cap, n_out, mono_index_out);
     h->in_fmt = saved;
     return rc;
+}
+
+int orbx_wire_process_frame(orbx_handle *h, const uint8_t *payload, size_t nbytes, int camera_rgb, int lap0, int lap1,
+                            orbx_keypoint *kp_out, uint8_t *desc_out, int cap, int *n_out, int *mono_index_out, int *width_out,
+                            int *height_out, double *timestamp_out, int *camera_id_out) {
+    if (!h) return ORBX_E_INVALID;
+    if (n_out) *n_out = 0;
+    if (mono_index_out) *mono_index_out = -1;
+    orbx_wire_frame m;
+    if (orbx_wire_parse_frame(payload, nbytes, &m) != ORBX_OK) return fail(h, ORBX_E_INVALID, "Failed to parse MessagePack payload");
+    if (m.type_len != 5 || std::memcmp(m.type, "frame", 5) != 0) return fail(h, ORBX_E_INVALID, "not a frame message");
+    // the receive loop's checks, in its order (orbslam3_mono_networked.cc:527-544); each one skips the message there
+    if (!m.has_camera_id || !m.camera_id) return fail(h, ORBX_E_EMPTY, "Frame message missing camera identifier.");
+    if (!m.image || !m.image_bytes) return fail(h, ORBX_E_EMPTY, "Frame message missing binary image data.");
+    if (!m.has_timestamp) return fail(h, ORBX_E_EMPTY, "Frame message missing timestamp.");
+    if (timestamp_out) *timestamp_out = m.timestamp;
+    if (camera_id_out) *camera_id_out = m.camera_id;
+    return orbx_extract_pnm(h, m.image, m.image_bytes, camera_rgb, lap0, lap1, kp_out, desc_out, cap, n_out, mono_index_out, width_out, height_out);
 }
 
 // ---- stage inspection ------------------------------------------------------------------------------------------

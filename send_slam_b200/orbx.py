@@ -36,11 +36,22 @@ class _Config(C.Structure):
                 ("max_batch", C.c_int)]
 
 
+class _WireFrame(C.Structure):          # orbx_wire_frame (include/orbx_wire.h)
+    _fields_ = [("type", C.c_void_p), ("type_len", C.c_size_t), ("image", C.c_void_p), ("image_bytes", C.c_size_t),
+                ("timestamp", C.c_double), ("camera_id", C.c_int), ("has_timestamp", C.c_int), ("has_camera_id", C.c_int)]
+
+
+class _WireFeatures(C.Structure):       # orbx_wire_features
+    _fields_ = [("timestamp", C.c_double), ("camera_id", C.c_int), ("width", C.c_int), ("height", C.c_int), ("mono_index", C.c_int),
+                ("n", C.c_int), ("keypoints", C.c_void_p), ("descriptors", C.c_void_p)]
+
+
 # every symbol include/orbx.h declares (tests check the library exports all of them)
 EXPORTS = [
     "orbx_create", "orbx_destroy", "orbx_last_error", "orbx_keypoint_capacity", "orbx_get_tables", "orbx_get_level_sizes",
     "orbx_extract", "orbx_extract_batch", "orbx_extract_batch_submit", "orbx_extract_batch_collect",
     "orbx_extract_batch_device", "orbx_sync", "orbx_launch_count", "orbx_pnm_header", "orbx_extract_pnm",
+    "orbx_wire_parse_frame", "orbx_wire_process_frame", "orbx_wire_features_bound", "orbx_wire_pack_features", "orbx_wire_parse_features",
     "orbx_debug_get_level", "orbx_debug_get_candidates", "orbx_debug_get_level_keypoints", "orbx_debug_resize",
     "orbx_debug_blur", "orbx_debug_octree", "orbx_debug_describe", "orbx_distance_batch", "orbx_match_windowed",
     "orbx_knn2_create_db", "orbx_knn2_create_db_device", "orbx_knn2_destroy_db", "orbx_knn2_last_error", "orbx_knn2_query",
@@ -67,6 +78,47 @@ def pnm_header(data: bytes):
     return w.value, h.value, ch.value, off.value
 
 
+def wire_parse_frame(payload: bytes):
+    """ParseMessage of the backend (orbslam3_mono_networked.cc:302-337) for a non-calibration message: dict with type, image
+    (bytes or None), timestamp / camera_id (None if absent); raises OrbxError where ParseMessage throws or returns false."""
+    buf = np.frombuffer(payload, np.uint8)
+    m = _WireFrame()
+    rc = lib().orbx_wire_parse_frame(_p(buf) if len(buf) else None, len(buf), C.byref(m))
+    if rc:
+        raise OrbxError(rc, "Failed to parse MessagePack payload")
+    base = buf.ctypes.data
+    return {"type": bytes(buf[m.type - base:m.type - base + m.type_len]).decode("utf-8", "replace"),
+            "image": bytes(buf[m.image - base:m.image - base + m.image_bytes]) if m.image else None,
+            "timestamp": m.timestamp if m.has_timestamp else None, "camera_id": m.camera_id if m.has_camera_id else None}
+
+
+def wire_pack_features(timestamp, camera_id, width, height, mono_index, kps, desc, framed=True) -> bytes:
+    """The 'features' message of SURVEY.md §8f-3 (include/orbx_wire.h)."""
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    n = len(kps)
+    out = np.zeros(lib().orbx_wire_features_bound(n, int(framed)), np.uint8)
+    wr = C.c_size_t()
+    rc = lib().orbx_wire_pack_features(float(timestamp), int(camera_id), int(width), int(height), int(mono_index), _p(kps) if n else None,
+                                       _p(desc) if n else None, n, int(framed), _p(out), len(out), C.byref(wr))
+    if rc:
+        raise OrbxError(rc, "orbx_wire_pack_features")
+    return out[:wr.value].tobytes()
+
+
+def wire_parse_features(payload: bytes):
+    buf = np.frombuffer(payload, np.uint8)
+    m = _WireFeatures()
+    rc = lib().orbx_wire_parse_features(_p(buf) if len(buf) else None, len(buf), C.byref(m))
+    if rc:
+        raise OrbxError(rc, "not a features message")
+    base = buf.ctypes.data
+    kp = np.frombuffer(bytes(buf[m.keypoints - base:m.keypoints - base + m.n * 28]), KP_DTYPE)
+    de = np.frombuffer(bytes(buf[m.descriptors - base:m.descriptors - base + m.n * 32]), np.uint8).reshape(m.n, 32)
+    return {"timestamp": m.timestamp, "camera_id": m.camera_id, "width": m.width, "height": m.height, "mono_index": m.mono_index,
+            "keypoints": kp, "descriptors": de}
+
+
 def lib():
     """Loads liborbx.so (built in-tree by __graft_entry__.build()); fails loudly if it is missing."""
     global _lib
@@ -91,6 +143,14 @@ def lib():
     L.orbx_extract_batch_submit.argtypes = [vp, C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp,
                                             C.c_int]
     L.orbx_extract_batch_collect.argtypes = [vp, vp, vp]
+    L.orbx_wire_parse_frame.argtypes = [vp, C.c_size_t, C.POINTER(_WireFrame)]
+    L.orbx_wire_process_frame.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, ip, ip, ip, ip,
+                                          C.POINTER(C.c_double), ip]
+    L.orbx_wire_features_bound.argtypes = [C.c_int, C.c_int]
+    L.orbx_wire_features_bound.restype = C.c_size_t
+    L.orbx_wire_pack_features.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, vp, C.c_size_t,
+                                          C.POINTER(C.c_size_t)]
+    L.orbx_wire_parse_features.argtypes = [vp, C.c_size_t, C.POINTER(_WireFeatures)]
     L.orbx_pnm_header.argtypes = [vp, C.c_size_t, ip, ip, ip, C.POINTER(C.c_size_t)]
     L.orbx_extract_pnm.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, ip, ip, ip, ip]
     L.orbx_extract_batch_device.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp,
@@ -267,6 +327,23 @@ class ORBextractor:
             return -1, np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8), None
         self._check(rc)
         return mono.value, kps[:n.value].copy(), desc[:n.value].copy(), (w.value, h.value)
+
+    def process_frame_message(self, payload: bytes, camera_rgb: bool = True, vLappingArea=(0, 1000)):
+        """One 'frame' message as it comes off the socket (the MessagePack map after the 4-byte length): what the backend's receive
+        loop does up to operator().  Returns dict(mono_index, keypoints, descriptors, size, timestamp, camera_id), or None where the
+        reference logs and skips the message; raises OrbxError where its ParseMessage throws / the message is not a frame."""
+        buf = np.frombuffer(payload, np.uint8)
+        kps = np.zeros(self.capacity, KP_DTYPE)
+        desc = np.zeros((self.capacity, 32), np.uint8)
+        n, mono, w, h, cam, ts = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_double()
+        rc = self._L.orbx_wire_process_frame(self._h, _p(buf) if len(buf) else None, len(buf), int(bool(camera_rgb)), int(vLappingArea[0]),
+                                             int(vLappingArea[1]), _p(kps), _p(desc), self.capacity, C.byref(n), C.byref(mono),
+                                             C.byref(w), C.byref(h), C.byref(ts), C.byref(cam))
+        if rc == ORBX_E_EMPTY:
+            return None
+        self._check(rc)
+        return {"mono_index": mono.value, "keypoints": kps[:n.value].copy(), "descriptors": desc[:n.value].copy(),
+                "size": (w.value, h.value), "timestamp": ts.value, "camera_id": cam.value}
 
     def _batch_args(self, frames, out):
         frames = np.asarray(frames)

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def declared_functions():
-    txt = open(os.path.join(ROOT, "include", "orbx.h")).read()
+    txt = "".join(open(os.path.join(ROOT, "include", f)).read() for f in ("orbx.h", "orbx_wire.h"))     # include/*.h
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
     return sorted(set(re.findall(r"\b(orbx_[a-z0-9_]+)\s*\(", txt)))
 
@@ -119,3 +119,61 @@ def test_pnm_header_host_logic(golden_dir):
         pay = np.frombuffer(data, np.uint8)[off:off + w * h * ch].reshape(h, w, ch)
         assert np.array_equal(pay[:, :, ::-1] if ch == 3 else pay[:, :, 0], m), data[:16]
     assert orbx.pnm_header(b"") is None
+
+
+def test_wire_messages_host_logic():
+    """include/orbx_wire.h against the Python msgpack package as the independent MessagePack implementation: the 'frame' message the
+    Elixir side builds (slam_handler.ex:140-156) parses to what ParseMessage extracts (orbslam3_mono_networked.cc:302-337), malformed
+    payloads are refused the way msgpack-c's unpack / convert throw, and the 'features' message round-trips both ways."""
+    msgpack = pytest.importorskip("msgpack")
+    ppm = b"P6\n4 2\n255\n" + bytes(range(24))
+    frame = {"type": "frame", "camera_id": 1, "encoding": "ppm", "timestamp": 12.5, "width": 4, "height": 2, "channels": 3, "frame": ppm}
+    m = orbx.wire_parse_frame(msgpack.packb(frame, use_bin_type=True))
+    assert m == {"type": "frame", "image": ppm, "timestamp": 12.5, "camera_id": 1}
+    # key order, the "image" alias, integer / float32 timestamps, unknown fields of every MessagePack family, big frames (bin32)
+    import struct
+    big = bytes(70000)
+    extra = {"nested": {"a": [1, -2, 3.5, None, True, {"b": b"x" * 300, "c": "y" * 40}], "d": [[]], "e": 2 ** 40, "f": -2 ** 33},
+             "ext": msgpack.ExtType(5, b"12345"), "ext8": msgpack.ExtType(1, b"12345678"), "calibration": {"fx": 1.0, "dist": [0.1, 0.2]}}
+    msg = dict(extra, image=big, camera_id=300, timestamp=7, type="frame")
+    m = orbx.wire_parse_frame(msgpack.packb(msg, use_bin_type=True))
+    assert m["image"] == big and m["camera_id"] == 300 and m["timestamp"] == 7.0 and m["type"] == "frame"
+    f32 = b"\x83" + msgpack.packb("type") + msgpack.packb("frame") + msgpack.packb("timestamp") + b"\xca" + struct.pack(">f", 1.25) + \
+        msgpack.packb("camera_id") + b"\xd1" + struct.pack(">h", -7)
+    m = orbx.wire_parse_frame(f32)
+    assert m["timestamp"] == 1.25 and m["camera_id"] == -7 and m["image"] is None
+    dup = b"\x83" + msgpack.packb("type") + msgpack.packb("frame") + msgpack.packb("camera_id") + msgpack.packb(1) + msgpack.packb("camera_id") + msgpack.packb(2)
+    assert orbx.wire_parse_frame(dup)["camera_id"] == 2                                   # later duplicate wins, as in the loop
+    assert orbx.wire_parse_frame(msgpack.packb({"type": "calibration", "calibration": {"fx": 1}}))["type"] == "calibration"
+    good = msgpack.packb(frame, use_bin_type=True)
+    bad = [b"", b"\xc1", msgpack.packb([1, 2]), msgpack.packb("frame"), good[:-1], good[:10],               # empty, reserved tag, non-map, truncated
+           msgpack.packb({"type": "frame", "frame": "not-bin"}, use_bin_type=True),                           # image must be bin
+           msgpack.packb({"type": "frame", "timestamp": "soon"}), msgpack.packb({"type": "frame", "camera_id": 1.5}),
+           msgpack.packb({"type": "frame", "camera_id": 2 ** 31}), msgpack.packb({"type": ""}), msgpack.packb({"camera_id": 1}),
+           msgpack.packb({1: "frame"}), msgpack.packb({"type": "frame", "x": [1, 2, 3]})[:-1], b"\xdf\xff\xff\xff\xff", b"\x81\xa4type\xdd\xff\xff\xff\xff"]
+    for b in bad:
+        with pytest.raises(orbx.OrbxError):
+            orbx.wire_parse_frame(b)
+    # the 'features' message: library -> msgpack package, msgpack package -> library, library -> library
+    rng = np.random.default_rng(3)
+    n = 37
+    kps = np.zeros(n, orbx.KP_DTYPE)
+    for name in ("x", "y", "size", "angle", "response"):
+        kps[name] = rng.uniform(0, 640, n).astype(np.float32)
+    kps["octave"] = rng.integers(0, 8, n); kps["class_id"] = -1
+    desc = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    wire = orbx.wire_pack_features(3.75, 2, 640, 480, 11, kps, desc, framed=True)
+    assert struct.unpack(">I", wire[:4])[0] == len(wire) - 4
+    d = msgpack.unpackb(wire[4:], raw=False)
+    assert d == {"type": "features", "camera_id": 2, "timestamp": 3.75, "width": 640, "height": 480, "mono_index": 11, "n": n,
+                 "keypoints": kps.tobytes(), "descriptors": desc.tobytes()}
+    for payload in (wire[4:], msgpack.packb(dict(reversed(list(d.items())), note="extra"), use_bin_type=True)):
+        f = orbx.wire_parse_features(payload)
+        assert (f["timestamp"], f["camera_id"], f["width"], f["height"], f["mono_index"]) == (3.75, 2, 640, 480, 11)
+        assert f["keypoints"].tobytes() == kps.tobytes() and np.array_equal(f["descriptors"], desc)
+    empty = orbx.wire_parse_features(orbx.wire_pack_features(1.0, 1, 64, 48, 0, kps[:0], desc[:0], framed=False))
+    assert len(empty["keypoints"]) == 0 and empty["descriptors"].shape == (0, 32)
+    for b in (msgpack.packb(frame, use_bin_type=True), wire[4:-1], msgpack.packb(dict(d, n=n + 1), use_bin_type=True),
+              msgpack.packb(dict(d, keypoints="str"), use_bin_type=True)):
+        with pytest.raises(orbx.OrbxError):
+            orbx.wire_parse_features(b)

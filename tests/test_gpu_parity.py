@@ -445,6 +445,35 @@ def test_wire_ppm_frames(ex, oracle, golden_dir):
         ex.extract_pnm(b"P6\n2 2\n65535\n" + bytes(24))
 
 
+def test_wire_frame_message_to_features(ex, oracle):
+    """A 'frame' message as the Elixir side builds it (slam_handler.ex:140-156; packed here with the Python msgpack package) goes
+    through orbx_wire_process_frame = the backend's receive loop up to operator(); the result equals imdecode -> cvtColor ->
+    operator() of the oracle, and leaves again as the 'features' message of SURVEY.md §8f-3, which decodes to the same records."""
+    msgpack = pytest.importorskip("msgpack")
+    w, h = 640, 480
+    bgr = np.stack([synth.textured_frame(60 + k, w, h) for k in range(3)], axis=2)
+    ppm = b"P6\n%d %d\n255\n" % (w, h) + bgr[:, :, ::-1].tobytes()
+    msg = {"type": "frame", "camera_id": 3, "encoding": "ppm", "timestamp": 41.0625, "width": w, "height": h, "channels": 3, "frame": ppm}
+    payload = msgpack.packb(msg, use_bin_type=True)
+    r = ex.process_frame_message(payload, camera_rgb=True)
+    gray = oracle.gray(oracle.pnm_decode(ppm), 1)
+    want = oracle.Oracle(1000).extract(gray)
+    assert_same_extraction((r["mono_index"], r["keypoints"], r["descriptors"]), want, "frame message")
+    assert r["size"] == (w, h) and r["timestamp"] == 41.0625 and r["camera_id"] == 3
+    out = orbx.wire_pack_features(r["timestamp"], r["camera_id"], w, h, r["mono_index"], r["keypoints"], r["descriptors"])
+    assert len(out) < len(payload) // 10                                  # 60 KB instead of 0.92 MB on the wire at 640x480
+    back = msgpack.unpackb(out[4:], raw=False)
+    assert back["n"] == len(want[0]) and back["descriptors"] == want[1].tobytes() and back["keypoints"] == want[0].tobytes()
+    # the loop's skip cases come back as None (camera_id 0 / missing, no image, no timestamp, undecodable image) ...
+    for bad in (dict(msg, camera_id=0), {k: v for k, v in msg.items() if k != "camera_id"}, {k: v for k, v in msg.items() if k != "frame"},
+                {k: v for k, v in msg.items() if k != "timestamp"}, dict(msg, frame=ppm[:-10]), dict(msg, frame=b"")):
+        assert ex.process_frame_message(msgpack.packb(bad, use_bin_type=True)) is None
+    # ... what ParseMessage throws on, and other message types, are errors
+    for bad in (payload[:-1], msgpack.packb(dict(msg, frame="text"), use_bin_type=True), msgpack.packb({"type": "calibration"})):
+        with pytest.raises(orbx.OrbxError):
+            ex.process_frame_message(bad)
+
+
 def test_frame_undistort_and_grid(ex, oracle):
     """SURVEY.md §8f-2: Frame::UndistortKeyPoints / ComputeImageBounds / AssignFeaturesToGrid on the device, bit-exact against
     the oracle (which equals cv2.undistortPoints bit for bit, tests/test_oracle_golden.py)."""
