@@ -835,7 +835,9 @@ int launch_fast(const LevelDev *h_levels, const CellRect *d_cells, int ncells, i
         }
         const int total = ncells * batch;
         const int want = (total + FW_WARPS - 1) / FW_WARPS;
-        const int grid = want < sm_count * per_sm ? want : sm_count * per_sm;
+        static const int cap_env = [] { const char *e = getenv("ORBX_FAST_CTAS"); return e ? atoi(e) : 0; }();
+        const int resident = cap_env > 0 && cap_env < per_sm ? cap_env : per_sm;
+        const int grid = want < sm_count * resident ? want : sm_count * resident;
         k_fast_tma<<<grid, FW_WARPS * 32, smem, stream>>>(P, d_cells, ncells, total, ini_th, min_th, f0, d_overflow);
         return 1;
     }
