@@ -1,9 +1,10 @@
 #!/usr/bin/env python
-"""Randomised parity sweep on a B200: random frame sizes / kinds / extractor parameters through orbx_extract (and a few batches through
-the device-resident and colour paths), every result compared with the CPU oracle bit for bit.  Usage: python tools/fuzz_parity.py [seconds] [seed]"""
+"""Randomised parity sweep on a B200: random frame sizes / kinds / extractor parameters through orbx_extract (and batches through
+the blocking, submit/collect, device-resident, colour, PPM and frame-message paths), every result compared with the CPU oracle bit for bit.  Usage: python tools/fuzz_parity.py [seconds] [seed]"""
 import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import msgpack
 import torch
 from send_slam_b200 import orbx, synth
 from oracle import oracle_lib as ol
@@ -29,7 +30,7 @@ while time.time() - t0 < budget:
         continue
     frames = np.stack([synth.textured_frame(int(rng.integers(0, 1 << 30)), w, h, kind) for _ in range(B)])
     e = orbx.ORBextractor(nf, scale, nlev, ini, mn, max_width=w, max_height=h, max_batch=B)
-    mode = int(rng.integers(0, 3)) if B > 1 else 0
+    mode = int(rng.integers(0, 4)) if B > 1 else 0
     try:
         e(frames[0])          # geometry the reference itself cannot handle (degenerate upper levels) is refused with ORBX_E_INVALID
     except orbx.OrbxError as err:
@@ -41,6 +42,12 @@ while time.time() - t0 < budget:
         got = [e(frames[i]) for i in range(B)]
     elif mode == 1:
         mono, n, kps, desc = e.extract_batch(frames)
+        got = [(int(mono[i]), kps[i, :n[i]], desc[i, :n[i]]) for i in range(B)]
+    elif mode == 3:       # asynchronous pair, pageable or page-locked buffers, twice (the second call may replay a graph)
+        src = torch.from_numpy(frames).pin_memory().numpy() if ncase & 1 else frames
+        for rep in range(2):
+            e.extract_batch_submit(src)
+            mono, n, kps, desc = e.extract_batch_collect()
         got = [(int(mono[i]), kps[i, :n[i]], desc[i, :n[i]]) for i in range(B)]
     else:
         cap = e.capacity
@@ -65,6 +72,14 @@ while time.time() - t0 < budget:
         k_g, d_g, m_g = o.extract(gray)
         if not (mono_c == m_g and np.array_equal(desc_c, d_g) and np.array_equal(kps_c.view(np.int32), k_g.view(np.int32))):
             print("MISMATCH colour", tag, fmt); sys.exit(1)
+        if ch == 3:           # the same pixels as a wire frame: binary PPM, bare and inside the MessagePack frame message
+            ppm = b"P6\n# fuzz\n%d %d\n255\n" % (w, h) + col.tobytes()
+            mono_p, kps_p, desc_p, size = e.extract_pnm(ppm, camera_rgb=(fmt == 2))
+            r = e.process_frame_message(msgpack.packb({"type": "frame", "camera_id": 1 + ncase, "timestamp": 0.5 * ncase, "frame": ppm}, use_bin_type=True),
+                                        camera_rgb=(fmt == 2))
+            if not (size == (w, h) and mono_p == m_g and np.array_equal(desc_p, d_g) and np.array_equal(kps_p.view(np.int32), k_g.view(np.int32)) and
+                    r["mono_index"] == m_g and np.array_equal(r["descriptors"], d_g) and r["camera_id"] == 1 + ncase):
+                print("MISMATCH ppm", tag, fmt); sys.exit(1)
         cam = (0.9 * w, 0.92 * w, 0.5 * w + 3, 0.5 * h - 2, float(rng.uniform(-0.3, 0.3)), float(rng.uniform(-0.1, 0.1)), 1e-3, -5e-4, 0.0)
         b = e.image_bounds(cam, w, h)
         if np.array_equal(b, ol.image_bounds(cam, w, h)) and b[2] > b[0] and b[3] > b[1]:
