@@ -30,6 +30,8 @@ W, H, NFEAT, NLEVELS, SCALE, INI_TH, MIN_TH = 640, 480, 1000, 8, 1.2, 20, 7
 BATCH = 64
 RING = 8                 # distinct input batches cycled through: 8 x 64 x 300 KB = 157 MB > 126 MB L2
 KNN_Q, KNN_ROWS = 2000, 1_000_000
+WORKLOAD = (f"ORB extraction, {BATCH} x {W}x{H} gray frames per GPU per step, nFeatures {NFEAT}, {NLEVELS} levels, scale {SCALE}, "
+            f"iniTh {INI_TH}, minTh {MIN_TH} (BASELINE configs[0] shape, 64-frame batches of configs[1])")
 METRIC = "ORB frames/s (640x480,1k kp) + Hamming pairs/s at 1/2/4/8 B200, %roofline"
 
 
@@ -155,8 +157,10 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"ORB extraction {W}x{H} gray, nFeatures {NFEAT}, {NLEVELS} levels, scale {SCALE}, CPU restatement of "
-                                   "ORB-SLAM3 ORBextractor (reference source not in tree / unbuildable: oracle port)"},
+            "config": {"workload": WORKLOAD,
+                       "implementation": "CPU restatement of ORB-SLAM3's ORBextractor (oracle/orb_oracle.c; the reference's own source is not in "
+                                         "its tree and needs OpenCV / Eigen / Boost: unbuildable here), one extractor per host thread",
+                       "sample_per_step": f"{nfr} of the workload's frames"},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -568,8 +572,7 @@ def main():
         line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8", "data": "synthetic",
-                "config": {"workload": f"ORB extraction, {BATCH} x {W}x{H} gray frames per GPU per step, nFeatures {NFEAT}, {NLEVELS} levels, "
-                                       f"scale {SCALE}, iniTh {INI_TH}, minTh {MIN_TH} (BASELINE configs[0] shape, 64-frame batches of configs[1])",
+                "config": {"workload": WORKLOAD,
                            "l2": f"inputs cycle through {RING} distinct batches = {RING * BATCH * W * H / 1e6:.0f} MB > 126 MB L2",
                            "sharding": "frames sharded by rank, no collective", "numa_binding": numa, "keypoints_per_frame": nkp,
                            "lanes": "two batches in flight per GPU: steps alternate between two handles, each with its own stream and result buffers"},
