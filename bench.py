@@ -3,8 +3,8 @@
 
 One "step" = one pass of the hot path over one batch of 64 synthetic 640x480 gray frames (nFeatures 1000, 8 levels,
 scale 1.2, iniTh 20, minTh 7) per GPU -- the configuration BASELINE.json's metric is quoted on.
-  value  frames/s, inputs resident in HBM when the timed region starts (orbx_extract_batch_device), whole job; two batches
-         in flight per GPU (steps alternate between two handles / streams); `single_lane` = one batch in flight.
+  value  frames/s, inputs resident in HBM when the timed region starts (orbx_extract_batch_device), whole job; four batches
+         in flight per GPU (steps go round-robin over four handles / streams); `single_lane` = one batch in flight.
   e2e    same metric through the reference-facing C ABI with HOST buffers (orbx_extract_batch_submit / _collect, one host
          thread): the host->device copy of the 64 frames and the device->host copy of keypoints + descriptors of every
          step are inside the timed region; `e2e.blocking_call` = one blocking orbx_extract_batch per batch.
@@ -225,71 +225,87 @@ def main():
         ex.extract_batch_device(t.data_ptr(), H * W, BATCH, W, H, W, d_kp.data_ptr(), d_desc.data_ptr(), cap,
                                 d_n.data_ptr(), d_mono.data_ptr())
 
-    # Second lane: a streaming job keeps two batches in flight, each on its own handle / stream / result buffers (two camera groups),
+    # More lanes: a streaming job keeps several batches in flight, each on its own handle / stream / result buffers (camera groups),
     # so that the latency-bound head (pyramid chain) and tail (quadtree, slots, descriptors) of one batch run under the machine-filling
-    # FAST pass of the other.  Every step is still one full pass over one 64-frame batch; steps alternate between the lanes.
-    exB = orbx.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank, max_width=W, max_height=H, max_batch=BATCH)
-    streamB = torch.cuda.Stream(device=dev)
-    exB.set_stream(streamB.cuda_stream)
-    d_kpB, d_descB, d_nB, d_monoB = torch.zeros_like(d_kp), torch.zeros_like(d_desc), torch.zeros_like(d_n), torch.zeros_like(d_mono)
-    evB = torch.cuda.Event()
+    # FAST pass of another.  Every step is still one full pass over one 64-frame batch; steps go round-robin over the lanes.
+    # Measured (tools/dev_two_handles.py): 1 lane 150 k, 2 lanes 164-165 k, 3 lanes 167 k, 4 lanes 170 k frames/s.  The lane count divides
+    # the ring of inputs, so every lane keeps meeting the same (input, output) buffer pairs (the library's graph replay keys on them).
+    NDL = max(1, int(os.environ.get("ORBX_BENCH_LANES", "4")))
+    more = []
+    for _ in range(NDL - 1):
+        e_ = orbx.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank, max_width=W, max_height=H, max_batch=BATCH)
+        s_ = torch.cuda.Stream(device=dev)
+        e_.set_stream(s_.cuda_stream)
+        more.append((e_, s_, (torch.zeros_like(d_kp), torch.zeros_like(d_desc), torch.zeros_like(d_n), torch.zeros_like(d_mono)), torch.cuda.Event()))
 
-    def step_two_lanes(i):
-        if i & 1:
-            t = d_in[i % RING]
-            exB.extract_batch_device(t.data_ptr(), H * W, BATCH, W, H, W, d_kpB.data_ptr(), d_descB.data_ptr(), cap,
-                                     d_nB.data_ptr(), d_monoB.data_ptr())
-        else:
+    def lane_call(lane, t):
+        e_, s_, (kp_, de_, n_, mo_), _ = lane
+        e_.extract_batch_device(t.data_ptr(), H * W, BATCH, W, H, W, kp_.data_ptr(), de_.data_ptr(), cap, n_.data_ptr(), mo_.data_ptr())
+
+    def step_lanes(i):
+        k = i % NDL
+        if k == 0:
             step_device(i)
+        else:
+            lane_call(more[k - 1], d_in[i % RING])
 
-    def timed(step_fn, nsteps, both):
+    def all_launches():
+        return ex.launch_count() + sum(m[0].launch_count() for m in more)
+
+    def timed(step_fn, nsteps, all_lanes):
         barrier()
-        l0 = ex.launch_count() + exB.launch_count()
+        l0 = all_launches()
         ev0.record(stream)
         for i in range(nsteps):
             step_fn(i)
-        if both:                                  # the clock stops when BOTH lanes are done
-            evB.record(streamB)
-            stream.wait_event(evB)
+        if all_lanes:                             # the clock stops when EVERY lane is done
+            for e_, s_, _, ev_ in more:
+                ev_.record(s_)
+                stream.wait_event(ev_)
         ev1.record(stream)
         ex.sync()
-        exB.sync()
+        for m in more:
+            m[0].sync()
         barrier()
         t = ev0.elapsed_time(ev1) * 1e-3
         if world > 1:
             tt = torch.tensor([t], dtype=torch.float64, device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             t = float(tt.item())
-        return t, ex.launch_count() + exB.launch_count() - l0
+        return t, all_launches() - l0
 
-    # the library replays a CUDA graph per (input, output) buffer pair from its third sighting on: each lane sees its half of the ring
-    args.warmup = max(args.warmup, 3 * RING + 2)
+    # the library replays a CUDA graph per (input, output) buffer pair from its third sighting on: each lane sees its share of the ring
+    args.warmup = max(args.warmup, 3 * RING + NDL)
     for i in range(args.warmup):
-        step_two_lanes(i)
+        step_lanes(i)
     ex.sync()
-    exB.sync()
+    for m in more:
+        m[0].sync()
     n_first = int(d_n.sum().item())
-    # lane B's results for a batch equal lane A's (checked once, outside the timed region)
+    # every lane returns for a batch what lane 0 returns (checked once, outside the timed region)
     step_device(1)
     ex.sync()
-    t1 = d_in[1]
-    exB.extract_batch_device(t1.data_ptr(), H * W, BATCH, W, H, W, d_kpB.data_ptr(), d_descB.data_ptr(), cap, d_nB.data_ptr(), d_monoB.data_ptr())
-    exB.sync()
-    if not (torch.equal(d_n, d_nB) and torch.equal(d_mono, d_monoB) and all(
-            torch.equal(d_desc[f, :int(d_n[f])], d_descB[f, :int(d_n[f])]) and torch.equal(d_kp[f, :int(d_n[f])].view(torch.int32), d_kpB[f, :int(d_n[f])].view(torch.int32))
-            for f in range(0, BATCH, 7))):
-        raise RuntimeError("the two lanes disagree")
+    for m in more:
+        lane_call(m, d_in[1])
+        m[0].sync()
+        kp_, de_, n_, mo_ = m[2]
+        if not (torch.equal(d_n, n_) and torch.equal(d_mono, mo_) and all(
+                torch.equal(d_desc[f, :int(d_n[f])], de_[f, :int(d_n[f])]) and
+                torch.equal(d_kp[f, :int(d_n[f])].view(torch.int32), kp_[f, :int(d_n[f])].view(torch.int32)) for f in range(0, BATCH, 7))):
+            raise RuntimeError("the lanes disagree")
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    dt, launches = timed(step_two_lanes, args.steps, True)
+    dt, launches = timed(step_lanes, args.steps, True)
     fps = world * args.steps * BATCH / dt
     # one lane alone (one batch in flight), same steps: reported beside the headline
     for i in range(2 * RING + 1):
         step_device(i)
     dt_single, _ = timed(step_device, args.steps, False)
     fps_single = world * args.steps * BATCH / dt_single
-    exB.close()
+    for m in more:
+        m[0].close()
+    del more
 
     # ---- per-kernel durations (CUDA events on the handle's stream, same inputs, right after the timed region)
     ex.set_profiling(True)
@@ -325,8 +341,8 @@ def main():
         dte = float(tt.item())
     e2e_fps = world * e2e_steps * BATCH / dte
     e2e_blocking_fps = e2e_fps
-    # The same host buffers through the asynchronous pair orbx_extract_batch_submit / _collect: ONE host thread keeps two handles
-    # busy (submit batch i, then collect batch i-1), so the upload of one batch overlaps the kernels and the download of the other.
+    # The same host buffers through the asynchronous pair orbx_extract_batch_submit / _collect: ONE host thread keeps several handles
+    # busy (submit batch i, then collect the oldest batch in flight), so the upload of one batch overlaps the kernels and the downloads of the others.
     # Every batch's H2D and D2H copies are inside the timed region; the last collect drains the device before the clock stops.
     ex2 = orbx.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank, max_width=W, max_height=H, max_batch=BATCH)
     pk2 = torch.empty((BATCH, cap, 7), dtype=torch.float32).pin_memory()
@@ -334,23 +350,34 @@ def main():
     out2 = (pk2.numpy().view(orbx.KP_DTYPE).reshape(BATCH, cap), pd2.numpy())
     ex.set_stream(0)          # each handle on its own stream
     lanes = [(ex, out_arrays), (ex2, out2)]
+    extra = []
+    # four batches in flight (measured: 2 handles 143-147 k, 4 handles 161 k frames/s; the lane count must divide the ring of input
+    # buffers so that every lane keeps meeting the same (input, output) pairs, which is what the library's graph replay keys on)
+    for _ in range(max(0, int(os.environ.get("ORBX_E2E_LANES", "4")) - 2)):
+        e3 = orbx.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank, max_width=W, max_height=H, max_batch=BATCH)
+        pk3 = torch.empty((BATCH, cap, 7), dtype=torch.float32).pin_memory()
+        pd3 = torch.empty((BATCH, cap, 32), dtype=torch.uint8).pin_memory()
+        lanes.append((e3, (pk3.numpy().view(orbx.KP_DTYPE).reshape(BATCH, cap), pd3.numpy())))
+        extra.append((e3, pk3, pd3))
+    NL = len(lanes)
 
     def run_streaming(nsteps):
-        busy = [False, False]
+        busy = [False] * NL
         for i in range(nsteps):
-            k = i & 1
+            k = i % NL
             e_, o_ = lanes[k]
             if busy[k]:
                 e_.extract_batch_collect()
             e_.extract_batch_submit(pinned_in[i % RING].numpy(), out=o_)
             busy[k] = True
-        for k in ((nsteps & 1), 1 - (nsteps & 1)):       # oldest first
+        for j in range(NL):                               # oldest first
+            k = (nsteps + j) % NL
             if busy[k]:
                 lanes[k][0].extract_batch_collect()
 
     e2e_async = None
     try:
-        run_streaming(2 * RING + 2)                       # graph capture for each lane's (input, output) pairs
+        run_streaming(NL * RING + NL)                     # graph capture for each lane's (input, output) pairs
         barrier()
         t0 = time.perf_counter()
         run_streaming(e2e_steps)
@@ -575,13 +602,13 @@ def main():
                 "config": {"workload": WORKLOAD,
                            "l2": f"inputs cycle through {RING} distinct batches = {RING * BATCH * W * H / 1e6:.0f} MB > 126 MB L2",
                            "sharding": "frames sharded by rank, no collective", "numa_binding": numa, "keypoints_per_frame": nkp,
-                           "lanes": "two batches in flight per GPU: steps alternate between two handles, each with its own stream and result buffers"},
+                           "lanes": f"{NDL} batches in flight per GPU: steps go round-robin over {NDL} handles, each with its own stream and result buffers"},
                 "clocks": clocks, "gpu_launches": launches,
                 "single_lane": {"value": fps_single, "unit": "frames/s", "ms_per_step": 1e3 * dt_single / args.steps,
                                 "note": "one handle, one batch in flight (every step waits for the previous one on the same stream)"},
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps,
-                        "api": ("orbx_extract_batch_submit / _collect from one host thread over two handles (batch i uploads while batch i-1 computes), "
+                        "api": (f"orbx_extract_batch_submit / _collect from one host thread over {NL} handles (batch i uploads while earlier batches compute and download), "
                                 "pinned host frames in / pinned keypoint + descriptor arrays out"
                                 if isinstance(e2e_async, float) else
                                 "orbx_extract_batch, pinned host frames in / pinned keypoint + descriptor arrays out"),

@@ -3,6 +3,7 @@
 # Every ncu run follows a plain run of the same command that exited 0.  Outputs land in gpurun_out/.
 set -u
 TAG=${1:-r01}
+export ORBX_DEV_SPLIT=1 ORBX_GRAPHS=0 ORBX_BENCH_LANES=1   # one lane, single-range launches, no graph replay: every launch is one whole-batch kernel
 CMD="python bench.py --steps 3 --warmup 3 --no-cpu"
 $CMD > gpurun_out/bench_plain_$TAG.json 2> gpurun_out/bench_plain_$TAG.err || { echo "plain run failed"; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launches_$TAG.log 2>&1

@@ -25,7 +25,7 @@ for r in rows:
 ours = {k: v for k, v in agg.items() if k.startswith("k_")}
 tot = sum(v[1] for k, v in ours.items() if not k.startswith("k_knn") and not k.startswith("k_expand"))
 with open(os.path.join(P, f"launches_{tag}_summary.md"), "w") as f:
-    f.write(f"# ncu launch list ({tag})\n\nCommand: `ORBX_DEV_SPLIT=1 ORBX_GRAPHS=0 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv python bench.py --steps 3 --warmup 3 --no-cpu`\n"
+    f.write(f"# ncu launch list ({tag})\n\nCommand: `ORBX_DEV_SPLIT=1 ORBX_GRAPHS=0 ORBX_BENCH_LANES=1 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv python bench.py --steps 3 --warmup 3 --no-cpu`\n"
             "(single-range launches without graph replay, so that every launch in the list is one whole-batch kernel; tools/capture_profiles.sh)\n"
             "(cold-cache, serialised: compare shares, not absolutes).  Share = fraction of the extraction kernels' time.\n\n"
             "| kernel | launches | total us | avg us | share of extraction time |\n|---|---|---|---|---|\n")
@@ -51,6 +51,7 @@ for fn in sorted(os.listdir(G)):
     if rd and wr:
         traffic[k] = {"dram_bytes_per_launch": float(rd.group(1)) * mult[rd.group(2)] + float(wr.group(1)) * mult[wr.group(2)],
                       "duration_under_ncu": f"{dur.group(1)} {dur.group(2)}" if dur else None}
-json.dump(traffic, open(os.path.join(P, f"traffic_{tag}.json"), "w"), indent=1)
+if traffic:      # launch-list-only refreshes (no .ncu-rep in gpurun_out/) keep the committed traffic file
+    json.dump(traffic, open(os.path.join(P, f"traffic_{tag}.json"), "w"), indent=1)
 print(open(os.path.join(P, f"launches_{tag}_summary.md")).read())
 print(json.dumps(traffic, indent=1))
