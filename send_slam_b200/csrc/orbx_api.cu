@@ -838,52 +838,6 @@ int orbx_extract(orbx_handle *h, const uint8_t *gray, int width, int height, int
 }
 
 // ---- frames as they arrive on the reference's wire: binary PNM (`encoding: "ppm"`) -------------------------------
-namespace {
-// Byte cursor with OpenCV's PxM header grammar: a number is preceded by any run of white space / '#' comments and followed by
-// exactly one consumed byte (so "255\n" leaves the cursor on the first sample).
-struct PnmCursor {
-    const uint8_t *d; size_t n, pos = 0; bool eos = false;
-    int get() { if (pos >= n) { eos = true; return -1; } return d[pos++]; }
-    static bool space(int c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
-    static bool digit(int c) { return c >= '0' && c <= '9'; }
-    bool number(long long &out) {
-        int c = get();
-        while (!eos && !digit(c)) {
-            if (c == '#') { do c = get(); while (!eos && c != '\n' && c != '\r'); c = get(); }
-            else if (space(c)) { do c = get(); while (!eos && space(c)); }
-            else return false;
-        }
-        if (eos) return false;
-        long long v = 0;
-        while (true) {
-            v = v * 10 + (c - '0');
-            if (v > INT32_MAX) return false;
-            c = get();
-            if (eos) return false;            // the reader needs the terminating byte
-            if (!digit(c)) break;
-        }
-        out = v;
-        return true;
-    }
-};
-}  // namespace
-
-int orbx_pnm_header(const uint8_t *data, size_t nbytes, int *width, int *height, int *channels, size_t *payload_offset) {
-    if ((!data && nbytes) || !width || !height || !channels || !payload_offset) return ORBX_E_INVALID;
-    if (nbytes < 2 || data[0] != 'P' || data[1] < '1' || data[1] > '6') return ORBX_E_EMPTY;   // imdecode: empty Mat
-    PnmCursor cur{data, nbytes, 2};
-    const int type = data[1] - '0';
-    long long w = 0, ht = 0, maxval = 1;
-    if (!cur.number(w) || !cur.number(ht)) return ORBX_E_EMPTY;
-    if (type != 1 && type != 4 && !cur.number(maxval)) return ORBX_E_EMPTY;
-    if (w <= 0 || ht <= 0 || maxval <= 0 || maxval > 65535) return ORBX_E_EMPTY;
-    if ((type != 5 && type != 6) || maxval > 255) return ORBX_E_INVALID;                          // decodable, but not CV_8U binary
-    const int ch = type == 6 ? 3 : 1;
-    if ((unsigned long long)w * (unsigned long long)ht * ch > nbytes - cur.pos) return ORBX_E_EMPTY;   // truncated payload
-    *width = (int)w; *height = (int)ht; *channels = ch; *payload_offset = cur.pos;
-    return ORBX_OK;
-}
-
 int orbx_extract_pnm(orbx_handle *h, const uint8_t *data, size_t nbytes, int camera_rgb, int lap0, int lap1, orbx_keypoint *kp_out,
                      uint8_t *desc_out, int cap, int *n_out, int *mono_index_out, int *width_out, int *height_out) {
     if (!h) return ORBX_E_INVALID;

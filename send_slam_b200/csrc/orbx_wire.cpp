@@ -1,5 +1,6 @@
 // MessagePack reader / writer for the two SEND-SLAM wire messages next to the ORB hot path (include/orbx_wire.h).
-// Host code only.  The reader walks the payload in place (no object tree, no allocation); the subset of MessagePack it
+// Also home of the binary-PNM header reader (orbx_pnm_header, declared in include/orbx.h): everything in this file parses untrusted
+// bytes and is host code only, so that it can be built and fuzzed on its own (tests/test_wire_fuzz_cpu.py: ASan + UBSan).  The reader walks the payload in place (no object tree, no allocation); the subset of MessagePack it
 // understands is the whole format, because unknown keys of any type have to be skipped the way msgpack-c's unpack accepts them.
 #include <cstdint>
 #include <cstring>
@@ -137,7 +138,53 @@ struct Writer {
 
 }  // namespace
 
+namespace {
+// Byte cursor with OpenCV's PxM header grammar: a number is preceded by any run of white space / '#' comments and followed by
+// exactly one consumed byte (so "255\n" leaves the cursor on the first sample).
+struct PnmCursor {
+    const uint8_t *d; size_t n, pos = 0; bool eos = false;
+    int get() { if (pos >= n) { eos = true; return -1; } return d[pos++]; }
+    static bool space(int c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
+    static bool digit(int c) { return c >= '0' && c <= '9'; }
+    bool number(long long &out) {
+        int c = get();
+        while (!eos && !digit(c)) {
+            if (c == '#') { do c = get(); while (!eos && c != '\n' && c != '\r'); c = get(); }
+            else if (space(c)) { do c = get(); while (!eos && space(c)); }
+            else return false;
+        }
+        if (eos) return false;
+        long long v = 0;
+        while (true) {
+            v = v * 10 + (c - '0');
+            if (v > INT32_MAX) return false;
+            c = get();
+            if (eos) return false;            // the reader needs the terminating byte
+            if (!digit(c)) break;
+        }
+        out = v;
+        return true;
+    }
+};
+}  // namespace
+
 extern "C" {
+
+int orbx_pnm_header(const uint8_t *data, size_t nbytes, int *width, int *height, int *channels, size_t *payload_offset) {
+    if ((!data && nbytes) || !width || !height || !channels || !payload_offset) return ORBX_E_INVALID;
+    if (nbytes < 2 || data[0] != 'P' || data[1] < '1' || data[1] > '6') return ORBX_E_EMPTY;   // imdecode: empty Mat
+    PnmCursor cur{data, nbytes, 2};
+    const int type = data[1] - '0';
+    long long w = 0, ht = 0, maxval = 1;
+    if (!cur.number(w) || !cur.number(ht)) return ORBX_E_EMPTY;
+    if (type != 1 && type != 4 && !cur.number(maxval)) return ORBX_E_EMPTY;
+    if (w <= 0 || ht <= 0 || maxval <= 0 || maxval > 65535) return ORBX_E_EMPTY;
+    if ((type != 5 && type != 6) || maxval > 255) return ORBX_E_INVALID;                          // decodable, but not CV_8U binary
+    const int ch = type == 6 ? 3 : 1;
+    if ((unsigned long long)w * (unsigned long long)ht * ch > nbytes - cur.pos) return ORBX_E_EMPTY;   // truncated payload
+    *width = (int)w; *height = (int)ht; *channels = ch; *payload_offset = cur.pos;
+    return ORBX_OK;
+}
 
 int orbx_wire_parse_frame(const uint8_t *payload, size_t nbytes, orbx_wire_frame *out) {
     if (!payload || !out) return ORBX_E_INVALID;
