@@ -138,6 +138,72 @@ def cpu_baseline(frames, nthreads):
     return len(frames) / dt
 
 
+def opencv_stage_times(frames):
+    """single-thread time of the REAL OpenCV primitives the reference's extractor spends its time in (cv2 =
+    the OpenCV code itself): the iterative resize pyramid, per-cell cv::FAST (20, fallback 7) and the 7x7 Gaussian per level, on the
+    benchmark's frames.  The control logic around them (quadtree, orientation, descriptors) is not in here.  `pyramid` and `blur` are
+    clean primitive times; `fast_cells` includes the Python binding's construction of a cv2.KeyPoint per corner (~13 k per frame), which
+    the C++ reference does not pay - read it as an upper bound.  Reported beside the C port's figure.  None where cv2 is not importable."""
+    try:
+        import cv2
+        from oracle import oracle_lib as ol
+    except Exception:
+        return None
+    cv2.setNumThreads(1)
+    o = ol.Oracle(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH)
+    sizes = [o.level_size(W, H, l) for l in range(NLEVELS)]
+    det20 = cv2.FastFeatureDetector_create(INI_TH, True, cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
+    det7 = cv2.FastFeatureDetector_create(MIN_TH, True, cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
+    t = {"pyramid": 0.0, "fast_cells": 0.0, "blur": 0.0}
+    for f in frames:
+        t0 = time.perf_counter()
+        levels = [f]
+        for l in range(1, NLEVELS):
+            levels.append(cv2.resize(levels[-1], sizes[l], interpolation=cv2.INTER_LINEAR))
+        t1 = time.perf_counter()
+        for lv in levels:                                   # the reference's cell loop: W = 35 cells with 6 px overlap inside the 16 px border
+            h, w = lv.shape
+            x0, y0, x1, y1 = 16 - 3, 16 - 3, w - 16 + 3, h - 16 + 3
+            ncx, ncy = max((x1 - x0) // 35, 1), max((y1 - y0) // 35, 1)
+            wc, hc = -(-(x1 - x0) // ncx), -(-(y1 - y0) // ncy)
+            for i in range(ncy):
+                iy = y0 + i * hc
+                if iy >= y1 - 3:
+                    continue
+                for j in range(ncx):
+                    ix = x0 + j * wc
+                    if ix >= x1 - 6:
+                        continue
+                    roi = lv[iy:min(iy + hc + 6, y1), ix:min(ix + wc + 6, x1)]
+                    if not det20.detect(roi):
+                        det7.detect(roi)
+        t2 = time.perf_counter()
+        for lv in levels:
+            cv2.GaussianBlur(lv, (7, 7), 2, None, 2, cv2.BORDER_REFLECT_101)
+        t3 = time.perf_counter()
+        t["pyramid"] += t1 - t0; t["fast_cells"] += t2 - t1; t["blur"] += t3 - t2
+    n = len(frames)
+    out = {k: 1e3 * v / n for k, v in t.items()}
+    out["sum"] = sum(out.values())
+    out["note"] = (f"cv2 {cv2.__version__}, cv2.setNumThreads(1), {n} frames; resize chain + per-cell FAST 20/7 + GaussianBlur only; "
+                   "fast_cells includes the Python binding's cv2.KeyPoint construction")
+    return out
+
+
+def opencv_bfmatcher_pairs_per_s(q, db, threads):
+    """SURVEY.md §8d(3): cv::BFMatcher(NORM_HAMMING).knnMatch(k=2) on a slice of the shard, all host threads.  None without cv2."""
+    try:
+        import cv2
+    except Exception:
+        return None
+    cv2.setNumThreads(threads)
+    bf = cv2.BFMatcher(cv2.NORM_HAMMING)
+    bf.knnMatch(q[:64], db[:10000], k=2)
+    t0 = time.perf_counter()
+    bf.knnMatch(q, db, k=2)
+    return len(q) * len(db) / (time.perf_counter() - t0)
+
+
 def run_reference(args, rank, world):
     """--impl reference: the CPU restatement of the reference's ORBextractor on all host threads (rank 0 only)."""
     if rank != 0:
@@ -540,6 +606,13 @@ def main():
             dtc = time.perf_counter() - t0
             hamming["cpu_baseline"] = {"value": KNN_Q * KNN_ROWS / dtc, "unit": "pairs/s", "cores": cores, "kind": "port",
                                        "sample": f"{KNN_Q} queries x {KNN_ROWS} rows, oracle/orb_oracle.c orb_oracle_knn2"}
+            try:                            # the real cv::BFMatcher beside the port, on a 100 k-row slice (linear in rows)
+                bfp = opencv_bfmatcher_pairs_per_s(q, db[:100000], cores)
+                if bfp:
+                    hamming["cpu_baseline"]["opencv_bfmatcher"] = {"value": bfp, "unit": "pairs/s", "cores": cores,
+                                                                   "sample": f"{KNN_Q} queries x 100000 rows, cv2.BFMatcher(NORM_HAMMING).knnMatch(k=2)"}
+            except Exception as err:
+                hamming["cpu_baseline"]["opencv_bfmatcher"] = {"error": repr(err)}
         index.close()
 
     # ---- cpu baseline (rank 0, N=1 only)
@@ -557,6 +630,10 @@ def main():
         ms1 = 1e3 * (time.perf_counter() - t1) / 24
         cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "single_thread_ms_per_frame": ms1,
                "sample": f"{nfr} of the benchmark's synthetic 640x480 frames, oracle/orb_oracle.c, one extractor per thread"}
+        try:
+            cpu["opencv_primitives_ms_per_frame"] = opencv_stage_times(sample_frames[:16])
+        except Exception as err:
+            cpu["opencv_primitives_ms_per_frame"] = {"error": repr(err)}
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
