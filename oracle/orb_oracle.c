@@ -19,6 +19,8 @@
  *   - cvtColor *2GRAY and cv::undistortPoints (the SURVEY.md 8f rows): bit-compared with cv2 4.13 in
  *     tests/test_oracle_golden.py, SHA pins of the verified outputs committed there.
  *   - steered BRIEF: bit-compared with cv2.ORB_create().compute() on the same keypoints/angles.
+ *   - binary-PNM decode (the wire's frame encoding, orbslam3_mono_networked.cc:546): accept / reject verdict, geometry and
+ *     Mat bytes compared with cv2.imdecode case by case (tests/golden/pnm_cases.npz, made by tests/golden/make_golden_pnm.py).
  *   - cell grid, DistributeOctTree, output ordering: "parity unpinned" -- restated from the published
  *     ORB-SLAM3 v1.0 algorithm; cross-checked only against the independent Python
  *     restatement in oracle/orb_cv2.py.  Known non-determinism in the reference itself: the final octree

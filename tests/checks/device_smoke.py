@@ -1,10 +1,10 @@
 #!/usr/bin/env python
-"""A small pass over every device path for compute-sanitizer (memcheck / racecheck / synccheck run it ~10-50x slower than native):
-single frame, a batch through submit/collect, a PPM wire frame, the device-resident path, windowed matching and kNN on both routes.
-Usage (on a B200): compute-sanitizer --tool memcheck python tools/sanitize_smoke.py"""
+"""A small pass over every device path, each result checked against the oracle: single frame, a batch through submit/collect, a PPM
+wire frame, windowed matching and kNN on both routes.  Small enough to run under a sanitizer or a debugger where those are available
+(compute-sanitizer is closed on the pool this repository was developed on).  Usage (on a B200): python tests/checks/device_smoke.py"""
 import os, sys
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from send_slam_b200 import orbx, synth
 from oracle import oracle_lib as ol
 

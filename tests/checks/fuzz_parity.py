@@ -1,9 +1,9 @@
 #!/usr/bin/env python
 """Randomised parity sweep on a B200: random frame sizes / kinds / extractor parameters through orbx_extract (and batches through
-the blocking, submit/collect, device-resident, colour, PPM and frame-message paths), every result compared with the CPU oracle bit for bit.  Usage: python tools/fuzz_parity.py [seconds] [seed]"""
+the blocking, submit/collect, device-resident, colour, PPM and frame-message paths), every result compared with the CPU oracle bit for bit.  Usage: python tests/checks/fuzz_parity.py [seconds] [seed]"""
 import os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import msgpack
 import torch
 from send_slam_b200 import orbx, synth

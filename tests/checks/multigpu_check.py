@@ -2,10 +2,10 @@
 """Multi-GPU check (run under torchrun, one rank per GPU): (1) row-sharded brute-force kNN, top-2 merged with one NCCL
 all-gather, compared on rank 0 with the CPU oracle on a bounded database; (2) frame-sharded extraction, every rank's
 shard compared with the oracle on a few frames; (3) timing of the config-4 shape (2000 queries vs rows-per-GPU x world).
-Usage: python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/multigpu_check.py [rows_per_gpu]"""
+Usage: python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 --master-port P tests/checks/multigpu_check.py [rows_per_gpu]"""
 import json, os, sys
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import torch.distributed as dist
 from send_slam_b200 import orbx, sharded, synth
