@@ -76,6 +76,7 @@ struct orbx_handle {
     uint8_t *d_desc = nullptr;      // [batch][kp_cap][32]
     int *d_n = nullptr, *d_mono = nullptr;
     FastTma ftma{};                 // tensor maps of the level planes (TMA-staged FAST kernel)
+    Fast2Tma ftma2{};               // ... and for the pair-plane FAST kernel (orbx_fast2.cu), the one the pipeline prefers
     DescTma dtma{};                 // ... and of the un-blurred / blurred planes for the descriptor kernel
     int sm_count = 148;
     // colour input (orbx_set_input_format): frames are uploaded to d_color and converted into the level-0 planes on the device
@@ -160,6 +161,15 @@ static void encode_fast_map(orbx_handle *h, int l) {
                                                        D.img_fstride, T.box_w[l], T.box_h[l]);
     T.ok = !getenv("ORBX_NO_TMA");
     for (int k = 0; k < h->plan.nlevels; k++) T.ok = T.ok && (T.level_ok[k] || h->plan.lv[k].ncells == 0);
+    Fast2Tma &T2 = h->ftma2;
+    T2.level_ok[l] = T2.pitch > 0 && T2.box_w[l] > 0 &&
+                     tma_make_plane_map(reinterpret_cast<CUtensorMap *>(T2.map[l]), D.img, D.w, D.h, h->batch_cap, (size_t)D.pitch, D.img_fstride,
+                                        T2.box_w[l], T2.box_h);
+    {
+        static const int fast_v = [] { const char *e = getenv("ORBX_FAST_V"); return e ? atoi(e) : 2; }();
+        T2.ok = !getenv("ORBX_NO_TMA") && fast_v == 2 && T2.pitch > 0;
+    }
+    for (int k = 0; k < h->plan.nlevels; k++) T2.ok = T2.ok && (T2.level_ok[k] || h->plan.lv[k].ncells == 0);
     // descriptor kernel: 64 x 31 box on the un-blurred plane, 64 x 39 box on the blurred plane
     DescTma &Q = h->dtma;
     Q.level_ok[l] = tma_make_plane_map(reinterpret_cast<CUtensorMap *>(Q.img[l]), D.img, D.w, D.h, h->batch_cap, (size_t)D.pitch, D.img_fstride, 64, 31) &&
@@ -185,6 +195,36 @@ static void build_fast_maps(orbx_handle *h) {
         T.box_w[l] = bw; T.box_h[l] = rh + 1;
         T.max_iw = std::max(T.max_iw, rw - 6); T.max_ih = std::max(T.max_ih, rh - 6);
         if (bw > 96 || rh + 1 > 80) { T.box_w[l] = 0; }   // larger than the shared-memory stage: no TMA for this plan
+    }
+    // pair-plane kernel: per level the bytes a row of the widest cell needs behind its 16-byte aligned box start (up to 12 bytes of
+    // lead + 4 (K + 1) bytes, K = byte words unpacked per row); one chunk height for the whole pyramid
+    Fast2Tma &T2 = h->ftma2;
+    std::memset(&T2, 0, sizeof(T2));
+    int kmax = 0;
+    for (int l = 0; l < h->plan.nlevels; l++) {
+        const LevelPlan &LP = h->plan.lv[l];
+        if (LP.ncells == 0) continue;
+        int iw = 0, ih = 0;
+        for (int c = LP.first_cell; c < LP.first_cell + LP.ncells; c++) {
+            iw = std::max(iw, h->plan.cells[c].x1 - h->plan.cells[c].x0 - 6);
+            ih = std::max(ih, h->plan.cells[c].y1 - h->plan.cells[c].y0 - 6);
+        }
+        const int np = (iw + 1) / 2, K = (2 * np + 8 + 3 + 7) / 8;      // 8-pixel groups unpacked per row
+        T2.box_w[l] = (12 + 4 * (2 * K + 1) + 15) / 16 * 16;
+        T2.max_np = std::max(T2.max_np, np); T2.max_iw = std::max(T2.max_iw, iw); T2.max_ih = std::max(T2.max_ih, ih);
+        kmax = std::max(kmax, K);
+    }
+    if (kmax > 0) {
+        static const int ch_env = [] { const char *e = getenv("ORBX_FAST_CH"); return e ? atoi(e) : 0; }();
+        const int ch_want = ch_env >= 4 ? ch_env : 24;
+        // balanced chunks: a cell of ih rows runs as ceil(ih / ch) chunks of ceil(ih / nch) rows
+        T2.ch = std::min(ch_want, T2.max_ih);
+        T2.box_h = T2.ch + 6;
+        T2.pitch = fast2_pick_pitch(8 * kmax + 1);
+        int bw = 0;
+        for (int l = 0; l < h->plan.nlevels; l++) bw = std::max(bw, T2.box_w[l]);
+        T2.stage_bytes = (bw * T2.box_h + 8 + 127) / 128 * 128;
+        if (bw > 256 || T2.box_h > 256) T2.pitch = 0;
     }
     for (int l = 0; l < h->plan.nlevels; l++) encode_fast_map(h, l);
 }
@@ -395,7 +435,12 @@ static int run_pipeline(orbx_handle *h, int f0, int batch, int lap0, int lap1, K
     // from running side by side.
     if (!fork) h->launches += launch_blur(h->h_levels, h->d_tiles, h->ntiles, f0, batch, stream);
     STAGE_MARK(2);
-    h->launches += launch_fast(h->h_levels, h->d_cells, (int)pl.cells.size(), f0, batch, h->P.ini_th, h->P.min_th, h->d_overflow, stream, &h->ftma, h->sm_count);
+    {
+        int nl2 = 0;
+        if (h->ftma2.ok) nl2 = launch_fast2(h->h_levels, h->d_cells, (int)pl.cells.size(), f0, batch, h->P.ini_th, h->P.min_th, h->d_overflow, stream, &h->ftma2, h->sm_count);
+        if (!nl2) nl2 = launch_fast(h->h_levels, h->d_cells, (int)pl.cells.size(), f0, batch, h->P.ini_th, h->P.min_th, h->d_overflow, stream, &h->ftma, h->sm_count);
+        h->launches += nl2;
+    }
     STAGE_MARK(3);
     cudaStream_t qs = fork ? side : stream;
     if (fork) {

@@ -63,6 +63,19 @@ struct FastTma {
 };
 int launch_fast(const LevelDev *h_levels, const CellRect *d_cells, int ncells, int f0, int batch,
                 int ini_th, int min_th, int *d_overflow, cudaStream_t stream, const FastTma *tma, int sm_count);
+// Tensor maps + geometry of the pair-plane FAST kernel (orbx_fast2.cu): one box of box_w[l] x box_h bytes per chunk of `ch` tested
+// cell rows; `pitch` = pair-plane pitch in words (one of the kernel's template instantiations).
+struct Fast2Tma {
+    alignas(64) unsigned char map[kMaxLevels][128];
+    int box_w[kMaxLevels];
+    int box_h, ch, stage_bytes, pitch;
+    int max_np, max_iw, max_ih;
+    bool level_ok[kMaxLevels];
+    bool ok;                    // every level has a valid map and a kernel instantiation fits
+};
+int fast2_pick_pitch(int min_words);   // smallest instantiated pair-plane pitch >= min_words, 0 if none
+int launch_fast2(const LevelDev *h_levels, const CellRect *d_cells, int ncells, int f0, int batch, int ini_th, int min_th, int *d_overflow,
+                 cudaStream_t stream, const Fast2Tma *tma, int sm_count);
 int launch_octree(const LevelDev *h_levels, int nlevels, int f0, int batch, int *d_overflow,
                   cudaStream_t stream);
 int launch_finalize(const LevelDev *h_levels, int nlevels, int f0, int batch, int total_out_cap, int lap0, int lap1,
