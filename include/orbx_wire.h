@@ -51,14 +51,18 @@ int orbx_wire_process_frame(orbx_handle *h, const uint8_t *payload, size_t nbyte
 typedef struct orbx_wire_features {
     double timestamp;
     int camera_id, width, height, mono_index, n;
-    const orbx_keypoint *keypoints;   /* may be unaligned: memcpy out of the payload */
-    const uint8_t *descriptors;
+    const uint8_t *keypoints;         /* n x 28 bytes (orbx_keypoint records) at an ARBITRARY byte offset of the payload: never cast
+                                         to orbx_keypoint *, copy them out (orbx_wire_copy_keypoints / memcpy) */
+    const uint8_t *descriptors;       /* n x 32 bytes */
 } orbx_wire_features;
 
 size_t orbx_wire_features_bound(int n, int framed);   /* bytes orbx_wire_pack_features needs at most */
 int orbx_wire_pack_features(double timestamp, int camera_id, int width, int height, int mono_index, const orbx_keypoint *kp,
                             const uint8_t *desc, int n, int framed, uint8_t *out, size_t out_cap, size_t *written);
 int orbx_wire_parse_features(const uint8_t *payload, size_t nbytes, orbx_wire_features *out);
+/* Copies the n keypoint records of a parsed features message into aligned caller memory (the std::vector<cv::KeyPoint> storage a
+ * Frame would be built from).  Returns n, or ORBX_E_CAPACITY when cap < n. */
+int orbx_wire_copy_keypoints(const orbx_wire_features *f, orbx_keypoint *dst, int cap);
 
 #ifdef __cplusplus
 }

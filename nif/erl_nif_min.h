@@ -10,10 +10,19 @@ typedef struct enif_resource_type_t ErlNifResourceType;
 typedef struct { size_t size; unsigned char *data; void *ref_bin; void *spare[2]; } ErlNifBinary;
 typedef struct { const char *name; unsigned arity; ERL_NIF_TERM (*fptr)(ErlNifEnv *, int, const ERL_NIF_TERM[]); unsigned flags; } ErlNifFunc;
 typedef void ErlNifResourceDtor(ErlNifEnv *, void *);
+typedef struct ErlNifMutex_ ErlNifMutex;
 typedef enum { ERL_NIF_RT_CREATE = 1, ERL_NIF_RT_TAKEOVER = 2 } ErlNifResourceFlags;
 #define ERL_NIF_DIRTY_JOB_IO_BOUND 2
 int enif_get_int(ErlNifEnv *, ERL_NIF_TERM, int *);
+int enif_get_long(ErlNifEnv *, ERL_NIF_TERM, long *);
 int enif_get_double(ErlNifEnv *, ERL_NIF_TERM, double *);
+void *enif_alloc(size_t);
+void enif_free(void *);
+ErlNifMutex *enif_mutex_create(char *name);
+void enif_mutex_destroy(ErlNifMutex *);
+int enif_mutex_trylock(ErlNifMutex *);   /* 0 = acquired, EBUSY otherwise */
+void enif_mutex_lock(ErlNifMutex *);
+void enif_mutex_unlock(ErlNifMutex *);
 int enif_get_tuple(ErlNifEnv *, ERL_NIF_TERM, int *, const ERL_NIF_TERM **);
 int enif_inspect_binary(ErlNifEnv *, ERL_NIF_TERM, ErlNifBinary *);
 int enif_get_resource(ErlNifEnv *, ERL_NIF_TERM, ErlNifResourceType *, void **);
@@ -25,7 +34,9 @@ ERL_NIF_TERM enif_make_int(ErlNifEnv *, int);
 ERL_NIF_TERM enif_make_badarg(ErlNifEnv *);
 ERL_NIF_TERM enif_make_tuple(ErlNifEnv *, unsigned, ...);
 #define enif_make_tuple2(e, a, b) enif_make_tuple(e, 2, a, b)
+#define enif_make_tuple3(e, a, b, c) enif_make_tuple(e, 3, a, b, c)
 #define enif_make_tuple5(e, a, b, c, d, f) enif_make_tuple(e, 5, a, b, c, d, f)
+#define enif_make_tuple6(e, a, b, c, d, f, g) enif_make_tuple(e, 6, a, b, c, d, f, g)
 #define enif_make_tuple7(e, a, b, c, d, f, g, i) enif_make_tuple(e, 7, a, b, c, d, f, g, i)
 unsigned char *enif_make_new_binary(ErlNifEnv *, size_t, ERL_NIF_TERM *);
 ERL_NIF_TERM enif_make_sub_binary(ErlNifEnv *, ERL_NIF_TERM, size_t, size_t);

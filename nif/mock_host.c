@@ -3,6 +3,7 @@
  * test harness, not part of the product: tests/test_gpu_parity.py builds  orbx_nif.c + mock_host.c -> one shared object and
  * drives it through the mock_* functions below (ctypes).  Terms live in a per-thread arena that mock_reset() clears; that is
  * enough for call-at-a-time use, which is how a dirty-scheduler NIF call looks from the C side. */
+#include <pthread.h>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -34,6 +35,15 @@ static term_t *T(ERL_NIF_TERM t) { return (t >= 1 && (int)t <= g_nterms) ? &g_te
 
 /* ---- erl_nif API used by the NIF --------------------------------------------------------------------------------------- */
 int enif_get_int(ErlNifEnv *e, ERL_NIF_TERM t, int *out) { (void)e; term_t *x = T(t); if (!x || x->kind != T_INT) return 0; *out = (int)x->i; return 1; }
+int enif_get_long(ErlNifEnv *e, ERL_NIF_TERM t, long *out) { (void)e; term_t *x = T(t); if (!x || x->kind != T_INT) return 0; *out = x->i; return 1; }
+void *enif_alloc(size_t n) { return malloc(n); }
+void enif_free(void *p) { free(p); }
+struct ErlNifMutex_ { pthread_mutex_t m; };
+ErlNifMutex *enif_mutex_create(char *name) { (void)name; ErlNifMutex *m = (ErlNifMutex *)calloc(1, sizeof(*m)); if (m) pthread_mutex_init(&m->m, NULL); return m; }
+void enif_mutex_destroy(ErlNifMutex *m) { if (m) { pthread_mutex_destroy(&m->m); free(m); } }
+int enif_mutex_trylock(ErlNifMutex *m) { return pthread_mutex_trylock(&m->m); }
+void enif_mutex_lock(ErlNifMutex *m) { pthread_mutex_lock(&m->m); }
+void enif_mutex_unlock(ErlNifMutex *m) { pthread_mutex_unlock(&m->m); }
 int enif_get_double(ErlNifEnv *e, ERL_NIF_TERM t, double *out) { (void)e; term_t *x = T(t); if (!x || x->kind != T_DOUBLE) return 0; *out = x->d; return 1; }
 int enif_get_tuple(ErlNifEnv *e, ERL_NIF_TERM t, int *arity, const ERL_NIF_TERM **arr) {
     (void)e; term_t *x = T(t); if (!x || x->kind != T_TUPLE) return 0; *arity = x->arity; *arr = x->elems; return 1;
@@ -94,10 +104,11 @@ unsigned long mock_resource_term(void *obj) { return enif_make_resource(NULL, ob
 void mock_resource_drop(void *obj) { res_unref(obj); }
 unsigned long mock_call(const char *name, int argc, const unsigned long *argv) {
     const ErlNifFunc *f = orbx_nif_funcs_for_check();
-    for (int i = 0; i < 16 && f[i].name; i++)
+    for (int i = 0; i < 32 && f[i].name; i++)
         if (!strcmp(f[i].name, name) && (int)f[i].arity == argc) return f[i].fptr(NULL, argc, argv);
     return enif_make_badarg(NULL);
 }
+unsigned long mock_long(long v) { ERL_NIF_TERM t = new_term(T_INT); T(t)->i = v; return t; }
 int mock_kind(unsigned long t) { term_t *x = T(t); return x ? (int)x->kind : 0; }
 long mock_get_int(unsigned long t) { return T(t)->i; }
 const char *mock_get_atom(unsigned long t) { return T(t)->atom; }

@@ -14,8 +14,28 @@ defmodule SendSlam.OrbNif do
     :erlang.load_nif(path, 0)
   end
 
+  @doc """
+  One handle = one GPU workspace.  A handle is single-flight: keep it in the state of ONE process (one camera, one consumer).
+  If the term does reach a second process, a call that finds the handle busy returns `{:error, :busy}`.
+  """
   def create(_nfeatures, _scale_factor, _nlevels, _ini_th, _min_th, _device, _max_width, _max_height),
     do: :erlang.nif_error(:nif_not_loaded)
+
+  @doc "as create/8 with room for `max_batch` frames per `extract_batch/5` call"
+  def create(_nfeatures, _scale_factor, _nlevels, _ini_th, _min_th, _device, _max_width, _max_height, _max_batch),
+    do: :erlang.nif_error(:nif_not_loaded)
+
+  @doc """
+  `batch` gray frames back to back in one binary -> `{:ok, counts, mono_indices, keypoints, descriptors, cap}`; frame i owns
+  records `i * cap .. i * cap + counts[i] - 1` of the two result binaries (counts / mono_indices: int32 little-endian).
+  """
+  def extract_batch(_handle, _frames_binary, _batch, _width, _height), do: :erlang.nif_error(:nif_not_loaded)
+
+  @doc "a row shard of a descriptor database resident on the GPU: rows x 32 bytes, `row_offset` = global index of its first row"
+  def knn2_create(_descriptors_binary, _device, _row_offset), do: :erlang.nif_error(:nif_not_loaded)
+
+  @doc "k = 2 nearest rows per query (cv::BFMatcher NORM_HAMMING): `{:ok, indices (nq x 2 int32), distances (nq x 2 int32)}`; backend 0 = POPC, 1 = tensor cores"
+  def knn2(_db, _queries_binary, _backend), do: :erlang.nif_error(:nif_not_loaded)
 
   def extract(_handle, _gray_binary, _width, _height), do: :erlang.nif_error(:nif_not_loaded)
 

@@ -28,10 +28,12 @@ static thread_local std::string g_create_error;
 struct GraphKey {
     const void *in, *kp, *desc, *aux0, *aux1;
     cudaStream_t stream;
-    int batch, width, height, stride, lap0, lap1, cap, chunk, fmt;
+    int batch, width, height, stride, lap0, lap1, cap, chunk, fmt, gray_shift;
+    size_t frame_stride;   // bytes between device-resident frames (0 for host-buffer calls)
     bool operator==(const GraphKey &o) const {
         return in == o.in && kp == o.kp && desc == o.desc && aux0 == o.aux0 && aux1 == o.aux1 && stream == o.stream && batch == o.batch && width == o.width &&
-               height == o.height && stride == o.stride && lap0 == o.lap0 && lap1 == o.lap1 && cap == o.cap && chunk == o.chunk && fmt == o.fmt;
+               height == o.height && stride == o.stride && lap0 == o.lap0 && lap1 == o.lap1 && cap == o.cap && chunk == o.chunk && fmt == o.fmt &&
+               gray_shift == o.gray_shift && frame_stride == o.frame_stride;
     }
 };
 struct GraphEntry { GraphKey key; cudaGraphExec_t exec; long long launches; bool disabled; };
@@ -166,7 +168,7 @@ static void encode_fast_map(orbx_handle *h, int l) {
                      tma_make_plane_map(reinterpret_cast<CUtensorMap *>(T2.map[l]), D.img, D.w, D.h, h->batch_cap, (size_t)D.pitch, D.img_fstride,
                                         T2.box_w[l], T2.box_h);
     {
-        static const int fast_v = [] { const char *e = getenv("ORBX_FAST_V"); return e ? atoi(e) : 2; }();
+        static const int fast_v = [] { const char *e = getenv("ORBX_FAST_V"); return e ? atoi(e) : 1; }();
         T2.ok = !getenv("ORBX_NO_TMA") && fast_v == 2 && T2.pitch > 0;
     }
     for (int k = 0; k < h->plan.nlevels; k++) T2.ok = T2.ok && (T2.level_ok[k] || h->plan.lv[k].ncells == 0);
@@ -217,9 +219,16 @@ static void build_fast_maps(orbx_handle *h) {
     if (kmax > 0) {
         static const int ch_env = [] { const char *e = getenv("ORBX_FAST_CH"); return e ? atoi(e) : 0; }();
         const int ch_want = ch_env >= 4 ? ch_env : 24;
-        // balanced chunks: a cell of ih rows runs as ceil(ih / ch) chunks of ceil(ih / nch) rows
+        // balanced chunks: a cell of ih rows runs as nch = ceil(ih / ch) chunks of ceil(ih / nch) rows; the per-warp buffers are sized
+        // for the tallest chunk that actually occurs
         T2.ch = std::min(ch_want, T2.max_ih);
-        T2.box_h = T2.ch + 6;
+        int crmax = 1;
+        for (const CellRect &c : h->plan.cells) {
+            const int ih = c.y1 - c.y0 - 6, nch = (ih + T2.ch - 1) / T2.ch;
+            crmax = std::max(crmax, (ih + nch - 1) / nch);
+        }
+        T2.rows = crmax;
+        T2.box_h = crmax + 6;
         T2.pitch = fast2_pick_pitch(8 * kmax + 1);
         int bw = 0;
         for (int l = 0; l < h->plan.nlevels; l++) bw = std::max(bw, T2.box_w[l]);
@@ -347,6 +356,11 @@ static int ensure_color(orbx_handle *h) {
     for (auto &g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     h->graphs.clear();
     if (h->h_color) { cudaFreeHost(h->h_color); h->h_color = nullptr; }
+    if (h->d_color) {   // a 3 <-> 4 bytes-per-pixel switch: the old staging goes now, not at the next re-plan
+        h->dev_allocs.erase(std::remove(h->dev_allocs.begin(), h->dev_allocs.end(), (void *)h->d_color), h->dev_allocs.end());
+        cudaFree(h->d_color);
+        h->d_color = nullptr;
+    }
     h->color_pitch = (h->plan.width * bpp + 15) / 16 * 16;
     h->color_fstride = (size_t)h->color_pitch * h->plan.height;
     CU_TRY(h, dev_alloc(h, &h->d_color, h->color_fstride * h->batch_cap + 64));   // freed with the plan
@@ -508,12 +522,12 @@ int orbx_create(const orbx_config *cfg, orbx_handle **out) {
         (e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming)) != cudaSuccess) {
         g_create_error = std::string("cuda init: ") + cudaGetErrorString(e);
-        cudaStreamDestroy(h->stream); delete h; return ORBX_E_CUDA;
+        orbx_destroy(h); return ORBX_E_CUDA;
     }
     upload_constants();
     if ((e = cudaGetLastError()) != cudaSuccess) {
         g_create_error = std::string("constant upload: ") + cudaGetErrorString(e);
-        cudaStreamDestroy(h->stream); delete h; return ORBX_E_CUDA;
+        orbx_destroy(h); return ORBX_E_CUDA;
     }
     *out = h;
     return ORBX_OK;
@@ -649,6 +663,7 @@ int orbx_extract_batch_device(orbx_handle *h, const uint8_t *d_frames, size_t fr
                               int height, int stride, int lap0, int lap1, orbx_keypoint *d_kp_out, uint8_t *d_desc_out,
                               int cap, int *d_n_out, int *d_mono_out) {
     if (!h) return ORBX_E_INVALID;
+    if (h->pending.active) return fail(h, ORBX_E_INVALID, "a submitted batch has not been collected");
     if (!d_frames || !d_kp_out || !d_desc_out || !d_n_out || !d_mono_out) return fail(h, ORBX_E_INVALID, "null argument");
     if (width < 1 || height < 1) return fail(h, ORBX_E_EMPTY, "empty image");
     const int bpp = h->in_fmt == ORBX_FMT_GRAY8 ? 1 : h->in_fmt >= ORBX_FMT_RGBA8 ? 4 : 3, rowb = width * bpp;
@@ -696,7 +711,7 @@ int orbx_extract_batch_device(orbx_handle *h, const uint8_t *d_frames, size_t fr
     // which takes the ~60 API calls of a call off the host (with several ranks per host the enqueue cost otherwise limits scaling).
     if (!graphs_enabled() || h->profiling) return enqueue(true);
     GraphKey key{d_frames, d_kp_out, d_desc_out, d_n_out, d_mono_out, h->stream, batch, width, height, stride, lap0, lap1, cap,
-                 0x1000 + parts, h->in_fmt * 100 + h->gray_shift + (int)(frame_stride_bytes % 1000003) * 1000};
+                 0x1000 + parts, h->in_fmt, h->gray_shift, frame_stride_bytes};
     return run_graphed(h, key, enqueue, [] {});
 }
 
@@ -827,7 +842,7 @@ int orbx_extract_batch_submit(orbx_handle *h, const uint8_t *const *frames, int 
     } else {
         GraphKey key{in_pinned ? frames[0] : nullptr, out_direct ? (const void *)kp_out : nullptr, out_direct ? (const void *)desc_out : nullptr,
                      nullptr, nullptr, h->stream, batch, width, height, stride, lap0, lap1, out_direct ? cap : 0, chunk,
-                     h->in_fmt * 100 + h->gray_shift};
+                     h->in_fmt, h->gray_shift, 0};
         if ((rc = run_graphed(h, key, enqueue, [&] { stage_in(0, batch); }))) return rc;
     }
     h->pending = orbx_handle::Pending{true, batch, cap, out_direct, kp_out, desc_out};

@@ -68,7 +68,7 @@ int launch_fast(const LevelDev *h_levels, const CellRect *d_cells, int ncells, i
 struct Fast2Tma {
     alignas(64) unsigned char map[kMaxLevels][128];
     int box_w[kMaxLevels];
-    int box_h, ch, stage_bytes, pitch;
+    int box_h, ch, rows, stage_bytes, pitch;   // ch: chunk height asked for; rows: tallest chunk that occurs (box_h = rows + 6)
     int max_np, max_iw, max_ih;
     bool level_ok[kMaxLevels];
     bool ok;                    // every level has a valid map and a kernel instantiation fits

@@ -146,6 +146,7 @@ struct Fast2Params {
     int stage_bytes;                    // per-warp shared memory: TMA stage (multiple of 128) ...
     int u_bytes;                        // ... pair plane, (ch + 6) rows x P words ...
     int sc_pitch, sc_bytes;             // ... score tile (pitch in words, even; ch + 4 rows) ...
+    int bits_pitch, bits_words;         // ... bitmap of the NMS survivors of a chunk (words per tile row, total) ...
     int list_cap;                       // ... candidate list (u32 entries) ...
     int warp_bytes;                     // ... total per warp (multiple of 128)
 };
@@ -160,16 +161,18 @@ __global__ void __launch_bounds__(128, 4) k_fast_pairs(const __grid_constant__ F
     const uint32_t *s_roi = reinterpret_cast<const uint32_t *>(wsm);
     uint32_t *s_u = reinterpret_cast<uint32_t *>(wsm + Q.stage_bytes);
     uint32_t *s_sc = reinterpret_cast<uint32_t *>(wsm + Q.stage_bytes + Q.u_bytes);
-    uint32_t *s_list = reinterpret_cast<uint32_t *>(wsm + Q.stage_bytes + Q.u_bytes + Q.sc_bytes);
+    uint32_t *s_bits = reinterpret_cast<uint32_t *>(wsm + Q.stage_bytes + Q.u_bytes + Q.sc_bytes);
+    uint32_t *s_list = s_bits + Q.bits_words;
     uint64_t *s_full = reinterpret_cast<uint64_t *>(s_list + Q.list_cap);
     int *s_cnt = reinterpret_cast<int *>(s_full + 1);                      // [above iniTh, rest]
-    const int SP = Q.sc_pitch, lcap = Q.list_cap, CH = Q.ch;
+    const int SP = Q.sc_pitch, lcap = Q.list_cap, CH = Q.ch, BW = Q.bits_pitch;
 
     if (lane == 0) {
         tma_mbar_init(s_full, 1);
         tma_mbar_fence_init();
         s_cnt[0] = 0; s_cnt[1] = 0;
     }
+    for (int i = lane; i < Q.bits_words; i += 32) s_bits[i] = 0;
     __syncwarp();
     const int stride = gridDim.x * nwarps;
     int item = blockIdx.x * nwarps + warp;
@@ -246,13 +249,17 @@ __global__ void __launch_bounds__(128, 4) k_fast_pairs(const __grid_constant__ F
                 const int H = (nrows + 1) >> 1;
                 const int nit = np * H;
                 const uint32_t inv = 65536u / (uint32_t)H + 1u;
-                const uint32_t ubase = tma_smem_u32(s_u) + (uint32_t)sh * 4u;
+                const uint32_t ubase = tma_smem_u32(s_u) + (uint32_t)sh * 4u;   // the centre of item (j, rr) sits at +(3 P + 3) words
+                const uint32_t hp4 = (uint32_t)(min(H, nrows - 1) * P) * 4u;     // second row of an item (clamped into the staged rows)
                 for (int it = lane; it < nit; it += 32) {
                     const int j = (int)(((uint32_t)it * inv) >> 16), rr = it - j * H;
                     const uint32_t ad = ubase + (uint32_t)(rr * P + 2 * j) * 4u;
                     uint32_t *so = s_sc + (rr + 2) * SP + j + 1;
-                    so[0] = score_at<P, NRELU, NIMAD>(ad);
-                    if (rr + H < nrows) so[H * SP] = score_at<P, NRELU, NIMAD>(ad + (uint32_t)(H * P) * 4u);
+                    // both rows unconditionally (two independent dependency graphs per thread); the second row of the last item of
+                    // a column may lie behind the chunk: it is computed on the staged halo rows and not stored
+                    const uint32_t s0 = score_at<P, NRELU, NIMAD>(ad), s1 = score_at<P, NRELU, NIMAD>(ad + hp4);
+                    so[0] = s0;
+                    if (rr + H < nrows) so[H * SP] = s1;
                 }
             }
             __syncwarp();
@@ -279,30 +286,42 @@ __global__ void __launch_bounds__(128, 4) k_fast_pairs(const __grid_constant__ F
                     if ((w[1][1] | w[1][2] | w[2][1] | w[2][2]) == 0) continue;
 #pragma unroll
                     for (int rr = 0; rr < 2; rr++) {
-                        if (rr == 1 && rt + 1 > lastrow) break;
                         uint32_t T[4];
 #pragma unroll
                         for (int cc = 0; cc < 4; cc++) T[cc] = umax3(w[rr][cc], w[rr + 1][cc], w[rr + 2][cc]);
                         const uint32_t x01 = __byte_perm(T[0], T[1], 0x5432), x12 = __byte_perm(T[1], T[2], 0x5432), x23 = __byte_perm(T[2], T[3], 0x5432);
-#pragma unroll
-                        for (int cc = 0; cc < 2; cc++) {
-                            const uint32_t mid = w[rr + 1][cc + 1];
-                            const uint32_t vv = umax3(w[rr][cc + 1], w[rr + 2][cc + 1], thr2);
-                            const uint32_t m = umax3(cc ? x12 : x01, cc ? x23 : x12, vv);
-                            const uint32_t fl = umax2(mid, m) ^ m;    // non-zero lane <=> strict maximum above minTh
-                            if (fl == 0) continue;
-                            const int j = 2 * jj + cc;
-                            if (j >= np) continue;
-#pragma unroll
-                            for (int k = 0; k < 2; k++) {
-                                if ((fl >> (16 * k)) & 0xFFFFu) {
-                                    const uint32_t sc = (mid >> (16 * k)) & 0xFFFFu;
-                                    const uint32_t e = ((uint32_t)(rt + rr) << 20) | ((uint32_t)(2 * j + k) << 8) | sc;
-                                    if ((int)sc > ini_th) s_list[atomicAdd(&s_cnt[0], 1)] = e;
-                                    else s_list[lcap - 1 - atomicAdd(&s_cnt[1], 1)] = e;
-                                }
-                            }
-                        }
+                        const uint32_t m0 = umax3(x01, x12, umax3(w[rr][1], w[rr + 2][1], thr2));
+                        const uint32_t m1 = umax3(x12, x23, umax3(w[rr][2], w[rr + 2][2], thr2));
+                        // strict maximum above minTh <=> NOT (ring maximum >= score) per lane: VIMNMX with predicate outputs
+                        bool h0, l0, h1, l1;
+                        __vibmax_u16x2(m0, w[rr + 1][1], &h0, &l0);
+                        __vibmax_u16x2(m1, w[rr + 1][2], &h1, &l1);
+                        uint32_t mask = (l0 ? 0u : 1u) | (h0 ? 0u : 2u) | (l1 ? 0u : 4u) | (h1 ? 0u : 8u);
+                        if (rr == 1 && rt + 1 > lastrow) mask = 0;
+                        // survivors are rare: one shared-memory OR per (item, row); the lists are filled once per chunk below
+                        if (mask) atomicOr(&s_bits[(rt + rr - a + 2) * BW + (jj >> 3)], mask << (4 * (jj & 7)));
+                    }
+                }
+            }
+            __syncwarp();
+            // ---- survivors of this chunk -> the cell's two lists (above iniTh from the front, the rest from the back)
+            {
+                const int nw = (nrows + 3) * BW;
+                for (int wi = lane; wi < nw; wi += 32) {
+                    uint32_t bits = s_bits[wi];
+                    if (!bits) continue;
+                    s_bits[wi] = 0;
+                    const int t = wi / BW, cw = wi - t * BW;
+                    const uint32_t *row = s_sc + t * SP + 1 + 16 * cw;
+                    while (bits) {
+                        const int bpos = __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        const int col = 32 * cw + bpos;
+                        if (col >= iw) continue;                      // the masked second pixel of an odd-width row's last pair
+                        const uint32_t sc = (row[bpos >> 1] >> (16 * (bpos & 1))) & 0xFFFFu;
+                        const uint32_t e = ((uint32_t)(t + a - 2) << 20) | ((uint32_t)col << 8) | sc;
+                        if ((int)sc > ini_th) s_list[atomicAdd(&s_cnt[0], 1)] = e;
+                        else s_list[lcap - 1 - atomicAdd(&s_cnt[1], 1)] = e;
                     }
                 }
             }
@@ -380,9 +399,12 @@ int launch_fast2(const LevelDev *h_levels, const CellRect *d_cells, int ncells, 
     Q.stage_bytes = tma->stage_bytes;
     Q.u_bytes = (tma->box_h * tma->pitch * 4 + 15) / 16 * 16;
     Q.sc_pitch = (tma->max_np + 3 + 1) & ~1;
-    Q.sc_bytes = (Q.sc_pitch * (tma->ch + 4) * 4 + 15) / 16 * 16;
+    if ((Q.sc_pitch & 3) == 0) Q.sc_pitch += 2;      // pitch = 2 mod 4: the score stores of a column-major warp spread over 16 banks
+    Q.sc_bytes = (Q.sc_pitch * (tma->rows + 4) * 4 + 15) / 16 * 16;
+    Q.bits_pitch = (tma->max_np * 2 + 31) / 32;
+    Q.bits_words = Q.bits_pitch * (tma->rows + 4);
     Q.list_cap = (((tma->max_iw + 1) / 2) * ((tma->max_ih + 1) / 2) + 8 + 3) / 4 * 4;
-    Q.warp_bytes = (Q.stage_bytes + Q.u_bytes + Q.sc_bytes + Q.list_cap * 4 + 8 + 2 * 4 + 127) / 128 * 128;
+    Q.warp_bytes = (Q.stage_bytes + Q.u_bytes + Q.sc_bytes + Q.bits_words * 4 + Q.list_cap * 4 + 8 + 2 * 4 + 127) / 128 * 128;
     static const int mix = env_int("ORBX_FAST_MIX", 2);
     const Fast2Variant *vars = fast2_mix(mix);
     Fast2Kernel fn = nullptr;

@@ -215,7 +215,10 @@ __global__ void __launch_bounds__(128) k_resize(const __grid_constant__ LevelTab
 int launch_resize(const LevelDev *h_levels, int level, int f0, int batch, cudaStream_t stream) {
     const LevelDev &D = h_levels[level];
     const LevelDev &S = h_levels[level - 1];
-    const bool aligned = ((reinterpret_cast<uintptr_t>(S.img) | (uintptr_t)S.pitch | (uintptr_t)S.img_fstride) & 3) == 0 && D.xpack != nullptr;
+    // the word loads of k_resize may touch up to 3 bytes behind the last pixel of a row: fine inside the workspace's padded planes,
+    // not behind the last row of caller-owned memory, so an unpadded source qualifies only when its rows end on a word boundary
+    const bool aligned = ((reinterpret_cast<uintptr_t>(S.img) | (uintptr_t)S.pitch | (uintptr_t)S.img_fstride) & 3) == 0 && D.xpack != nullptr &&
+                         (S.padded || (S.w & 3) == 0);
     if (aligned) {
         const int ngx = (D.w + 3) / 4, nitems = ngx * ((D.h + RR - 1) / RR);
         dim3 grid((nitems + 127) / 128, batch);

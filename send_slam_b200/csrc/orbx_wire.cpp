@@ -270,7 +270,7 @@ int orbx_wire_parse_features(const uint8_t *payload, size_t nbytes, orbx_wire_fe
         else if (key_is(key, "n")) { if (!to_int(val, &out->n)) return ORBX_E_INVALID; have_n = true; }
         else if (key_is(key, "keypoints")) {
             if (val.kind != K_BIN) return ORBX_E_INVALID;
-            out->keypoints = reinterpret_cast<const orbx_keypoint *>(val.data); kp_bytes = (size_t)val.u;
+            out->keypoints = val.data; kp_bytes = (size_t)val.u;
         } else if (key_is(key, "descriptors")) {
             if (val.kind != K_BIN) return ORBX_E_INVALID;
             out->descriptors = val.data; desc_bytes = (size_t)val.u;
@@ -282,6 +282,13 @@ int orbx_wire_parse_features(const uint8_t *payload, size_t nbytes, orbx_wire_fe
     if (!is_features || !have_n || out->n < 0 || !out->keypoints || !out->descriptors) return ORBX_E_INVALID;
     if (kp_bytes != (size_t)out->n * sizeof(orbx_keypoint) || desc_bytes != (size_t)out->n * ORBX_DESC_BYTES) return ORBX_E_INVALID;
     return ORBX_OK;
+}
+
+int orbx_wire_copy_keypoints(const orbx_wire_features *f, orbx_keypoint *dst, int cap) {
+    if (!f || f->n < 0 || (f->n > 0 && (!f->keypoints || !dst))) return ORBX_E_INVALID;
+    if (cap < f->n) return ORBX_E_CAPACITY;
+    if (f->n) std::memcpy(dst, f->keypoints, (size_t)f->n * sizeof(orbx_keypoint));
+    return f->n;
 }
 
 }  // extern "C"

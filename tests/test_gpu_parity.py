@@ -539,28 +539,37 @@ def test_distance_batch(ex, oracle):
     assert m.DescriptorDistance(a[33], b[33]) == int(d[33])
 
 
-def test_knn2_golden_and_oracle(oracle, golden_dir):
+@pytest.mark.parametrize("backend", [orbx.Knn2Index.POPC, orbx.Knn2Index.TENSOR], ids=["popc", "tensor"])
+def test_knn2_golden_and_oracle(oracle, golden_dir, backend):
+    """Both distance backends (XOR + POPC on the CUDA cores, tcgen05 int8 tiles) against the committed golden vector and the oracle."""
+    def index(rows, **kw):
+        ix = orbx.Knn2Index(rows, **kw)
+        ix.set_backend(backend)
+        return ix
     g = np.load(os.path.join(golden_dir, "knn2_4096x128.npz"))
     db = synth.descriptor_db(4096, seed=int(g["db_seed"]))
     q, _ = synth.queries_from_db(db, 128, seed=int(g["q_seed"]))
     db[100] = db[7]
     db[2000] = db[7]
-    idx, dist = orbx.Knn2Index(db).knnMatch(q)
+    idx, dist = index(db).knnMatch(q)
     assert np.array_equal(idx, g["idx"]) and np.array_equal(dist, g["dist"])
-    # ragged sizes: rows not a multiple of the tile, queries not a multiple of the CTA, tiny shards, row offset
+    # ragged sizes: rows not a multiple of the tile, queries not a multiple of the CTA, tiny shards, row offset; 5000 queries run
+    # as several query blocks (the tensor route takes at most 2048 per pass)
     rng = np.random.default_rng(4)
-    for nrows, nq in [(1, 3), (2, 1), (127, 5), (129, 257), (70001, 300), (300000, 2000)]:
+    for nrows, nq in [(1, 3), (2, 1), (127, 5), (129, 257), (70001, 300), (300000, 2000), (40000, 5000)]:
         db = rng.integers(0, 256, (nrows, 32), dtype=np.uint8)
         q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
         q[0] = db[nrows // 2]
-        idx, dist = orbx.Knn2Index(db, row_offset=1000).knnMatch(q)
+        q[nq - 1] = db[nrows - 1]
+        idx, dist = index(db, row_offset=1000).knnMatch(q)
         idx_o, dist_o = oracle.knn2(q, db, nthreads=os.cpu_count() or 1)
         idx_o = np.where(idx_o >= 0, idx_o + 1000, idx_o)
         assert np.array_equal(idx, idx_o) and np.array_equal(dist, dist_o), (nrows, nq)
-        assert dist[0, 0] == 0
+        assert dist[0, 0] == 0 and dist[nq - 1, 0] == 0
 
 
-def test_knn2_full_size_properties():
+@pytest.mark.parametrize("backend", [orbx.Knn2Index.POPC, orbx.Knn2Index.TENSOR], ids=["popc", "tensor"])
+def test_knn2_full_size_properties(backend):
     """2000 queries x 1M rows per shard (config 4's per-GPU share at 8+ GPUs is 1.25M): known answers instead of an
     oracle pass -- queries are database rows with <= 40 flipped bits, so the nearest row and its distance are known and
     the ratio test passes; merging the two half-shard results equals the whole-shard result (checksum of checksums)."""
@@ -569,10 +578,12 @@ def test_knn2_full_size_properties():
     q, src = synth.queries_from_db(db, 2000, seed=99)
     flips = np.unpackbits(q ^ db[src], axis=1).sum(1)
     whole = orbx.Knn2Index(db)
+    whole.set_backend(backend)
     idx, dist = whole.knnMatch(q)
     assert np.array_equal(idx[:, 0], src) and np.array_equal(dist[:, 0], flips)
     assert np.all(dist[:, 1] > 60) and np.all(dist[:, 0] < 0.7 * dist[:, 1])
     lo, hi = orbx.Knn2Index(db[:500_000]), orbx.Knn2Index(db[500_000:], row_offset=500_000)
+    lo.set_backend(backend); hi.set_backend(backend)
     d_q = torch.from_numpy(q).cuda()
     parts = torch.zeros((2, 2000, 2), dtype=torch.int64, device="cuda")
     lo.query_device(d_q.data_ptr(), 2000, parts[0].data_ptr()); lo.sync()

@@ -26,10 +26,11 @@ def nif(tmp_path_factory):
     libdir = os.path.join(ROOT, "send_slam_b200")
     subprocess.check_call(["gcc", "-std=c11", "-O1", "-Wall", "-Werror", "-DORBX_NIF_MIN", "-I", os.path.join(ROOT, "include"), "-I",
                            os.path.join(ROOT, "nif"), "-shared", "-fPIC", os.path.join(ROOT, "nif", "orbx_nif.c"),
-                           os.path.join(ROOT, "nif", "mock_host.c"), "-L", libdir, "-lorbx", "-Wl,-rpath," + libdir, "-o", so])
+                           os.path.join(ROOT, "nif", "mock_host.c"), "-L", libdir, "-lorbx", "-lpthread", "-Wl,-rpath," + libdir, "-o", so])
     L = C.CDLL(so)
     ul = C.c_ulong
     L.mock_int.restype = ul; L.mock_int.argtypes = [C.c_int]
+    L.mock_long.restype = ul; L.mock_long.argtypes = [C.c_long]
     L.mock_double.restype = ul; L.mock_double.argtypes = [C.c_double]
     L.mock_binary.restype = ul; L.mock_binary.argtypes = [C.c_void_p, C.c_size_t]
     L.mock_tuple4.restype = ul; L.mock_tuple4.argtypes = [ul, ul, ul, ul]
@@ -66,9 +67,11 @@ def decode(L, t):
     return ("term", k)
 
 
-def nif_create(L, nfeatures, w, h):
-    r = call(L, "create", L.mock_int(nfeatures), L.mock_double(1.2), L.mock_int(8), L.mock_int(20), L.mock_int(7), L.mock_int(0),
-             L.mock_int(w), L.mock_int(h))
+def nif_create(L, nfeatures, w, h, max_batch=None):
+    args = [L.mock_int(nfeatures), L.mock_double(1.2), L.mock_int(8), L.mock_int(20), L.mock_int(7), L.mock_int(0), L.mock_int(w), L.mock_int(h)]
+    if max_batch is not None:
+        args.append(L.mock_int(max_batch))
+    r = call(L, "create", *args)
     assert L.mock_kind(r) == T_TUPLE and decode(L, L.mock_tuple_elem(r, 0)) == "ok", decode(L, r)
     res = L.mock_resource_keep(L.mock_tuple_elem(r, 1))      # the "process" keeps the handle term alive across calls
     L.mock_reset()
@@ -178,3 +181,85 @@ def test_eight_concurrent_streams(nif, oracle):
                 want = oracle.match_windowed(pd, quvr, qlev, kps, desc, np.array([0, 0, w, h], np.float32))
                 assert np.array_equal(bi, want[0]) and np.array_equal(bd, want[1]) and np.array_equal(si, want[2]) and np.array_equal(sd, want[3])
                 assert ((bi >= 0) & (bd <= 100)).mean() > 0.4
+
+
+def test_one_handle_shared_by_several_processes(nif, oracle):
+    """A resource term can reach several BEAM processes; the handle underneath is single-flight.  Every call either runs alone
+    (result identical to the oracle's) or comes back as {:error, :busy} -- never a torn result, never a crash."""
+    L = nif
+    w, h, nf = 640, 480, 1000
+    res = nif_create(L, nf, w, h)
+    frames = [synth.textured_frame(900 + k, w, h) for k in range(4)]
+    want = [oracle.Oracle(nf).extract(f) for f in frames]
+    stats = {"ok": 0, "busy": 0}
+    errs = []
+    lock = threading.Lock()
+
+    def proc(k):
+        try:
+            for it in range(12):
+                f = frames[(k + it) % 4]
+                buf = np.ascontiguousarray(f)
+                r = decode(L, call(L, "extract", L.mock_resource_term(res), L.mock_binary(buf.ctypes.data, buf.nbytes), L.mock_int(w), L.mock_int(h)))
+                L.mock_reset()
+                if r == ("error", "busy"):
+                    with lock:
+                        stats["busy"] += 1
+                    continue
+                assert r[0] == "ok", r
+                k_o, d_o, m_o = want[(k + it) % 4]
+                assert r[1] == len(k_o) and r[2] == m_o and r[4] == d_o.tobytes() and r[3] == k_o.tobytes()
+                with lock:
+                    stats["ok"] += 1
+        except Exception as e:
+            errs.append(repr(e))
+
+    th = [threading.Thread(target=proc, args=(k,)) for k in range(6)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    assert stats["ok"] >= 4 and stats["ok"] + stats["busy"] == 72, stats
+    L.mock_resource_drop(res)
+
+
+def test_nif_extract_batch_and_knn2(nif, oracle):
+    L = nif
+    w, h, nf, B = 640, 480, 1000, 5
+    res = nif_create(L, nf, w, h, max_batch=8)
+    frames = np.stack([synth.textured_frame(950 + k, w, h, "mixed" if k == 2 else "textured") for k in range(B)])
+    r = decode(L, call(L, "extract_batch", L.mock_resource_term(res), L.mock_binary(frames.ctypes.data, frames.nbytes), L.mock_int(B),
+                       L.mock_int(w), L.mock_int(h)))
+    L.mock_reset()
+    assert r[0] == "ok", r
+    _, nb, mb, kpb, deb, cap = r
+    n, mono = np.frombuffer(nb, np.int32), np.frombuffer(mb, np.int32)
+    kps = np.frombuffer(kpb, orbx.KP_DTYPE).reshape(B, cap)
+    desc = np.frombuffer(deb, np.uint8).reshape(B, cap, 32)
+    o = oracle.Oracle(nf)
+    for i in range(B):
+        k_o, d_o, m_o = o.extract(frames[i])
+        assert n[i] == len(k_o) and mono[i] == m_o and np.array_equal(desc[i, :n[i]], d_o) and kps[i, :n[i]].tobytes() == k_o.tobytes(), i
+    r = decode(L, call(L, "extract_batch", L.mock_resource_term(res), L.mock_binary(frames.ctypes.data, frames.nbytes), L.mock_int(9),
+                       L.mock_int(w), L.mock_int(h)))
+    L.mock_reset()
+    assert r == ("error", "capacity")
+    L.mock_resource_drop(res)
+    # brute-force kNN (k = 2) through the NIF: a database shard as one binary, both distance backends, global row indices
+    db = synth.descriptor_db(30011, seed=21)
+    q, _ = synth.queries_from_db(db, 77, seed=22)
+    r = call(L, "knn2_create", L.mock_binary(db.ctypes.data, db.nbytes), L.mock_int(0), L.mock_long(4_000_000_000))
+    assert decode(L, L.mock_tuple_elem(r, 0)) == "ok", decode(L, r)
+    dbres = L.mock_resource_keep(L.mock_tuple_elem(r, 1))
+    L.mock_reset()
+    idx_o, dist_o = oracle.knn2(q, db)
+    for backend in (orbx.Knn2Index.POPC, orbx.Knn2Index.TENSOR):
+        r = decode(L, call(L, "knn2", L.mock_resource_term(dbres), L.mock_binary(q.ctypes.data, q.nbytes), L.mock_int(backend)))
+        L.mock_reset()
+        assert r[0] == "ok", r
+        idx, dist = np.frombuffer(r[1], np.int32).reshape(-1, 2), np.frombuffer(r[2], np.int32).reshape(-1, 2)
+        # the 32-bit index field carries the low word of (row_offset + row): row_offset + row modulo 2^32 (the ABI keeps row_offset + rows below 2^32)
+        assert np.array_equal(dist, dist_o) and np.array_equal(idx.astype(np.int64) & 0xFFFFFFFF, (idx_o.astype(np.int64) + 4_000_000_000) & 0xFFFFFFFF), backend
+    r = decode(L, call(L, "knn2", L.mock_resource_term(dbres), L.mock_binary(q.ctypes.data, 33), L.mock_int(1)))
+    L.mock_reset()
+    assert r == ("error", "size_mismatch")
+    L.mock_resource_drop(dbres)
