@@ -204,6 +204,31 @@ int orbx_knn2_query_device(orbx_db *db, const uint8_t *d_queries, int nq, unsign
  * orbx_knn2_query_device output) into d_packed_out[nq*2]; all pointers in HBM on the db's device. */
 int orbx_knn2_merge_device(orbx_db *db, const unsigned long long *d_partials, int nparts, int nq,
                            unsigned long long *d_packed_out);
+/* ---- multi-GPU brute-force kNN: row-sharded database, top-2 merge over NCCL (BASELINE config 4) -------------------------
+ * One process per GPU.  Every rank holds one row shard as an orbx_db (row_offset = global index of its first row) and passes the SAME
+ * queries; orbx_knn2_query_sharded* computes the local top-2 (orbx_knn2_query_device), exchanges the nq x 2 x 8-byte partials with
+ * ONE ncclAllGather over NVLink (32 KB per rank at 2000 queries) on the db's stream and merges them on every rank (orbx_knn2_merge_device):
+ * identical results on all ranks, ties to the lowest global row as cv::BFMatcher(NORM_HAMMING) does.  The reference has no
+ * counterpart (its matcher sources, slam_backends/orb_slam_3/CMakeLists.txt:53, run on one CPU); this is the seam a backend that
+ * relocalises against a large map database would link.
+ * NCCL is bound at run time (dlopen of libnccl.so.2, or of the path in ORBX_NCCL_LIB): liborbx.so itself does not link it, and a
+ * process that already has NCCL loaded (e.g. through torch) shares that copy.  orbx_comm wraps one communicator:
+ *   orbx_comm_unique_id  ncclGetUniqueId on ONE rank; ship the 128 bytes to the others by any means (file, socket, MPI, torch)
+ *   orbx_comm_create     ncclCommInitRank on `device` -- collective over all ranks
+ *   orbx_comm_adopt      wrap a ncclComm_t the caller already owns (not destroyed with the orbx_comm)                              */
+typedef struct orbx_comm orbx_comm;
+#define ORBX_NCCL_ID_BYTES 128
+int orbx_comm_unique_id(uint8_t *id_out /* ORBX_NCCL_ID_BYTES */);
+int orbx_comm_create(int device, int rank, int nranks, const uint8_t *id /* ORBX_NCCL_ID_BYTES */, orbx_comm **out);
+int orbx_comm_adopt(void *nccl_comm, int rank, int nranks, orbx_comm **out);
+void orbx_comm_destroy(orbx_comm *c);
+const char *orbx_comm_last_error(const orbx_comm *c);   /* c == NULL: last error of a failed create / unique_id on this thread */
+/* d_queries (nq x 32 B, identical on every rank) -> d_packed_out[nq*2] = (dist << 32 | global row) over the WHOLE database, on every
+ * rank.  Asynchronous on the db's stream (orbx_knn2_sync to wait).  Collective: every rank of the communicator must call it. */
+int orbx_knn2_query_sharded_device(orbx_db *db, orbx_comm *comm, const uint8_t *d_queries, int nq, unsigned long long *d_packed_out);
+/* Same with HOST queries / results (idx = global row, -1 if the database has fewer than two rows); waits for the result. */
+int orbx_knn2_query_sharded(orbx_db *db, orbx_comm *comm, const uint8_t *queries, int nq, int32_t *idx_out, int32_t *dist_out);
+
 /* ---- Frame post-extraction steps ---------------------------------------------------------------------------
  * What UPSTREAM ORB-SLAM3 src/Frame.cc runs between ORBextractor::operator() and the matchers, on the device:
  *   Frame::UndistortKeyPoints   = cv::undistortPoints(pts, pts, K, mDistCoef, cv::Mat(), K)  (5 iterations, double precision)

@@ -74,12 +74,14 @@ struct orbx_handle {
     int *d_counts = nullptr;        // [2][nlevels][batch]: cand_count then sel_count
     int *d_overflow = nullptr;
     int *d_slot = nullptr;          // [batch][total_out_cap]
+    uint2 *d_items = nullptr;       // [batch][total_out_cap]  dense work list of the descriptor kernel, written by the slot kernel
     KeypointRec *d_kp = nullptr;    // [batch][kp_cap]
     uint8_t *d_desc = nullptr;      // [batch][kp_cap][32]
     int *d_n = nullptr, *d_mono = nullptr;
     FastTma ftma{};                 // tensor maps of the level planes (TMA-staged FAST kernel)
     Fast2Tma ftma2{};               // ... and for the pair-plane FAST kernel (orbx_fast2.cu), the one the pipeline prefers
     DescTma dtma{};                 // ... and of the un-blurred / blurred planes for the descriptor kernel
+    BlurTma btma{};                 // ... and of the un-blurred planes for the Gaussian pass
     int sm_count = 148;
     // colour input (orbx_set_input_format): frames are uploaded to d_color and converted into the level-0 planes on the device
     int in_fmt = ORBX_FMT_GRAY8, gray_shift = ORBX_GRAY_Q15;
@@ -178,6 +180,12 @@ static void encode_fast_map(orbx_handle *h, int l) {
                     tma_make_plane_map(reinterpret_cast<CUtensorMap *>(Q.blur[l]), D.blur, D.w, D.h, h->batch_cap, (size_t)D.blur_pitch, D.blur_fstride, 64, 39);
     Q.ok = !getenv("ORBX_NO_TMA");
     for (int k = 0; k < h->plan.nlevels; k++) Q.ok = Q.ok && Q.level_ok[k];
+    // Gaussian pass: 96 x 118 box on the un-blurred plane; planes under 16 x 16 keep the word-load kernel (multiple reflections)
+    BlurTma &G = h->btma;
+    G.level_ok[l] = D.w >= 16 && D.h >= 16 &&
+                    tma_make_plane_map(reinterpret_cast<CUtensorMap *>(G.map[l]), D.img, D.w, D.h, h->batch_cap, (size_t)D.pitch, D.img_fstride, 96, 118);
+    G.ok = !getenv("ORBX_NO_TMA") && !getenv("ORBX_BLUR_WORDS");
+    for (int k = 0; k < h->plan.nlevels; k++) G.ok = G.ok && G.level_ok[k];
 }
 
 // Box of a level = the largest ROI of its cells plus the 4-pixel-group / row-pair overhang the scoring items read.
@@ -185,6 +193,7 @@ static void build_fast_maps(orbx_handle *h) {
     FastTma &T = h->ftma;
     std::memset(&T, 0, sizeof(T));
     std::memset(&h->dtma, 0, sizeof(h->dtma));
+    std::memset(&h->btma, 0, sizeof(h->btma));
     for (int l = 0; l < h->plan.nlevels; l++) {
         const LevelPlan &LP = h->plan.lv[l];
         int rw = 0, rh = 0;
@@ -254,6 +263,7 @@ static int ensure_plan(orbx_handle *h, int w, int ht, int batch) {
     CU_TRY(h, dev_upload(h, &h->d_cells, pl.cells));
     CU_TRY(h, dev_alloc(h, &h->d_counts, (size_t)2 * nl * B));
     CU_TRY(h, dev_alloc(h, &h->d_slot, (size_t)B * pl.total_out_cap));
+    CU_TRY(h, dev_alloc(h, &h->d_items, (size_t)B * pl.total_out_cap));
     CU_TRY(h, dev_alloc(h, &h->d_kp, (size_t)B * h->kp_cap));
     CU_TRY(h, dev_alloc(h, &h->d_desc, (size_t)B * h->kp_cap * 32));
     // counts, mono indices and the overflow flag share one block (same layout as the pinned h_n block): one D2H copy per call
@@ -447,7 +457,7 @@ static int run_pipeline(orbx_handle *h, int f0, int batch, int lap0, int lap1, K
     // which has the highest priority so that its few CTAs are placed first, while the Gaussian pass fills the rest of
     // the machine from the main stream.  The fork comes after FAST because two machine-filling kernels gain nothing
     // from running side by side.
-    if (!fork) h->launches += launch_blur(h->h_levels, h->d_tiles, h->ntiles, f0, batch, stream);
+    if (!fork) h->launches += launch_blur(h->h_levels, h->d_tiles, h->ntiles, f0, batch, stream, &h->btma);
     STAGE_MARK(2);
     {
         int nl2 = 0;
@@ -463,14 +473,14 @@ static int run_pipeline(orbx_handle *h, int f0, int batch, int lap0, int lap1, K
     }
     h->launches += launch_octree(h->h_levels, nl, f0, batch, h->d_overflow, qs);
     STAGE_MARK(4);
-    h->launches += launch_finalize(h->h_levels, nl, f0, batch, pl.total_out_cap, lap0, lap1, d_kp, cap, h->d_slot, d_n, d_mono, h->d_overflow, qs);
+    h->launches += launch_finalize(h->h_levels, nl, f0, batch, pl.total_out_cap, lap0, lap1, d_kp, cap, h->d_slot, h->d_items, d_n, d_mono, h->d_overflow, qs);
     STAGE_MARK(5);
     if (fork) {
         CU_TRY(h, cudaEventRecord(ev_join, side));
-        h->launches += launch_blur(h->h_levels, h->d_tiles, h->ntiles, f0, batch, stream);
+        h->launches += launch_blur(h->h_levels, h->d_tiles, h->ntiles, f0, batch, stream, &h->btma);
         CU_TRY(h, cudaStreamWaitEvent(stream, ev_join, 0));
     }
-    h->launches += launch_describe(h->h_levels, nl, f0, batch, pl.total_out_cap, h->d_slot, d_kp, d_desc, cap, stream, &h->dtma, h->sm_count);
+    h->launches += launch_describe(h->h_levels, nl, f0, batch, pl.total_out_cap, h->d_slot, h->d_items, d_kp, d_desc, cap, stream, &h->dtma, h->sm_count);
     STAGE_MARK(6);
 #undef STAGE_MARK
     if (stream == h->stream) h->ev_valid = prof;

@@ -3,6 +3,8 @@
 #include <cstddef>
 #include <cstdint>
 
+#include <vector_types.h>
+
 #include "orbx_plan.h"
 
 namespace orbx {
@@ -51,7 +53,13 @@ struct KeypointRec {           // == orbx_keypoint == cv::KeyPoint
 int launch_gray(const uint8_t *d_src, size_t src_fstride, int src_pitch, int format, int shift, uint8_t *d_dst, size_t dst_fstride,
                 int dst_pitch, int w, int h, int f0, int batch, cudaStream_t stream);
 int launch_resize(const LevelDev *h_levels, int level, int f0, int batch, cudaStream_t stream);
-int launch_blur(const LevelDev *h_levels, const BlurTile *d_tiles, int ntiles, int f0, int batch, cudaStream_t stream);
+// Tensor maps of the un-blurred level planes for the TMA-staged Gaussian (box 96 x 118); ok = every level has one and is >= 16 x 16.
+struct BlurTma {
+    alignas(64) unsigned char map[kMaxLevels][128];
+    bool level_ok[kMaxLevels];
+    bool ok;
+};
+int launch_blur(const LevelDev *h_levels, const BlurTile *d_tiles, int ntiles, int f0, int batch, cudaStream_t stream, const BlurTma *tma = nullptr);
 // Tensor maps of the level planes for the TMA-staged FAST kernel (host side: orbx_api.cu builds them; 128 bytes each,
 // stored opaquely so that this header does not need <cuda.h>).
 struct FastTma {
@@ -78,8 +86,10 @@ int launch_fast2(const LevelDev *h_levels, const CellRect *d_cells, int ncells, 
                  cudaStream_t stream, const Fast2Tma *tma, int sm_count);
 int launch_octree(const LevelDev *h_levels, int nlevels, int f0, int batch, int *d_overflow,
                   cudaStream_t stream);
+// d_items [frames][total_out_cap]: per frame the dense list of its keypoints in sequence order, .x = level << 24 | y << 12 | x (level
+// coordinates), .y = output slot; 0xFFFFFFFF in .x behind the last one.  The descriptor kernel walks it instead of the level tables.
 int launch_finalize(const LevelDev *h_levels, int nlevels, int f0, int batch, int total_out_cap, int lap0, int lap1,
-                    KeypointRec *d_kp, int cap, int *d_slot, int *d_n, int *d_mono, int *d_overflow, cudaStream_t stream);
+                    KeypointRec *d_kp, int cap, int *d_slot, uint2 *d_items, int *d_n, int *d_mono, int *d_overflow, cudaStream_t stream);
 // Tensor maps of the un-blurred and blurred level planes for the TMA-staged descriptor kernel (boxes 64 x 31 and 64 x 39).
 struct DescTma {
     alignas(64) unsigned char img[kMaxLevels][128];
@@ -87,7 +97,7 @@ struct DescTma {
     bool level_ok[kMaxLevels];
     bool ok;
 };
-int launch_describe(const LevelDev *h_levels, int nlevels, int f0, int batch, int total_out_cap, const int *d_slot,
+int launch_describe(const LevelDev *h_levels, int nlevels, int f0, int batch, int total_out_cap, const int *d_slot, const uint2 *d_items,
                     KeypointRec *d_kp, uint8_t *d_desc, int cap, cudaStream_t stream, const DescTma *tma, int sm_count);
 // Frame post-extraction steps (orbx_frame.cu): cv::undistortPoints of Frame::UndistortKeyPoints and the 64 x 48 feature grid
 constexpr int kGridCols = 64, kGridRows = 48;

@@ -397,9 +397,127 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ LevelTable
     }
 }
 
-int launch_blur(const LevelDev *h_levels, const BlurTile *d_tiles, int ntiles, int f0, int batch, cudaStream_t stream) {
+// TMA-staged variant (the one the pipeline runs when every plane meets the TMA alignment rules and is at least 16 x 16): the halo
+// tile arrives as ONE box of 96 x 118 bytes at (x0 - 16, y0 - 3) -- a TMA box starts on a 16-byte boundary, bytes outside the plane
+// arrive as 0 -- and the BORDER_REFLECT_101 rows / columns are patched in shared memory afterwards.  That takes the ~6.6 staging
+// instructions per pixel of k_blur off the SM (measured by tools/blur_tma_probe.cu on 64 x 640x480: 23.1 -> 18.8 us); the two passes
+// are k_blur's, with the row pairs and the pixel quads packed by byte permutes instead of shift / mask pairs.
+constexpr int BTP = 96;                 // staged row pitch: image columns x0-16 .. x0+79
+struct BlurTmaParams { CUtensorMap map[kMaxLevels]; };
+
+__global__ void __launch_bounds__(256) k_blur_tma(const __grid_constant__ BlurTmaParams M, const __grid_constant__ LevelTable T,
+                                                  const BlurTile *__restrict__ tiles, int f0) {
+    const LevelDev *lv = T.lv;
+    __shared__ __align__(128) uint8_t s_in[BROWS * BTP];
+    __shared__ __align__(16) uint32_t s_h[(BROWS / 2) * BTW];
+    __shared__ __align__(8) uint64_t bar;
+    const BlurTile t = tiles[blockIdx.x];
+    const LevelDev &L = lv[t.level];
+    const int f = f0 + blockIdx.y;
+    const int x0 = t.tx * BTW, y0 = t.ty * BTH;
+    const int w = L.w, h = L.h;
+    const int nseg = (min(BTH, h - y0) + 3) >> 2, srows = 4 * nseg + 6, npairs = srows >> 1;
+    if (threadIdx.x == 0) { tma_mbar_init(&bar, 1); tma_mbar_fence_init(); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tma_mbar_expect_tx(&bar, (uint32_t)(BTP * BROWS));
+        tma_load_3d(s_in, &M.map[t.level], x0 - 16, y0 - 3, f, &bar);
+    }
+    tma_mbar_wait(&bar, 0);
+    // rows outside the plane <- their reflections (staged row r holds image row y0 - 3 + r)
+    const bool top = y0 == 0, bottom = y0 - 3 + srows > h;
+    if (top || bottom) {
+        for (int i = threadIdx.x; i < 3 * (BTP / 4); i += 256) {
+            const int k = i / (BTP / 4), wq = i - k * (BTP / 4);
+            uint32_t *S = reinterpret_cast<uint32_t *>(s_in);
+            if (top) S[(2 - k) * (BTP / 4) + wq] = S[(4 + k) * (BTP / 4) + wq];                  // rows -1-k <- rows 1+k
+            if (bottom) {
+                const int r = h + k - (y0 - 3), sr = h - 2 - k - (y0 - 3);                       // row h+k <- row h-2-k
+                if (r < srows && sr >= 0) S[r * (BTP / 4) + wq] = S[sr * (BTP / 4) + wq];
+            }
+        }
+        __syncthreads();
+    }
+    const bool left = x0 == 0, right = x0 + 76 > w;
+    if (left || right) {
+        for (int r = threadIdx.x; r < srows; r += 256) {
+            uint8_t *row = s_in + r * BTP + 12;                                                  // row[c]: image column x0 - 4 + c
+            if (left) { row[1] = row[7]; row[2] = row[6]; row[3] = row[5]; }                     // x = -3, -2, -1 <- x = 3, 2, 1
+            if (right) {
+                const int c = w - x0 + 4;                                                        // staged column of image column w
+#pragma unroll
+                for (int k = 0; k < 3; k++) if (c + k < BTP - 12) row[c + k] = row[c - 2 - k];   // x = w + k <- x = w - 2 - k
+            }
+        }
+    }
+    __syncthreads();
+    // horizontal: item = (row pair p, group g of 8 output columns)
+    for (int it = threadIdx.x; it < npairs * 8; it += 256) {
+        const int p = it >> 3, g = it & 7;
+        constexpr uint32_t KA = 18u | (34u << 8) | (48u << 16) | (56u << 24), KB = 48u | (34u << 8) | (18u << 16);
+        uint32_t hs[2][8];
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++) {
+            const uint32_t *q = reinterpret_cast<const uint32_t *>(s_in + (2 * p + rr) * BTP + 12 + 8 * g);   // image columns x0-4+8g ..
+            const uint32_t W[4] = {q[0], q[1], q[2], q[3]};
+            uint32_t U[13];
+#pragma unroll
+            for (int o = 1; o <= 12; o++) U[o] = (o & 3) ? __funnelshift_r(W[o >> 2], W[(o >> 2) + 1], 8 * (o & 3)) : W[o >> 2];
+#pragma unroll
+            for (int i = 0; i < 8; i++) hs[rr][i] = __dp4a(U[i + 5], KB, __dp4a(U[i + 1], KA, 0u));
+        }
+        uint32_t o[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) o[i] = __byte_perm(hs[0][i], hs[1][i], 0x5410);   // lo16(row 2p) | lo16(row 2p+1) << 16
+        uint4 *d4 = reinterpret_cast<uint4 *>(s_h + p * BTW + 8 * g);
+        d4[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        d4[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+    __syncthreads();
+    // vertical: item = (4-column group cg, segment of 4 output rows), as in k_blur
+    uint8_t *__restrict__ dstp = L.blur + (size_t)f * L.blur_fstride;
+    const int bp = L.blur_pitch;
+    for (int it = threadIdx.x; it < 16 * nseg; it += 256) {
+        const int cg = it & 15, seg = it >> 4;
+        const int gx = x0 + 4 * cg;
+        if (gx >= w) continue;
+        constexpr uint32_t EA = 18u | (34u << 8) | (48u << 16) | (56u << 24), EB = 48u | (34u << 8) | (18u << 16);
+        constexpr uint32_t OA = (18u << 8) | (34u << 16) | (48u << 24), OB = 56u | (48u << 8) | (34u << 16) | (18u << 24);
+        uint32_t Pq[5][4];
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const uint4 q = *reinterpret_cast<const uint4 *>(s_h + (2 * seg + k) * BTW + 4 * cg);
+            Pq[k][0] = q.x; Pq[k][1] = q.y; Pq[k][2] = q.z; Pq[k][3] = q.w;
+        }
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int gy = y0 + 4 * seg + r, pb = r >> 1;
+            const uint32_t ka = (r & 1) ? OA : EA, kb = (r & 1) ? OB : EB;
+            uint32_t acc[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                uint32_t a = __dp2a_lo(Pq[pb][c], ka, 32768u);
+                a = __dp2a_hi(Pq[pb + 1][c], ka, a);
+                a = __dp2a_lo(Pq[pb + 2][c], kb, a);
+                acc[c] = __dp2a_hi(Pq[pb + 3][c], kb, a);
+            }
+            // byte 2 of every accumulator is the pixel (acc < 2^24): three permutes for four pixels
+            const uint32_t px = __byte_perm(__byte_perm(acc[0], acc[1], 0x0062), __byte_perm(acc[2], acc[3], 0x0062), 0x5410);
+            if (gy < h) *reinterpret_cast<uint32_t *>(dstp + (size_t)gy * bp + gx) = px;
+        }
+    }
+}
+
+int launch_blur(const LevelDev *h_levels, const BlurTile *d_tiles, int ntiles, int f0, int batch, cudaStream_t stream, const BlurTma *tma) {
     if (ntiles <= 0) return 0;
     dim3 grid(ntiles, batch);
+    if (tma && tma->ok) {
+        static_assert(sizeof(BlurTma::map) == sizeof(BlurTmaParams::map), "tensor map storage mismatch");
+        BlurTmaParams M;
+        memcpy(M.map, tma->map, sizeof(M.map));
+        k_blur_tma<<<grid, 256, 0, stream>>>(M, make_table(h_levels), d_tiles, f0);
+        return 1;
+    }
     k_blur<<<grid, 256, 0, stream>>>(make_table(h_levels), d_tiles, f0);
     return 1;
 }
@@ -1224,7 +1342,8 @@ int launch_octree(const LevelDev *h_levels, int nlevels, int f0, int batch, int 
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_finalize(const __grid_constant__ LevelTable T, int nlevels, int total_out_cap, int lap0,
                                                   int lap1, KeypointRec *__restrict__ kp, int cap, int *__restrict__ slot,
-                                                  int *__restrict__ n_out, int *__restrict__ mono_out, int f0, int *__restrict__ overflow) {
+                                                  uint2 *__restrict__ items, int *__restrict__ n_out, int *__restrict__ mono_out, int f0,
+                                                  int *__restrict__ overflow) {
     const LevelDev *lv = T.lv;   // level table in the kernel parameter (constant) bank: no dependent global loads
     const int f = f0 + blockIdx.x, tid = threadIdx.x;
     __shared__ int s_cnt[kMaxLevels + 1];
@@ -1237,16 +1356,22 @@ __global__ void __launch_bounds__(256) k_finalize(const __grid_constant__ LevelT
     }
     __syncthreads();
     const int ntot = s_cnt[nlevels];
-    if (ntot > cap) { if (tid == 0) { *overflow = 4; n_out[f] = 0; mono_out[f] = 0; } return; }
+    if (ntot > cap) {
+        if (tid == 0) { *overflow = 4; n_out[f] = 0; mono_out[f] = 0; }
+        for (int i = tid; i < total_out_cap; i += 256) items[(size_t)f * total_out_cap + i] = make_uint2(0xFFFFFFFFu, 0u);
+        return;
+    }
+    for (int i = ntot + tid; i < total_out_cap; i += 256) items[(size_t)f * total_out_cap + i] = make_uint2(0xFFFFFFFFu, 0u);
     const float flap0 = (float)lap0, flap1 = (float)lap1;
     // chunks of 256 keypoints in sequence order; running count of lapping-area keypoints carried across chunks
     for (int base = 0; base < ntot; base += 256) {
         const int i = base + tid;
         int l = 0, inlap = 0;
         float x = 0.f, y = 0.f, resp = 0.f;
+        uint32_t c = 0;
         if (i < ntot) {
             while (i >= s_cnt[l + 1]) l++;
-            const uint32_t c = lv[l].sel[(size_t)f * lv[l].out_cap + (i - s_cnt[l])];
+            c = lv[l].sel[(size_t)f * lv[l].out_cap + (i - s_cnt[l])];
             x = (float)((c >> 8) & 0xFFF); y = (float)(c >> 20); resp = (float)(c & 0xFF);
             if (l != 0) { x = __fmul_rn(x, lv[l].scale); y = __fmul_rn(y, lv[l].scale); }
             inlap = (x >= flap0 && x <= flap1) ? 1 : 0;
@@ -1267,6 +1392,7 @@ __global__ void __launch_bounds__(256) k_finalize(const __grid_constant__ LevelT
             r.x = x; r.y = y; r.size = lv[l].kp_size; r.angle = -1.f; r.response = resp; r.octave = l; r.class_id = -1;
             kp[(size_t)f * cap + sl] = r;
             slot[(size_t)f * total_out_cap + lv[l].out_base + (i - s_cnt[l])] = sl;
+            items[(size_t)f * total_out_cap + i] = make_uint2(((uint32_t)l << 24) | ((c >> 20) << 12) | ((c >> 8) & 0xFFFu), (uint32_t)sl);
         }
         __syncthreads();
         if (tid == 0) s_run += tot;
@@ -1276,8 +1402,8 @@ __global__ void __launch_bounds__(256) k_finalize(const __grid_constant__ LevelT
 }
 
 int launch_finalize(const LevelDev *h_levels, int nlevels, int f0, int batch, int total_out_cap, int lap0, int lap1,
-                    KeypointRec *d_kp, int cap, int *d_slot, int *d_n, int *d_mono, int *d_overflow, cudaStream_t stream) {
-    k_finalize<<<batch, 256, 0, stream>>>(make_table(h_levels), nlevels, total_out_cap, lap0, lap1, d_kp, cap, d_slot, d_n, d_mono, f0, d_overflow);
+                    KeypointRec *d_kp, int cap, int *d_slot, uint2 *d_items, int *d_n, int *d_mono, int *d_overflow, cudaStream_t stream) {
+    k_finalize<<<batch, 256, 0, stream>>>(make_table(h_levels), nlevels, total_out_cap, lap0, lap1, d_kp, cap, d_slot, d_items, d_n, d_mono, f0, d_overflow);
     return 1;
 }
 
@@ -1430,6 +1556,27 @@ __device__ __forceinline__ uint8_t warp_brief_byte_smem(uint32_t center, float a
     return (uint8_t)val;
 }
 
+// warp_brief_byte on a patch in shared memory with the lane's 8 pattern tests already in fp32 registers (pq[j] = x0, y0, x1, y1) and
+// cvRound as the fp32 magic-number addition: for |x| < 2^22, fadd.rn(x, 1.5 * 2^23) has rint(x) (ties to even, as cvRound) in its low
+// mantissa bits, so bits(x + M) = bits(M) + rint(x).  center65 = shared-space address of the keypoint minus 65 * bits(M): the byte
+// offset iy * 64 + ix then comes out of one IMAD on the raw bit patterns (all arithmetic modulo 2^32).  No I2F / F2I in the loop:
+// conversions issue at a quarter of the FMA rate and were ~28 of the kernel's 71 us (profiles/k_describe_tma_r01_summary.txt).
+__device__ __forceinline__ uint8_t warp_brief_byte_regs(uint32_t center65, float a, float b, const float4 (&pq)[8]) {
+    const float M = 12582912.f;
+    uint32_t val = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const float4 p = pq[j];
+        const uint32_t ix0 = __float_as_uint(__fadd_rn(__fsub_rn(__fmul_rn(p.x, a), __fmul_rn(p.y, b)), M));
+        const uint32_t iy0 = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(p.x, b), __fmul_rn(p.y, a)), M));
+        const uint32_t ix1 = __float_as_uint(__fadd_rn(__fsub_rn(__fmul_rn(p.z, a), __fmul_rn(p.w, b)), M));
+        const uint32_t iy1 = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(p.z, b), __fmul_rn(p.w, a)), M));
+        const uint32_t t0 = lds_u8(center65 + iy0 * 64u + ix0), t1 = lds_u8(center65 + iy1 * 64u + ix1);
+        val |= (uint32_t)(t0 < t1) << j;
+    }
+    return (uint8_t)val;
+}
+
 // TMA-staged, persistent variant (the one the pipeline runs when every plane meets the TMA alignment rules).  One warp owns one
 // keypoint at a time and walks the (frame, slot) items with a grid stride.  The 31-row patch of the un-blurred level (IC_Angle)
 // and the 39-row patch of the blurred level (the rotated test points lie within radius 18.4 of the keypoint) are brought into
@@ -1450,7 +1597,7 @@ struct DescTmaParams {
 struct DescItem { int level, x, y, sl, f; };         // level < 0: nothing to do for this item
 
 __global__ void __launch_bounds__(DT_WARPS * 32, 6) k_describe_tma(const __grid_constant__ DescTmaParams P, const __grid_constant__ LevelTable T,
-                                                                   int nlevels, int total_out_cap, int nframes, const int *__restrict__ slot,
+                                                                   int nlevels, int total_out_cap, int nframes, const uint2 *__restrict__ items,
                                                                    KeypointRec *__restrict__ kp, uint8_t *__restrict__ desc, int cap, int f0) {
     extern __shared__ __align__(128) uint8_t smem[];
     const LevelDev *lv = T.lv;
@@ -1460,18 +1607,14 @@ __global__ void __launch_bounds__(DT_WARPS * 32, 6) k_describe_tma(const __grid_
     if (lane == 0) { tma_mbar_init(&s_full[0], 1); tma_mbar_init(&s_full[1], 1); tma_mbar_fence_init(); }
     __syncwarp();
     const int total = nframes * total_out_cap, stride = gridDim.x * DT_WARPS;
+    // work list written by k_finalize: one 8-byte record per keypoint (level, position, output slot), dense per frame
     auto load_item = [&](int i) -> DescItem {
         DescItem d; d.level = -1; d.x = d.y = d.sl = d.f = 0;
         if (i >= total) return d;
-        const int fi = i / total_out_cap, item = i - fi * total_out_cap;
-        int l = 0;
-        while (l + 1 < nlevels && item >= lv[l + 1].out_base) l++;
-        const LevelDev &L = lv[l];
-        const int idx = item - L.out_base, f = f0 + fi;
-        if (idx >= L.sel_count[f]) return d;
-        const uint32_t c = L.sel[(size_t)f * L.out_cap + idx];
-        d.level = l; d.x = (c >> 8) & 0xFFF; d.y = c >> 20; d.f = f;
-        d.sl = slot[(size_t)f * total_out_cap + item];
+        const int fi = i / total_out_cap, k = i - fi * total_out_cap, f = f0 + fi;
+        const uint2 r = __ldg(items + (size_t)f * total_out_cap + k);
+        if (r.x == 0xFFFFFFFFu) return d;
+        d.level = (int)(r.x >> 24); d.x = (int)(r.x & 0xFFFu); d.y = (int)((r.x >> 12) & 0xFFFu); d.f = f; d.sl = (int)r.y;
         return d;
     };
     auto issue = [&](const DescItem &d, int st) {        // lane 0 only
@@ -1487,6 +1630,13 @@ __global__ void __launch_bounds__(DT_WARPS * 32, 6) k_describe_tma(const __grid_
     uint32_t phase = 0;                                   // bit st = parity to wait for on stage st
     constexpr int UM[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
     const int u = lane - kHalfPatch, au = u < 0 ? -u : u;
+    // the lane's 8 BRIEF tests (bits 8 lane .. 8 lane + 7) as fp32, once per persistent warp
+    float4 pq[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const char4 p = reinterpret_cast<const char4 *>(g_pattern)[lane * 8 + j];
+        pq[j] = make_float4((float)p.x, (float)p.y, (float)p.z, (float)p.w);
+    }
     for (int q = 0; i_cur < total; q++, i_cur += stride) {
         const int st = q & 1;
         const DescItem Cn = load_item(i_cur + 2 * stride);                 // descriptor prefetch for the item after next
@@ -1513,7 +1663,7 @@ __global__ void __launch_bounds__(DT_WARPS * 32, 6) k_describe_tma(const __grid_
                 steer_trig(angle, a, b);
             }
             angle = __shfl_sync(0xFFFFFFFFu, angle, 0); a = __shfl_sync(0xFFFFFFFFu, a, 0); b = __shfl_sync(0xFFFFFFFFu, b, 0);
-            const uint8_t byte = warp_brief_byte_smem(tma_smem_u32(bp) + (uint32_t)(DT_R * DT_BOXW + xo), a, b, lane);
+            const uint8_t byte = warp_brief_byte_regs(tma_smem_u32(bp) + (uint32_t)(DT_R * DT_BOXW + xo) - 65u * 0x4B400000u, a, b, pq);
             desc[((size_t)A.f * cap + A.sl) * 32 + lane] = byte;
             if (lane == 0) kp[(size_t)A.f * cap + A.sl].angle = angle;
         }
@@ -1523,7 +1673,7 @@ __global__ void __launch_bounds__(DT_WARPS * 32, 6) k_describe_tma(const __grid_
     }
 }
 
-int launch_describe(const LevelDev *h_levels, int nlevels, int f0, int batch, int total_out_cap, const int *d_slot,
+int launch_describe(const LevelDev *h_levels, int nlevels, int f0, int batch, int total_out_cap, const int *d_slot, const uint2 *d_items,
                     KeypointRec *d_kp, uint8_t *d_desc, int cap, cudaStream_t stream, const DescTma *tma, int sm_count) {
     if (tma && tma->ok) {
         static_assert(sizeof(DescTma::img) == sizeof(DescTmaParams::img), "tensor map storage mismatch");
@@ -1541,7 +1691,7 @@ int launch_describe(const LevelDev *h_levels, int nlevels, int f0, int batch, in
         const int total = batch * total_out_cap;
         const int want = (total + DT_WARPS - 1) / DT_WARPS;
         const int grid = want < sm_count * per_sm ? want : sm_count * per_sm;
-        k_describe_tma<<<grid, DT_WARPS * 32, smem, stream>>>(P, make_table(h_levels), nlevels, total_out_cap, batch, d_slot, d_kp, d_desc, cap, f0);
+        k_describe_tma<<<grid, DT_WARPS * 32, smem, stream>>>(P, make_table(h_levels), nlevels, total_out_cap, batch, d_items, d_kp, d_desc, cap, f0);
         return 1;
     }
     dim3 grid((total_out_cap + 8 * DG - 1) / (8 * DG), batch);

@@ -10,6 +10,8 @@
 // streams database rows through shared memory (broadcast reads), so the POPC pipe is the bound.
 #include <cuda_runtime.h>
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -242,6 +244,8 @@ struct orbx_db {
     int8_t *d_dbe = nullptr;
     int8_t *d_qe = nullptr; int qe_cap = 0;
     unsigned long long *d_partial_tc = nullptr; size_t partial_tc_cap = 0;
+    // row-sharded queries: this rank's top-2 and the all-gathered [ranks][nq][2] partials
+    unsigned long long *d_sh_local = nullptr, *d_sh_gather = nullptr; size_t sh_cap = 0;
 };
 
 #define DB_TRY(db, expr)                                                                       \
@@ -335,6 +339,8 @@ void orbx_knn2_destroy_db(orbx_db *db) {
     if (db->d_dbe) cudaFree(db->d_dbe);
     if (db->d_qe) cudaFree(db->d_qe);
     if (db->d_partial_tc) cudaFree(db->d_partial_tc);
+    if (db->d_sh_local) cudaFree(db->d_sh_local);
+    if (db->d_sh_gather) cudaFree(db->d_sh_gather);
     if (db->own_stream) cudaStreamDestroy(db->own_stream);
     delete db;
 }
@@ -434,6 +440,147 @@ int orbx_knn2_query(orbx_db *db, const uint8_t *queries, int nq, int32_t *idx_ou
     if (rc) return rc;
     DB_TRY(db, cudaMemcpyAsync(db->d_q, queries, (size_t)nq * 32, cudaMemcpyHostToDevice, db->stream));
     if ((rc = orbx_knn2_query_device(db, db->d_q, nq, db->d_out))) return rc;
+    DB_TRY(db, cudaMemcpyAsync(db->h_out, db->d_out, (size_t)nq * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, db->stream));
+    DB_TRY(db, cudaStreamSynchronize(db->stream));
+    for (int i = 0; i < 2 * nq; i++) {
+        const unsigned long long k = db->h_out[i];
+        if (k == NONE64) { idx_out[i] = -1; dist_out[i] = -1; }
+        else { idx_out[i] = (int32_t)(k & 0xFFFFFFFFull); dist_out[i] = (int32_t)(k >> 32); }
+    }
+    return ORBX_OK;
+}
+
+}  // extern "C"
+
+// ---- row-sharded kNN over NCCL ---------------------------------------------------------------------------------------------
+// NCCL is bound at run time: the entry points used here have had the same C signatures since NCCL 2.0 (nccl.h: ncclGetUniqueId,
+// ncclCommInitRank, ncclCommDestroy, ncclAllGather, ncclGetErrorString; ncclUniqueId = 128 opaque bytes passed by value,
+// ncclUint64 = 5).
+namespace {
+struct NcclId { char internal[ORBX_NCCL_ID_BYTES]; };
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(NcclId *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    std::string why;
+};
+NcclApi *nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api.AllGather ? &api : nullptr;
+    tried = true;
+    const char *env = getenv("ORBX_NCCL_LIB");
+    if (env && *env) api.lib = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+    if (!api.lib) api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);   // the copy the process already uses (torch)
+    if (!api.lib) api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!api.lib) { api.why = std::string("cannot load libnccl.so.2 (set ORBX_NCCL_LIB): ") + (dlerror() ? dlerror() : ""); return nullptr; }
+    api.GetUniqueId = (int (*)(NcclId *))dlsym(api.lib, "ncclGetUniqueId");
+    api.CommInitRank = (int (*)(void **, int, NcclId, int))dlsym(api.lib, "ncclCommInitRank");
+    api.CommDestroy = (int (*)(void *))dlsym(api.lib, "ncclCommDestroy");
+    api.GetErrorString = (const char *(*)(int))dlsym(api.lib, "ncclGetErrorString");
+    api.AllGather = (int (*)(const void *, void *, size_t, int, void *, cudaStream_t))dlsym(api.lib, "ncclAllGather");
+    if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather) { api.AllGather = nullptr; api.why = "libnccl.so.2 lacks the expected symbols"; return nullptr; }
+    return &api;
+}
+thread_local std::string g_comm_error;
+std::string nccl_err(NcclApi *a, const char *what, int rc) { return std::string(what) + ": " + (a->GetErrorString ? a->GetErrorString(rc) : "nccl error"); }
+}  // namespace
+
+struct orbx_comm {
+    void *comm = nullptr;
+    int rank = 0, nranks = 1, device = -1;
+    bool owned = false;
+    mutable std::string err;
+};
+
+extern "C" {
+
+int orbx_comm_unique_id(uint8_t *id_out) {
+    if (!id_out) { g_comm_error = "null argument"; return ORBX_E_INVALID; }
+    NcclApi *a = nccl_api();
+    if (!a) { static NcclApi *dummy = nullptr; (void)dummy; g_comm_error = "NCCL unavailable"; return ORBX_E_CUDA; }
+    NcclId id;
+    const int rc = a->GetUniqueId(&id);
+    if (rc) { g_comm_error = nccl_err(a, "ncclGetUniqueId", rc); return ORBX_E_CUDA; }
+    std::memcpy(id_out, id.internal, ORBX_NCCL_ID_BYTES);
+    return ORBX_OK;
+}
+
+int orbx_comm_create(int device, int rank, int nranks, const uint8_t *id, orbx_comm **out) {
+    if (!out || !id || nranks < 1 || rank < 0 || rank >= nranks) { g_comm_error = "bad argument"; return ORBX_E_INVALID; }
+    *out = nullptr;
+    NcclApi *a = nccl_api();
+    if (!a) { g_comm_error = "NCCL unavailable: cannot load libnccl.so.2 (set ORBX_NCCL_LIB to its path)"; return ORBX_E_CUDA; }
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) { g_comm_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e); return ORBX_E_CUDA; }
+    NcclId nid;
+    std::memcpy(nid.internal, id, ORBX_NCCL_ID_BYTES);
+    void *comm = nullptr;
+    const int rc = a->CommInitRank(&comm, nranks, nid, rank);
+    if (rc) { g_comm_error = nccl_err(a, "ncclCommInitRank", rc); return ORBX_E_CUDA; }
+    orbx_comm *c = new (std::nothrow) orbx_comm();
+    if (!c) { a->CommDestroy(comm); g_comm_error = "out of host memory"; return ORBX_E_INVALID; }
+    c->comm = comm; c->rank = rank; c->nranks = nranks; c->device = device; c->owned = true;
+    *out = c;
+    return ORBX_OK;
+}
+
+int orbx_comm_adopt(void *nccl_comm, int rank, int nranks, orbx_comm **out) {
+    if (!out || !nccl_comm || nranks < 1 || rank < 0 || rank >= nranks) { g_comm_error = "bad argument"; return ORBX_E_INVALID; }
+    *out = nullptr;
+    if (!nccl_api()) { g_comm_error = "NCCL unavailable: cannot load libnccl.so.2 (set ORBX_NCCL_LIB to its path)"; return ORBX_E_CUDA; }
+    orbx_comm *c = new (std::nothrow) orbx_comm();
+    if (!c) { g_comm_error = "out of host memory"; return ORBX_E_INVALID; }
+    c->comm = nccl_comm; c->rank = rank; c->nranks = nranks; c->owned = false;
+    *out = c;
+    return ORBX_OK;
+}
+
+void orbx_comm_destroy(orbx_comm *c) {
+    if (!c) return;
+    if (c->owned && c->comm) {
+        if (c->device >= 0) cudaSetDevice(c->device);
+        NcclApi *a = nccl_api();
+        if (a) a->CommDestroy(c->comm);
+    }
+    delete c;
+}
+
+const char *orbx_comm_last_error(const orbx_comm *c) { return c ? c->err.c_str() : g_comm_error.c_str(); }
+
+int orbx_knn2_query_sharded_device(orbx_db *db, orbx_comm *comm, const uint8_t *d_queries, int nq, unsigned long long *d_packed_out) {
+    if (!db || !comm || !d_queries || !d_packed_out || nq < 1) return ORBX_E_INVALID;
+    NcclApi *a = nccl_api();
+    if (!a) { db->err = "NCCL unavailable"; return ORBX_E_CUDA; }
+    DB_TRY(db, cudaSetDevice(db->device));
+    const size_t need = (size_t)nq * 2;
+    if (need > db->sh_cap) {
+        if (db->d_sh_local) cudaFree(db->d_sh_local);
+        if (db->d_sh_gather) cudaFree(db->d_sh_gather);
+        db->d_sh_local = db->d_sh_gather = nullptr; db->sh_cap = 0;
+        DB_TRY(db, cudaMalloc((void **)&db->d_sh_local, need * sizeof(unsigned long long)));
+        DB_TRY(db, cudaMalloc((void **)&db->d_sh_gather, need * sizeof(unsigned long long) * 64));   // room for 64 ranks
+        db->sh_cap = need;
+    }
+    if (comm->nranks > 64) { db->err = "more than 64 ranks"; return ORBX_E_CAPACITY; }
+    int rc = orbx_knn2_query_device(db, d_queries, nq, db->d_sh_local);
+    if (rc) return rc;
+    if (comm->nranks == 1) return orbx_knn2_merge_device(db, db->d_sh_local, 1, nq, d_packed_out);
+    const int nrc = a->AllGather(db->d_sh_local, db->d_sh_gather, need, 5 /* ncclUint64 */, comm->comm, db->stream);   // rank-major [ranks][nq][2]
+    if (nrc) { db->err = nccl_err(a, "ncclAllGather", nrc); comm->err = db->err; return ORBX_E_CUDA; }
+    return orbx_knn2_merge_device(db, db->d_sh_gather, comm->nranks, nq, d_packed_out);
+}
+
+int orbx_knn2_query_sharded(orbx_db *db, orbx_comm *comm, const uint8_t *queries, int nq, int32_t *idx_out, int32_t *dist_out) {
+    if (!db || !comm || !queries || !idx_out || !dist_out || nq < 1) return ORBX_E_INVALID;
+    DB_TRY(db, cudaSetDevice(db->device));
+    int rc = db_reserve(db, nq);
+    if (rc) return rc;
+    DB_TRY(db, cudaMemcpyAsync(db->d_q, queries, (size_t)nq * 32, cudaMemcpyHostToDevice, db->stream));
+    if ((rc = orbx_knn2_query_sharded_device(db, comm, db->d_q, nq, db->d_out))) return rc;
     DB_TRY(db, cudaMemcpyAsync(db->h_out, db->d_out, (size_t)nq * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, db->stream));
     DB_TRY(db, cudaStreamSynchronize(db->stream));
     for (int i = 0; i < 2 * nq; i++) {
