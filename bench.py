@@ -204,12 +204,171 @@ def opencv_bfmatcher_pairs_per_s(q, db, threads):
     return len(q) * len(db) / (time.perf_counter() - t0)
 
 
+def profile_facts(kernel):
+    """ncu facts of one kernel from the newest profiles/*_r02 capture (tools/make_profile_summaries.py writes profiles/ncu_facts_r02.json):
+    dram bytes per launch, pipe busy fractions.  None where the round's capture does not hold the kernel -- nothing is hard-coded here."""
+    for name in ("ncu_facts_r02.json",):
+        try:
+            facts = json.load(open(os.path.join(ROOT, "profiles", name)))
+            if kernel in facts:
+                return dict(facts[kernel], source=f"profiles/{name}")
+        except Exception:
+            pass
+    return None
+
+
+def ubench_rate(op):
+    """thread-ops / clk / SM of one instruction kind from the committed pipe microbenchmark (tools/ubench_pipes.cu)."""
+    for name in ("ubench_pipes_r02.jsonl", "ubench_pipes_r01.jsonl"):
+        try:
+            for line in open(os.path.join(ROOT, "profiles", name)):
+                d = json.loads(line)
+                if d.get("op") == op:
+                    return float(d["thread_ops_per_clk_per_sm"]), f"profiles/{name}"
+        except Exception:
+            pass
+    return None, None
+
+
+def device_leg(torch, dist, orbx, synth, dev, local_rank, rank, world, stream, barrier, ev0, ev1, W1, H1, NF1, B1, R1, steps, seed0,
+               baseline_bytes=None, match=False):
+    """Device-resident extraction on another BASELINE shape (same measurement as the headline: CUDA events on the launching stream,
+    inputs cycling through R1 resident batches larger than L2).  match=True adds Frame::UndistortKeyPoints + AssignFeaturesToGrid
+    (orbx_frame_grid_batch_device) and the previous-frame windowed search (orbx_match_windowed_grid_device: every keypoint of frame i
+    searched in frame i+1 of the batch, radius 15 x scale[octave], octave +-1, static camera) to the step -- BASELINE config 3."""
+    ex1 = orbx.ORBextractor(NF1, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank, max_width=W1, max_height=H1, max_batch=B1)
+    cap1 = ex1.capacity
+    ex1.set_stream(stream.cuda_stream)
+    nd = min(B1, 8)                                      # distinct synthetic frames per batch; batches differ by a roll
+    base = np.stack([synth.textured_frame(seed0 + 1000 * rank + i, W1, H1) for i in range(nd)])
+    d_in1 = []
+    for r in range(R1):
+        b = np.stack([np.roll(base[i % nd], 7 * r + 3 * (i // nd), axis=1) for i in range(B1)])
+        d_in1.append(torch.from_numpy(b).to(dev))
+    k1 = torch.zeros((B1, cap1, 7), dtype=torch.float32, device=dev)
+    de1 = torch.zeros((B1, cap1, 32), dtype=torch.uint8, device=dev)
+    n1 = torch.zeros(B1, dtype=torch.int32, device=dev)
+    m1 = torch.zeros(B1, dtype=torch.int32, device=dev)
+    cam = (0.73 * W1, 0.73 * W1, W1 / 2.0, H1 / 2.0, -0.05, 0.01, 0.0005, -0.0003, 0.0)
+    mstate = None
+    if match:
+        un1 = torch.zeros_like(k1)
+        st1 = torch.zeros((B1, 64 * 48 + 1), dtype=torch.int32, device=dev)
+        it1 = torch.zeros((B1, cap1), dtype=torch.int32, device=dev)
+        bounds = ex1.image_bounds(cam, W1, H1)
+        outs = [torch.zeros((B1, cap1), dtype=torch.int32, device=dev) for _ in range(4)]
+        mstate = {"q": [None] * R1}
+
+    def step1(i):
+        r = i % R1
+        ex1.extract_batch_device(d_in1[r].data_ptr(), H1 * W1, B1, W1, H1, W1, k1.data_ptr(), de1.data_ptr(), cap1, n1.data_ptr(), m1.data_ptr())
+        if match:
+            ex1.frame_grid_batch_device(k1.data_ptr(), n1.data_ptr(), B1, cap1, cam, bounds, un1.data_ptr(), st1.data_ptr(), it1.data_ptr())
+            q = mstate["q"][r]
+            if q is not None:
+                quvr, qlev, nq = q
+                for f in range(B1):
+                    t = (f + 1) % B1
+                    ex1.match_windowed_grid_device(de1[f].data_ptr(), quvr[f].data_ptr(), qlev[f].data_ptr(), nq[f], un1[t].data_ptr(), de1[t].data_ptr(),
+                                                   st1[t].data_ptr(), it1[t].data_ptr(), bounds, *[o[f].data_ptr() for o in outs])
+
+    if match:
+        # queries of every ring entry, prepared once outside the clock (in the reference this is CPU geometry: projection by the
+        # motion model): window centre = the keypoint's own undistorted position, radius 15 x scale[octave], octaves o-1 .. o+1
+        scale = torch.tensor(ex1.GetScaleFactors(), dtype=torch.float32, device=dev)
+        for r in range(R1):
+            step1(r)
+            ex1.sync()
+            octv = un1[:, :, 5].contiguous().view(torch.int32).clamp(0, NLEVELS - 1).long()
+            quvr = torch.stack([un1[:, :, 0], un1[:, :, 1], 15.0 * scale[octv]], dim=2).contiguous()
+            qlev = torch.stack([octv - 1, octv + 1], dim=2).to(torch.int32).contiguous()
+            mstate["q"][r] = (quvr, qlev, [int(v) for v in n1.cpu().tolist()])
+    for i in range(2 * R1 + 1):
+        step1(i)
+    ex1.sync()
+    barrier()
+    ev0.record(stream)
+    for i in range(steps):
+        step1(i)
+    ev1.record(stream)
+    ex1.sync()
+    barrier()
+    dt1 = ev0.elapsed_time(ev1) * 1e-3
+    if world > 1:
+        tt = torch.tensor([dt1], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt1 = float(tt.item())
+    fps1 = world * steps * B1 / dt1
+    bytes1 = orbx.plan_probe(NF1, SCALE, NLEVELS, INI_TH, MIN_TH, W1, H1)["algorithmic_bytes"]
+    peaks1, _ = measured_peaks()
+    out = {"workload": f"ORB extraction{' + feature grid + previous-frame windowed search' if match else ''}, {B1} x {W1}x{H1} gray frames per GPU per step, "
+                       f"nFeatures {NF1}", "value": fps1, "unit": "frames/s", "ms_per_step": 1e3 * dt1 / steps,
+           "keypoints_per_frame": float(n1.float().mean().item()), "algorithmic_bytes_per_frame": bytes1,
+           "baseline_md_bytes_per_frame": baseline_bytes,
+           "whole_step_hbm_frac": bytes1 * fps1 / world / 1e9 / float(peaks1["hbm_gbs"]),
+           "l2": f"inputs cycle through {R1} distinct batches = {R1 * B1 * W1 * H1 / 1e6:.0f} MB > 126 MB L2"}
+    if match:
+        # the search alone: queries/s of orbx_match_windowed_grid_device on the resident results of the last step
+        quvr, qlev, nq = mstate["q"][(steps - 1) % R1]
+        reps = 20
+        barrier()
+        ev0.record(stream)
+        for _ in range(reps):
+            for f in range(B1):
+                t = (f + 1) % B1
+                ex1.match_windowed_grid_device(de1[f].data_ptr(), quvr[f].data_ptr(), qlev[f].data_ptr(), nq[f], un1[t].data_ptr(), de1[t].data_ptr(),
+                                               st1[t].data_ptr(), it1[t].data_ptr(), bounds, *[o[f].data_ptr() for o in outs])
+        ev1.record(stream)
+        ex1.sync()
+        tm = ev0.elapsed_time(ev1) * 1e-3
+        matched = float(((outs[0][0, :nq[0]] >= 0) & (outs[1][0, :nq[0]] <= 100)).float().mean().item())
+        out["windowed_match"] = {"queries_per_s": world * reps * sum(nq) / tm, "us_per_frame_pair": 1e6 * tm / (reps * B1), "queries_per_frame": sum(nq) / B1,
+                                 "matched_fraction_th_high": matched,
+                                 "api": "orbx_match_windowed_grid_device, device-resident queries / grid / descriptors, one launch per frame pair"}
+    ex1.close()
+    return out
+
+
+def latency_leg(orbx, synth, local_rank, cpu_too):
+    """What the reference's seam actually issues: ONE frame per ORBextractor::operator() call (orbslam3_mono_networked.cc:594), pageable
+    memory in (a cv::Mat), keypoints + descriptors out (std::vector / cv::Mat).  200 orbx_extract calls per shape, median / p99 ms, with the
+    CPU restatement's single-thread time per frame beside it.  Shapes: the bench's 640x480 / 1000, and the reference's own camera:
+    1280x800 (application.ex:49-57) with its YAML's nFeatures 1250 and the 5x initialisation extractor (6250)."""
+    out = []
+    for (w, h, nf) in ((640, 480, 1000), (1280, 800, 1250), (1280, 800, 6250)):
+        ex = orbx.ORBextractor(nf, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank, max_width=w, max_height=h, max_batch=1)
+        frames = [synth.textured_frame(4000 + i, w, h) for i in range(4)]
+        for i in range(12):
+            ex(frames[i % 4])
+        l0 = ex.launch_count()
+        ts = []
+        for i in range(200):
+            t0 = time.perf_counter()
+            mono, kps, desc = ex(frames[i % 4])
+            ts.append(time.perf_counter() - t0)
+        launches = (ex.launch_count() - l0) / 200.0
+        ts = np.sort(np.array(ts)) * 1e3
+        rec = {"shape": f"{w}x{h}", "nfeatures": nf, "keypoints": int(len(kps)), "median_ms": float(ts[100]), "p99_ms": float(ts[197]), "min_ms": float(ts[0]),
+               "calls": 200, "kernel_launches_per_frame": launches,
+               "api": "orbx_extract (one frame per call, pageable numpy frame in, keypoints + descriptors out, ctypes overhead included)"}
+        if cpu_too:
+            from oracle import oracle_lib as ol
+            ol.extract_batch(np.stack(frames[:2]), nf, SCALE, NLEVELS, INI_TH, MIN_TH, nthreads=1)
+            t0 = time.perf_counter()
+            ol.extract_batch(np.stack(frames), nf, SCALE, NLEVELS, INI_TH, MIN_TH, nthreads=1)
+            rec["cpu_single_thread_ms"] = 1e3 * (time.perf_counter() - t0) / len(frames)
+            rec["speedup_vs_cpu_single_thread"] = rec["cpu_single_thread_ms"] / rec["median_ms"]
+        ex.close()
+        out.append(rec)
+    return out
+
+
 def run_reference(args, rank, world):
     """--impl reference: the CPU restatement of the reference's ORBextractor on all host threads (rank 0 only)."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    nfr = max(cores * 16, 128)          # frames per step: ~0.25 s of wall time on 16 threads
+    nfr = BATCH                         # one step = one 64-frame batch, as in the main arm (about 50 ms on 16 threads)
     frames = make_frames(nfr, 0)
     from oracle import oracle_lib as ol
     for _ in range(args.warmup):
@@ -223,10 +382,9 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD,
-                       "implementation": "CPU restatement of ORB-SLAM3's ORBextractor (oracle/orb_oracle.c; the reference's own source is not in "
-                                         "its tree and needs OpenCV / Eigen / Boost: unbuildable here), one extractor per host thread",
-                       "sample_per_step": f"{nfr} of the workload's frames"},
+            "config": {"workload": WORKLOAD},
+            "implementation": "CPU restatement of ORB-SLAM3's ORBextractor (oracle/orb_oracle.c; the reference's own source is not in its tree and "
+                              "needs OpenCV / Eigen / Boost: unbuildable here), one extractor per host thread",
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -241,7 +399,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-knn", action="store_true", help="skip the Hamming kNN leg")
     ap.add_argument("--no-two-callers", action="store_true", help="skip the two-concurrent-callers e2e figure")
-    ap.add_argument("--no-euroc", action="store_true", help="skip the 752x480 / 1200-feature (configs[1]) leg")
+    ap.add_argument("--no-euroc", action="store_true", help="skip the legs on the other BASELINE frame shapes (configs[1], [2], [4])")
+    ap.add_argument("--no-latency", action="store_true", help="skip the one-frame-per-call latency leg")
     args = ap.parse_args()
     # the library replays a CUDA graph per (input buffer, output buffers) pair from the third sighting on: the warm-up runs the
     # ring of input batches twice (+1) so that the timed region is the steady state of a streaming caller; reported as done
@@ -364,6 +523,20 @@ def main():
         sampler.start()
     dt, launches = timed(step_lanes, args.steps, True)
     fps = world * args.steps * BATCH / dt
+    # the same step loop for >= 2 s: the headline's timed region is a few milliseconds (a burst); this one is long enough for the
+    # power management to settle and for the 20 ms clock sampler to see it
+    sustained = None
+    try:
+        sus_steps = int(min(40000, max(200, 2.4 / (dt / args.steps))))
+        sus_steps -= sus_steps % NDL
+        sampler_s = ClockSampler(local_rank)
+        if rank == 0:
+            sampler_s.start()
+        dt_s, _ = timed(step_lanes, sus_steps, True)
+        sustained = {"value": world * sus_steps * BATCH / dt_s, "unit": "frames/s", "seconds": dt_s, "steps": sus_steps,
+                     "ms_per_step": 1e3 * dt_s / sus_steps, "clocks": sampler_s.stop() if rank == 0 else None}
+    except Exception as err:
+        sustained = {"error": repr(err)}
     # one lane alone (one batch in flight), same steps: reported beside the headline
     for i in range(2 * RING + 1):
         step_device(i)
@@ -492,6 +665,45 @@ def main():
           e2e_two = world * 2 * e2e_steps * BATCH / dt2
       except Exception as err:          # an auxiliary figure must not cost the headline line
         e2e_two = {"error": repr(err)}
+    # what the platform allows: every rank copies the same page-locked ring to its GPU at the same time, no kernels (plain
+    # cudaMemcpyAsync through torch, two streams so that copies queue back to back); the e2e figure is reported against it
+    h2d_ceiling = None
+    try:
+        s_a, s_b = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        d_tmp = [torch.empty((BATCH, H, W), dtype=torch.uint8, device=dev) for _ in range(2)]
+        d_res = torch.empty((BATCH, cap, 15), dtype=torch.float32, device=dev)       # 60 bytes per keypoint slot, as the results
+        p_res = torch.empty((BATCH, cap, 15), dtype=torch.float32).pin_memory()
+
+        def copy_loop(n, with_d2h):
+            for i in range(n):
+                with torch.cuda.stream(s_a if i & 1 else s_b):
+                    d_tmp[i & 1].copy_(pinned_in[i % RING], non_blocking=True)
+                if with_d2h:
+                    with torch.cuda.stream(stream):
+                        p_res.copy_(d_res, non_blocking=True)
+            torch.cuda.synchronize()
+
+        res = {}
+        for name, dup in (("h2d_only", False), ("h2d_with_d2h", True)):
+            copy_loop(8, dup)
+            barrier()
+            t0 = time.perf_counter()
+            copy_loop(160, dup)
+            barrier()
+            dtc = time.perf_counter() - t0
+            if world > 1:
+                tt = torch.tensor([dtc], dtype=torch.float64, device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dtc = float(tt.item())
+            res[name] = world * 160 * BATCH / dtc
+        h2d_ceiling = {"value": res["h2d_with_d2h"], "unit": "frames/s", "h2d_only": res["h2d_only"],
+                       "gb_per_s_per_gpu": res["h2d_with_d2h"] / world * W * H / 1e9,
+                       "e2e_over_ceiling": (e2e_fps / res["h2d_with_d2h"]) if isinstance(e2e_fps, float) else None,
+                       "how": "all ranks copy the bench's page-locked 64-frame batches to their GPU concurrently (cudaMemcpyAsync, no kernels), "
+                              "with the result-sized device->host copy running beside it; frames/s = frames copied / wall time, max over ranks"}
+        del d_tmp, d_res, p_res
+    except Exception as err:
+        h2d_ceiling = {"error": repr(err)}
     ex2.close()
     ex.set_stream(stream.cuda_stream)
     # the clock sampler (nvidia-smi, 20 ms period) covers the device-timed region, the per-stage pass and the e2e region
@@ -499,56 +711,186 @@ def main():
     h2d = BATCH * W * H
     d2h = BATCH * cap * (28 + 32) + BATCH * 8 + 4
 
-    # ---- BASELINE configs[1] shape beside the headline: EuRoC-sized 752x480 frames, nFeatures 1200, 64-frame batches per GPU
-    euroc = None
+    # ---- the other BASELINE frame shapes, same device-resident measurement (auxiliary figures must not cost the headline line)
+    from send_slam_b200 import synth
+    legs = {}
+    for key, (w1, h1, nf1, b1, r1, bb, mt) in {"config1_752x480_nf1200": (752, 480, 1200, 64, 6, 6782935, False),
+                                                "config3_1920x1080_nf2000": (1920, 1080, 2000, 16, 5, 32503669, True),
+                                                "config5_1280x720_nf1250": (1280, 720, 1250, 32, 5, 14923333, False)}.items():
+        if args.no_euroc:
+            legs[key] = None
+            continue
+        try:
+            legs[key] = device_leg(torch, dist if world > 1 else None, orbx, synth, dev, local_rank, rank, world, stream, barrier, ev0, ev1,
+                                   w1, h1, nf1, b1, r1, max(5, args.steps // (2 if w1 > 1000 else 1)), 5000, baseline_bytes=bb, match=mt)
+        except Exception as err:
+            legs[key] = {"error": repr(err)}
+        torch.cuda.empty_cache()
+    euroc = legs["config1_752x480_nf1200"]
+    # config 5's other half: one camera stream per GPU, one frame per call through the entry point the NIF calls (orbx_extract with
+    # pageable memory; nif/orbx_nif.c nif_extract), then the previous-frame search of that frame on host buffers (orbx_match_windowed)
+    stream5 = None
     if not args.no_euroc:
-      try:
-          from send_slam_b200 import synth
-          W1, H1, NF1, R1 = 752, 480, 1200, 6                      # 6 x 64 x 361 KB = 139 MB > 126 MB L2
-          ex1 = orbx.ORBextractor(NF1, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank, max_width=W1, max_height=H1, max_batch=BATCH)
-          cap1 = ex1.capacity
-          ex1.set_stream(stream.cuda_stream)
-          d_in1 = [torch.from_numpy(np.stack([synth.textured_frame(5000 + 1000 * rank + BATCH * r + i, W1, H1) for i in range(BATCH)])).to(dev)
-                   for r in range(R1)]
-          k1 = torch.zeros((BATCH, cap1, 7), dtype=torch.float32, device=dev)
-          de1 = torch.zeros((BATCH, cap1, 32), dtype=torch.uint8, device=dev)
-          n1 = torch.zeros(BATCH, dtype=torch.int32, device=dev)
-          m1 = torch.zeros(BATCH, dtype=torch.int32, device=dev)
+        try:
+            w5, h5, nf5 = 1280, 720, 1250
+            ex5 = orbx.ORBextractor(nf5, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank, max_width=w5, max_height=h5, max_batch=1)
+            f5 = [synth.shifted_frame(synth.textured_frame(7000 + rank, w5, h5), 2 * t, -t, seed=t) for t in range(4)]
+            sc5 = np.asarray(ex5.GetScaleFactors(), np.float32)
+            prev = None
 
-          def step1(i):
-              ex1.extract_batch_device(d_in1[i % R1].data_ptr(), H1 * W1, BATCH, W1, H1, W1, k1.data_ptr(), de1.data_ptr(), cap1,
-                                       n1.data_ptr(), m1.data_ptr())
+            def one(i):
+                nonlocal prev
+                mono, kps, desc = ex5(f5[i % 4])
+                if prev is not None:
+                    pk, pd = prev
+                    quvr = np.stack([pk["x"], pk["y"], 15.0 * sc5[pk["octave"]]], 1).astype(np.float32)
+                    qlev = np.stack([pk["octave"] - 1, pk["octave"] + 1], 1).astype(np.int32)
+                    ex5.match_windowed(pd, quvr, qlev, kps, desc, np.array([0, 0, w5, h5], np.float32))
+                prev = (kps, desc)
 
-          for i in range(2 * R1 + 1):
-              step1(i)
-          ex1.sync()
-          barrier()
-          ev0.record(stream)
-          for i in range(args.steps):
-              step1(i)
-          ev1.record(stream)
-          ex1.sync()
-          barrier()
-          dt1 = ev0.elapsed_time(ev1) * 1e-3
-          if world > 1:
-              tt = torch.tensor([dt1], dtype=torch.float64, device=dev)
-              dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-              dt1 = float(tt.item())
-          fps1 = world * args.steps * BATCH / dt1
-          bytes1 = orbx.plan_probe(NF1, SCALE, NLEVELS, INI_TH, MIN_TH, W1, H1)["algorithmic_bytes"]
-          peaks1, _ = measured_peaks()
-          euroc = {"workload": f"ORB extraction, {BATCH} x {W1}x{H1} gray frames per GPU per step, nFeatures {NF1} (BASELINE configs[1])",
-                   "value": fps1, "unit": "frames/s", "ms_per_step": 1e3 * dt1 / args.steps, "keypoints_per_frame": float(n1.float().mean().item()),
-                   "whole_step_hbm_frac": bytes1 * fps1 / world / 1e9 / float(peaks1["hbm_gbs"])}
-          ex1.close()
-          del d_in1
-      except Exception as err:          # an auxiliary figure must not cost the headline line
-        euroc = {"error": repr(err)}
+            for i in range(8):
+                one(i)
+            barrier()
+            t0 = time.perf_counter()
+            n5 = 60
+            for i in range(n5):
+                one(i)
+            barrier()
+            d5 = time.perf_counter() - t0
+            if world > 1:
+                tt = torch.tensor([d5], dtype=torch.float64, device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                d5 = float(tt.item())
+            stream5 = {"value": world * n5 / d5, "unit": "frames/s", "streams": world, "ms_per_frame": 1e3 * d5 / n5,
+                       "workload": f"{world} camera stream(s), one per GPU: per frame orbx_extract (1280x720, nFeatures 1250, pageable frame in) + "
+                                   "orbx_match_windowed against the previous frame (host buffers), one blocking call each, Python caller"}
+            ex5.close()
+        except Exception as err:
+            stream5 = {"error": repr(err)}
 
-    # ---- Hamming kNN leg (k=2): 2000 queries vs a 1M-row shard per GPU, device resident
+    # ---- Hamming kNN legs (k=2)
+    #   cfg4      BASELINE config 4 as written: 2000 queries x 10 M database rows, row-sharded over the N ranks (strong scaling: the
+    #             total work is fixed), top-2 merged over NCCL -- orbx_knn2_query_sharded_device = local query + ncclAllGather +
+    #             merge, all inside the CUDA-event region; the merged result is checked against the known answers on every rank.
+    #   per_shard 2000 queries x a 1 M-row shard per GPU, both distance backends (the per-GPU figure of round 1; weak scaling)
     hamming = None
     if not args.no_knn:
-        from send_slam_b200 import synth
+        peaks_k, _src_k = measured_peaks()
+        # tensor route: descriptors expanded to {-1,+1} int8, q.d = 256 - 2H by tcgen05.mma kind::i8 = 2 x 256 int8 ops per
+        # pair; kind::i8 issues at twice the dense bf16 rate, so the peak is 2 x the measured cuBLAS bf16 figure
+        tensor_peak_ops = 2.0 * float(peaks_k["bf16_tflops"]) * 1e12
+        tensor_pairs_peak = tensor_peak_ops / 512.0
+        # CUDA-core route: 8 POPC32 per pair on the POPC pipe.  16 / clk / SM is the CUDA guide's figure; this part's own
+        # rate is the microbenchmark's (tools/ubench_pipes.cu, profiles/ubench_pipes_r0x.jsonl)
+        popc_pairs_peak = 148 * 16.0 * 1.965e9 / 8.0
+        popc_rate, popc_src = ubench_rate("POPC")
+        ksteps = 10
+
+        def time_queries(fn, n):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            barrier()
+            ev0.record(stream)
+            for _ in range(n):
+                fn()
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            barrier()
+            t = ev0.elapsed_time(ev1) * 1e-3
+            if world > 1:
+                tt = torch.tensor([t], dtype=torch.float64, device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                t = float(tt.item())
+            return t
+
+        # -- cfg4
+        cfg4 = None
+        try:
+            from send_slam_b200 import sharded
+            ROWS4, BLK = 10_000_000, 1_250_000                  # the database is 8 blocks of 1.25 M rows with fixed seeds: identical at every N
+            r0, r1 = sharded.row_shard(ROWS4, world, rank)
+            rng_q = np.random.default_rng(99)
+            src4 = np.sort(rng_q.integers(0, ROWS4, size=KNN_Q))
+            q4 = np.zeros((KNN_Q, 32), np.uint8)
+            parts = []
+            for bk in range(ROWS4 // BLK):
+                blk = np.random.default_rng(1234 + bk).integers(0, 256, size=(BLK, 32), dtype=np.uint8)
+                lo, hi = bk * BLK, (bk + 1) * BLK
+                sel = (src4 >= lo) & (src4 < hi)
+                q4[sel] = blk[src4[sel] - lo]
+                a_, b_ = max(r0, lo), min(r1, hi)
+                if b_ > a_:
+                    parts.append(blk[a_ - lo:b_ - lo])
+                del blk
+            flips4 = rng_q.integers(0, 41, size=KNN_Q)
+            for i in range(KNN_Q):                               # 0..40 flipped bits per query: nearest row and distance are known
+                if flips4[i]:
+                    bits = rng_q.choice(256, size=int(flips4[i]), replace=False)
+                    np.bitwise_xor.at(q4[i], bits >> 3, (1 << (bits & 7)).astype(np.uint8))
+            d_db4 = torch.from_numpy(np.concatenate(parts) if len(parts) > 1 else parts[0]).to(dev)
+            del parts
+            d_q4 = torch.from_numpy(q4).to(dev)
+            d_out4 = torch.zeros((KNN_Q, 2), dtype=torch.int64, device=dev)
+            idx4 = orbx.Knn2Index(device=local_rank, device_ptr=d_db4.data_ptr(), nrows=r1 - r0, row_offset=r0)
+            idx4.set_stream(stream.cuda_stream)
+            comm, route = None, None
+            try:
+                uid = torch.zeros(orbx.NCCL_ID_BYTES, dtype=torch.uint8, device=dev)
+                if rank == 0:
+                    uid.copy_(torch.frombuffer(bytearray(orbx.comm_unique_id()), dtype=torch.uint8))
+                if world > 1:
+                    dist.broadcast(uid, 0)
+                comm = orbx.Comm(local_rank, rank, world, bytes(uid.cpu().numpy().tobytes()))
+                route = "orbx_knn2_query_sharded_device (C ABI: local top-2 + ncclAllGather + merge on the shard's stream)"
+            except Exception as err:                            # NCCL not loadable through the C ABI: the torch collective does the exchange
+                route = f"send_slam_b200.sharded.knn2_sharded (torch all_gather_into_tensor + orbx_knn2_merge_device); C ABI route failed: {err!r}"
+
+            def q_sharded():
+                if comm is not None:
+                    idx4.query_sharded_device(comm, d_q4.data_ptr(), KNN_Q, d_out4.data_ptr())
+                else:
+                    with torch.cuda.stream(stream):
+                        d_out4.copy_(sharded.knn2_sharded(idx4, d_q4, stream=stream.cuda_stream))
+
+            t4 = time_queries(q_sharded, ksteps)
+            got_idx, got_dist = orbx.unpack_knn(d_out4.cpu().numpy().view(np.uint64))
+            ok4 = bool(np.array_equal(got_idx[:, 0], src4) and np.array_equal(got_dist[:, 0], flips4))
+            chk = d_out4.sum().reshape(1).clone()
+            same = True
+            if world > 1:
+                lo_, hi_ = chk.clone(), chk.clone()
+                dist.all_reduce(lo_, op=dist.ReduceOp.MIN); dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+                same = bool((lo_ == hi_).item())
+            # where the time goes: the local query alone, the exchange alone (NCCL all-gather of nq x 2 x 8 B per rank), the merge alone
+            d_loc = torch.zeros((KNN_Q, 2), dtype=torch.int64, device=dev)
+            t_local = time_queries(lambda: idx4.query_device(d_q4.data_ptr(), KNN_Q, d_loc.data_ptr()), ksteps)
+            d_gath = torch.zeros((world, KNN_Q, 2), dtype=torch.int64, device=dev)
+            t_gather = 0.0
+            if world > 1:
+                def gather_only():
+                    with torch.cuda.stream(stream):
+                        dist.all_gather_into_tensor(d_gath.view(-1), d_loc.view(-1))
+                t_gather = time_queries(gather_only, ksteps)
+            else:
+                d_gath[0].copy_(d_loc)
+            t_merge = time_queries(lambda: idx4.merge_device(d_gath.data_ptr(), world, KNN_Q, d_out4.data_ptr()), ksteps)
+            cfg4 = {"workload": f"{KNN_Q} queries x {ROWS4} database rows row-sharded over {world} GPU(s) ({r1 - r0} rows on rank 0), k = 2, NCCL top-2 merge",
+                    "pairs_per_s": ksteps * KNN_Q * ROWS4 / t4, "ms_per_query_batch": 1e3 * t4 / ksteps, "scaling": "strong",
+                    "local_query_us": 1e6 * t_local / ksteps, "allgather_us": 1e6 * t_gather / ksteps, "merge_us": 1e6 * t_merge / ksteps,
+                    "known_answers_ok": ok4, "identical_on_all_ranks": same, "ranks": world, "route": route,
+                    "roofline_frac_per_gpu": ksteps * KNN_Q * ROWS4 / t4 / world / tensor_pairs_peak}
+            if not (ok4 and same):
+                cfg4["error"] = "merged result differs from the known answers / between ranks"
+            if comm is not None:
+                comm.close()
+            idx4.close()
+            del d_db4
+            torch.cuda.empty_cache()
+        except Exception as err:
+            cfg4 = {"error": repr(err)}
+
+        # -- per-shard figure, both backends
         db = synth.descriptor_db(KNN_ROWS, seed=1234 + rank)
         q, _src = synth.queries_from_db(db, KNN_Q, seed=99)
         d_db = torch.from_numpy(db).to(dev)
@@ -556,44 +898,37 @@ def main():
         d_out = torch.zeros((KNN_Q, 2), dtype=torch.int64, device=dev)
         index = orbx.Knn2Index(device=local_rank, device_ptr=d_db.data_ptr(), nrows=KNN_ROWS, row_offset=rank * KNN_ROWS)
         index.set_stream(stream.cuda_stream)
+
         def time_backend(backend):
             index.set_backend(backend)
-            for _ in range(3):
-                index.query_device(d_q.data_ptr(), KNN_Q, d_out.data_ptr())
-            index.sync()
-            barrier()
             l0 = index.launch_count()
-            ev0.record(stream)
-            for _ in range(ksteps):
-                index.query_device(d_q.data_ptr(), KNN_Q, d_out.data_ptr())
-            ev1.record(stream)
-            index.sync()
-            barrier()
-            t = ev0.elapsed_time(ev1) * 1e-3
-            if world > 1:
-                tt = torch.tensor([t], dtype=torch.float64, device=dev)
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-                t = float(tt.item())
-            return world * ksteps * KNN_Q * KNN_ROWS / t, index.launch_count() - l0
+            t = time_queries(lambda: index.query_device(d_q.data_ptr(), KNN_Q, d_out.data_ptr()), ksteps)
+            return world * ksteps * KNN_Q * KNN_ROWS / t, (index.launch_count() - l0) * ksteps // (ksteps + 3)
 
-        ksteps = 10
         pairs_popc, _ = time_backend(orbx.Knn2Index.POPC)
         pairs, klaunches = time_backend(orbx.Knn2Index.TENSOR)
-        peaks_k, _src_k = measured_peaks()
-        # tensor route: descriptors expanded to {-1,+1} int8, q.d = 256 - 2H by tcgen05.mma kind::i8 = 2 x 256 int8 ops per
-        # pair; kind::i8 issues at twice the dense bf16 rate, so the peak is 2 x the measured cuBLAS bf16 figure
-        tensor_peak_ops = 2.0 * float(peaks_k["bf16_tflops"]) * 1e12
-        tensor_pairs_peak = tensor_peak_ops / 512.0
-        # CUDA-core route: 8 POPC32 per pair on the POPC pipe (16 / clk / SM)
-        popc_pairs_peak = 148 * 16.0 * 1.965e9 / 8.0
+        # the same shard through the host-buffer entry point (orbx_knn2_query: pageable queries in, indices + distances out)
+        index.knnMatch(q)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            index.knnMatch(q)
+        pairs_e2e = 5 * KNN_Q * KNN_ROWS / (time.perf_counter() - t0)
+        popc_note = {"value": pairs_popc, "unit": "pairs/s",
+                     "roofline": {"bound": "popc-pipe", "peak": popc_pairs_peak, "frac": pairs_popc / world / popc_pairs_peak,
+                                  "note": "148 SM x 16 POPC/clk/SM x 1.965 GHz / 8 POPC per pair (CUDA guide figure)"}}
+        if popc_rate:
+            pk = 148 * popc_rate * 1.965e9 / 8.0
+            popc_note["roofline_measured_pipe"] = {"peak": pk, "frac": pairs_popc / world / pk,
+                                                   "note": f"POPC rate of this part by microbenchmark: {popc_rate} thread-ops/clk/SM ({popc_src})"}
+        tc_facts = profile_facts("k_knn2_tc")
         hamming = {"metric": "Hamming pairs/s (k=2 brute force)", "value": pairs, "unit": "pairs/s",
                    "config": {"queries": KNN_Q, "db_rows_per_gpu": KNN_ROWS, "k": 2, "backend": "tcgen05.mma kind::i8 on {-1,+1} expansion"},
                    "roofline": {"bound": "tensor", "achieved": pairs / world * 512.0 / 1e12, "peak": tensor_peak_ops / 1e12, "unit": "TOP/s (int8)",
                                 "frac": pairs / world / tensor_pairs_peak,
-                                "note": "512 int8 ops per pair; peak = 2 x measured dense bf16 TFLOP/s (MEASURED_PEAKS.json); nominal int8 dense 4500 TOP/s; "
-                                        "ncu sm__pipe_tensor_cycles_active of the main pass: 73 % (profiles/k_knn2_tc_r01_summary.txt)"},
-                   "popc_backend": {"value": pairs_popc, "unit": "pairs/s", "roofline": {"bound": "popc-pipe", "peak": popc_pairs_peak,
-                                    "frac": pairs_popc / world / popc_pairs_peak, "note": "148 SM x 16 POPC/clk/SM x 1.965 GHz / 8 POPC per pair"}},
+                                "note": "512 int8 ops per pair; peak = 2 x measured dense bf16 TFLOP/s (MEASURED_PEAKS.json); nominal int8 dense 4500 TOP/s",
+                                "ncu": tc_facts},
+                   "e2e": {"value": pairs_e2e, "unit": "pairs/s", "api": "orbx_knn2_query (host queries in, host indices + distances out), one rank"},
+                   "popc_backend": popc_note, "cfg4": cfg4,
                    "gpu_launches": klaunches}
         if rank == 0 and world == 1 and not args.no_cpu:
             # CPU baseline of the matcher: the oracle's brute-force k = 2 search (XOR + popcount on 64-bit words,
@@ -614,6 +949,14 @@ def main():
             except Exception as err:
                 hamming["cpu_baseline"]["opencv_bfmatcher"] = {"error": repr(err)}
         index.close()
+
+    # ---- one frame per call: the latency of the seam the reference issues (rank 0)
+    latency = None
+    if rank == 0 and not args.no_latency:
+        try:
+            latency = latency_leg(orbx, synth, local_rank, world == 1 and not args.no_cpu)
+        except Exception as err:
+            latency = {"error": repr(err)}
 
     # ---- cpu baseline (rank 0, N=1 only)
     cpu = None
@@ -648,31 +991,25 @@ def main():
         hbm = float(peaks["hbm_gbs"])
         ach = stage_bytes[dom] * BATCH / (acc[dom] * 1e-3) / 1e9
         total_bytes = plan["algorithmic_bytes"]
-        kname = {"pyramid": "k_resize", "blur": "k_blur", "fast": "k_fast_tma", "describe": "k_describe"}[dom]
-        traffic = None      # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel (profiles/)
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))
-            if kname in tj and dom != "pyramid":      # the pyramid is 7 launches; its capture is one level only
-                traffic = tj[kname]["dram_bytes_per_launch"]
-        except Exception:
-            pass
+        kname = {"pyramid": "k_resize", "blur": "k_blur_tma", "fast": "k_fast_tma", "describe": "k_describe_tma"}[dom]
+        # ncu facts of the dominant kernel come from the round's committed capture (profiles/ncu_facts_r02.json, written by
+        # tools/make_profile_summaries.py from the .ncu-rep files); nothing is hard-coded: null where the capture lacks the kernel
+        facts = profile_facts(kname) if dom != "pyramid" else None      # the pyramid is 7 launches; a capture holds one level
+        traffic = facts.get("dram_bytes_per_launch") if facts else None
         roofline = {"bound": "hbm", "kernel": kname + (" (7 launches)" if dom == "pyramid" else ""),
                     "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": traffic,
-                    "note": "the contract's bound for byte work is HBM; ncu shows this kernel bound by the integer ALU pipe "
-                            "(sm__pipe_alu_cycles_active, profiles/k_fast_tma_r01_summary.txt): FAST scoring costs ~40 min/max ops "
-                            "per pixel and 59 % of the synthetic frames' pixels are corners" if dom == "fast" else None,
+                    "note": ("the contract's bound for byte work is HBM; what binds this kernel is instruction issue: ncu sm__inst_executed per cycle and the "
+                             "pipe microbenchmarks (profiles/ubench_mix_r02.jsonl: one pipe alone retires ~83, any two-pipe mix <= ~98 thread-instructions / clk / SM) "
+                             "-- FAST scoring is ~87 instructions per pixel on frames where 59 % of the pixels are corners" if dom == "fast" else None),
                     "peak_source": peak_src,
-                    # what actually binds the dominant kernel (FAST): the integer ALU pipe.  Algorithmic work = 57 u16x2 min/max per
-                    # pixel pair and pass on the ALU pipe (the 16 pair maxima per pass run as IMAD on the FMA pipe), 4 passes per 8
-                    # pixels; peak = VIMNMX.U16x2 rate measured by tools/ubench_pipes.cu (profiles/ubench_pipes_r01.jsonl)
-                    "alu_pipe": ({"achieved_Gops": S * BATCH * 28.5 / (acc["fast"] * 1e-3) / 1e9, "peak_Gops": 82.7 * 148 * 1.965,
-                                  "frac": S * BATCH * 28.5 / (acc["fast"] * 1e-3) / 1e9 / (82.7 * 148 * 1.965),
-                                  "ncu_pipe_alu_busy": 0.686, "source": "profiles/k_fast_tma_r01_summary.txt"} if dom == "fast" else None),
+                    "ncu": facts,
                     "algorithmic_bytes_per_launch": stage_bytes[dom] * BATCH,
                     "launch_ms": acc[dom],
                     "whole_step": {"algorithmic_bytes_per_frame": total_bytes,
                                    "achieved": total_bytes * fps / world / 1e9, "frac": total_bytes * fps / world / 1e9 / hbm},
                     "stage_ms": acc}
+        if isinstance(sustained, dict) and "value" in sustained:
+            sustained["whole_step_hbm_frac"] = total_bytes * sustained["value"] / world / 1e9 / hbm
         line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8", "data": "synthetic",
@@ -683,8 +1020,9 @@ def main():
                 "clocks": clocks, "gpu_launches": launches,
                 "single_lane": {"value": fps_single, "unit": "frames/s", "ms_per_step": 1e3 * dt_single / args.steps,
                                 "note": "one handle, one batch in flight (every step waits for the previous one on the same stream)"},
+                "sustained": sustained,
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "steps": e2e_steps,
+                        "steps": e2e_steps, "h2d_ceiling": h2d_ceiling,
                         "api": (f"orbx_extract_batch_submit / _collect from one host thread over {NL} handles (batch i uploads while earlier batches compute and download), "
                                 "pinned host frames in / pinned keypoint + descriptor arrays out"
                                 if isinstance(e2e_async, float) else
@@ -692,7 +1030,10 @@ def main():
                         "blocking_call": {"value": e2e_blocking_fps, "unit": "frames/s", "api": "orbx_extract_batch (one blocking call per batch)"},
                         "async_pair": e2e_async,
                         "two_concurrent_callers": e2e_two},
-                "roofline": roofline, "cpu_baseline": cpu, "config1_752x480_nf1200": euroc, "hamming": hamming, "keypoints_first_batch": n_first}
+                "roofline": roofline, "cpu_baseline": cpu, "latency": latency,
+                "config1_752x480_nf1200": euroc, "config3_1920x1080_nf2000": legs.get("config3_1920x1080_nf2000"),
+                "config5_1280x720_nf1250": dict(legs.get("config5_1280x720_nf1250") or {}, per_frame_stream=stream5),
+                "hamming": hamming, "keypoints_first_batch": n_first}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -501,7 +501,7 @@ extern "C" {
 int orbx_comm_unique_id(uint8_t *id_out) {
     if (!id_out) { g_comm_error = "null argument"; return ORBX_E_INVALID; }
     NcclApi *a = nccl_api();
-    if (!a) { static NcclApi *dummy = nullptr; (void)dummy; g_comm_error = "NCCL unavailable"; return ORBX_E_CUDA; }
+    if (!a) { g_comm_error = "NCCL unavailable: cannot load libnccl.so.2 (set ORBX_NCCL_LIB to its path)"; return ORBX_E_CUDA; }
     NcclId id;
     const int rc = a->GetUniqueId(&id);
     if (rc) { g_comm_error = nccl_err(a, "ncclGetUniqueId", rc); return ORBX_E_CUDA; }

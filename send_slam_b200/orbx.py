@@ -52,7 +52,8 @@ EXPORTS = [
     "orbx_extract", "orbx_extract_batch", "orbx_extract_batch_submit", "orbx_extract_batch_collect",
     "orbx_extract_batch_device", "orbx_sync", "orbx_launch_count", "orbx_pnm_header", "orbx_extract_pnm",
     "orbx_wire_parse_frame", "orbx_wire_process_frame", "orbx_wire_features_bound", "orbx_wire_pack_features", "orbx_wire_parse_features",
-    "orbx_wire_copy_keypoints",
+    "orbx_wire_copy_keypoints", "orbx_comm_unique_id", "orbx_comm_create", "orbx_comm_adopt", "orbx_comm_destroy", "orbx_comm_last_error",
+    "orbx_knn2_query_sharded_device", "orbx_knn2_query_sharded",
     "orbx_debug_get_level", "orbx_debug_get_candidates", "orbx_debug_get_level_keypoints", "orbx_debug_resize",
     "orbx_debug_blur", "orbx_debug_octree", "orbx_debug_describe", "orbx_distance_batch", "orbx_match_windowed",
     "orbx_knn2_create_db", "orbx_knn2_create_db_device", "orbx_knn2_destroy_db", "orbx_knn2_last_error", "orbx_knn2_query",
@@ -196,6 +197,16 @@ def lib():
     L.orbx_plan_probe.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, ip, ip, ip, ip, ip, ip,
                                   C.POINTER(C.c_longlong)]
     L.orbx_version.restype = C.c_char_p
+    L.orbx_comm_unique_id.argtypes = [vp]
+    L.orbx_comm_create.argtypes = [C.c_int, C.c_int, C.c_int, vp, C.POINTER(vp)]
+    L.orbx_comm_adopt.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp)]
+    L.orbx_comm_destroy.argtypes = [vp]
+    L.orbx_comm_destroy.restype = None
+    L.orbx_comm_last_error.argtypes = [vp]
+    L.orbx_comm_last_error.restype = C.c_char_p
+    L.orbx_knn2_query_sharded_device.argtypes = [vp, vp, vp, C.c_int, vp]
+    L.orbx_knn2_query_sharded.argtypes = [vp, vp, vp, C.c_int, vp, vp]
+    L.orbx_wire_copy_keypoints.argtypes = [C.POINTER(_WireFeatures), vp, C.c_int]
     L.orbx_set_stream.argtypes = [vp, vp]
     L.orbx_knn2_set_stream.argtypes = [vp, vp]
     L.orbx_knn2_set_backend.argtypes = [vp, C.c_int]
@@ -631,6 +642,16 @@ class Knn2Index:
     def set_stream(self, cuda_stream: int):
         self._check(self._L.orbx_knn2_set_stream(self._db, C.c_void_p(cuda_stream)))
 
+    def query_sharded_device(self, comm: "Comm", d_queries_ptr, nq, d_packed_out_ptr):
+        """Top-2 over the WHOLE row-sharded database on every rank: local query + ncclAllGather + merge on this shard's stream (collective)."""
+        self._check(self._L.orbx_knn2_query_sharded_device(self._db, comm._c, C.c_void_p(d_queries_ptr), nq, C.c_void_p(d_packed_out_ptr)))
+
+    def knnMatch_sharded(self, comm: "Comm", queries):
+        q = np.ascontiguousarray(queries, np.uint8).reshape(-1, 32)
+        idx, dist = np.zeros((len(q), 2), np.int32), np.zeros((len(q), 2), np.int32)
+        self._check(self._L.orbx_knn2_query_sharded(self._db, comm._c, _p(q), len(q), _p(idx), _p(dist)))
+        return idx, dist
+
     POPC, TENSOR = 0, 1
 
     def set_backend(self, backend: int):
@@ -639,6 +660,42 @@ class Knn2Index:
 
     def launch_count(self):
         return int(self._L.orbx_knn2_launch_count(self._db))
+
+
+NCCL_ID_BYTES = 128
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (call on ONE rank, ship the bytes to the others)."""
+    buf = (C.c_uint8 * NCCL_ID_BYTES)()
+    rc = lib().orbx_comm_unique_id(buf)
+    if rc != ORBX_OK:
+        raise OrbxError(rc, (lib().orbx_comm_last_error(None) or b"").decode())
+    return bytes(buf)
+
+
+class Comm:
+    """One NCCL communicator of this process (one rank = one GPU) for the row-sharded kNN: orbx_comm of include/orbx.h."""
+
+    def __init__(self, device: int, rank: int, nranks: int, unique_id: bytes):
+        self._L = lib()
+        self._c = C.c_void_p()
+        idb = (C.c_uint8 * NCCL_ID_BYTES).from_buffer_copy(unique_id)
+        rc = self._L.orbx_comm_create(device, rank, nranks, idb, C.byref(self._c))
+        if rc != ORBX_OK:
+            raise OrbxError(rc, (self._L.orbx_comm_last_error(None) or b"").decode())
+        self.rank, self.nranks = rank, nranks
+
+    def close(self):
+        if getattr(self, "_c", None) and self._c.value:
+            self._L.orbx_comm_destroy(self._c)
+            self._c = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def unpack_knn(packed: np.ndarray):

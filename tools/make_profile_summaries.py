@@ -2,7 +2,9 @@
 """Turn the captures of tools/capture_profiles.sh (gpurun_out/) into the tracked summaries under profiles/:
   profiles/launches_<tag>_summary.md   per-kernel launch counts, total/avg duration and share of the step (ncu launch list)
   profiles/<kernel>_<tag>_summary.txt  headline metrics + SASS hot segments of the `ncu --set full` capture
-  profiles/traffic_<tag>.json          dram bytes per launch of each captured kernel (bench.py reads it for roofline.traffic)
+  profiles/traffic_<tag>.json          dram bytes per launch of each captured kernel
+  profiles/ncu_facts_<tag>.json        per kernel: dram bytes per launch, duration, pipe / issue busy fractions, instructions (bench.py reads
+                                       roofline.traffic and roofline.ncu from it; nothing of this is hard-coded in bench.py)
 Usage: python tools/make_profile_summaries.py r01"""
 import collections, csv, io, json, os, re, subprocess, sys
 
@@ -36,7 +38,12 @@ with open(os.path.join(P, f"launches_{tag}_summary.md"), "w") as f:
     f.write("\nNon-orbx kernels in the capture (torch fills / copies of the harness): " + ", ".join(f"{k} x{v[0]}" for k, v in list(others.items())[:8]) + "\n")
 
 # ---- per-kernel captures
-traffic = {}
+traffic, facts = {}, {}
+FACT_KEYS = {"sm__issue_active.avg.pct_of_peak_sustained_elapsed": "issue_active_pct", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_elapsed": "pipe_alu_pct",
+             "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_elapsed": "pipe_fma_pct", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed": "pipe_tensor_pct",
+             "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed": "smem_wavefronts_pct", "smsp__inst_executed.sum": "warp_instructions",
+             "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_pct", "launch__registers_per_thread": "registers", "launch__grid_size": "grid",
+             "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed": "dram_throughput_pct", "lts__t_sector_hit_rate.pct": "l2_hit_pct"}
 for fn in sorted(os.listdir(G)):
     m = re.match(rf"prof_(k_\w+)_{tag}\.ncu-rep$", fn)
     if not m:
@@ -51,7 +58,13 @@ for fn in sorted(os.listdir(G)):
     if rd and wr:
         traffic[k] = {"dram_bytes_per_launch": float(rd.group(1)) * mult[rd.group(2)] + float(wr.group(1)) * mult[wr.group(2)],
                       "duration_under_ncu": f"{dur.group(1)} {dur.group(2)}" if dur else None}
+        facts[k] = dict(traffic[k], capture=f"profiles/{k}_{tag}_summary.txt")
+        for mk, short in FACT_KEYS.items():
+            mm = re.search(re.escape(mk) + r": ([\d.]+)", out)
+            if mm:
+                facts[k][short] = float(mm.group(1))
 if traffic:      # launch-list-only refreshes (no .ncu-rep in gpurun_out/) keep the committed traffic file
     json.dump(traffic, open(os.path.join(P, f"traffic_{tag}.json"), "w"), indent=1)
+    json.dump(facts, open(os.path.join(P, f"ncu_facts_{tag}.json"), "w"), indent=1)
 print(open(os.path.join(P, f"launches_{tag}_summary.md")).read())
 print(json.dumps(traffic, indent=1))
