@@ -239,12 +239,21 @@ def device_leg(torch, dist, orbx, synth, dev, local_rank, rank, world, stream, b
     ex1 = orbx.ORBextractor(NF1, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank, max_width=W1, max_height=H1, max_batch=B1)
     cap1 = ex1.capacity
     ex1.set_stream(stream.cuda_stream)
-    nd = min(B1, 8)                                      # distinct synthetic frames per batch; batches differ by a roll
-    base = np.stack([synth.textured_frame(seed0 + 1000 * rank + i, W1, H1) for i in range(nd)])
     d_in1 = []
-    for r in range(R1):
-        b = np.stack([np.roll(base[i % nd], 7 * r + 3 * (i // nd), axis=1) for i in range(B1)])
-        d_in1.append(torch.from_numpy(b).to(dev))
+    if match:
+        # a camera sequence: frame i+1 = frame i moved by (3, -2) px plus sensor noise, so that the previous-frame search finds what
+        # a tracker would find; the ring entries are different sequences
+        for r in range(R1):
+            seq = [synth.textured_frame(seed0 + 1000 * rank + r, W1, H1)]
+            for i in range(1, B1):
+                seq.append(synth.shifted_frame(seq[-1], 3, -2, seed=seed0 + i))
+            d_in1.append(torch.from_numpy(np.stack(seq)).to(dev))
+    else:
+        nd = min(B1, 8)                                  # distinct synthetic frames per batch; batches differ by a roll
+        base = np.stack([synth.textured_frame(seed0 + 1000 * rank + i, W1, H1) for i in range(nd)])
+        for r in range(R1):
+            b = np.stack([np.roll(base[i % nd], 7 * r + 3 * (i // nd), axis=1) for i in range(B1)])
+            d_in1.append(torch.from_numpy(b).to(dev))
     k1 = torch.zeros((B1, cap1, 7), dtype=torch.float32, device=dev)
     de1 = torch.zeros((B1, cap1, 32), dtype=torch.uint8, device=dev)
     n1 = torch.zeros(B1, dtype=torch.int32, device=dev)
@@ -274,13 +283,13 @@ def device_leg(torch, dist, orbx, synth, dev, local_rank, rank, world, stream, b
 
     if match:
         # queries of every ring entry, prepared once outside the clock (in the reference this is CPU geometry: projection by the
-        # motion model): window centre = the keypoint's own undistorted position, radius 15 x scale[octave], octaves o-1 .. o+1
+        # motion model): window centre = the keypoint's undistorted position moved by the sequence's motion, radius 15 x scale[octave], octaves o-1 .. o+1
         scale = torch.tensor(ex1.GetScaleFactors(), dtype=torch.float32, device=dev)
         for r in range(R1):
             step1(r)
             ex1.sync()
             octv = un1[:, :, 5].contiguous().view(torch.int32).clamp(0, NLEVELS - 1).long()
-            quvr = torch.stack([un1[:, :, 0], un1[:, :, 1], 15.0 * scale[octv]], dim=2).contiguous()
+            quvr = torch.stack([un1[:, :, 0] + 3.0, un1[:, :, 1] - 2.0, 15.0 * scale[octv]], dim=2).contiguous()
             qlev = torch.stack([octv - 1, octv + 1], dim=2).to(torch.int32).contiguous()
             mstate["q"][r] = (quvr, qlev, [int(v) for v in n1.cpu().tolist()])
     for i in range(2 * R1 + 1):

@@ -150,7 +150,7 @@ bool build_plan(const ExtractorParams &p, int width, int height, Plan &plan, std
         L.n_ini = 0; L.depth0 = 0; L.nbins = 0;
         if (L.reg_w > 0 && L.reg_h > 0) {
             L.n_ini = (int)std::round((float)L.reg_w / (float)L.reg_h);
-            if (L.n_ini < 1 || L.n_ini > kMaxRoots) { err = "unsupported aspect ratio (quadtree roots outside 1..8)"; return false; }
+            if (L.n_ini < 1 || L.n_ini > kMaxRoots) { err = "unsupported aspect ratio (quadtree roots outside 1..16: a level wider than 16.5 x its height, or flatter than 0.5)"; return false; }
             const float hX = (float)L.reg_w / (float)L.n_ini;
             for (int i = 0; i < L.n_ini; i++) {
                 L.root_ulx[i] = (int)(hX * (float)i);

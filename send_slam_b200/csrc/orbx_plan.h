@@ -17,7 +17,7 @@ constexpr int kMinBorder = 16;   // EDGE_THRESHOLD - 3
 constexpr int kMaxLevels = 16;
 constexpr int kPitchAlign = 32;
 constexpr int kMaxBins = 4096;   // quadtree histogram bins per (frame, level) problem
-constexpr int kMaxRoots = 8;
+constexpr int kMaxRoots = 16;   // quadtree roots of a level = round(width / height) of its tested region: aspect ratios up to 16.5 : 1
 
 struct ExtractorParams {
     int nfeatures = 1000;

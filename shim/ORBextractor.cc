@@ -2,7 +2,9 @@
 // (slam_backends/orb_slam_3/CMakeLists.txt:52); see INTEGRATION.md for the two-line CMake change.
 #include "ORBextractor.h"
 
+#include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../include/orbx.h"
@@ -11,12 +13,21 @@ namespace ORB_SLAM3 {
 
 static_assert(sizeof(cv::KeyPoint) == sizeof(orbx_keypoint), "cv::KeyPoint must be 7 x 4 bytes");
 
+static std::atomic<int> g_device{-1};   // -1: not chosen by the program -> ORBX_DEVICE, else 0
+void ORBextractor::SetDevice(int cuda_device) { g_device.store(cuda_device); }
+int ORBextractor::GetDevice() {
+    const int d = g_device.load();
+    if (d >= 0) return d;
+    const char *e = std::getenv("ORBX_DEVICE");
+    return e && *e ? std::atoi(e) : 0;
+}
+
 ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int _iniThFAST, int _minThFAST)
     : nfeatures(_nfeatures), scaleFactor(_scaleFactor), nlevels(_nlevels), iniThFAST(_iniThFAST), minThFAST(_minThFAST) {
     orbx_config cfg;
     cfg.nfeatures = _nfeatures; cfg.scale_factor = _scaleFactor; cfg.nlevels = _nlevels;
     cfg.ini_th_fast = _iniThFAST; cfg.min_th_fast = _minThFAST;
-    cfg.device = 0; cfg.max_width = 4095; cfg.max_height = 4095; cfg.max_batch = 1;   // workspace is sized on first use
+    cfg.device = GetDevice(); cfg.max_width = 4095; cfg.max_height = 4095; cfg.max_batch = 1;   // workspace is sized on first use
     if (orbx_create(&cfg, &mHandle) != ORBX_OK) {
         // the reference never throws here; keep the process alive and fail every call loudly instead
         std::fprintf(stderr, "ORBextractor(orbx): %s\n", orbx_last_error(nullptr));

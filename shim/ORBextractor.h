@@ -35,6 +35,12 @@ public:
     // not in upstream: colour frames converted on the device (cv::cvtColor *2GRAY of Tracking::GrabImageMonocular)
     bool SetInputFormat(int orbx_fmt, int gray_shift = 15 /* ORBX_GRAY_Q15 */);
 
+    // not in upstream: the CUDA device the extractors constructed AFTER this call live on (System constructs them inside Tracking, so
+    // a backend that wants GPU 3 calls ORB_SLAM3::ORBextractor::SetDevice(3) before `new ORB_SLAM3::System(...)`,
+    // orbslam3_mono_networked.cc:511).  Without a call the environment variable ORBX_DEVICE decides, else device 0.
+    static void SetDevice(int cuda_device);
+    static int GetDevice();
+
     int inline GetLevels() { return nlevels; }
     float inline GetScaleFactor() { return (float)scaleFactor; }
     std::vector<float> inline GetScaleFactors() { return mvScaleFactor; }
@@ -42,8 +48,9 @@ public:
     std::vector<float> inline GetScaleSigmaSquares() { return mvLevelSigma2; }
     std::vector<float> inline GetInverseScaleSigmaSquares() { return mvInvLevelSigma2; }
 
-    // Only stereo matching reads the pyramid; the mono path of SEND-SLAM (System::MONOCULAR,
-    // orbslam3_mono_networked.cc:511) never does, so it stays empty.
+    // INTENTIONALLY EMPTY Mats (nlevels of them): upstream fills this with the bordered pyramid planes, and only the stereo matcher
+    // (Frame::ComputeStereoMatches) reads it.  The mono path of SEND-SLAM (System::MONOCULAR, orbslam3_mono_networked.cc:511) never
+    // does, and the planes live in HBM here; a stereo port would download them with orbx_debug_get_level.
     std::vector<cv::Mat> mvImagePyramid;
 
 protected:
