@@ -544,13 +544,16 @@ __device__ __forceinline__ uint32_t umin3(uint32_t a, uint32_t b, uint32_t c) { 
 // a + b - min(a, b) on the FMA pipe: two IMADs with multiplier 1 (an asm block keeps ptxas from folding them back into one
 // ALU-pipe IADD3)
 __constant__ uint32_t c_one = 1u;   // a multiplier ptxas cannot fold: keeps the two adds of pair_max as IMADs (FMA pipe)
+template <int PM>
 __device__ __forceinline__ uint32_t pair_max(uint32_t a, uint32_t b, uint32_t mn) {
+    if (PM == 1 || PM == 4 || PM == 6) return umax2(a, b);   // one VIMNMX (ALU pipe): fewer instructions, more ALU-pipe work
     const uint32_t one = c_one;
-    return (a + b * one) - mn * one;
+    return (a + b * one) - mn * one;           // two IMAD (FMA pipe)
 }
 
 // r[0..15] ring lanes, v centre lanes (pixel value in the high byte of each u16 lane).  Returns the two scores as
 // clean u16 lanes.
+template <int PM>
 __device__ __forceinline__ uint32_t fast_score_lanes(const uint32_t (&r)[16], uint32_t v) {
     uint32_t qx[8], qn[8];
 #pragma unroll
@@ -558,7 +561,7 @@ __device__ __forceinline__ uint32_t fast_score_lanes(const uint32_t (&r)[16], ui
         // max = a + b - min holds for the whole word (exact integer identity per lane, carries cancel): the additions
         // can issue on the FMA pipe (IMAD.IADD) while the ALU pipe, which bounds this kernel, does the min/max
         qn[j] = umin2(r[2 * j + 1], r[(2 * j + 2) & 15]);
-        qx[j] = pair_max(r[2 * j + 1], r[(2 * j + 2) & 15], qn[j]);
+        qx[j] = pair_max<PM>(r[2 * j + 1], r[(2 * j + 2) & 15], qn[j]);
     }
     uint32_t q2x[8], q2n[8];
 #pragma unroll
@@ -572,7 +575,7 @@ __device__ __forceinline__ uint32_t fast_score_lanes(const uint32_t (&r)[16], ui
         const uint32_t a = r[2 * i], b = r[(2 * i + 9) & 15];
         const uint32_t mn = umin2(a, b);
         fx[i] = umax3(q2x[i], q2x[(i + 2) & 7], mn);   // max over arc, smaller of the two arcs sharing 8 pixels
-        fn[i] = umin3(q2n[i], q2n[(i + 2) & 7], pair_max(a, b, mn));
+        fn[i] = umin3(q2n[i], q2n[(i + 2) & 7], pair_max<(PM == 2 ? 1 : PM)>(a, b, mn));
     }
     uint32_t min_arc_max = umin3(umin3(fx[0], fx[1], fx[2]), umin3(fx[3], fx[4], fx[5]), umin2(fx[6], fx[7]));
     uint32_t max_arc_min = umax3(umax3(fn[0], fn[1], fn[2]), umax3(fn[3], fn[4], fn[5]), umax2(fn[6], fn[7]));
@@ -585,10 +588,19 @@ __device__ __forceinline__ uint32_t fast_score_lanes(const uint32_t (&r)[16], ui
 
 // w[7][4]: staged words of rows y-3..y+3, 16 bytes each; the four pixels of interest sit at bytes M+3 .. M+6 (M = 0..3 is
 // the misalignment of the ROI inside its 16-byte aligned TMA box; the fallback kernel stages aligned ROIs, M = 0).
-template <int M>
+// funnel shift right by 8 k bits as IMAD.HI + IMAD on the FMA pipe: (lo * 2^(32-8k)) >> 32 + hi * 2^(32-8k); the multipliers come from
+// the constant bank so that ptxas cannot turn the pair back into one ALU-pipe SHF
+__constant__ uint32_t c_fsh[4] = {0u, 1u << 24, 1u << 16, 1u << 8};
+template <int PM>
+__device__ __forceinline__ uint32_t slice_r(uint32_t lo, uint32_t hi, int k) {
+    if (PM >= 5) { const uint32_t c = c_fsh[k]; return __umulhi(lo, c) + hi * c; }
+    return __funnelshift_r(lo, hi, 8 * k);
+}
+
+template <int M, int PM>
 __device__ __forceinline__ uint32_t fast_score4(const uint32_t (&w)[7][4]) {
     // 4-byte slices at byte offset o of a row
-#define SL(row, o) ((((o) + M) & 3) == 0 ? w[row][((o) + M) >> 2] : __funnelshift_r(w[row][((o) + M) >> 2], w[row][(((o) + M) >> 2) + 1], 8 * (((o) + M) & 3)))
+#define SL(row, o) ((((o) + M) & 3) == 0 ? w[row][((o) + M) >> 2] : slice_r<PM>(w[row][((o) + M) >> 2], w[row][(((o) + M) >> 2) + 1], ((o) + M) & 3))
     uint32_t r[16];
     r[0] = SL(6, 3);  r[1] = SL(6, 4);  r[2] = SL(5, 5);  r[3] = SL(4, 6);
     r[4] = SL(3, 6);  r[5] = SL(2, 6);  r[6] = SL(1, 5);  r[7] = SL(0, 4);
@@ -596,16 +608,16 @@ __device__ __forceinline__ uint32_t fast_score4(const uint32_t (&w)[7][4]) {
     r[12] = SL(3, 0); r[13] = SL(4, 0); r[14] = SL(5, 1); r[15] = SL(6, 2);
     const uint32_t c = SL(3, 3);
 #undef SL
-    const uint32_t odd = fast_score_lanes(r, c);          // pixels 1, 3
+    const uint32_t odd = fast_score_lanes<PM>(r, c);      // pixels 1, 3
     uint32_t re[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) re[k] = r[k] << 8;
-    const uint32_t even = fast_score_lanes(re, c << 8);   // pixels 0, 2
+    const uint32_t even = fast_score_lanes<PM>(re, c << 8);   // pixels 0, 2
     return even | (odd << 8);
 }
 
 // scores of a 4-pixel x 2-row item: p = first staged word of row 2s of the item, pitch in bytes
-template <int M>
+template <int M, int PM>
 __device__ __forceinline__ void fast_item(const uint8_t *p, int pitch, uint32_t &sa, uint32_t &sb) {
     uint32_t w[8][4];
 #pragma unroll
@@ -619,7 +631,7 @@ __device__ __forceinline__ void fast_item(const uint8_t *p, int pitch, uint32_t 
     for (int r = 0; r < 7; r++)
 #pragma unroll
         for (int k = 0; k < 4; k++) { wa[r][k] = w[r][k]; wb[r][k] = w[r + 1][k]; }
-    sa = fast_score4<M>(wa); sb = fast_score4<M>(wb);
+    sa = fast_score4<M, PM>(wa); sb = fast_score4<M, PM>(wb);
 }
 
 __global__ void __launch_bounds__(192) k_fast_cells(const __grid_constant__ LevelTable T, const CellRect *__restrict__ cells,
@@ -679,7 +691,7 @@ __global__ void __launch_bounds__(192) k_fast_cells(const __grid_constant__ Leve
     for (int it = threadIdx.x; it < ng * ns; it += blockDim.x) {
         const int s = (int)(((uint32_t)it * (65536u / (uint32_t)ng + 1u)) >> 16), g = it - s * ng;
         uint32_t sa, sb;
-        fast_item<0>(s_roi + (2 * s) * FT_PITCH + 4 * g, FT_PITCH, sa, sb);
+        fast_item<0, 0>(s_roi + (2 * s) * FT_PITCH + 4 * g, FT_PITCH, sa, sb);
         // mask pixels beyond the interior (group / row-pair overhang)
         const int valid = iw - 4 * g;
         if (valid < 4) { const uint32_t m = 0xFFFFFFFFu >> (8 * (4 - valid)); sa &= m; sb &= m; }
@@ -778,6 +790,9 @@ struct FastTmaParams {
     int warp_bytes;                     // ... total per warp (multiple of 128)
 };
 
+// PM: how the 16 pair maxima per pass are formed -- 0: a + b - min as two IMAD (FMA pipe), 1: VIMNMX (ALU pipe), 2: the Q pairs by IMAD,
+// the (r[2i], r[2i+9]) pairs by VIMNMX; 3 / 4: as 0 / 1 with the NMS flags taken from VIMNMX predicate outputs; 5 / 6: as 3 / 4 with the ring slices cut by IMAD.HI + IMAD
+template <int PM>
 __global__ void __launch_bounds__(FW_WARPS * 32, 6) k_fast_tma(const __grid_constant__ FastTmaParams P, const CellRect *__restrict__ cells,
                                                                int ncells, int total, int ini_th, int min_th, int f0,
                                                                int *__restrict__ overflow) {
@@ -840,7 +855,7 @@ __global__ void __launch_bounds__(FW_WARPS * 32, 6) k_fast_tma(const __grid_cons
         for (int wi = lane; wi < ng * ns; wi += 32) {
             const int s2 = (int)(((uint32_t)wi * inv_ng) >> 16), g = wi - s2 * ng;
             uint32_t sa, sb;
-            fast_item<0>(s_roi + (2 * s2) * rp + wbase + 4 * g, rp, sa, sb);
+            fast_item<0, PM>(s_roi + (2 * s2) * rp + wbase + 4 * g, rp, sa, sb);
             // mask pixels outside the tested columns (leading lanes of group 0, trailing lanes of the last group)
             const int lo = lead_px - 4 * g, hi = lead_px + iw - 4 * g;       // valid lanes: lo <= k < hi
             uint32_t m = 0xFFFFFFFFu;
@@ -879,8 +894,16 @@ __global__ void __launch_bounds__(FW_WARPS * 32, 6) k_fast_tma(const __grid_cons
                 const uint32_t mo = umax3(Ho[c - 1], Ho[c + 1], LRo[c]) | 0x00FF00FFu;
                 const uint32_t me = umax3(He[c - 1], He[c + 1], LRe[c]) | 0x00FF00FFu;
                 const uint32_t so = c_m & 0xFF00FF00u, se = (c_m << 8) & 0xFF00FF00u;
-                const uint32_t fo = umax2(so, mo) ^ mo, fe = umax2(se, me) ^ me;   // non-zero lane <=> strict maximum above minTh
-                uint32_t mask = ((fe & 0xFFFFu) ? 1u : 0u) | ((fo & 0xFFFFu) ? 2u : 0u) | ((fe >> 16) ? 4u : 0u) | ((fo >> 16) ? 8u : 0u);
+                uint32_t mask;
+                if (PM >= 3) {       // strict maximum above minTh <=> NOT (ring maximum >= score): VIMNMX with predicate outputs
+                    bool oh, ol, eh, el;
+                    __vibmax_u16x2(mo, so, &oh, &ol);
+                    __vibmax_u16x2(me, se, &eh, &el);
+                    mask = (el ? 0u : 1u) | (ol ? 0u : 2u) | (eh ? 0u : 4u) | (oh ? 0u : 8u);
+                } else {
+                    const uint32_t fo = umax2(so, mo) ^ mo, fe = umax2(se, me) ^ me;   // non-zero lane <=> strict maximum above minTh
+                    mask = ((fe & 0xFFFFu) ? 1u : 0u) | ((fo & 0xFFFFu) ? 2u : 0u) | ((fe >> 16) ? 4u : 0u) | ((fo >> 16) ? 8u : 0u);
+                }
                 while (mask) {
                     const int k = __ffs(mask) - 1;
                     mask &= mask - 1;
@@ -946,12 +969,15 @@ int launch_fast(const LevelDev *h_levels, const CellRect *d_cells, int ncells, i
         std::lock_guard<std::mutex> lock(g_attr_mutex);
         size_t &configured = configured_[dv], &last = last_[dv];
         int &per_sm = per_sm_[dv];
+        static const int pm_env = [] { const char *e = getenv("ORBX_FAST_PM"); return e ? atoi(e) : 3; }();   // measured: 0 225-227, 1 238, 2 232, 3 223-225, 4 236, 5 230, 6 240 us
+        typedef void (*FastKernel)(const FastTmaParams, const CellRect *, int, int, int, int, int, int *);
+        const FastKernel fn = pm_env == 1 ? k_fast_tma<1> : pm_env == 2 ? k_fast_tma<2> : pm_env == 3 ? k_fast_tma<3> : pm_env == 4 ? k_fast_tma<4> : pm_env == 5 ? k_fast_tma<5> : pm_env == 6 ? k_fast_tma<6> : k_fast_tma<0>;
         if (smem > configured) {
-            cudaFuncSetAttribute(k_fast_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             configured = smem;
         }
         if (smem != last) {
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fast_tma, FW_WARPS * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, FW_WARPS * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
             last = smem;
         }
         const int total = ncells * batch;
@@ -959,7 +985,7 @@ int launch_fast(const LevelDev *h_levels, const CellRect *d_cells, int ncells, i
         static const int cap_env = [] { const char *e = getenv("ORBX_FAST_CTAS"); return e ? atoi(e) : 0; }();
         const int resident = cap_env > 0 && cap_env < per_sm ? cap_env : per_sm;
         const int grid = want < sm_count * resident ? want : sm_count * resident;
-        k_fast_tma<<<grid, FW_WARPS * 32, smem, stream>>>(P, d_cells, ncells, total, ini_th, min_th, f0, d_overflow);
+        fn<<<grid, FW_WARPS * 32, smem, stream>>>(P, d_cells, ncells, total, ini_th, min_th, f0, d_overflow);
         return 1;
     }
     dim3 grid(ncells, batch);
