@@ -123,6 +123,13 @@ int orbx_extract_batch_device(orbx_handle *h, const uint8_t *d_frames, size_t fr
                               uint8_t *d_desc_out, int cap, int *d_n_out, int *d_mono_out);
 int orbx_sync(orbx_handle *h);
 
+/* Page-locked host memory for frames / results (cudaHostAlloc through the library, for hosts that do not link the CUDA runtime themselves:
+ * the BEAM, a Go or Java process).  Page-locked buffers are DMA'd directly by orbx_extract_batch (no staging copy) and are what its
+ * CUDA-graph replay keys on.  write_combined != 0 asks for write-combined memory: faster for the device to read over PCIe and fine for
+ * upload-only frame buffers that the CPU fills sequentially, but slow for the CPU to read back -- never use it for result buffers. */
+void *orbx_host_alloc(size_t bytes, int write_combined);
+void orbx_host_free(void *p);
+
 /* Pixel format of the frames handed to orbx_extract / orbx_extract_batch / orbx_extract_batch_device.
  * Replaces the cv::cvtColor(RGB2GRAY / BGR2GRAY / RGBA2GRAY / BGRA2GRAY) that UPSTREAM Tracking::GrabImageMonocular runs
  * on the CPU between cv::imdecode (orbslam3_mono_networked.cc:546) and the Frame constructor; which of RGB / BGR applies

@@ -497,7 +497,14 @@ struct Scratch {
 
 extern "C" {
 
-const char *orbx_version(void) { return "orbx 0.1 sm_100a"; }
+const char *orbx_version(void) { return "orbx 0.2 sm_100a"; }
+
+void *orbx_host_alloc(size_t bytes, int write_combined) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void orbx_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 int orbx_create(const orbx_config *cfg, orbx_handle **out) {
     if (!cfg || !out) return fail(nullptr, ORBX_E_INVALID, "null argument");

@@ -53,7 +53,7 @@ EXPORTS = [
     "orbx_extract_batch_device", "orbx_sync", "orbx_launch_count", "orbx_pnm_header", "orbx_extract_pnm",
     "orbx_wire_parse_frame", "orbx_wire_process_frame", "orbx_wire_features_bound", "orbx_wire_pack_features", "orbx_wire_parse_features",
     "orbx_wire_copy_keypoints", "orbx_comm_unique_id", "orbx_comm_create", "orbx_comm_adopt", "orbx_comm_destroy", "orbx_comm_last_error",
-    "orbx_knn2_query_sharded_device", "orbx_knn2_query_sharded",
+    "orbx_knn2_query_sharded_device", "orbx_knn2_query_sharded", "orbx_host_alloc", "orbx_host_free",
     "orbx_debug_get_level", "orbx_debug_get_candidates", "orbx_debug_get_level_keypoints", "orbx_debug_resize",
     "orbx_debug_blur", "orbx_debug_octree", "orbx_debug_describe", "orbx_distance_batch", "orbx_match_windowed",
     "orbx_knn2_create_db", "orbx_knn2_create_db_device", "orbx_knn2_destroy_db", "orbx_knn2_last_error", "orbx_knn2_query",
@@ -197,6 +197,10 @@ def lib():
     L.orbx_plan_probe.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, ip, ip, ip, ip, ip, ip,
                                   C.POINTER(C.c_longlong)]
     L.orbx_version.restype = C.c_char_p
+    L.orbx_host_alloc.argtypes = [C.c_size_t, C.c_int]
+    L.orbx_host_alloc.restype = vp
+    L.orbx_host_free.argtypes = [vp]
+    L.orbx_host_free.restype = None
     L.orbx_comm_unique_id.argtypes = [vp]
     L.orbx_comm_create.argtypes = [C.c_int, C.c_int, C.c_int, vp, C.POINTER(vp)]
     L.orbx_comm_adopt.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp)]
@@ -660,6 +664,31 @@ class Knn2Index:
 
     def launch_count(self):
         return int(self._L.orbx_knn2_launch_count(self._db))
+
+
+class PinnedArray:
+    """A numpy array in page-locked host memory from orbx_host_alloc (optionally write-combined, for upload-only frame buffers)."""
+
+    def __init__(self, shape, dtype=np.uint8, write_combined=False):
+        self._L = lib()
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self._p = self._L.orbx_host_alloc(self.nbytes, 1 if write_combined else 0)
+        if not self._p:
+            raise OrbxError(ORBX_E_CUDA, "cudaHostAlloc failed")
+        buf = (C.c_uint8 * self.nbytes).from_address(self._p)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def close(self):
+        if getattr(self, "_p", None):
+            self.array = None
+            self._L.orbx_host_free(C.c_void_p(self._p))
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 NCCL_ID_BYTES = 128
