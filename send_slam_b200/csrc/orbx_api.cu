@@ -82,6 +82,8 @@ struct orbx_handle {
     Fast2Tma ftma2{};               // ... and for the pair-plane FAST kernel (orbx_fast2.cu), the one the pipeline prefers
     DescTma dtma{};                 // ... and of the un-blurred / blurred planes for the descriptor kernel
     BlurTma btma{};                 // ... and of the un-blurred planes for the Gaussian pass
+    std::vector<ConeLaunch> cones;  // fused pyramid launches (empty or a failed map: the per-level resize kernels run)
+    bool cones_ok = false;
     int sm_count = 148;
     // colour input (orbx_set_input_format): frames are uploaded to d_color and converted into the level-0 planes on the device
     int in_fmt = ORBX_FMT_GRAY8, gray_shift = ORBX_GRAY_Q15;
@@ -180,6 +182,12 @@ static void encode_fast_map(orbx_handle *h, int l) {
                     tma_make_plane_map(reinterpret_cast<CUtensorMap *>(Q.blur[l]), D.blur, D.w, D.h, h->batch_cap, (size_t)D.blur_pitch, D.blur_fstride, 64, 39);
     Q.ok = !getenv("ORBX_NO_TMA");
     for (int k = 0; k < h->plan.nlevels; k++) Q.ok = Q.ok && Q.level_ok[k];
+    // fused pyramid: the launch whose source is this level
+    for (ConeLaunch &cl : h->cones)
+        if (cl.src == l)
+            cl.ok = tma_make_plane_map(reinterpret_cast<CUtensorMap *>(cl.map), D.img, D.w, D.h, h->batch_cap, (size_t)D.pitch, D.img_fstride, cl.box_w, cl.box_h);
+    h->cones_ok = !h->cones.empty() && !getenv("ORBX_NO_TMA") && !getenv("ORBX_NO_CONE");
+    for (const ConeLaunch &cl : h->cones) h->cones_ok = h->cones_ok && cl.ok;
     // Gaussian pass: 96 x 118 box on the un-blurred plane; planes under 16 x 16 keep the word-load kernel (multiple reflections)
     BlurTma &G = h->btma;
     G.level_ok[l] = D.w >= 16 && D.h >= 16 &&
@@ -309,6 +317,16 @@ static int ensure_plan(orbx_handle *h, int w, int ht, int batch) {
     }
     h->ntiles = (int)tiles.size();
     CU_TRY(h, dev_upload(h, &h->d_tiles, tiles));
+    h->cones.clear();
+    for (const ConePlan &cp : pl.cones) {
+        ConeLaunch cl;
+        std::memset(&cl, 0, sizeof(cl));
+        ConeLevel *d = nullptr;
+        CU_TRY(h, dev_upload(h, &d, cp.lv));
+        cl.d_tiles = d; cl.src = cp.src; cl.nl = cp.last - cp.src + 1; cl.ntiles = cp.ntiles; cl.box_w = cp.box_w; cl.box_h = cp.box_h;
+        cl.pitch = cp.pitch; cl.buf0_bytes = cp.buf0_bytes; cl.buf1_bytes = cp.buf1_bytes; cl.ok = false;
+        h->cones.push_back(cl);
+    }
     build_fast_maps(h);
     // pinned staging
     h->h_in_bytes = (size_t)B * pl.lv[0].plane_bytes;
@@ -438,6 +456,8 @@ static int run_pipeline(orbx_handle *h, int f0, int batch, int lap0, int lap1, K
     const bool prof = h->profiling && stream == h->stream;
     const bool fork = !prof && side != nullptr;
     static const bool dbg_sync = getenv("ORBX_DEBUG_SYNC") != nullptr;   // localise a faulting kernel: sync after every stage
+    // what-if timing only (results are wrong): bit 0 pyramid, 1 blur, 2 FAST, 3 quadtree + slots, 4 descriptors are not launched
+    static const int skip = [] { const char *e = getenv("ORBX_SKIP_STAGES"); return e ? atoi(e) : 0; }();
 #define STAGE_MARK(i)                                                                                             \
     do {                                                                                                          \
         if (prof) CU_TRY(h, cudaEventRecord(h->ev[i], stream));                                                   \
@@ -450,16 +470,19 @@ static int run_pipeline(orbx_handle *h, int f0, int batch, int lap0, int lap1, K
         h->launches += launch_gray(color.ptr, color.fstride, color.pitch, h->in_fmt, h->gray_shift, h->l0_own, h->l0_own_fstride, h->l0_own_pitch,
                                    pl.width, pl.height, f0, batch, stream);
     STAGE_MARK(0);
-    for (int l = 1; l < nl; l++) h->launches += launch_resize(h->h_levels, l, f0, batch, stream);
+    if (!(skip & 1)) {
+        if (h->cones_ok) for (const ConeLaunch &cl : h->cones) h->launches += launch_pyramid_cone(h->h_levels, cl, f0, batch, stream);
+        else for (int l = 1; l < nl; l++) h->launches += launch_resize(h->h_levels, l, f0, batch, stream);
+    }
     STAGE_MARK(1);
     // The blurred planes are only needed by the descriptor stage, and the quadtree kernel (one CTA per frame x level,
     // latency-bound) cannot fill the machine: outside profiling mode quadtree + slot assignment run on the side stream,
     // which has the highest priority so that its few CTAs are placed first, while the Gaussian pass fills the rest of
     // the machine from the main stream.  The fork comes after FAST because two machine-filling kernels gain nothing
     // from running side by side.
-    if (!fork) h->launches += launch_blur(h->h_levels, h->d_tiles, h->ntiles, f0, batch, stream, &h->btma);
+    if (!fork && !(skip & 2)) h->launches += launch_blur(h->h_levels, h->d_tiles, h->ntiles, f0, batch, stream, &h->btma);
     STAGE_MARK(2);
-    {
+    if (!(skip & 4)) {
         int nl2 = 0;
         if (h->ftma2.ok) nl2 = launch_fast2(h->h_levels, h->d_cells, (int)pl.cells.size(), f0, batch, h->P.ini_th, h->P.min_th, h->d_overflow, stream, &h->ftma2, h->sm_count);
         if (!nl2) nl2 = launch_fast(h->h_levels, h->d_cells, (int)pl.cells.size(), f0, batch, h->P.ini_th, h->P.min_th, h->d_overflow, stream, &h->ftma, h->sm_count);
@@ -471,16 +494,16 @@ static int run_pipeline(orbx_handle *h, int f0, int batch, int lap0, int lap1, K
         CU_TRY(h, cudaEventRecord(ev_fork, stream));
         CU_TRY(h, cudaStreamWaitEvent(side, ev_fork, 0));
     }
-    h->launches += launch_octree(h->h_levels, nl, f0, batch, h->d_overflow, qs);
+    if (!(skip & 8)) h->launches += launch_octree(h->h_levels, nl, f0, batch, h->d_overflow, qs);
     STAGE_MARK(4);
-    h->launches += launch_finalize(h->h_levels, nl, f0, batch, pl.total_out_cap, lap0, lap1, d_kp, cap, h->d_slot, h->d_items, d_n, d_mono, h->d_overflow, qs);
+    if (!(skip & 8)) h->launches += launch_finalize(h->h_levels, nl, f0, batch, pl.total_out_cap, lap0, lap1, d_kp, cap, h->d_slot, h->d_items, d_n, d_mono, h->d_overflow, qs);
     STAGE_MARK(5);
     if (fork) {
         CU_TRY(h, cudaEventRecord(ev_join, side));
-        h->launches += launch_blur(h->h_levels, h->d_tiles, h->ntiles, f0, batch, stream, &h->btma);
+        if (!(skip & 2)) h->launches += launch_blur(h->h_levels, h->d_tiles, h->ntiles, f0, batch, stream, &h->btma);
         CU_TRY(h, cudaStreamWaitEvent(stream, ev_join, 0));
     }
-    h->launches += launch_describe(h->h_levels, nl, f0, batch, pl.total_out_cap, h->d_slot, h->d_items, d_kp, d_desc, cap, stream, &h->dtma, h->sm_count);
+    if (!(skip & 16)) h->launches += launch_describe(h->h_levels, nl, f0, batch, pl.total_out_cap, h->d_slot, h->d_items, d_kp, d_desc, cap, stream, &h->dtma, h->sm_count);
     STAGE_MARK(6);
 #undef STAGE_MARK
     if (stream == h->stream) h->ev_valid = prof;
@@ -736,8 +759,12 @@ int orbx_extract_batch_device(orbx_handle *h, const uint8_t *d_frames, size_t fr
 // returns as soon as the copies and kernels are queued; orbx_extract_batch_collect waits and finishes the host side.
 // A caller that keeps two handles busy (submit A, submit B, collect A, submit A', collect B, ...) overlaps the upload
 // of one batch with the kernels and the download of the other from a single host thread.
-int orbx_extract_batch_submit(orbx_handle *h, const uint8_t *const *frames, int batch, int width, int height, int stride, int lap0,
-                              int lap1, orbx_keypoint *kp_out, uint8_t *desc_out, int cap) {
+// `blocking` = the caller will wait for this very batch (orbx_extract_batch): the batch is then issued as several frame ranges so that its
+// own upload, kernels and download overlap.  A caller that streams batches through _submit / _collect over several handles gets the
+// overlap from the batches in flight, and one range per batch is cheaper (measured, four handles, 64 x 640x480: 32-frame ranges
+// 164.3 k frames/s, one 64-frame range 167.4 k of a 178.7 k copy ceiling; ORBX_CHUNK overrides both).
+static int submit_impl(orbx_handle *h, const uint8_t *const *frames, int batch, int width, int height, int stride, int lap0,
+                       int lap1, orbx_keypoint *kp_out, uint8_t *desc_out, int cap, bool blocking) {
     if (!h) return ORBX_E_INVALID;
     if (h->pending.active) return fail(h, ORBX_E_INVALID, "a submitted batch has not been collected");
     if (!frames || !kp_out || !desc_out) return fail(h, ORBX_E_INVALID, "null argument");
@@ -799,7 +826,8 @@ int orbx_extract_batch_submit(orbx_handle *h, const uint8_t *const *frames, int 
     };
     h->last_batch = batch;
     if ((rc = set_level0(h, h->l0_own, h->l0_own_pitch, h->l0_own_fstride))) return rc;
-    const int chunk = h->profiling ? batch : pipeline_chunk(batch);
+    static const bool chunk_forced = getenv("ORBX_CHUNK") != nullptr;
+    const int chunk = h->profiling || (!blocking && !chunk_forced) ? batch : pipeline_chunk(batch);
     if (chunk < batch && (rc = ensure_pipeline(h))) return rc;
     // Everything the device does for this call, issued relative to the handle's stream.  `cpu_stage` = do the pageable
     // repacking inline (false when it was done up front because the device work is replayed from a CUDA graph).
@@ -866,6 +894,11 @@ int orbx_extract_batch_submit(orbx_handle *h, const uint8_t *const *frames, int 
     return ORBX_OK;
 }
 
+int orbx_extract_batch_submit(orbx_handle *h, const uint8_t *const *frames, int batch, int width, int height, int stride, int lap0,
+                              int lap1, orbx_keypoint *kp_out, uint8_t *desc_out, int cap) {
+    return submit_impl(h, frames, batch, width, height, stride, lap0, lap1, kp_out, desc_out, cap, false);
+}
+
 int orbx_extract_batch_collect(orbx_handle *h, int *n_out, int *mono_index_out) {
     if (!h) return ORBX_E_INVALID;
     if (!h->pending.active) return fail(h, ORBX_E_INVALID, "no submitted batch to collect");
@@ -899,7 +932,7 @@ int orbx_extract_batch(orbx_handle *h, const uint8_t *const *frames, int batch, 
         for (int i = 0; i < batch; i++) { n_out[i] = 0; mono_index_out[i] = -1; }
         return fail(h, ORBX_E_EMPTY, "empty image");
     }
-    const int rc = orbx_extract_batch_submit(h, frames, batch, width, height, stride, lap0, lap1, kp_out, desc_out, cap);
+    const int rc = submit_impl(h, frames, batch, width, height, stride, lap0, lap1, kp_out, desc_out, cap, true);
     return rc ? rc : orbx_extract_batch_collect(h, n_out, mono_index_out);
 }
 

@@ -53,6 +53,14 @@ struct KeypointRec {           // == orbx_keypoint == cv::KeyPoint
 int launch_gray(const uint8_t *d_src, size_t src_fstride, int src_pitch, int format, int shift, uint8_t *d_dst, size_t dst_fstride,
                 int dst_pitch, int w, int h, int f0, int batch, cudaStream_t stream);
 int launch_resize(const LevelDev *h_levels, int level, int f0, int batch, cudaStream_t stream);
+// One launch of the fused pyramid kernel (orbx_plan.h: ConePlan): levels src + 1 .. src + nl - 1 from level src.
+struct ConeLaunch {
+    alignas(64) unsigned char map[128];   // tensor map of the source level plane, box = box_w x box_h
+    const ConeLevel *d_tiles;             // [ntiles][nl] on the device
+    int src, nl, ntiles, box_w, box_h, pitch, buf0_bytes, buf1_bytes;
+    bool ok;
+};
+int launch_pyramid_cone(const LevelDev *h_levels, const ConeLaunch &cl, int f0, int batch, cudaStream_t stream);
 // Tensor maps of the un-blurred level planes for the TMA-staged Gaussian (box 96 x 118); ok = every level has one and is >= 16 x 16.
 struct BlurTma {
     alignas(64) unsigned char map[kMaxLevels][128];

@@ -232,6 +232,125 @@ int launch_resize(const LevelDev *h_levels, int level, int f0, int batch, cudaSt
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// K1c  fused pyramid ("cone" tiling).  The per-level kernels above are seven dependent, latency-bound launches per frame range; with four
+//      ranges per batch that is 28 small launches per step, and they cost the overlapped step more than their own duration (measured with
+//      stages switched off, tools/whatif.py: 350 -> 238 us per 64-frame step without the pyramid).  Here ONE CTA carries a tile of the
+//      source level down up to four levels in shared memory: the source region arrives as one TMA box, level l's region is computed from
+//      level l-1's region (same item arithmetic as k_resize: 4 pixels x 4 rows, taps from the host tables) into the other half of a
+//      ping-pong buffer, and the part of it this tile owns is written to the level's plane.  Regions overlap between neighbouring tiles
+//      by what the bilinear taps of the levels above need (orbx_plan.cpp: build_cone_plan; ~15 % redundant pixels), so CTAs never wait
+//      for each other.  Every pixel, owned or redundant, is the same arithmetic on the same inputs: bit-identical to the per-level path.
+// ---------------------------------------------------------------------------------------------------------------
+struct ConeParams {
+    CUtensorMap map;                    // source level plane [frames][h][w], box = box_w x box_h x 1
+    int src, nl;                        // source level; entries per tile (levels src .. src + nl - 1)
+    int box_w, box_h, pitch, buf0_bytes;
+};
+
+__global__ void __launch_bounds__(256) k_pyramid_cone(const __grid_constant__ ConeParams C, const __grid_constant__ LevelTable T,
+                                                      const ConeLevel *__restrict__ tiles, int f0) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ __align__(16) uint32_t s_xt[256];        // x taps of the current region (rw <= 256 - 16)
+    __shared__ __align__(8) uint2 s_yt[272];            // y taps of its rows, padded to item blocks of four
+    uint8_t *buf0 = smem, *buf1 = smem + C.buf0_bytes;
+    const ConeLevel *R = tiles + (size_t)blockIdx.x * C.nl;
+    const int f = f0 + blockIdx.y, tid = threadIdx.x;
+    const ConeLevel box = R[0];
+    if (box.rw <= 0 || box.rh <= 0) return;             // a tile without pixels (grids finer than a tiny level); uniform for the CTA
+    if (tid == 0) { tma_mbar_init(&bar, 1); tma_mbar_fence_init(); }
+    __syncthreads();
+    if (tid == 0) {
+        tma_mbar_expect_tx(&bar, (uint32_t)(C.box_w * C.box_h));
+        tma_load_3d(buf0, &C.map, box.rx0, box.ry0, f, &bar);
+    }
+    tma_mbar_wait(&bar, 0);
+    const uint8_t *src = buf0;
+    int spitch = C.box_w, sx0 = box.rx0, sy0 = box.ry0;
+    for (int k = 1; k < C.nl; k++) {
+        const LevelDev &D = T.lv[C.src + k];
+        const ConeLevel r = R[k];
+        uint8_t *dst = (k & 1) ? buf1 : buf0;
+        const int ngx = r.rw >> 2, nry = (r.rh + 3) >> 2, nitems = ngx * nry, dh = D.h, dpitch = C.pitch;
+        uint8_t *__restrict__ gplane = D.img + (size_t)f * D.img_fstride;
+        // the region's taps go to shared memory once (the items of a level would otherwise start with dependent global loads)
+        for (int i = tid; i < r.rw; i += 256) s_xt[i] = __ldg(D.xpack + r.rx0 + i);
+        for (int i = tid; i < 4 * nry; i += 256) s_yt[i] = __ldg(reinterpret_cast<const uint2 *>(D.ytap + min(r.ry0 + i, dh - 1)));
+        __syncthreads();
+        const uint32_t inv_ngx = 65536u / (uint32_t)ngx + 1u;
+        for (int it = tid; it < nitems; it += 256) {
+            const int ry = (int)(((uint32_t)it * inv_ngx) >> 16), gxi = it - ry * ngx;
+            const int dx0 = r.rx0 + 4 * gxi, dy0 = r.ry0 + 4 * ry;
+            const uint4 tp = *reinterpret_cast<const uint4 *>(s_xt + 4 * gxi);
+            const uint32_t t[4] = {tp.x, tp.y, tp.z, tp.w};
+            const int ofs0 = (int)(t[0] >> 16);
+            const uint32_t mis8 = 8u * (uint32_t)(ofs0 & 3);
+            const uint8_t *col = src + ((ofs0 & ~3) - sx0);
+            ResizeTap ty[RR];
+            uint32_t w[RR][2][3];
+#pragma unroll
+            for (int rr = 0; rr < RR; rr++) {
+                const uint2 q = s_yt[4 * ry + rr];
+                ty[rr].ofs = (int16_t)(q.x & 0xFFFF); ty[rr].c0 = (int16_t)(q.x >> 16); ty[rr].c1 = (int16_t)(q.y & 0xFFFF); ty[rr].ofs1 = (int16_t)(q.y >> 16);
+            }
+#pragma unroll
+            for (int rr = 0; rr < RR; rr++)
+#pragma unroll
+                for (int k2 = 0; k2 < 2; k2++) {
+                    const uint32_t *q = reinterpret_cast<const uint32_t *>(col + ((k2 ? ty[rr].ofs1 : ty[rr].ofs) - sy0) * spitch);
+                    w[rr][k2][0] = q[0]; w[rr][k2][1] = q[1]; w[rr][k2][2] = q[2];
+                }
+            uint32_t sel[4], coef[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint32_t d = (t[i] >> 16) - (uint32_t)ofs0;   // 0..6: byte offset of the first tap inside the window
+                sel[i] = d | ((d + 1) << 4);                          // PRMT: bytes d, d+1 -> result bytes 0, 1
+                const uint32_t c1 = t[i] & 0xFFFFu;
+                coef[i] = (c1 << 16) | (2048u - c1);                  // IDP.2A: lo16 * byte0 + hi16 * byte1
+            }
+            const bool own_x = dx0 >= r.ox0 && dx0 < r.ox1;
+            uint32_t *drow = reinterpret_cast<uint32_t *>(dst + (dy0 - r.ry0) * dpitch + (dx0 - r.rx0));
+#pragma unroll
+            for (int rr = 0; rr < RR; rr++) {
+                uint32_t rv[2][4];
+#pragma unroll
+                for (int k2 = 0; k2 < 2; k2++) {
+                    const uint32_t a = __funnelshift_r(w[rr][k2][0], w[rr][k2][1], mis8), b = __funnelshift_r(w[rr][k2][1], w[rr][k2][2], mis8);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) rv[k2][i] = __dp2a_lo(coef[i], __byte_perm(a, b, sel[i]), 0u);
+                }
+                const uint32_t c0s = (uint32_t)ty[rr].c0 << 16, c1s = (uint32_t)ty[rr].c1 << 16;
+                uint32_t packed = 0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) packed |= ((__umulhi(c0s, rv[0][i] >> 4) + __umulhi(c1s, rv[1][i] >> 4) + 2u) >> 2) << (8 * i);
+                drow[rr * (dpitch >> 2)] = packed;
+                const int dy = dy0 + rr;
+                if (own_x && dy >= r.oy0 && dy < r.oy1) *reinterpret_cast<uint32_t *>(gplane + (size_t)dy * D.pitch + dx0) = packed;
+            }
+        }
+        __syncthreads();
+        src = dst; spitch = dpitch; sx0 = r.rx0; sy0 = r.ry0;
+    }
+}
+
+int launch_pyramid_cone(const LevelDev *h_levels, const ConeLaunch &cl, int f0, int batch, cudaStream_t stream) {
+    static_assert(sizeof(cl.map) == sizeof(CUtensorMap), "tensor map storage mismatch");
+    ConeParams C;
+    memcpy(&C.map, cl.map, sizeof(C.map));
+    C.src = cl.src; C.nl = cl.nl; C.box_w = cl.box_w; C.box_h = cl.box_h; C.pitch = cl.pitch; C.buf0_bytes = cl.buf0_bytes;
+    const size_t smem = (size_t)cl.buf0_bytes + cl.buf1_bytes;
+    static size_t configured_[kMaxDevices];
+    {
+        std::lock_guard<std::mutex> lock(g_attr_mutex);
+        size_t &configured = configured_[current_device_slot()];
+        if (smem > configured) { cudaFuncSetAttribute(k_pyramid_cone, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = smem; }
+    }
+    dim3 grid(cl.ntiles, batch);
+    k_pyramid_cone<<<grid, 256, smem, stream>>>(C, make_table(h_levels), cl.d_tiles, f0);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // K5  7x7 Gaussian, fixed point [18,34,48,56,48,34,18]/256 per axis, exact 16.16 accumulation, REFLECT_101.
 //     Output tile 64 x 112 per CTA (two rounds of items per thread amortise the per-thread set-up; 64 x 56 cost 20 % more
 //     instructions).  The halo tile (118 rows x 80 bytes) is staged with word loads; the horizontal pass is
@@ -474,13 +593,16 @@ __global__ void __launch_bounds__(256) k_blur_tma(const __grid_constant__ BlurTm
         d4[1] = make_uint4(o[4], o[5], o[6], o[7]);
     }
     __syncthreads();
-    // vertical: item = (4-column group cg, segment of 4 output rows), as in k_blur
-    uint8_t *__restrict__ dstp = L.blur + (size_t)f * L.blur_fstride;
-    const int bp = L.blur_pitch;
+    // vertical: item = (4-column group cg, segment of 4 output rows), as in k_blur.  The output address is formed once per item and
+    // pinned in a register: left to itself the compiler re-derives it per row from the parameter bank (17 instructions per store).
+    uint8_t *dstp = L.blur + (size_t)f * L.blur_fstride + (size_t)y0 * L.blur_pitch + x0;
+    int bp = L.blur_pitch;
+    asm volatile("" : "+l"(dstp), "+r"(bp));
     for (int it = threadIdx.x; it < 16 * nseg; it += 256) {
         const int cg = it & 15, seg = it >> 4;
         const int gx = x0 + 4 * cg;
         if (gx >= w) continue;
+        uint8_t *orow = dstp + (4 * seg) * bp + 4 * cg;
         constexpr uint32_t EA = 18u | (34u << 8) | (48u << 16) | (56u << 24), EB = 48u | (34u << 8) | (18u << 16);
         constexpr uint32_t OA = (18u << 8) | (34u << 16) | (48u << 24), OB = 56u | (48u << 8) | (34u << 16) | (18u << 24);
         uint32_t Pq[5][4];
@@ -503,7 +625,7 @@ __global__ void __launch_bounds__(256) k_blur_tma(const __grid_constant__ BlurTm
             }
             // byte 2 of every accumulator is the pixel (acc < 2^24): three permutes for four pixels
             const uint32_t px = __byte_perm(__byte_perm(acc[0], acc[1], 0x0062), __byte_perm(acc[2], acc[3], 0x0062), 0x5410);
-            if (gy < h) *reinterpret_cast<uint32_t *>(dstp + (size_t)gy * bp + gx) = px;
+            if (gy < h) *reinterpret_cast<uint32_t *>(orow + r * bp) = px;
         }
     }
 }

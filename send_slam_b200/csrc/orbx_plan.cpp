@@ -2,6 +2,7 @@
 // orbx_plan_* debug exports at the bottom of orbx_api.cu.
 #include "orbx_plan.h"
 
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstring>
@@ -68,6 +69,94 @@ static inline uint32_t spread_bits(uint32_t v) {   // bit i -> bit 2i
     uint32_t r = 0;
     for (int i = 0; i < 16; i++) r |= ((v >> i) & 1u) << (2 * i);
     return r;
+}
+
+static inline int floor4(int v) { return v & ~3; }
+static inline int ceil4(int v) { return (v + 3) & ~3; }
+
+// One attempt with a given tile grid; false when a region does not fit the kernel's limits.
+static bool cone_try(const Plan &plan, int src, int last, int gx, int gy, ConePlan &c) {
+    const int NL = last - src + 1;
+    c = ConePlan();
+    c.src = src; c.last = last; c.gx = gx; c.gy = gy; c.ntiles = gx * gy;
+    c.lv.assign((size_t)c.ntiles * NL, ConeLevel{0, 0, 0, 0, 0, 0, 0, 0});
+    int pitch = 0, b0 = 0, b1 = 0;
+    // what the region `r` of level l reads from level l - 1: columns [nx0, nx1), rows [ny0, ny1)
+    auto needs = [&](int l, const ConeLevel &r, int &nx0, int &nx1, int &ny0, int &ny1) {
+        const LevelPlan &N = plan.lv[l];
+        const int a = r.rx0, b = r.rx0 + r.rw;
+        nx0 = N.xtap[std::min(a, N.w - 1)].ofs; nx1 = N.xtap[std::min(b - 1, N.w - 1)].ofs + 2;
+        const int r0 = r.ry0, r1 = std::min(r.ry0 + ceil4(r.rh) - 1, N.h - 1);
+        ny0 = N.ytap[r0].ofs; ny1 = N.ytap[r1].ofs1 + 1;
+        for (int y = r0; y <= r1; y++) { ny0 = std::min<int>(ny0, N.ytap[y].ofs); ny1 = std::max<int>(ny1, N.ytap[y].ofs1 + 1); }
+    };
+    for (int j = 0; j < gy; j++)
+        for (int i = 0; i < gx; i++) {
+            ConeLevel *R = &c.lv[(size_t)(j * gx + i) * NL] - src;      // R[l] = entry of level l
+            for (int l = last; l > src; l--) {
+                const int W = plan.lv[l].w, H = plan.lv[l].h;
+                int ox0 = i == 0 ? 0 : floor4((int)((long long)i * W / gx)), ox1 = i == gx - 1 ? W : floor4((int)((long long)(i + 1) * W / gx));
+                int oy0 = (int)((long long)j * H / gy), oy1 = j == gy - 1 ? H : (int)((long long)(j + 1) * H / gy);
+                if (ox1 <= ox0 || oy1 <= oy0) { ox1 = ox0; oy1 = oy0; }
+                int x0 = ox0, x1 = ox1, y0 = oy0, y1 = oy1;
+                if (l < last && R[l + 1].rw > 0 && R[l + 1].rh > 0) {
+                    int nx0, nx1, ny0, ny1;
+                    needs(l + 1, R[l + 1], nx0, nx1, ny0, ny1);
+                    if (x1 > x0 && y1 > y0) { x0 = std::min(x0, nx0); x1 = std::max(x1, nx1); y0 = std::min(y0, ny0); y1 = std::max(y1, ny1); }
+                    else { x0 = nx0; x1 = nx1; y0 = ny0; y1 = ny1; }
+                }
+                const int rx0 = floor4(x0), rx1 = std::min(ceil4(x1), ceil4(W));
+                R[l] = ConeLevel{(int16_t)rx0, (int16_t)y0, (int16_t)std::max(rx1 - rx0, 0), (int16_t)std::max(std::min(y1, H) - y0, 0),
+                                 (int16_t)ox0, (int16_t)ox1, (int16_t)oy0, (int16_t)oy1};
+                pitch = std::max(pitch, R[l].rw + 16);
+            }
+            if (R[src + 1].rw > 0 && R[src + 1].rh > 0) {               // the TMA box of the source level
+                int nx0, nx1, ny0, ny1;
+                needs(src + 1, R[src + 1], nx0, nx1, ny0, ny1);
+                const int bx0 = nx0 & ~15;
+                R[src] = ConeLevel{(int16_t)bx0, (int16_t)ny0, (int16_t)(nx1 - bx0), (int16_t)(ny1 - ny0), 0, 0, 0, 0};
+                c.box_w = std::max(c.box_w, (nx1 + 10 - bx0 + 15) / 16 * 16);   // the 3-word read window of an item reaches 11 bytes past its first word
+                c.box_h = std::max(c.box_h, ny1 - ny0);
+            }
+        }
+    c.pitch = (pitch + 3) & ~3;
+    for (int t = 0; t < c.ntiles; t++)
+        for (int k = 1; k < NL; k++) {
+            const ConeLevel &r = c.lv[(size_t)t * NL + k];
+            const int bytes = c.pitch * ceil4(r.rh) + 16;
+            if (k & 1) b1 = std::max(b1, bytes); else b0 = std::max(b0, bytes);
+        }
+    c.buf0_bytes = (std::max(b0, c.box_w * c.box_h + 16) + 127) / 128 * 128;
+    c.buf1_bytes = (b1 + 127) / 128 * 128;
+    if (c.box_w < 16 || c.box_h < 1 || c.box_w > 256 || c.box_h > 256) return false;
+    if (c.buf0_bytes + c.buf1_bytes > 56 * 1024) return false;
+    // self-check: the own parts partition every level and lie inside their regions
+    for (int k = 1; k < NL; k++) {
+        long long area = 0;
+        for (int t = 0; t < c.ntiles; t++) {
+            const ConeLevel &r = c.lv[(size_t)t * NL + k];
+            area += (long long)(r.ox1 - r.ox0) * (r.oy1 - r.oy0);
+            if (r.ox1 > r.ox0 && (r.ox0 < r.rx0 || r.ox1 > r.rx0 + r.rw || r.oy0 < r.ry0 || r.oy1 > r.ry0 + r.rh || (r.ox0 & 3))) return false;
+            if ((r.rx0 & 3) || (r.rw & 3) || r.rw > 240 || ceil4(r.rh) > 272) return false;   // the kernel's tap staging arrays
+        }
+        if (area != (long long)plan.lv[src + k].w * plan.lv[src + k].h) return false;
+    }
+    c.ok = true;
+    return true;
+}
+
+// Tiles of about 128 x 120 pixels of the source level (a ~22 KB box + a ~14 KB first region per CTA); finer grids until everything fits.
+bool build_cone_plan(const Plan &plan, int src, int last, ConePlan &cone) {
+    cone = ConePlan();
+    if (src < 0 || last <= src || last >= plan.nlevels) return false;
+    for (int l = src + 1; l <= last; l++) if (plan.lv[l].xpack.empty() || plan.lv[l].w < 8 || plan.lv[l].h < 8) return false;
+    int gx = std::max(1, (plan.lv[src].w + 64) / 128), gy = std::max(1, (plan.lv[src].h + 60) / 120);
+    for (int attempt = 0; attempt < 6; attempt++) {
+        if (cone_try(plan, src, last, gx, gy, cone)) return true;
+        gx = gx * 5 / 4 + 1; gy = gy * 5 / 4 + 1;
+    }
+    cone = ConePlan();
+    return false;
 }
 
 bool build_plan(const ExtractorParams &p, int width, int height, Plan &plan, std::string &err) {
@@ -203,6 +292,12 @@ bool build_plan(const ExtractorParams &p, int width, int height, Plan &plan, std
         const int minout = 4 * (L.n_ini > 0 ? L.n_ini : 1);
         L.out_cap = (L.quota + 3 > minout ? L.quota + 3 : minout);
         plan.total_out_cap += L.out_cap;
+    }
+    // fused pyramid launches of up to four levels each (optional: an empty list means the per-level kernels run)
+    for (int src = 0; src + 1 < p.nlevels; src += 4) {
+        ConePlan c;
+        if (!build_cone_plan(plan, src, std::min(src + 4, p.nlevels - 1), c)) { plan.cones.clear(); break; }
+        plan.cones.push_back(std::move(c));
     }
     return true;
 }

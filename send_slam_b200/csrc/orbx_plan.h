@@ -45,6 +45,26 @@ struct CellRect {     // one FAST cell: ROI [x0,x1) x [y0,y1) in level coordinat
 };
 static_assert(sizeof(CellRect) == 16, "CellRect must be 16 bytes");
 
+// Fused pyramid ("cone" tiling, k_pyramid_cone): the frame is cut into gx x gy tiles; ONE CTA carries a tile down all levels in shared
+// memory.  At level l it computes the region R_l = its own part of the level (what it writes to global memory; the own parts partition
+// the level, interior x boundaries on multiples of 4) plus everything the next level's region reads through its bilinear taps, so no CTA
+// ever waits for another one.  The source level enters as one TMA box per tile.  Deep cones are wasteful (the halo a level needs grows by
+// about two pixels of every level above it), so a pyramid runs as a few launches of up to four levels each.
+struct ConeLevel {
+    int16_t rx0, ry0, rw, rh;        // region held in shared memory: columns [rx0, rx0 + rw) (both multiples of 4), rows [ry0, ry0 + rh)
+    int16_t ox0, ox1, oy0, oy1;      // the part written to global memory; level 0 entry: rx0 / ry0 = origin of the TMA box
+};
+static_assert(sizeof(ConeLevel) == 16, "ConeLevel must be 16 bytes");
+struct ConePlan {
+    bool ok = false;
+    int src = 0, last = 0;           // this launch reads level `src` (TMA) and produces levels src + 1 .. last; nl = last - src + 1 entries per tile
+    int gx = 0, gy = 0, ntiles = 0;
+    int box_w = 0, box_h = 0;        // TMA box of level 0: bytes per row (multiple of 16), rows
+    int pitch = 0;                   // row pitch in bytes of the level >= 1 regions (multiple of 4, >= widest region + 16)
+    int buf0_bytes = 0, buf1_bytes = 0;   // ping-pong buffers: buf0 = TMA box, then the even levels; buf1 = the odd levels
+    std::vector<ConeLevel> lv;       // [tile][last - src + 1]: entry k describes level src + k (entry 0: the TMA box)
+};
+
 struct LevelPlan {
     int w = 0, h = 0, pitch = 0;
     size_t plane_bytes = 0;          // pitch * h
@@ -75,9 +95,11 @@ struct Plan {
     std::vector<LevelPlan> lv;
     std::vector<CellRect> cells;     // all levels, level-major
     int total_out_cap = 0;           // sum of out_cap
+    std::vector<ConePlan> cones;     // fused pyramid launches (levels 1..4 from level 0, 5..7 from level 4, ...); empty: per-level kernels
     size_t algorithmic_bytes(int nkeypoints) const;   // 5S - P0 - P(L-1) + 1321 N
 };
 
+bool build_cone_plan(const Plan &plan, int src_level, int last_level, ConePlan &cone);
 void build_resize_taps(int dst, int src, bool is_x, std::vector<ResizeTap> &taps);
 
 // Builds the plan; returns false and sets err on unsupported geometry.

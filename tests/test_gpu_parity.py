@@ -259,7 +259,7 @@ def test_device_resident_batch(oracle):
         k_o, d_o, m_o = o.extract(frames[i])
         assert n[i] == len(k_o) and np.array_equal(desc[i, :n[i]], d_o)
         assert np.array_equal(kp[i, :n[i], 0], k_o["x"]) and np.array_equal(kp[i, :n[i], 3], k_o["angle"])
-    assert e.launch_count() >= 12
+    assert e.launch_count() >= 7      # fused pyramid (2) + FAST + quadtree + slots + blur + descriptors
     # caller memory that misses the TMA / word-load alignment rules (odd base address, odd row stride): the byte-wise
     # resize and the CTA-per-cell FAST kernel take over; results must not change
     stride = w + 3
