@@ -288,6 +288,7 @@ int orbx_vocab_transform(orbx_vocab *v, const uint8_t *desc, int n, int levelsup
  * tcgen05.mma kind::i8 with the top-2 taken from TMEM; ORBX_KNN_POPC = XOR + POPC on the CUDA cores.  Identical results. */
 #define ORBX_KNN_POPC 0
 #define ORBX_KNN_TENSOR 1
+#define ORBX_KNN_TENSOR_FP4 2   /* {-1,+1} as E2M1 nibbles, tcgen05.mma kind::mxf4 with unit block scales: half the operand bytes, twice the MMA rate */
 int orbx_knn2_set_backend(orbx_db *db, int backend);
 int orbx_knn2_sync(orbx_db *db);
 int orbx_knn2_set_stream(orbx_db *db, void *cuda_stream);

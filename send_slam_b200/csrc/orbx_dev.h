@@ -131,6 +131,16 @@ int launch_knn2_tc(const int8_t *d_qe, int nq, const int8_t *d_dbe, long long nr
                    unsigned long long *d_partial, int *nparts_out,
                    void (*merge)(const unsigned long long *, int, int, unsigned long long *, cudaStream_t), cudaStream_t stream,
                    std::string &err);
+// FP4 variant (orbx_knn_fp4.cu): descriptors expanded to E2M1 nibbles (128 bytes per row), tcgen05.mma kind::mxf4 with unit block scales
+size_t knn_fp4_smem_bytes();
+int knn_fp4_max_queries();
+long long knn_fp4_padded_rows(long long nrows);
+int knn_fp4_padded_queries(int nq);
+int launch_expand_fp4(const uint8_t *d_bits, long long nrows, long long nrows_pad, uint8_t *d_out, cudaStream_t stream);
+int launch_knn2_fp4(const uint8_t *d_qe, int nq, const uint8_t *d_dbe, long long nrows, long long row_offset, int sm_count,
+                    unsigned long long *d_partial, int *nparts_out,
+                    void (*merge)(const unsigned long long *, int, int, unsigned long long *, cudaStream_t), cudaStream_t stream,
+                    std::string &err);
 }  // namespace orbx
 
 namespace orbx {

@@ -243,6 +243,8 @@ struct orbx_db {
     int sm_count = 0;
     int8_t *d_dbe = nullptr;
     int8_t *d_qe = nullptr; int qe_cap = 0;
+    uint8_t *d_dbe4 = nullptr;       // FP4 backend: E2M1 expansion of the shard (128 B per row) and of the queries
+    uint8_t *d_qe4 = nullptr; int qe4_cap = 0;
     unsigned long long *d_partial_tc = nullptr; size_t partial_tc_cap = 0;
     // row-sharded queries: this rank's top-2 and the all-gathered [ranks][nq][2] partials
     unsigned long long *d_sh_local = nullptr, *d_sh_gather = nullptr; size_t sh_cap = 0;
@@ -338,6 +340,8 @@ void orbx_knn2_destroy_db(orbx_db *db) {
     if (db->h_out) cudaFreeHost(db->h_out);
     if (db->d_dbe) cudaFree(db->d_dbe);
     if (db->d_qe) cudaFree(db->d_qe);
+    if (db->d_dbe4) cudaFree(db->d_dbe4);
+    if (db->d_qe4) cudaFree(db->d_qe4);
     if (db->d_partial_tc) cudaFree(db->d_partial_tc);
     if (db->d_sh_local) cudaFree(db->d_sh_local);
     if (db->d_sh_gather) cudaFree(db->d_sh_gather);
@@ -366,7 +370,7 @@ int orbx_knn2_sync(orbx_db *db) {
 }
 
 int orbx_knn2_set_backend(orbx_db *db, int backend) {
-    if (!db || (backend != ORBX_KNN_POPC && backend != ORBX_KNN_TENSOR)) return ORBX_E_INVALID;
+    if (!db || (backend != ORBX_KNN_POPC && backend != ORBX_KNN_TENSOR && backend != ORBX_KNN_TENSOR_FP4)) return ORBX_E_INVALID;
     db->backend = backend;
     return ORBX_OK;
 }
@@ -408,11 +412,49 @@ static int query_device_tensor(orbx_db *db, const uint8_t *d_queries, int nq, un
     return ORBX_OK;
 }
 
+// FP4 tensor-core path: same flow as query_device_tensor on the E2M1 expansion
+static int query_device_fp4(orbx_db *db, const uint8_t *d_queries, int nq, unsigned long long *d_packed_out) {
+    if (!db->d_dbe4) {
+        const long long rows_pad = knn_fp4_padded_rows(db->nrows);
+        DB_TRY(db, cudaMalloc((void **)&db->d_dbe4, (size_t)rows_pad * 128));
+        db->launches += launch_expand_fp4(db->d_rows, db->nrows, rows_pad, db->d_dbe4, db->stream);
+        DB_TRY(db, cudaGetLastError());
+    }
+    const int maxq = knn_fp4_max_queries();
+    const int qcap = knn_fp4_padded_queries(std::min(nq, maxq));
+    if (qcap > db->qe4_cap) {
+        if (db->d_qe4) cudaFree(db->d_qe4);
+        db->d_qe4 = nullptr; db->qe4_cap = 0;
+        DB_TRY(db, cudaMalloc((void **)&db->d_qe4, (size_t)qcap * 128));
+        db->qe4_cap = qcap;
+    }
+    const size_t need = (size_t)(db->sm_count + 1) * std::min(nq, maxq) * 2;
+    if (need > db->partial_tc_cap) {
+        if (db->d_partial_tc) cudaFree(db->d_partial_tc);
+        db->d_partial_tc = nullptr; db->partial_tc_cap = 0;
+        DB_TRY(db, cudaMalloc((void **)&db->d_partial_tc, need * sizeof(unsigned long long)));
+        db->partial_tc_cap = need;
+    }
+    for (int q0 = 0; q0 < nq; q0 += maxq) {
+        const int n = std::min(maxq, nq - q0);
+        db->launches += launch_expand_fp4(d_queries + (size_t)q0 * 32, n, knn_fp4_padded_queries(n), db->d_qe4, db->stream);
+        int nparts = 0;
+        const int l = launch_knn2_fp4(db->d_qe4, n, db->d_dbe4, db->nrows, db->row_offset, db->sm_count, db->d_partial_tc, &nparts, merge_launch,
+                                      db->stream, db->err);
+        if (!l) return ORBX_E_CUDA;
+        k_knn2_merge<<<(n + 255) / 256, 256, 0, db->stream>>>(db->d_partial_tc, nparts, n, d_packed_out + (size_t)q0 * 2);
+        db->launches += l + 1;
+        DB_TRY(db, cudaGetLastError());
+    }
+    return ORBX_OK;
+}
+
 int orbx_knn2_query_device(orbx_db *db, const uint8_t *d_queries, int nq, unsigned long long *d_packed_out) {
     if (!db || !d_queries || !d_packed_out || nq < 1) return ORBX_E_INVALID;
     if (((uintptr_t)d_queries & 15) != 0) { db->err = "device queries must be 16-byte aligned"; return ORBX_E_INVALID; }
     DB_TRY(db, cudaSetDevice(db->device));
     if (db->backend == ORBX_KNN_TENSOR && db->nrows > 0) return query_device_tensor(db, d_queries, nq, d_packed_out);
+    if (db->backend == ORBX_KNN_TENSOR_FP4 && db->nrows > 0) return query_device_fp4(db, d_queries, nq, d_packed_out);
     int rc = db_reserve(db, nq);
     if (rc) return rc;
     dim3 grid((nq + KQ_THREADS * KQ_QPT - 1) / (KQ_THREADS * KQ_QPT), db->nchunks);

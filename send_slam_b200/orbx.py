@@ -656,7 +656,7 @@ class Knn2Index:
         self._check(self._L.orbx_knn2_query_sharded(self._db, comm._c, _p(q), len(q), _p(idx), _p(dist)))
         return idx, dist
 
-    POPC, TENSOR = 0, 1
+    POPC, TENSOR, TENSOR_FP4 = 0, 1, 2
 
     def set_backend(self, backend: int):
         """Knn2Index.TENSOR (default: tcgen05 int8 GEMM tiles) or Knn2Index.POPC (CUDA-core XOR + POPC)."""

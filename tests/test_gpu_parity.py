@@ -539,7 +539,7 @@ def test_distance_batch(ex, oracle):
     assert m.DescriptorDistance(a[33], b[33]) == int(d[33])
 
 
-@pytest.mark.parametrize("backend", [orbx.Knn2Index.POPC, orbx.Knn2Index.TENSOR], ids=["popc", "tensor"])
+@pytest.mark.parametrize("backend", [orbx.Knn2Index.POPC, orbx.Knn2Index.TENSOR, orbx.Knn2Index.TENSOR_FP4], ids=["popc", "tensor", "tensor_fp4"])
 def test_knn2_golden_and_oracle(oracle, golden_dir, backend):
     """Both distance backends (XOR + POPC on the CUDA cores, tcgen05 int8 tiles) against the committed golden vector and the oracle."""
     def index(rows, **kw):
@@ -568,7 +568,7 @@ def test_knn2_golden_and_oracle(oracle, golden_dir, backend):
         assert dist[0, 0] == 0 and dist[nq - 1, 0] == 0
 
 
-@pytest.mark.parametrize("backend", [orbx.Knn2Index.POPC, orbx.Knn2Index.TENSOR], ids=["popc", "tensor"])
+@pytest.mark.parametrize("backend", [orbx.Knn2Index.POPC, orbx.Knn2Index.TENSOR, orbx.Knn2Index.TENSOR_FP4], ids=["popc", "tensor", "tensor_fp4"])
 def test_knn2_full_size_properties(backend):
     """2000 queries x 1M rows per shard (config 4's per-GPU share at 8+ GPUs is 1.25M): known answers instead of an
     oracle pass -- queries are database rows with <= 40 flipped bits, so the nearest row and its distance are known and
