@@ -790,7 +790,10 @@ def main():
         peaks_k, _src_k = measured_peaks()
         # tensor route: descriptors expanded to {-1,+1} int8, q.d = 256 - 2H by tcgen05.mma kind::i8 = 2 x 256 int8 ops per
         # pair; kind::i8 issues at twice the dense bf16 rate, so the peak is 2 x the measured cuBLAS bf16 figure
-        tensor_peak_ops = 2.0 * float(peaks_k["bf16_tflops"]) * 1e12
+        i8_peak_ops = 2.0 * float(peaks_k["bf16_tflops"]) * 1e12
+        # default route: the same +-1 values as E2M1 FP4 (kind::mxf4.block_scale, unit scales, fp32 accumulators -- exact): the
+        # block-scaled FP4 MMA issues at four times the dense bf16 rate
+        tensor_peak_ops = 4.0 * float(peaks_k["bf16_tflops"]) * 1e12
         tensor_pairs_peak = tensor_peak_ops / 512.0
         # CUDA-core route: 8 POPC32 per pair on the POPC pipe.  16 / clk / SM is the CUDA guide's figure; this part's own
         # rate is the microbenchmark's (tools/ubench_pipes.cu, profiles/ubench_pipes_r0x.jsonl)
@@ -918,7 +921,8 @@ def main():
             return world * ksteps * KNN_Q * KNN_ROWS / t, (index.launch_count() - l0) * ksteps // (ksteps + 3)
 
         pairs_popc, _ = time_backend(orbx.Knn2Index.POPC)
-        pairs, klaunches = time_backend(orbx.Knn2Index.TENSOR)
+        pairs_i8, _ = time_backend(orbx.Knn2Index.TENSOR)
+        pairs, klaunches = time_backend(orbx.Knn2Index.TENSOR_FP4)
         # the same shard through the host-buffer entry point (orbx_knn2_query: pageable queries in, indices + distances out)
         index.knnMatch(q)
         t0 = time.perf_counter()
@@ -932,13 +936,17 @@ def main():
             pk = 148 * popc_rate * 1.965e9 / 8.0
             popc_note["roofline_measured_pipe"] = {"peak": pk, "frac": pairs_popc / world / pk,
                                                    "note": f"POPC rate of this part by microbenchmark: {popc_rate} thread-ops/clk/SM ({popc_src})"}
-        tc_facts = profile_facts("k_knn2_tc")
+        tc_facts = profile_facts("k_knn2_fp4")
+        i8_note = {"value": pairs_i8, "unit": "pairs/s", "backend": "tcgen05.mma kind::i8 on the {-1,+1} int8 expansion",
+                   "roofline": {"bound": "tensor", "peak": i8_peak_ops / 1e12, "unit": "TOP/s (int8)", "frac": pairs_i8 / world * 512.0 / i8_peak_ops,
+                                "note": "peak = 2 x measured dense bf16 TFLOP/s", "ncu": profile_facts("k_knn2_tc")}}
         hamming = {"metric": "Hamming pairs/s (k=2 brute force)", "value": pairs, "unit": "pairs/s",
-                   "config": {"queries": KNN_Q, "db_rows_per_gpu": KNN_ROWS, "k": 2, "backend": "tcgen05.mma kind::i8 on {-1,+1} expansion"},
-                   "roofline": {"bound": "tensor", "achieved": pairs / world * 512.0 / 1e12, "peak": tensor_peak_ops / 1e12, "unit": "TOP/s (int8)",
+                   "config": {"queries": KNN_Q, "db_rows_per_gpu": KNN_ROWS, "k": 2, "backend": "tcgen05.mma kind::mxf4.block_scale on the {-1,+1} E2M1 expansion (unit scales, fp32 accumulators, exact)"},
+                   "roofline": {"bound": "tensor", "achieved": pairs / world * 512.0 / 1e12, "peak": tensor_peak_ops / 1e12, "unit": "TOP/s (fp4)",
                                 "frac": pairs / world / tensor_pairs_peak,
-                                "note": "512 int8 ops per pair; peak = 2 x measured dense bf16 TFLOP/s (MEASURED_PEAKS.json); nominal int8 dense 4500 TOP/s",
+                                "note": "512 fp4 ops per pair; peak = 4 x measured dense bf16 TFLOP/s (MEASURED_PEAKS.json); nominal fp4 dense 9000 TOP/s",
                                 "ncu": tc_facts},
+                   "int8_backend": i8_note,
                    "e2e": {"value": pairs_e2e, "unit": "pairs/s", "api": "orbx_knn2_query (host queries in, host indices + distances out), one rank"},
                    "popc_backend": popc_note, "cfg4": cfg4,
                    "gpu_launches": klaunches}
@@ -1003,7 +1011,7 @@ def main():
         hbm = float(peaks["hbm_gbs"])
         ach = stage_bytes[dom] * BATCH / (acc[dom] * 1e-3) / 1e9
         total_bytes = plan["algorithmic_bytes"]
-        kname = {"pyramid": "k_resize", "blur": "k_blur_tma", "fast": "k_fast_tma", "describe": "k_describe_tma"}[dom]
+        kname = {"pyramid": "k_pyramid_cone", "blur": "k_blur_tma", "fast": "k_fast_tma", "describe": "k_describe_tma"}[dom]
         # ncu facts of the dominant kernel come from the round's committed capture (profiles/ncu_facts_r02.json, written by
         # tools/make_profile_summaries.py from the .ncu-rep files); nothing is hard-coded: null where the capture lacks the kernel
         facts = profile_facts(kname) if dom != "pyramid" else None      # the pyramid is 7 launches; a capture holds one level

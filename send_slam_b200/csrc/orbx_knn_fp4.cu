@@ -34,6 +34,8 @@ constexpr int TC_MAX_QTILES = 16;     // 2048 queries per launch
 constexpr int TC_EPI_PARTS = 4;         // epilogue warps per TMEM lane quarter: each takes TC_DT / 4 = 56 accumulator columns
 constexpr int TC_THREADS = 64 + 4 * TC_EPI_PARTS * 32;   // warp 0 TMA, warp 1 MMA, then 4 x TC_EPI_PARTS epilogue warps
 constexpr uint32_t TC_SENTINEL = 0x7FFFFFu;   // row field of a seeded (virtual) key
+constexpr int TC_NA = 4;               // query-tile stages: a stage is refilled only after its MMAs retire, and the refill takes one TMA
+                                       // latency from L2 -- two stages left the tensor pipe waiting for query tiles
 constexpr uint32_t TC_A_BYTES = TC_QT * TC_K;          // 16 KB per query tile (one 128 x 128 B swizzle box)
 constexpr uint32_t TC_B_BYTES = TC_DT * TC_K;          // 28 KB per database tile (one 224 x 128 B box)
 constexpr uint32_t TC_SF_COL = 2 * TC_DT;              // TMEM columns 448 .. 511: scale factors (A at 448, B at 480)
@@ -60,6 +62,13 @@ __global__ void __launch_bounds__(256) k_expand_fp4(const uint8_t *__restrict__ 
 // ---- PTX helpers -----------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// one lane of a converged warp; the role loops below run warp-uniform (so their addresses and descriptors stay in uniform registers and
+// each tcgen05 / TMA instruction is a single issue, not a per-thread loop) and only the issue itself is predicated on the elected lane
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -131,7 +140,7 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
                  : "r"(taddr) : "memory")
 
 struct TcShared {
-    uint64_t full_a[2], empty_a[2], full_b[2], empty_b[2], tmem_full[2], tmem_empty[2];
+    uint64_t full_a[TC_NA], empty_a[TC_NA], full_b[2], empty_b[2], tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
     uint32_t pad;
     uint32_t top[TC_MAX_QTILES][TC_EPI_PARTS][TC_QT][2];   // [query tile][column part][row]: running (H << 23 | row-in-CTA) keys
@@ -145,11 +154,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_fp4(const __grid_constan
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment: round the dynamic shared-memory base up (1 KB of slack is requested)
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    // carve-up: A stages (2 x 32 KB), B stages (2 x 64 KB), then barriers + top-2 state
+    // carve-up: A stages (TC_NA x 16 KB), B stages (2 x 28 KB), then barriers + top-2 state
     uint8_t *smem_a = smem;
-    uint8_t *smem_b = smem + 2 * TC_A_BYTES;
-    TcShared &S = *reinterpret_cast<TcShared *>(smem + 2 * TC_A_BYTES + 2 * TC_B_BYTES);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t *smem_b = smem + TC_NA * TC_A_BYTES;
+    TcShared &S = *reinterpret_cast<TcShared *>(smem + TC_NA * TC_A_BYTES + 2 * TC_B_BYTES);
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp index, provably uniform
     const int cta = blockIdx.x, G = gridDim.x;
     const int my_tiles = cta < ntiles ? (ntiles - cta + G - 1) / G : 0;
 
@@ -165,8 +174,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_fp4(const __grid_constan
         (&S.top[0][0][0][0])[2 * i] = v; (&S.top[0][0][0][0])[2 * i + 1] = v;
     }
     if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_NA; s++) { mbar_init(&S.full_a[s], 1); mbar_init(&S.empty_a[s], 1); }
         for (int s = 0; s < 2; s++) {
-            mbar_init(&S.full_a[s], 1); mbar_init(&S.empty_a[s], 1);
             mbar_init(&S.full_b[s], 1); mbar_init(&S.empty_b[s], 1);
             mbar_init(&S.tmem_full[s], 1); mbar_init(&S.tmem_empty[s], 4 * TC_EPI_PARTS);   // one arrival per epilogue warp
         }
@@ -194,48 +203,53 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_fp4(const __grid_constan
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int k = 0; k < my_tiles; k++) {
-                const int t = tile0 + cta + k * G, bs = k & 1;
-                mbar_wait(&S.empty_b[bs], ((k >> 1) & 1) ^ 1);
+        // ===== TMA producer (whole warp in the loop, one elected lane issues) =====
+        uint32_t it = 0;
+        for (int k = 0; k < my_tiles; k++) {
+            const int t = tile0 + cta + k * G, bs = k & 1;
+            mbar_wait(&S.empty_b[bs], ((k >> 1) & 1) ^ 1);
+            if (elect_one()) {
                 mbar_expect_tx(&S.full_b[bs], TC_B_BYTES);
                 tma_load_2d(smem_b + bs * TC_B_BYTES, &map_db, 0, t * TC_DT, &S.full_b[bs]);
-                for (int q = 0; q < nqt; q++, it++) {
-                    const int as = it & 1;
-                    mbar_wait(&S.empty_a[as], ((it >> 1) & 1) ^ 1);
+            }
+            for (int q = 0; q < nqt; q++, it++) {
+                const int as = it % TC_NA;
+                mbar_wait(&S.empty_a[as], ((it / TC_NA) & 1) ^ 1);
+                if (elect_one()) {
                     mbar_expect_tx(&S.full_a[as], TC_A_BYTES);
                     tma_load_2d(smem_a + as * TC_A_BYTES, &map_q, 0, q * TC_QT, &S.full_a[as]);
                 }
             }
         }
+        __syncwarp();
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            // block-scaled instruction descriptor (cute::UMMA::InstrDescriptorBlockScaled): A = B = E2M1 (MXF4 format 1) at bits 7 / 10, both
-            // K-major, N >> 3 at bit 17, scale format UE8M0 at bit 23, M >> 4 at bit 24, scale-factor ids 0, K = 64 per instruction
-            const uint32_t idesc = (1u << 7) | (1u << 10) | ((uint32_t)(TC_DT >> 3) << 17) | (1u << 23) | ((uint32_t)(TC_QT >> 4) << 24);
-            const uint32_t tsfa = tmem_base + TC_SF_COL, tsfb = tmem_base + TC_SF_COL + 32;
-            uint32_t it = 0;
-            for (int k = 0; k < my_tiles; k++) {
-                const int bs = k & 1;
-                mbar_wait(&S.full_b[bs], (k >> 1) & 1);
-                for (int q = 0; q < nqt; q++, it++) {
-                    const int as = it & 1, acc = it & 1;
-                    mbar_wait(&S.full_a[as], (it >> 1) & 1);
-                    mbar_wait(&S.tmem_empty[acc], ((it >> 1) & 1) ^ 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t d = tmem_base + acc * TC_DT;
-                    const uint64_t da = umma_desc_sw128(smem_u32(smem_a + as * TC_A_BYTES));
-                    const uint64_t db = umma_desc_sw128(smem_u32(smem_b + bs * TC_B_BYTES));
+        // ===== MMA issuer (whole warp in the loop, one elected lane issues) =====
+        // block-scaled instruction descriptor (cute::UMMA::InstrDescriptorBlockScaled): A = B = E2M1 (MXF4 format 1) at bits 7 / 10, both
+        // K-major, N >> 3 at bit 17, scale format UE8M0 at bit 23, M >> 4 at bit 24, scale-factor ids 0, K = 64 per instruction
+        const uint32_t idesc = (1u << 7) | (1u << 10) | ((uint32_t)(TC_DT >> 3) << 17) | (1u << 23) | ((uint32_t)(TC_QT >> 4) << 24);
+        const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t tsfa = tb + TC_SF_COL, tsfb = tb + TC_SF_COL + 32;
+        uint32_t it = 0;
+        for (int k = 0; k < my_tiles; k++) {
+            const int bs = k & 1;
+            mbar_wait(&S.full_b[bs], (k >> 1) & 1);
+            const uint64_t db = umma_desc_sw128(smem_u32(smem_b + bs * TC_B_BYTES));
+            for (int q = 0; q < nqt; q++, it++) {
+                const int as = it % TC_NA, acc = it & 1;
+                mbar_wait(&S.full_a[as], (it / TC_NA) & 1);
+                mbar_wait(&S.tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d = tb + acc * TC_DT;
+                const uint64_t da = umma_desc_sw128(smem_u32(smem_a + as * TC_A_BYTES));
+                if (elect_one()) {
 #pragma unroll
                     for (int ks = 0; ks < 4; ks++)   // 64 elements = 32 bytes of K per MMA: advance the start address by 2 x 16 B
                         umma_mxf4(d, da + 2 * ks, db + 2 * ks, idesc, ks ? 1u : 0u, tsfa, tsfb);
                     umma_commit(&S.empty_a[as]);        // A stage reusable once these MMAs retire
                     umma_commit(&S.tmem_full[acc]);     // accumulator ready for the epilogue
+                    if (q == nqt - 1) umma_commit(&S.empty_b[bs]);
                 }
-                umma_commit(&S.empty_b[bs]);
+                __syncwarp();
             }
         }
     } else {
@@ -260,28 +274,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_fp4(const __grid_constan
                 TMEM_LD16(tcol + 32, (v + 32));
                 TMEM_LD8(tcol + 48, (v + 48));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                // groups of 8 accumulators (fp32, exact integers): only a group whose maximum beats the threshold enters the update
-#pragma unroll
-                for (int g = 0; g < PW / 8; g++) {
-                    const float m = fmaxf(fmaxf(fmaxf(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1])), fmaxf(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3]))),
-                                          fmaxf(fmaxf(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])), fmaxf(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7]))));
-                    if (m > thr) {
-#pragma unroll
-                        for (int j = 0; j < 8; j++) {
-                            const int col = half * PW + 8 * g + j;
-                            if (col < valid_cols) {
-                                const uint32_t hd = (uint32_t)(256 - __float2int_rn(__uint_as_float(v[8 * g + j]))) >> 1;
-                                const uint32_t key = (hd << 23) | (uint32_t)(k * TC_DT + col);
-                                k2 = min(k2, max(k1, key)); k1 = min(k1, key);
-                            }
-                        }
-                        thr = (float)(256 - 2 * (int)(k2 >> 23));
-                    }
-                }
-                S.top[q][half][row_in_tile][0] = k1; S.top[q][half][row_in_tile][1] = k2;
+                // the accumulator stage is free as soon as every epilogue warp holds its columns in registers: the next-but-one MMA
+                // runs under the scan below
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&S.tmem_empty[acc]);
+                // fast path: one three-input max tree over the warp's 56 accumulators (fp32, exact integers) and one branch; only a
+                // row whose maximum beats the threshold looks at its groups of 8
+                float gm[PW / 8];
+#pragma unroll
+                for (int g = 0; g < PW / 8; g++) {
+                    const float m0 = fmaxf(fmaxf(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1])), __uint_as_float(v[8 * g + 2]));
+                    const float m1 = fmaxf(fmaxf(__uint_as_float(v[8 * g + 3]), __uint_as_float(v[8 * g + 4])), __uint_as_float(v[8 * g + 5]));
+                    gm[g] = fmaxf(fmaxf(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])), fmaxf(m0, m1));
+                }
+                const float mall = fmaxf(fmaxf(fmaxf(fmaxf(gm[0], gm[1]), gm[2]), fmaxf(fmaxf(gm[3], gm[4]), gm[5])), gm[6]);
+                if (mall > thr) {
+#pragma unroll
+                    for (int g = 0; g < PW / 8; g++) {
+                        if (gm[g] > thr) {
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                const int col = half * PW + 8 * g + j;
+                                if (col < valid_cols) {
+                                    const uint32_t hd = (uint32_t)(256 - __float2int_rn(__uint_as_float(v[8 * g + j]))) >> 1;
+                                    const uint32_t key = (hd << 23) | (uint32_t)(k * TC_DT + col);
+                                    k2 = min(k2, max(k1, key)); k1 = min(k1, key);
+                                }
+                            }
+                            thr = (float)(256 - 2 * (int)(k2 >> 23));
+                        }
+                    }
+                }
+                S.top[q][half][row_in_tile][0] = k1; S.top[q][half][row_in_tile][1] = k2;
             }
         }
         // merge the two column halves and write this CTA's partial result
@@ -351,7 +376,7 @@ static bool make_map(CUtensorMap *map, const void *base, long long rows, int box
     return true;
 }
 
-size_t knn_fp4_smem_bytes() { return 2 * TC_A_BYTES + 2 * TC_B_BYTES + sizeof(TcShared) + 1024; }
+size_t knn_fp4_smem_bytes() { return TC_NA * TC_A_BYTES + 2 * TC_B_BYTES + sizeof(TcShared) + 1024; }
 int knn_fp4_max_queries() { return TC_MAX_QTILES * TC_QT; }
 long long knn_fp4_padded_rows(long long nrows) { return (nrows + TC_DT - 1) / TC_DT * TC_DT; }
 int knn_fp4_padded_queries(int nq) { return (nq + TC_QT - 1) / TC_QT * TC_QT; }

@@ -222,6 +222,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const __grid_constant
                     uint32_t v[64];
                     TMEM_LD64(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TC_DT + c0), v);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (c0 + 64 == (half + 1) * (TC_DT / 2)) {
+                        // last chunk in registers: the accumulator stage is free, the next-but-one MMA runs under the scan below
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&S.tmem_empty[acc]);
+                    }
 #pragma unroll
                     for (int g = 0; g < 8; g++) {
                         const int m = max(max(max((int)v[8 * g], (int)v[8 * g + 1]), max((int)v[8 * g + 2], (int)v[8 * g + 3])),
@@ -241,9 +247,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const __grid_constant
                     }
                 }
                 S.top[q][half][row_in_tile][0] = k1; S.top[q][half][row_in_tile][1] = k2;
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&S.tmem_empty[acc]);
             }
         }
         // merge the two column halves and write this CTA's partial result

@@ -239,7 +239,7 @@ struct orbx_db {
     mutable std::string err;
     long long launches = 0;
     // tensor-core backend (orbx_knn_tc.cu): {-1,+1} int8 expansion of the shard (built on first use) and of the queries
-    int backend = 1;                 // ORBX_KNN_TENSOR
+    int backend = 2;                 // ORBX_KNN_TENSOR_FP4 (the fastest of the three; all three give identical results)
     int sm_count = 0;
     int8_t *d_dbe = nullptr;
     int8_t *d_qe = nullptr; int qe_cap = 0;
