@@ -20,6 +20,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <mutex>
+#include <cstdlib>
 #include <string>
 
 #include "orbx_dev.h"
@@ -148,9 +149,9 @@ struct TcShared {
 
 __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_fp4(const __grid_constant__ CUtensorMap map_q,
                                                            const __grid_constant__ CUtensorMap map_db, int nq, int nqt,
-                                                           long long nrows, int tile0, int ntiles, long long row_offset,
+                                                           long long nrows, int tile0, int ntiles, long long row_offset, int qsplit,
                                                            const unsigned long long *__restrict__ seed,
-                                                           unsigned long long *__restrict__ partial) {
+                                                           unsigned long long *__restrict__ partial, unsigned int *gthr) {
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment: round the dynamic shared-memory base up (1 KB of slack is requested)
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -159,8 +160,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_fp4(const __grid_constan
     uint8_t *smem_b = smem + TC_NA * TC_A_BYTES;
     TcShared &S = *reinterpret_cast<TcShared *>(smem + TC_NA * TC_A_BYTES + 2 * TC_B_BYTES);
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp index, provably uniform
-    const int cta = blockIdx.x, G = gridDim.x;
-    const int my_tiles = cta < ntiles ? (ntiles - cta + G - 1) / G : 0;
+    // qsplit consecutive CTAs share one database-tile slot and split the query tiles between them (the seeding pass: one query tile per
+    // CTA, so that its latency is one tile, not sixteen); qsplit = 1 is the main pass: every CTA takes all query tiles of its tiles
+    const int cta = blockIdx.x / qsplit, G = gridDim.x / qsplit, qpart = blockIdx.x % qsplit;
+    const int q_per = (nqt + qsplit - 1) / qsplit, q_lo = qpart * q_per, q_hi = min(nqt, q_lo + q_per);
+    const int my_tiles = (cta < ntiles && q_lo < q_hi) ? (ntiles - cta + G - 1) / G : 0;
 
     // running top-2 state; with a seed (top-2 of an earlier pass over lower rows) only strictly closer rows can matter,
     // so both slots start at the virtual key (seed second-best distance, sentinel row)
@@ -212,7 +216,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_fp4(const __grid_constan
                 mbar_expect_tx(&S.full_b[bs], TC_B_BYTES);
                 tma_load_2d(smem_b + bs * TC_B_BYTES, &map_db, 0, t * TC_DT, &S.full_b[bs]);
             }
-            for (int q = 0; q < nqt; q++, it++) {
+            for (int q = q_lo; q < q_hi; q++, it++) {
                 const int as = it % TC_NA;
                 mbar_wait(&S.empty_a[as], ((it / TC_NA) & 1) ^ 1);
                 if (elect_one()) {
@@ -234,7 +238,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_fp4(const __grid_constan
             const int bs = k & 1;
             mbar_wait(&S.full_b[bs], (k >> 1) & 1);
             const uint64_t db = umma_desc_sw128(smem_u32(smem_b + bs * TC_B_BYTES));
-            for (int q = 0; q < nqt; q++, it++) {
+            for (int q = q_lo; q < q_hi; q++, it++) {
                 const int as = it % TC_NA, acc = it & 1;
                 mbar_wait(&S.full_a[as], (it / TC_NA) & 1);
                 mbar_wait(&S.tmem_empty[acc], ((it >> 1) & 1) ^ 1);
@@ -247,7 +251,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_fp4(const __grid_constan
                         umma_mxf4(d, da + 2 * ks, db + 2 * ks, idesc, ks ? 1u : 0u, tsfa, tsfb);
                     umma_commit(&S.empty_a[as]);        // A stage reusable once these MMAs retire
                     umma_commit(&S.tmem_full[acc]);     // accumulator ready for the epilogue
-                    if (q == nqt - 1) umma_commit(&S.empty_b[bs]);
+                    if (q == q_hi - 1) umma_commit(&S.empty_b[bs]);
                 }
                 __syncwarp();
             }
@@ -261,10 +265,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_fp4(const __grid_constan
             const int t = tile0 + cta + k * G;
             const long long tile_row0 = (long long)t * TC_DT;
             const int valid_cols = (int)min((long long)TC_DT, nrows - tile_row0);
-            for (int q = 0; q < nqt; q++, it++) {
+            for (int q = q_lo; q < q_hi; q++, it++) {
                 const int acc = it & 1;
                 uint32_t k1 = S.top[q][half][row_in_tile][0], k2 = S.top[q][half][row_in_tile][1];
-                float thr = (float)(256 - 2 * (int)(k2 >> 23));   // a dot product must exceed this to enter the top 2
+                const uint32_t k2_in = k2;
+                // thresholds shared between the CTAs: gthr[query] = the smallest second-best distance any CTA has published.  A row of the final
+                // top 2 has a distance <= that (ties with rows of other CTAs are decided by row number later, so "<=" here, "<" against this
+                // CTA's own second best, whose rows come first).  The load is in flight during the wait for the accumulator.
+                unsigned int *gq = gthr + q * TC_QT + row_in_tile;
+                const float thr_g = (float)(255 - 2 * (int)min(__ldcg(gq), 511u));
+                float thr = fmaxf((float)(256 - 2 * (int)(k2 >> 23)), thr_g);   // a dot product must exceed this to enter the top 2
                 mbar_wait(&S.tmem_full[acc], (it >> 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 constexpr int PW = TC_DT / TC_EPI_PARTS;     // 56 columns per warp: one x32, one x16 and one x8 load
@@ -302,9 +312,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_fp4(const __grid_constan
                                     k2 = min(k2, max(k1, key)); k1 = min(k1, key);
                                 }
                             }
-                            thr = (float)(256 - 2 * (int)(k2 >> 23));
+                            thr = fmaxf((float)(256 - 2 * (int)(k2 >> 23)), thr_g);
                         }
                     }
+                    if (k2 != k2_in && (k2 & 0x7FFFFFu) != TC_SENTINEL) atomicMin(gq, k2 >> 23);
                 }
                 S.top[q][half][row_in_tile][0] = k1; S.top[q][half][row_in_tile][1] = k2;
             }
@@ -323,7 +334,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_fp4(const __grid_constan
                             const uint32_t key = S.top[q][pp][row_in_tile][j];
                             k2 = min(k2, max(k1, key)); k1 = min(k1, key);
                         }
-                    unsigned long long *o = partial + ((size_t)cta * nq + qi) * 2;
+                    unsigned long long *o = partial + ((size_t)blockIdx.x * nq + qi) * 2;
                     const uint32_t keys[2] = {k1, k2};
 #pragma unroll
                     for (int j = 0; j < 2; j++) {
@@ -417,15 +428,22 @@ int launch_knn2_fp4(const uint8_t *d_qe, int nq, const uint8_t *d_dbe, long long
         }
         configured = true;
     }
+    unsigned int *gthr = reinterpret_cast<unsigned int *>(d_partial + (size_t)(sm_count + 1) * nq * 2);
+    cudaMemsetAsync(gthr, 0xFF, (size_t)TC_MAX_QTILES * TC_QT * sizeof(unsigned int), stream);
     if (ntiles <= 2 * grid) {   // small shard: one pass
-        k_knn2_fp4<<<grid, TC_THREADS, smem, stream>>>(mq, mdb, nq, nqt, nrows, 0, ntiles, row_offset, nullptr, d_partial);
+        k_knn2_fp4<<<grid, TC_THREADS, smem, stream>>>(mq, mdb, nq, nqt, nrows, 0, ntiles, row_offset, 1, nullptr, d_partial, gthr);
         *nparts_out = grid;
         return 1;
     }
     unsigned long long *seed = d_partial + (size_t)grid * nq * 2;
-    k_knn2_fp4<<<grid, TC_THREADS, smem, stream>>>(mq, mdb, nq, nqt, nrows, 0, grid, row_offset, nullptr, d_partial);
-    merge(d_partial, grid, nq, seed, stream);
-    k_knn2_fp4<<<grid, TC_THREADS, smem, stream>>>(mq, mdb, nq, nqt, nrows, grid, ntiles - grid, row_offset, seed, d_partial);
+    // seeding pass: (query tile, database tile) pairs spread over the CTAs, one pair each -- t1 tiles x nqt query tiles <= grid
+    static const bool split_seed = getenv("ORBX_KNN_SEED_SPLIT") && atoi(getenv("ORBX_KNN_SEED_SPLIT")) != 0;
+    const bool sp = split_seed && grid / nqt > 0;
+    const int t1 = sp ? grid / nqt : 1, qs = sp ? nqt : 1, g1 = sp ? t1 * nqt : grid;
+    const int first = sp ? t1 : grid;
+    k_knn2_fp4<<<g1, TC_THREADS, smem, stream>>>(mq, mdb, nq, nqt, nrows, 0, first, row_offset, qs, nullptr, d_partial, gthr);
+    merge(d_partial, g1, nq, seed, stream);
+    k_knn2_fp4<<<grid, TC_THREADS, smem, stream>>>(mq, mdb, nq, nqt, nrows, first, ntiles - first, row_offset, 1, seed, d_partial, gthr);
     *nparts_out = grid + 1;
     return 3;
 }

@@ -201,26 +201,42 @@ __global__ void __launch_bounds__(KQ_THREADS) k_knn2(const uint4 *__restrict__ d
     emit(qb, kb1, kb2);
 }
 
-__global__ void __launch_bounds__(256) k_knn2_merge(const unsigned long long *__restrict__ partial, int nparts, int nq,
+// 32 queries per CTA (lanes), 16 warps striding over the partial blocks (coalesced 512-byte reads per warp), then one pass over the 16
+// per-warp results in shared memory.  The two smallest distinct keys do not depend on the visiting order.
+__device__ __forceinline__ void top2_insert(unsigned long long key, unsigned long long &k1, unsigned long long &k2) {
+    if (key < k1) { k2 = k1; k1 = key; } else if (key < k2 && key != k1) k2 = key;
+}
+
+__global__ void __launch_bounds__(512) k_knn2_merge(const unsigned long long *__restrict__ partial, int nparts, int nq,
                                                     unsigned long long *__restrict__ out) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nq) return;
+    __shared__ unsigned long long sm[16][32][2];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, q = blockIdx.x * 32 + lane;
     unsigned long long k1 = NONE64, k2 = NONE64;
-    for (int p = 0; p < nparts; p++) {
-        const unsigned long long *v = partial + ((size_t)p * nq + q) * 2;
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-            const unsigned long long key = v[j];
-            if (key < k1) { k2 = k1; k1 = key; } else if (key < k2 && key != k1) k2 = key;
+    if (q < nq) {
+#pragma unroll 4
+        for (int p = w; p < nparts; p += 16) {
+            const unsigned long long *v = partial + ((size_t)p * nq + q) * 2;
+            const unsigned long long a = v[0], b = v[1];
+            top2_insert(a, k1, k2); top2_insert(b, k1, k2);
         }
     }
-    out[2 * q] = k1; out[2 * q + 1] = k2;
+    sm[w][lane][0] = k1; sm[w][lane][1] = k2;
+    __syncthreads();
+    if (w == 0 && q < nq) {
+#pragma unroll
+        for (int i = 1; i < 16; i++) { top2_insert(sm[i][lane][0], k1, k2); top2_insert(sm[i][lane][1], k1, k2); }
+        out[2 * q] = k1; out[2 * q + 1] = k2;
+    }
+}
+
+static inline void launch_merge(const unsigned long long *parts, int nparts, int nq, unsigned long long *out, cudaStream_t stream) {
+    k_knn2_merge<<<(nq + 31) / 32, 512, 0, stream>>>(parts, nparts, nq, out);
 }
 
 thread_local std::string g_db_error;
 
 void merge_launch(const unsigned long long *parts, int nparts, int nq, unsigned long long *out, cudaStream_t stream) {
-    k_knn2_merge<<<(nq + 255) / 256, 256, 0, stream>>>(parts, nparts, nq, out);
+    launch_merge(parts, nparts, nq, out, stream);
 }
 
 }  // namespace
@@ -405,7 +421,7 @@ static int query_device_tensor(orbx_db *db, const uint8_t *d_queries, int nq, un
         const int l = launch_knn2_tc(db->d_qe, n, db->d_dbe, db->nrows, db->row_offset, db->sm_count, db->d_partial_tc, &nparts,
                                      merge_launch, db->stream, db->err);
         if (!l) return ORBX_E_CUDA;
-        k_knn2_merge<<<(n + 255) / 256, 256, 0, db->stream>>>(db->d_partial_tc, nparts, n, d_packed_out + (size_t)q0 * 2);
+        launch_merge(db->d_partial_tc, nparts, n, d_packed_out + (size_t)q0 * 2, db->stream);
         db->launches += l + 1;
         DB_TRY(db, cudaGetLastError());
     }
@@ -428,7 +444,7 @@ static int query_device_fp4(orbx_db *db, const uint8_t *d_queries, int nq, unsig
         DB_TRY(db, cudaMalloc((void **)&db->d_qe4, (size_t)qcap * 128));
         db->qe4_cap = qcap;
     }
-    const size_t need = (size_t)(db->sm_count + 1) * std::min(nq, maxq) * 2;
+    const size_t need = (size_t)(db->sm_count + 1) * std::min(nq, maxq) * 2 + (size_t)maxq / 2;   // + one u32 per query: the thresholds the CTAs share
     if (need > db->partial_tc_cap) {
         if (db->d_partial_tc) cudaFree(db->d_partial_tc);
         db->d_partial_tc = nullptr; db->partial_tc_cap = 0;
@@ -442,7 +458,7 @@ static int query_device_fp4(orbx_db *db, const uint8_t *d_queries, int nq, unsig
         const int l = launch_knn2_fp4(db->d_qe4, n, db->d_dbe4, db->nrows, db->row_offset, db->sm_count, db->d_partial_tc, &nparts, merge_launch,
                                       db->stream, db->err);
         if (!l) return ORBX_E_CUDA;
-        k_knn2_merge<<<(n + 255) / 256, 256, 0, db->stream>>>(db->d_partial_tc, nparts, n, d_packed_out + (size_t)q0 * 2);
+        launch_merge(db->d_partial_tc, nparts, n, d_packed_out + (size_t)q0 * 2, db->stream);
         db->launches += l + 1;
         DB_TRY(db, cudaGetLastError());
     }
@@ -460,7 +476,7 @@ int orbx_knn2_query_device(orbx_db *db, const uint8_t *d_queries, int nq, unsign
     dim3 grid((nq + KQ_THREADS * KQ_QPT - 1) / (KQ_THREADS * KQ_QPT), db->nchunks);
     k_knn2<<<grid, KQ_THREADS, 0, db->stream>>>(reinterpret_cast<const uint4 *>(db->d_rows), db->nrows, db->row_offset,
                                                 reinterpret_cast<const uint4 *>(d_queries), nq, db->rows_per_chunk, db->d_partial);
-    k_knn2_merge<<<(nq + 255) / 256, 256, 0, db->stream>>>(db->d_partial, db->nchunks, nq, d_packed_out);
+    launch_merge(db->d_partial, db->nchunks, nq, d_packed_out, db->stream);
     db->launches += 2;
     DB_TRY(db, cudaGetLastError());
     return ORBX_OK;
@@ -469,7 +485,7 @@ int orbx_knn2_query_device(orbx_db *db, const uint8_t *d_queries, int nq, unsign
 int orbx_knn2_merge_device(orbx_db *db, const unsigned long long *d_partials, int nparts, int nq, unsigned long long *d_packed_out) {
     if (!db || !d_partials || !d_packed_out || nparts < 1 || nq < 1) return ORBX_E_INVALID;
     DB_TRY(db, cudaSetDevice(db->device));
-    k_knn2_merge<<<(nq + 255) / 256, 256, 0, db->stream>>>(d_partials, nparts, nq, d_packed_out);
+    launch_merge(d_partials, nparts, nq, d_packed_out, db->stream);
     db->launches += 1;
     DB_TRY(db, cudaGetLastError());
     return ORBX_OK;
