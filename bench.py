@@ -267,6 +267,7 @@ def device_leg(torch, dist, orbx, synth, dev, local_rank, rank, world, stream, b
         bounds = ex1.image_bounds(cam, W1, H1)
         outs = [torch.zeros((B1, cap1), dtype=torch.int32, device=dev) for _ in range(4)]
         mstate = {"q": [None] * R1}
+        pairs1 = [(f, (f + 1) % B1) for f in range(B1)]
 
     def step1(i):
         r = i % R1
@@ -276,10 +277,9 @@ def device_leg(torch, dist, orbx, synth, dev, local_rank, rank, world, stream, b
             q = mstate["q"][r]
             if q is not None:
                 quvr, qlev, nq = q
-                for f in range(B1):
-                    t = (f + 1) % B1
-                    ex1.match_windowed_grid_device(de1[f].data_ptr(), quvr[f].data_ptr(), qlev[f].data_ptr(), nq[f], un1[t].data_ptr(), de1[t].data_ptr(),
-                                                   st1[t].data_ptr(), it1[t].data_ptr(), bounds, *[o[f].data_ptr() for o in outs])
+                # every frame searched in its successor, all B1 pairs in one launch (query counts are read from n1 on the device)
+                ex1.match_windowed_grid_batch_device(pairs1, B1, cap1, de1.data_ptr(), quvr.data_ptr(), qlev.data_ptr(), n1.data_ptr(), un1.data_ptr(),
+                                                     de1.data_ptr(), st1.data_ptr(), it1.data_ptr(), bounds, *[o.data_ptr() for o in outs])
 
     if match:
         # queries of every ring entry, prepared once outside the clock (in the reference this is CPU geometry: projection by the
@@ -323,17 +323,23 @@ def device_leg(torch, dist, orbx, synth, dev, local_rank, rank, world, stream, b
         barrier()
         ev0.record(stream)
         for _ in range(reps):
-            for f in range(B1):
-                t = (f + 1) % B1
-                ex1.match_windowed_grid_device(de1[f].data_ptr(), quvr[f].data_ptr(), qlev[f].data_ptr(), nq[f], un1[t].data_ptr(), de1[t].data_ptr(),
-                                               st1[t].data_ptr(), it1[t].data_ptr(), bounds, *[o[f].data_ptr() for o in outs])
+            ex1.match_windowed_grid_batch_device(pairs1, B1, cap1, de1.data_ptr(), quvr.data_ptr(), qlev.data_ptr(), n1.data_ptr(), un1.data_ptr(),
+                                                 de1.data_ptr(), st1.data_ptr(), it1.data_ptr(), bounds, *[o.data_ptr() for o in outs])
         ev1.record(stream)
         ex1.sync()
         tm = ev0.elapsed_time(ev1) * 1e-3
+        # one frame pair per launch (the call a per-frame tracker makes): the latency of a single search
+        ev0.record(stream)
+        for _ in range(reps):
+            ex1.match_windowed_grid_device(de1[0].data_ptr(), quvr[0].data_ptr(), qlev[0].data_ptr(), nq[0], un1[1].data_ptr(), de1[1].data_ptr(),
+                                           st1[1].data_ptr(), it1[1].data_ptr(), bounds, *[o[0].data_ptr() for o in outs])
+        ev1.record(stream)
+        ex1.sync()
+        t_single = ev0.elapsed_time(ev1) * 1e-3 / reps
         matched = float(((outs[0][0, :nq[0]] >= 0) & (outs[1][0, :nq[0]] <= 100)).float().mean().item())
         out["windowed_match"] = {"queries_per_s": world * reps * sum(nq) / tm, "us_per_frame_pair": 1e6 * tm / (reps * B1), "queries_per_frame": sum(nq) / B1,
-                                 "matched_fraction_th_high": matched,
-                                 "api": "orbx_match_windowed_grid_device, device-resident queries / grid / descriptors, one launch per frame pair"}
+                                 "matched_fraction_th_high": matched, "us_single_pair_launch": 1e6 * t_single,
+                                 "api": "orbx_match_windowed_grid_batch_device, device-resident queries / grid / descriptors, all frame pairs of the batch in one launch"}
     ex1.close()
     return out
 
@@ -624,6 +630,7 @@ def main():
                 lanes[k][0].extract_batch_collect()
 
     e2e_async = None
+    e2e_per_rank = None
     e2e_stream_steps = e2e_steps
     try:
         run_streaming(NL * RING + NL)                     # graph capture for each lane's (input, output) pairs
@@ -632,12 +639,18 @@ def main():
         # long enough that filling and draining the four batches in flight (about one batch latency, ~1 ms) is noise: 240 steps ~ 90 ms
         e2e_stream_steps = max(e2e_steps, 240)
         run_streaming(e2e_stream_steps)
+        dt_own = time.perf_counter() - t0                 # this rank's own stream, before it waits for the others
         barrier()
         dta = time.perf_counter() - t0
+        e2e_per_rank = [e2e_stream_steps * BATCH / dt_own]
         if world > 1:
             tt = torch.tensor([dta], dtype=torch.float64, device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dta = float(tt.item())
+            own = torch.zeros(world, dtype=torch.float64, device=dev)
+            own[rank] = dt_own
+            dist.all_reduce(own)
+            e2e_per_rank = [e2e_stream_steps * BATCH / float(x) for x in own.cpu()]
         e2e_async = world * e2e_stream_steps * BATCH / dta
         # check on the spot that the streamed results are the blocking call's
         mono_b, n_b, kps_b, desc_b = ex.extract_batch(pinned_in[1].numpy())
@@ -1042,7 +1055,7 @@ def main():
                                 "note": "one handle, one batch in flight (every step waits for the previous one on the same stream)"},
                 "sustained": sustained,
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "steps": e2e_stream_steps if isinstance(e2e_async, float) else e2e_steps, "h2d_ceiling": h2d_ceiling,
+                        "steps": e2e_stream_steps if isinstance(e2e_async, float) else e2e_steps, "h2d_ceiling": h2d_ceiling, "per_rank": e2e_per_rank,
                         "api": (f"orbx_extract_batch_submit / _collect from one host thread over {NL} handles (batch i uploads while earlier batches compute and download), "
                                 "pinned host frames in / pinned keypoint + descriptor arrays out"
                                 if isinstance(e2e_async, float) else

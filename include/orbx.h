@@ -270,6 +270,16 @@ int orbx_match_windowed_grid_device(orbx_handle *h, const uint8_t *d_q_desc, con
                                     const orbx_keypoint *d_t_kp_un, const uint8_t *d_t_desc, const int32_t *d_cell_start,
                                     const int32_t *d_cell_items, const float *bounds4, int32_t *d_best_idx, int32_t *d_best_dist,
                                     int32_t *d_second_idx, int32_t *d_second_dist);
+/* The same search for npairs (query frame, train frame) pairs of ONE batch in one launch -- e.g. frame i against frame i + 1 for a whole
+ * batch of a camera sequence (UPSTREAM Tracking::TrackWithMotionModel -> ORBmatcher::SearchByProjection once per frame).  Every device array
+ * is laid out [batch][cap] as orbx_extract_batch_device / orbx_frame_grid_batch_device leave it (d_cell_start: [batch][ORBX_GRID_CELLS + 1]);
+ * d_q_* and the four outputs are indexed by the pair's query frame, the train arrays by its train frame; the number of queries of a
+ * frame is read from d_n[frame] on the device (no host round trip between extraction and search).  pair_*_frame are HOST arrays. */
+int orbx_match_windowed_grid_batch_device(orbx_handle *h, int npairs, const int32_t *pair_query_frame, const int32_t *pair_train_frame, int batch,
+                                          int cap, const uint8_t *d_q_desc, const float *d_q_uvr, const int32_t *d_q_levels, const int32_t *d_n,
+                                          const orbx_keypoint *d_t_kp_un, const uint8_t *d_t_desc, const int32_t *d_cell_start,
+                                          const int32_t *d_cell_items, const float *bounds4, int32_t *d_best_idx, int32_t *d_best_dist,
+                                          int32_t *d_second_idx, int32_t *d_second_dist);
 
 /* ---- Vocabulary-tree descent ------------------------------------------------------------------------------------
  * DBoW2 TemplatedVocabulary<ORB>::transform as UPSTREAM Frame::ComputeBoW calls it (mpORBvocabulary->transform(desc, BowVec, FeatVec, 4)):

@@ -1309,6 +1309,30 @@ int orbx_match_windowed_grid_device(orbx_handle *h, const uint8_t *d_q_desc, con
     return ORBX_OK;
 }
 
+int orbx_match_windowed_grid_batch_device(orbx_handle *h, int npairs, const int32_t *pair_query_frame, const int32_t *pair_train_frame, int batch,
+                                          int cap, const uint8_t *d_q_desc, const float *d_q_uvr, const int32_t *d_q_levels, const int32_t *d_n,
+                                          const orbx_keypoint *d_t_kp_un, const uint8_t *d_t_desc, const int32_t *d_cell_start,
+                                          const int32_t *d_cell_items, const float *bounds4, int32_t *d_best_idx, int32_t *d_best_dist,
+                                          int32_t *d_second_idx, int32_t *d_second_dist) {
+    if (!h) return ORBX_E_INVALID;
+    if (npairs < 0 || batch < 1 || cap < 1 || !bounds4 ||
+        (npairs > 0 && (!pair_query_frame || !pair_train_frame || !d_q_desc || !d_q_uvr || !d_q_levels || !d_n || !d_t_kp_un || !d_t_desc ||
+                        !d_cell_start || !d_cell_items || !d_best_idx || !d_best_dist || !d_second_idx || !d_second_dist)))
+        return fail(h, ORBX_E_INVALID, "null argument");
+    for (int i = 0; i < npairs; i++)
+        if (pair_query_frame[i] < 0 || pair_query_frame[i] >= batch || pair_train_frame[i] < 0 || pair_train_frame[i] >= batch)
+            return fail(h, ORBX_E_INVALID, "frame index of a pair outside the batch");
+    if (((uintptr_t)d_q_desc | (uintptr_t)d_t_desc) & 15) return fail(h, ORBX_E_INVALID, "descriptor arrays must be 16-byte aligned");
+    if (!(bounds4[2] > bounds4[0]) || !(bounds4[3] > bounds4[1])) return fail(h, ORBX_E_INVALID, "empty image bounds");
+    if (npairs == 0) return ORBX_OK;
+    CU_TRY(h, cudaSetDevice(h->device));
+    h->launches += match_windowed_grid_batch_device(h->stream, npairs, pair_query_frame, pair_train_frame, cap, d_q_desc, d_q_uvr, d_q_levels, d_n,
+                                                    reinterpret_cast<const KeypointRec *>(d_t_kp_un), d_t_desc, d_cell_start, d_cell_items, bounds4,
+                                                    d_best_idx, d_best_dist, d_second_idx, d_second_dist);
+    CU_TRY(h, cudaGetLastError());
+    return ORBX_OK;
+}
+
 // ---- plan inspection without a GPU (used by the CPU-only tests) --------------------------------------------------
 // Fills level sizes, cell counts, quotas and candidate capacities of the plan for (params, w, h); returns nlevels or < 0.
 int orbx_plan_probe(int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th, int width, int height,

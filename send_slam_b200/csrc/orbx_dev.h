@@ -144,6 +144,11 @@ int launch_knn2_fp4(const uint8_t *d_qe, int nq, const uint8_t *d_dbe, long long
 }  // namespace orbx
 
 namespace orbx {
+constexpr int kMaxMatchPairs = 64;   // (query frame, train frame) pairs per launch of the batched grid search (kernel-parameter table)
+int match_windowed_grid_batch_device(cudaStream_t stream, int npairs, const int32_t *pair_q, const int32_t *pair_t, int cap, const uint8_t *d_q_desc,
+                                     const float *d_q_uvr, const int32_t *d_q_levels, const int32_t *d_n, const KeypointRec *d_t_kp,
+                                     const uint8_t *d_t_desc, const int32_t *d_cell_start, const int32_t *d_cell_items, const float *bounds4,
+                                     int32_t *d_best_idx, int32_t *d_best_dist, int32_t *d_second_idx, int32_t *d_second_dist);
 int match_windowed_grid_device(cudaStream_t stream, const uint8_t *d_q_desc, const float *d_q_uvr, const int32_t *d_q_levels, int nq,
                                const KeypointRec *d_t_kp, const uint8_t *d_t_desc, const int32_t *d_cell_start, const int32_t *d_cell_items,
                                const float *bounds4, int32_t *d_best_idx, int32_t *d_best_dist, int32_t *d_second_idx, int32_t *d_second_dist);

@@ -92,6 +92,75 @@ __global__ void __launch_bounds__(256) k_match_windowed(const uint4 *__restrict_
 // (ix outer, iy inner) of the query window; in the CSR layout (cell = ix * 48 + iy) the cells iy0..iy1 of one grid column are
 // one contiguous item range, so a warp strides over a few dozen candidates instead of every train keypoint.  The CSR position
 // is monotone in the reference's visiting order (grid column, grid row, train index), which makes it the tie-break key.
+// One warp, one query.  The cells iy0..iy1 of every grid column of the window are one CSR range; the ranges of all columns are fetched
+// at once (lane = column), laid end to end by a warp scan, and the lanes stride over the concatenated candidate list -- four dependent
+// load latencies per query (cell_start -> cell_items -> keypoint -> descriptor) instead of four per grid column.
+__device__ __forceinline__ void match_grid_query(int lane, uint4 q0, uint4 q1, float x, float y, float r, int minLevel, int maxLevel,
+                                                 const KeypointRec *__restrict__ tkp, const uint4 *__restrict__ tdesc,
+                                                 const int32_t *__restrict__ cell_start, const int32_t *__restrict__ cell_items,
+                                                 float minX, float minY, float invW, float invH, int32_t *best_idx, int32_t *best_dist,
+                                                 int32_t *second_idx, int32_t *second_dist) {
+    const bool check = (minLevel > 0) || (maxLevel >= 0);
+    const int cx0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, minX), r), invW)));
+    const int cx1 = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, minX), r), invW)));
+    const int cy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, minY), r), invH)));
+    const int cy1 = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, minY), r), invH)));
+    unsigned long long k1 = NONE64, k2 = NONE64;
+    if (cx0 < GRID_COLS && cx1 >= 0 && cy0 < GRID_ROWS && cy1 >= 0 && cy0 <= cy1 && cx0 <= cx1) {
+        const int ncol = cx1 - cx0 + 1;                                    // <= 64: lane holds columns cx0 + lane and cx0 + 32 + lane
+        int lo[2] = {0, 0}, cnt[2] = {0, 0}, off[2];
+#pragma unroll
+        for (int hlf = 0; hlf < 2; hlf++) {
+            const int c = 32 * hlf + lane;
+            if (c < ncol) {
+                lo[hlf] = cell_start[(cx0 + c) * GRID_ROWS + cy0];
+                cnt[hlf] = cell_start[(cx0 + c) * GRID_ROWS + cy1 + 1] - lo[hlf];
+            }
+        }
+        int carry = 0;
+#pragma unroll
+        for (int hlf = 0; hlf < 2; hlf++) {                                 // inclusive scan of the counts, columns in visiting order
+            int v = cnt[hlf];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xFFFFFFFFu, v, o); if (lane >= o) v += u; }
+            off[hlf] = v + carry;
+            carry = __shfl_sync(0xFFFFFFFFu, off[hlf], 31);
+        }
+        const int total = carry;
+        for (int j0 = 0; j0 < total; j0 += 32) {
+            const int j = j0 + lane;
+            int p = -1;                                                     // CSR position of candidate j
+            for (int c = 0; c < ncol; c++) {
+                const int oc = __shfl_sync(0xFFFFFFFFu, c < 32 ? off[0] : off[1], c & 31);
+                const int lc = __shfl_sync(0xFFFFFFFFu, c < 32 ? lo[0] : lo[1], c & 31);
+                const int nc = __shfl_sync(0xFFFFFFFFu, c < 32 ? cnt[0] : cnt[1], c & 31);
+                if (p < 0 && j < oc) p = lc + (j - (oc - nc));
+            }
+            if (j >= total || p < 0) continue;
+            const int t = cell_items[p];
+            const KeypointRec kp = tkp[t];
+            if (check) {
+                if (kp.octave < minLevel) continue;
+                if (maxLevel >= 0 && kp.octave > maxLevel) continue;
+            }
+            if (!(fabsf(__fsub_rn(kp.x, x)) < r && fabsf(__fsub_rn(kp.y, y)) < r)) continue;
+            const int d = hamming256(q0, q1, tdesc[2 * t], tdesc[2 * t + 1]);
+            const unsigned long long key = ((unsigned long long)d << 40) | (unsigned long long)p;
+            if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
+        }
+    }
+    unsigned long long b = k1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(0xFFFFFFFFu, b, o); b = v < b ? v : b; }
+    unsigned long long s = (k1 == b) ? k2 : k1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(0xFFFFFFFFu, s, o); s = v < s ? v : s; }
+    if (lane == 0) {
+        *best_idx = b == NONE64 ? -1 : cell_items[(int)(b & 0xFFFFFFFFull)];  *best_dist = b == NONE64 ? 256 : (int32_t)(b >> 40);
+        *second_idx = s == NONE64 ? -1 : cell_items[(int)(s & 0xFFFFFFFFull)]; *second_dist = s == NONE64 ? 256 : (int32_t)(s >> 40);
+    }
+}
+
 __global__ void __launch_bounds__(256) k_match_windowed_grid(const uint4 *__restrict__ qdesc, const float *__restrict__ quvr,
                                                              const int32_t *__restrict__ qlev, int nq,
                                                              const KeypointRec *__restrict__ tkp, const uint4 *__restrict__ tdesc,
@@ -102,42 +171,29 @@ __global__ void __launch_bounds__(256) k_match_windowed_grid(const uint4 *__rest
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= nq) return;
-    const uint4 q0 = qdesc[2 * q], q1 = qdesc[2 * q + 1];
-    const float x = quvr[3 * q], y = quvr[3 * q + 1], r = quvr[3 * q + 2];
-    const int minLevel = qlev[2 * q], maxLevel = qlev[2 * q + 1];
-    const bool check = (minLevel > 0) || (maxLevel >= 0);
-    const int cx0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, minX), r), invW)));
-    const int cx1 = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, minX), r), invW)));
-    const int cy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, minY), r), invH)));
-    const int cy1 = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, minY), r), invH)));
-    unsigned long long k1 = NONE64, k2 = NONE64;
-    if (cx0 < GRID_COLS && cx1 >= 0 && cy0 < GRID_ROWS && cy1 >= 0 && cy0 <= cy1) {
-        for (int ix = cx0; ix <= cx1; ix++) {
-            const int lo = cell_start[ix * GRID_ROWS + cy0], hi = cell_start[ix * GRID_ROWS + cy1 + 1];
-            for (int p = lo + lane; p < hi; p += 32) {
-                const int t = cell_items[p];
-                const KeypointRec kp = tkp[t];
-                if (check) {
-                    if (kp.octave < minLevel) continue;
-                    if (maxLevel >= 0 && kp.octave > maxLevel) continue;
-                }
-                if (!(fabsf(__fsub_rn(kp.x, x)) < r && fabsf(__fsub_rn(kp.y, y)) < r)) continue;
-                const int d = hamming256(q0, q1, tdesc[2 * t], tdesc[2 * t + 1]);
-                const unsigned long long key = ((unsigned long long)d << 40) | (unsigned long long)p;
-                if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
-            }
-        }
-    }
-    unsigned long long b = k1;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(0xFFFFFFFFu, b, o); b = v < b ? v : b; }
-    unsigned long long s = (k1 == b) ? k2 : k1;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(0xFFFFFFFFu, s, o); s = v < s ? v : s; }
-    if (lane == 0) {
-        best_idx[q] = b == NONE64 ? -1 : cell_items[(int)(b & 0xFFFFFFFFull)];  best_dist[q] = b == NONE64 ? 256 : (int32_t)(b >> 40);
-        second_idx[q] = s == NONE64 ? -1 : cell_items[(int)(s & 0xFFFFFFFFull)]; second_dist[q] = s == NONE64 ? 256 : (int32_t)(s >> 40);
-    }
+    match_grid_query(lane, qdesc[2 * q], qdesc[2 * q + 1], quvr[3 * q], quvr[3 * q + 1], quvr[3 * q + 2], qlev[2 * q], qlev[2 * q + 1], tkp, tdesc,
+                     cell_start, cell_items, minX, minY, invW, invH, best_idx + q, best_dist + q, second_idx + q, second_dist + q);
+}
+
+// Several (query frame, train frame) pairs of one batch in one launch: every per-frame array is [batch][cap] as orbx_extract_batch_device
+// and orbx_frame_grid_batch_device leave it; blockIdx.y = pair, the query count of a frame is read from the device-resident n[].
+struct MatchPairs { int qf[kMaxMatchPairs], tf[kMaxMatchPairs]; };
+
+__global__ void __launch_bounds__(256) k_match_windowed_grid_batch(const __grid_constant__ MatchPairs prs, int cap, const uint4 *__restrict__ qdesc,
+                                                                   const float *__restrict__ quvr, const int32_t *__restrict__ qlev,
+                                                                   const int32_t *__restrict__ nq_of, const KeypointRec *__restrict__ tkp,
+                                                                   const uint4 *__restrict__ tdesc, const int32_t *__restrict__ cell_start,
+                                                                   const int32_t *__restrict__ cell_items, float minX, float minY, float invW,
+                                                                   float invH, int32_t *__restrict__ best_idx, int32_t *__restrict__ best_dist,
+                                                                   int32_t *__restrict__ second_idx, int32_t *__restrict__ second_dist) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int qf = prs.qf[blockIdx.y], tf = prs.tf[blockIdx.y];
+    if (q >= min(nq_of[qf], cap)) return;
+    const size_t qi = (size_t)qf * cap + q, tb = (size_t)tf * cap;
+    match_grid_query(lane, qdesc[2 * qi], qdesc[2 * qi + 1], quvr[3 * qi], quvr[3 * qi + 1], quvr[3 * qi + 2], qlev[2 * qi], qlev[2 * qi + 1],
+                     tkp + tb, tdesc + 2 * tb, cell_start + (size_t)tf * (GRID_COLS * GRID_ROWS + 1), cell_items + tb, minX, minY, invW, invH,
+                     best_idx + qi, best_dist + qi, second_idx + qi, second_dist + qi);
 }
 
 // ---- brute-force kNN, k = 2 -----------------------------------------------------------------------------------
@@ -708,6 +764,28 @@ int match_windowed(int device, cudaStream_t stream, const uint8_t *q_desc, const
     cleanup();
 #undef M_TRY
     return ORBX_OK;
+}
+}  // namespace orbx
+
+namespace orbx {
+int match_windowed_grid_batch_device(cudaStream_t stream, int npairs, const int32_t *pair_q, const int32_t *pair_t, int cap, const uint8_t *d_q_desc,
+                                     const float *d_q_uvr, const int32_t *d_q_levels, const int32_t *d_n, const KeypointRec *d_t_kp,
+                                     const uint8_t *d_t_desc, const int32_t *d_cell_start, const int32_t *d_cell_items, const float *bounds4,
+                                     int32_t *d_best_idx, int32_t *d_best_dist, int32_t *d_second_idx, int32_t *d_second_dist) {
+    int launches = 0;
+    const float minX = bounds4[0], minY = bounds4[1], maxX = bounds4[2], maxY = bounds4[3];
+    const float invW = (float)GRID_COLS / (maxX - minX), invH = (float)GRID_ROWS / (maxY - minY);
+    for (int p0 = 0; p0 < npairs; p0 += kMaxMatchPairs) {
+        const int np = std::min(kMaxMatchPairs, npairs - p0);
+        MatchPairs prs;
+        for (int i = 0; i < kMaxMatchPairs; i++) { prs.qf[i] = i < np ? pair_q[p0 + i] : 0; prs.tf[i] = i < np ? pair_t[p0 + i] : 0; }
+        k_match_windowed_grid_batch<<<dim3((cap + 7) / 8, np), 256, 0, stream>>>(prs, cap, reinterpret_cast<const uint4 *>(d_q_desc), d_q_uvr, d_q_levels, d_n,
+                                                                                d_t_kp, reinterpret_cast<const uint4 *>(d_t_desc), d_cell_start,
+                                                                                d_cell_items, minX, minY, invW, invH, d_best_idx, d_best_dist,
+                                                                                d_second_idx, d_second_dist);
+        launches++;
+    }
+    return launches;
 }
 }  // namespace orbx
 

@@ -61,7 +61,7 @@ EXPORTS = [
     "orbx_version", "orbx_set_profiling", "orbx_get_stage_times", "orbx_set_stream",
     "orbx_knn2_set_stream", "orbx_knn2_set_backend", "orbx_set_input_format", "orbx_debug_gray",
     "orbx_undistort_points", "orbx_image_bounds", "orbx_frame_grid", "orbx_frame_grid_batch_device",
-    "orbx_match_windowed_grid_device",
+    "orbx_match_windowed_grid_device", "orbx_match_windowed_grid_batch_device",
     "orbx_vocab_create", "orbx_vocab_destroy", "orbx_vocab_last_error", "orbx_vocab_depth", "orbx_vocab_transform",
 ]
 
@@ -171,6 +171,7 @@ def lib():
     L.orbx_frame_grid.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp]
     L.orbx_frame_grid_batch_device.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp]
     L.orbx_match_windowed_grid_device.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.orbx_match_windowed_grid_batch_device.argtypes = [vp, C.c_int, vp, vp, C.c_int, C.c_int] + [vp] * 13
     L.orbx_vocab_create.argtypes = [C.c_int, vp, vp, vp, C.c_int, C.POINTER(vp)]
     L.orbx_vocab_destroy.argtypes = [vp]
     L.orbx_vocab_last_error.restype = C.c_char_p
@@ -473,6 +474,17 @@ class ORBextractor:
         t = [C.c_void_p(x) for x in (d_t_kp_un, d_t_desc, d_cell_start, d_cell_items)]
         o = [C.c_void_p(x) for x in (d_best_idx, d_best_dist, d_second_idx, d_second_dist)]
         self._check(self._L.orbx_match_windowed_grid_device(self._h, p[0], p[1], p[2], int(nq), t[0], t[1], t[2], t[3], _p(b), *o))
+
+    def match_windowed_grid_batch_device(self, pairs, batch, cap, d_q_desc, d_q_uvr, d_q_levels, d_n, d_t_kp_un, d_t_desc, d_cell_start,
+                                         d_cell_items, bounds, d_best_idx, d_best_dist, d_second_idx, d_second_dist):
+        """pairs: sequence of (query frame, train frame) inside one batch; every device array is [batch][cap] (raw pointers); one launch
+        per 64 pairs, asynchronous, see sync()."""
+        b = np.ascontiguousarray(bounds, np.float32)
+        pq = np.ascontiguousarray([p[0] for p in pairs], np.int32)
+        pt = np.ascontiguousarray([p[1] for p in pairs], np.int32)
+        ptrs = [C.c_void_p(x) for x in (d_q_desc, d_q_uvr, d_q_levels, d_n, d_t_kp_un, d_t_desc, d_cell_start, d_cell_items)]
+        o = [C.c_void_p(x) for x in (d_best_idx, d_best_dist, d_second_idx, d_second_dist)]
+        self._check(self._L.orbx_match_windowed_grid_batch_device(self._h, len(pairs), _p(pq), _p(pt), int(batch), int(cap), *ptrs[:8], _p(b), *o))
 
     def debug_gray(self, src, fmt, gray_shift=15):
         src = np.ascontiguousarray(src, np.uint8)

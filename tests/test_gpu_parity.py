@@ -696,6 +696,30 @@ def test_device_resident_frame_to_frame_matching(oracle):
         assert np.array_equal(g_, w_), name
         assert np.array_equal(b_, w_), name
     assert ((got[0] >= 0) & (got[1] <= orbx.ORBmatcher.TH_HIGH)).mean() > 0.5
+    # the batched entry point: both directions (frame 0 in frame 1, frame 1 in frame 0) in ONE launch, arrays laid out [batch][cap],
+    # query counts read from the device-resident n[]
+    k1_ = un[1]
+    quvr1 = np.stack([k1_["x"] - 5, k1_["y"] + 4, 15.0 * scale[k1_["octave"]]], 1).astype(np.float32)
+    qlev1 = np.stack([k1_["octave"] - 1, k1_["octave"] + 1], 1).astype(np.int32)
+    b_quvr = torch.zeros((2, cap, 3), dtype=torch.float32, device=dev)
+    b_qlev = torch.zeros((2, cap, 2), dtype=torch.int32, device=dev)
+    b_quvr[0, :nq] = d_quvr; b_qlev[0, :nq] = d_qlev
+    b_quvr[1, :n[1]] = torch.from_numpy(quvr1).to(dev); b_qlev[1, :n[1]] = torch.from_numpy(qlev1).to(dev)
+    bouts = [torch.full((2, cap), -7, dtype=torch.int32, device=dev) for _ in range(4)]
+    l0 = e.launch_count()
+    e.match_windowed_grid_batch_device([(0, 1), (1, 0)], 2, cap, d_desc.data_ptr(), b_quvr.data_ptr(), b_qlev.data_ptr(), d_n.data_ptr(),
+                                       d_un.data_ptr(), d_desc.data_ptr(), d_start.data_ptr(), d_items.data_ptr(), bounds, *[o.data_ptr() for o in bouts])
+    e.sync()
+    assert e.launch_count() - l0 == 1
+    want1 = oracle.match_windowed(desc[1], quvr1, qlev1, un[0], desc[0], bounds)
+    for o_, w0_, w1_, name in zip(bouts, want, want1, ["best_idx", "best_dist", "second_idx", "second_dist"]):
+        o_ = o_.cpu().numpy()
+        assert np.array_equal(o_[0, :nq], w0_), name
+        assert np.array_equal(o_[1, :n[1]], w1_), name
+        assert (o_[0, nq:] == -7).all() and (o_[1, n[1]:] == -7).all(), name       # nothing written beyond a frame's query count
+    with pytest.raises(orbx.OrbxError):
+        e.match_windowed_grid_batch_device([(0, 2)], 2, cap, d_desc.data_ptr(), b_quvr.data_ptr(), b_qlev.data_ptr(), d_n.data_ptr(),
+                                           d_un.data_ptr(), d_desc.data_ptr(), d_start.data_ptr(), d_items.data_ptr(), bounds, *[o.data_ptr() for o in bouts])
     e.close()
 
 

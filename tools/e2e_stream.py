@@ -22,14 +22,21 @@ for _ in range(NL):
     lanes.append((e, (pk.numpy().view(orbx.KP_DTYPE).reshape(B, cap), pd.numpy()), pk, pd))
 
 
+host = {"submit": 0.0, "collect": 0.0, "n": 0}
+
+
 def run(n):
     busy = [False] * NL
     for i in range(n):
         k = i % NL
         e, o, _, _ = lanes[k]
+        ta = time.perf_counter()
         if busy[k]:
             e.extract_batch_collect()
+        tb = time.perf_counter()
         e.extract_batch_submit(pin[i % RING].numpy(), out=o)
+        tc = time.perf_counter()
+        host["collect"] += tb - ta; host["submit"] += tc - tb; host["n"] += 1
         busy[k] = True
     for j in range(NL):
         k = (n + j) % NL
@@ -39,6 +46,7 @@ def run(n):
 
 run(NL * RING + NL)
 torch.cuda.synchronize()
+host.update(submit=0.0, collect=0.0, n=0)
 t0 = time.perf_counter()
 run(steps)
 dt = time.perf_counter() - t0
@@ -57,4 +65,6 @@ t0 = time.perf_counter()
 copies(160)
 ceil = 160 * B / (time.perf_counter() - t0)
 print(json.dumps({"env": {k: v for k, v in os.environ.items() if k.startswith("ORBX_")}, "lanes": NL, "e2e_fps": round(fps), "h2d_ceiling_fps": round(ceil),
-                  "ratio": round(fps / ceil, 3)}), flush=True)
+                  "ratio": round(fps / ceil, 3),
+                  "host_us_per_step": {"submit": round(1e6 * host["submit"] / max(host["n"], 1), 1), "collect_incl_wait": round(1e6 * host["collect"] / max(host["n"], 1), 1)},
+                  "step_us": round(1e6 * dt / steps, 1)}), flush=True)
