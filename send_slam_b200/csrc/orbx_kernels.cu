@@ -1134,11 +1134,16 @@ struct __align__(8) QNode {
     int depth;
 };
 
-constexpr int OT_THREADS = 256;
+constexpr int OT_THREADS = 256;       // threads per (frame, level) problem when many problems run side by side
+constexpr int OT_THREADS_WIDE = 512;   // ... for single-frame calls and for large problems (1080p, the 6250-feature initialisation extractor): the
+                                       // breadth-first replay is a chain of block-wide passes over up to 4096 nodes.  Measured (quadtree stage,
+                                       // us, 256 / 512 / 1024 threads): 640x480 x1 27 / 25 / 27, 1280x800 x1 46 / 39 / 41, 6250 features 86 / 60 / 62,
+                                       // 1080p x16 112 / 67 / 68 -- but 64 x 640x480 39 / 52 and 7 k frames/s off the four-lane step
 
-// exclusive scan of a[0..n) in place; returns the total to every thread.  s_warp: 8 ints of scratch.
+// exclusive scan of a[0..n) in place; returns the total to every thread.  s_warp: NT / 32 ints of scratch.
+template <int NT>
 __device__ int block_excl_scan(int *a, int n, int *s_warp) {
-    const int tid = threadIdx.x, per = (n + OT_THREADS - 1) / OT_THREADS;
+    const int tid = threadIdx.x, per = (n + NT - 1) / NT;
     const int b = tid * per, e = min(b + per, n);
     int sum = 0;
     for (int i = b; i < e; i++) sum += a[i];
@@ -1148,9 +1153,11 @@ __device__ int block_excl_scan(int *a, int n, int *s_warp) {
     __syncthreads();           // s_warp may still be read from a previous call
     if ((tid & 31) == 31) s_warp[tid >> 5] = inc;
     __syncthreads();
-    int woff = 0, total = 0;
+    // offsets of the warps: one scan of the (at most 32) warp totals, done redundantly by every warp
+    int wv = (tid & 31) < NT / 32 ? s_warp[tid & 31] : 0, winc = wv;
 #pragma unroll
-    for (int w = 0; w < OT_THREADS / 32; w++) { const int v = s_warp[w]; if (w < (tid >> 5)) woff += v; total += v; }
+    for (int o = 1; o < NT / 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, winc, o); if ((tid & 31) >= o) winc += t; }
+    const int woff = __shfl_sync(0xFFFFFFFFu, winc - wv, tid >> 5), total = __shfl_sync(0xFFFFFFFFu, winc, NT / 32 - 1);
     int run = woff + inc - sum;
     for (int i = b; i < e; i++) { const int v = a[i]; a[i] = run; run += v; }
     __syncthreads();
@@ -1206,7 +1213,8 @@ __device__ void split_node(const LevelDev &L, const QNode &p, const int *bin_sta
     }
 }
 
-__global__ void __launch_bounds__(OT_THREADS) k_octree(const __grid_constant__ LevelTable T, int nlevels, int cap_nodes,
+template <int NT>
+__global__ void __launch_bounds__(NT) k_octree(const __grid_constant__ LevelTable T, int nlevels, int cap_nodes,
                                                        int f0, int *__restrict__ overflow) {
     const LevelDev *lv = T.lv;   // level table in the kernel parameter (constant) bank: no dependent global loads
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1214,7 +1222,7 @@ __global__ void __launch_bounds__(OT_THREADS) k_octree(const __grid_constant__ L
     const LevelDev &L = lv[level];
     const int tid = threadIdx.x;
     __shared__ OctShared S;
-    __shared__ int s_warp[8];
+    __shared__ int s_warp[NT / 32];
     if (L.n_ini <= 0 || L.nbins <= 0) { if (tid == 0) L.sel_count[f] = 0; return; }
     int n = L.cand_count[f];
     if (n > L.cand_cap) n = L.cand_cap;
@@ -1232,17 +1240,17 @@ __global__ void __launch_bounds__(OT_THREADS) k_octree(const __grid_constant__ L
     const uint32_t *__restrict__ cand = L.cand + (size_t)f * L.cand_cap;
     uint32_t *sorted = L.sorted + (size_t)f * L.cand_cap;
 
-    for (int i = tid; i < L.nbins; i += OT_THREADS) { bin_start[i] = 0; best[i] = 0; }
+    for (int i = tid; i < L.nbins; i += NT) { bin_start[i] = 0; best[i] = 0; }
     if (tid == 0) { bin_start[L.nbins] = 0; S.len = 0; S.phase = 0; S.finish = 0; S.need_sorted = 0; S.sorted_done = 0; }
     __syncthreads();
     // pass A: histogram + per-bin winner.  Four candidates per thread are in flight (candidate word, then its four LUT
     // entries) before the shared-memory atomics of any of them: the loop is bound by the dependent global loads.
     {
         const uint32_t *__restrict__ xbin = L.xbin, *__restrict__ ybin = L.ybin, *__restrict__ xord = L.xord, *__restrict__ yord = L.yord;
-        for (int k0 = tid; k0 < n; k0 += 4 * OT_THREADS) {
+        for (int k0 = tid; k0 < n; k0 += 4 * NT) {
             uint32_t c[4], bb[4], oo[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) { const int k = k0 + u * OT_THREADS; c[u] = k < n ? __ldg(cand + k) : 0u; }
+            for (int u = 0; u < 4; u++) { const int k = k0 + u * NT; c[u] = k < n ? __ldg(cand + k) : 0u; }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 const uint32_t xr = (c[u] >> 8) & 0xFFF, yr = c[u] >> 20;
@@ -1251,7 +1259,7 @@ __global__ void __launch_bounds__(OT_THREADS) k_octree(const __grid_constant__ L
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                if (k0 + u * OT_THREADS < n) {
+                if (k0 + u * NT < n) {
                     atomicAdd(&bin_start[bb[u]], 1);
                     atomicMax(&best[bb[u]], ((c[u] & 0xFFu) << 24) | (0xFFFFFFu - oo[u]));
                 }
@@ -1259,7 +1267,7 @@ __global__ void __launch_bounds__(OT_THREADS) k_octree(const __grid_constant__ L
         }
     }
     __syncthreads();
-    block_excl_scan(bin_start, L.nbins + 1, s_warp);   // bin_start[b] = first key of bin b, bin_start[nbins] = n
+    block_excl_scan<NT>(bin_start, L.nbins + 1, s_warp);   // bin_start[b] = first key of bin b, bin_start[nbins] = n
     // roots (push_back order), empty ones erased
     if (tid == 0) {
         int len = 0;
@@ -1282,7 +1290,7 @@ __global__ void __launch_bounds__(OT_THREADS) k_octree(const __grid_constant__ L
         if (tid == 0) S.need_sorted = 0;
         __syncthreads();
         const bool sorted_ok = S.sorted_done != 0;
-        for (int i = tid; i < len; i += OT_THREADS) {
+        for (int i = tid; i < len; i += NT) {
             int cc = 0;
             a_kp[i] = 0;
             if (i < region) {
@@ -1300,9 +1308,9 @@ __global__ void __launch_bounds__(OT_THREADS) k_octree(const __grid_constant__ L
         if (S.need_sorted) {
             // the tree wants to go below depth0: build the bin-sorted key copy once, then redo this step
             uint32_t *cursor = L.bin_cursor + (size_t)f * L.nbins;
-            for (int i = tid; i < L.nbins; i += OT_THREADS) cursor[i] = 0;
+            for (int i = tid; i < L.nbins; i += NT) cursor[i] = 0;
             __syncthreads();
-            for (int k = tid; k < n; k += OT_THREADS) {
+            for (int k = tid; k < n; k += NT) {
                 const uint32_t c = cand[k];
                 const uint32_t b = L.xbin[(c >> 8) & 0xFFF] | L.ybin[c >> 20];
                 sorted[bin_start[b] + atomicAdd(&cursor[b], 1u)] = c;
@@ -1318,13 +1326,13 @@ __global__ void __launch_bounds__(OT_THREADS) k_octree(const __grid_constant__ L
         if (!final_phase) {
             // ---- full round: every divided node is replaced by its non-empty children (pushed to the front in
             //      creation order => reversed), single-key nodes keep their relative order behind them
-            for (int i = tid; i < len; i += OT_THREADS) a_kp[i] = (a_cc[i] == 0) ? 1 : 0;
+            for (int i = tid; i < len; i += NT) a_kp[i] = (a_cc[i] == 0) ? 1 : 0;
             __syncthreads();
-            ctot = block_excl_scan(a_cc, len, s_warp);
-            const int kept = block_excl_scan(a_kp, len, s_warp);
+            ctot = block_excl_scan<NT>(a_cc, len, s_warp);
+            const int kept = block_excl_scan<NT>(a_kp, len, s_warp);
             new_len = ctot + kept;
             if (new_len > cap_nodes) { if (tid == 0) { *overflow = 2; L.sel_count[f] = 0; } return; }
-            for (int i = tid; i < len; i += OT_THREADS) {
+            for (int i = tid; i < len; i += NT) {
                 const QNode p = cur[i];
                 if (p.hi - p.lo <= 1) { nxt[ctot + a_kp[i]] = p; continue; }
                 const int s[5] = {p.lo, a_s1[i], a_s2[i], a_s3[i], p.hi};
@@ -1342,7 +1350,7 @@ __global__ void __launch_bounds__(OT_THREADS) k_octree(const __grid_constant__ L
             // ---- final phase: candidates (count > 1, created by the previous step = list positions [0, region))
             //      are divided largest first, ties by creation order descending = list position ascending, until
             //      the list holds N nodes
-            for (int i = tid; i < region; i += OT_THREADS) {
+            for (int i = tid; i < region; i += NT) {
                 int rank = -1;
                 if (a_cc[i] > 0) {
                     const int sz = cur[i].hi - cur[i].lo;
@@ -1358,18 +1366,18 @@ __global__ void __launch_bounds__(OT_THREADS) k_octree(const __grid_constant__ L
             }
             __syncthreads();
             // number of candidates
-            for (int i = tid; i < region; i += OT_THREADS) if (a_rank[i] >= 0) a_ord[a_rank[i]] = i;
+            for (int i = tid; i < region; i += NT) if (a_rank[i] >= 0) a_ord[a_rank[i]] = i;
             if (tid == 0) { S.rstar = 0x7FFFFFFF; S.ctot = 0; }
             __syncthreads();
             // total candidates via scan of flags
-            for (int i = tid; i < region; i += OT_THREADS) a_kp[i] = a_rank[i] >= 0 ? 1 : 0;
+            for (int i = tid; i < region; i += NT) a_kp[i] = a_rank[i] >= 0 ? 1 : 0;
             __syncthreads();
-            const int ncand = block_excl_scan(a_kp, region, s_warp);
+            const int ncand = block_excl_scan<NT>(a_kp, region, s_warp);
             // growth in processing order: a_s? reused as scratch is not possible (split points live there) -> use a_kp
-            for (int r = tid; r < ncand; r += OT_THREADS) a_kp[r] = a_cc[a_ord[r]] - 1;
+            for (int r = tid; r < ncand; r += NT) a_kp[r] = a_cc[a_ord[r]] - 1;
             __syncthreads();
-            block_excl_scan(a_kp, ncand, s_warp);          // a_kp[r] = growth before rank r
-            for (int r = tid; r < ncand; r += OT_THREADS) {
+            block_excl_scan<NT>(a_kp, ncand, s_warp);          // a_kp[r] = growth before rank r
+            for (int r = tid; r < ncand; r += NT) {
                 const int after = len + a_kp[r] + a_cc[a_ord[r]] - 1;
                 if (after >= N) atomicMin(&S.rstar, r);
             }
@@ -1377,22 +1385,22 @@ __global__ void __launch_bounds__(OT_THREADS) k_octree(const __grid_constant__ L
             const int rstar = min(S.rstar, ncand - 1);     // last processed rank (-1 if no candidates)
             const int nproc = rstar + 1;
             // children offsets in processing order
-            for (int r = tid; r < ncand; r += OT_THREADS) a_kp[r] = (r < nproc) ? a_cc[a_ord[r]] : 0;
+            for (int r = tid; r < ncand; r += NT) a_kp[r] = (r < nproc) ? a_cc[a_ord[r]] : 0;
             __syncthreads();
-            ctot = block_excl_scan(a_kp, ncand, s_warp);   // a_kp[r] = children created before rank r
+            ctot = block_excl_scan<NT>(a_kp, ncand, s_warp);   // a_kp[r] = children created before rank r
             // a_rank[i] (list position) -> child offset, or -1 if the node is not processed
-            for (int i = tid; i < len; i += OT_THREADS) {
+            for (int i = tid; i < len; i += NT) {
                 int v = -1;
                 if (i < region && a_rank[i] >= 0 && a_rank[i] < nproc) v = a_kp[a_rank[i]];
                 a_ord[i] = v;      // a_ord no longer needed as rank->position map
             }
             __syncthreads();
-            for (int i = tid; i < len; i += OT_THREADS) a_kp[i] = a_ord[i] >= 0 ? 1 : 0;
+            for (int i = tid; i < len; i += NT) a_kp[i] = a_ord[i] >= 0 ? 1 : 0;
             __syncthreads();
-            block_excl_scan(a_kp, len, s_warp);            // a_kp[i] = processed nodes before list position i
+            block_excl_scan<NT>(a_kp, len, s_warp);            // a_kp[i] = processed nodes before list position i
             new_len = len - nproc + ctot;
             if (new_len > cap_nodes) { if (tid == 0) { *overflow = 2; L.sel_count[f] = 0; } return; }
-            for (int i = tid; i < len; i += OT_THREADS) {
+            for (int i = tid; i < len; i += NT) {
                 const QNode p = cur[i];
                 if (a_ord[i] < 0) { nxt[ctot + i - a_kp[i]] = p; continue; }
                 const int s[5] = {p.lo, a_s1[i], a_s2[i], a_s3[i], p.hi};
@@ -1432,7 +1440,7 @@ __global__ void __launch_bounds__(OT_THREADS) k_octree(const __grid_constant__ L
     const int len = S.len;
     uint32_t *__restrict__ sel = L.sel + (size_t)f * L.out_cap;
     if (len > L.out_cap) { if (tid == 0) { *overflow = 3; L.sel_count[f] = 0; } return; }
-    for (int i = tid; i < len; i += OT_THREADS) {
+    for (int i = tid; i < len; i += NT) {
         const QNode p = cur[i];
         uint32_t bv = 0;
         if (p.depth <= L.depth0) {
@@ -1475,12 +1483,18 @@ int launch_octree(const LevelDev *h_levels, int nlevels, int f0, int batch, int 
     {
         std::lock_guard<std::mutex> lock(g_attr_mutex);
         if (smem > configured) {
-            cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_octree<OT_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_octree<OT_THREADS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             configured = smem;
         }
     }
     dim3 grid(nlevels, batch);
-    k_octree<<<grid, OT_THREADS, smem, stream>>>(make_table(h_levels), nlevels, cap, f0, d_overflow);
+    // ORBX_OCTREE_WIDE=0/1 overrides the choice
+    static const int wide_env = getenv("ORBX_OCTREE_WIDE") ? atoi(getenv("ORBX_OCTREE_WIDE")) : -1;
+    const bool big = (long long)h_levels[0].w * h_levels[0].h >= 1500000 || h_levels[0].quota >= 1000;
+    const bool wide = wide_env >= 0 ? wide_env != 0 : (batch <= 4 || big);
+    if (wide) k_octree<OT_THREADS_WIDE><<<grid, OT_THREADS_WIDE, smem, stream>>>(make_table(h_levels), nlevels, cap, f0, d_overflow);
+    else k_octree<OT_THREADS><<<grid, OT_THREADS, smem, stream>>>(make_table(h_levels), nlevels, cap, f0, d_overflow);
     return 1;
 }
 
