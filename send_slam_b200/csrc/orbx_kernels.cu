@@ -1502,31 +1502,36 @@ int launch_octree(const LevelDev *h_levels, int nlevels, int f0, int batch, int 
 // K7  output slots.  One CTA per frame: walks levels 0..L-1 in list order, scales to image coordinates and assigns
 //     the reference's slot (lapping-area keypoints fill from the back, the rest from the front).
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_finalize(const __grid_constant__ LevelTable T, int nlevels, int total_out_cap, int lap0,
+template <int NT>
+__global__ void __launch_bounds__(NT) k_finalize(const __grid_constant__ LevelTable T, int nlevels, int total_out_cap, int lap0,
                                                   int lap1, KeypointRec *__restrict__ kp, int cap, int *__restrict__ slot,
                                                   uint2 *__restrict__ items, int *__restrict__ n_out, int *__restrict__ mono_out, int f0,
                                                   int *__restrict__ overflow) {
     const LevelDev *lv = T.lv;   // level table in the kernel parameter (constant) bank: no dependent global loads
     const int f = f0 + blockIdx.x, tid = threadIdx.x;
     __shared__ int s_cnt[kMaxLevels + 1];
-    __shared__ int s_warp[8];
+    __shared__ int s_warp[NT / 32];
     __shared__ int s_run;
-    if (tid == 0) {
-        int acc = 0;
-        for (int l = 0; l < nlevels; l++) { s_cnt[l] = acc; acc += lv[l].sel_count[f]; }
-        s_cnt[nlevels] = acc; s_run = 0;
+    if (tid < 32) {   // level offsets: the counts of all levels are fetched at once (lane = level), then one warp scan
+        const int v = tid < nlevels ? lv[tid].sel_count[f] : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (tid >= o) inc += t; }
+        if (tid < nlevels) s_cnt[tid] = inc - v;
+        if (tid == nlevels - 1) s_cnt[nlevels] = inc;
+        if (tid == 0) s_run = 0;
     }
     __syncthreads();
     const int ntot = s_cnt[nlevels];
     if (ntot > cap) {
         if (tid == 0) { *overflow = 4; n_out[f] = 0; mono_out[f] = 0; }
-        for (int i = tid; i < total_out_cap; i += 256) items[(size_t)f * total_out_cap + i] = make_uint2(0xFFFFFFFFu, 0u);
+        for (int i = tid; i < total_out_cap; i += NT) items[(size_t)f * total_out_cap + i] = make_uint2(0xFFFFFFFFu, 0u);
         return;
     }
-    for (int i = ntot + tid; i < total_out_cap; i += 256) items[(size_t)f * total_out_cap + i] = make_uint2(0xFFFFFFFFu, 0u);
+    for (int i = ntot + tid; i < total_out_cap; i += NT) items[(size_t)f * total_out_cap + i] = make_uint2(0xFFFFFFFFu, 0u);
     const float flap0 = (float)lap0, flap1 = (float)lap1;
-    // chunks of 256 keypoints in sequence order; running count of lapping-area keypoints carried across chunks
-    for (int base = 0; base < ntot; base += 256) {
+    // chunks of NT keypoints in sequence order; running count of lapping-area keypoints carried across chunks
+    for (int base = 0; base < ntot; base += NT) {
         const int i = base + tid;
         int l = 0, inlap = 0;
         float x = 0.f, y = 0.f, resp = 0.f;
@@ -1544,9 +1549,10 @@ __global__ void __launch_bounds__(256) k_finalize(const __grid_constant__ LevelT
         for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if ((tid & 31) >= o) inc += t; }
         if ((tid & 31) == 31) s_warp[tid >> 5] = inc;
         __syncthreads();
-        int woff = 0, tot = 0;
+        int wv = (tid & 31) < NT / 32 ? s_warp[tid & 31] : 0, winc = wv;
 #pragma unroll
-        for (int w = 0; w < 8; w++) { const int v = s_warp[w]; if (w < (tid >> 5)) woff += v; tot += v; }
+        for (int o = 1; o < NT / 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, winc, o); if ((tid & 31) >= o) winc += t; }
+        const int woff = __shfl_sync(0xFFFFFFFFu, winc - wv, tid >> 5), tot = __shfl_sync(0xFFFFFFFFu, winc, NT / 32 - 1);
         const int before = s_run + woff + inc - inlap;     // lapping keypoints before i
         if (i < ntot) {
             const int sl = inlap ? (ntot - 1 - before) : (i - before);
@@ -1565,7 +1571,10 @@ __global__ void __launch_bounds__(256) k_finalize(const __grid_constant__ LevelT
 
 int launch_finalize(const LevelDev *h_levels, int nlevels, int f0, int batch, int total_out_cap, int lap0, int lap1,
                     KeypointRec *d_kp, int cap, int *d_slot, uint2 *d_items, int *d_n, int *d_mono, int *d_overflow, cudaStream_t stream) {
-    k_finalize<<<batch, 256, 0, stream>>>(make_table(h_levels), nlevels, total_out_cap, lap0, lap1, d_kp, cap, d_slot, d_items, d_n, d_mono, f0, d_overflow);
+    // a handful of frames: 1024 threads each (the chunks of a frame are a serial chain); a full batch: 256, so that the CTAs fit beside
+    // the machine-filling kernels of the other frame ranges
+    if (batch <= 8) k_finalize<1024><<<batch, 1024, 0, stream>>>(make_table(h_levels), nlevels, total_out_cap, lap0, lap1, d_kp, cap, d_slot, d_items, d_n, d_mono, f0, d_overflow);
+    else k_finalize<256><<<batch, 256, 0, stream>>>(make_table(h_levels), nlevels, total_out_cap, lap0, lap1, d_kp, cap, d_slot, d_items, d_n, d_mono, f0, d_overflow);
     return 1;
 }
 
