@@ -34,7 +34,7 @@ defmodule SendSlam.OrbNif do
   @doc "a row shard of a descriptor database resident on the GPU: rows x 32 bytes, `row_offset` = global index of its first row"
   def knn2_create(_descriptors_binary, _device, _row_offset), do: :erlang.nif_error(:nif_not_loaded)
 
-  @doc "k = 2 nearest rows per query (cv::BFMatcher NORM_HAMMING): `{:ok, indices (nq x 2 int32), distances (nq x 2 int32)}`; backend 0 = POPC, 1 = tensor cores"
+  @doc "k = 2 nearest rows per query (cv::BFMatcher NORM_HAMMING): `{:ok, indices (nq x 2 int32), distances (nq x 2 int32)}`; backend 0 = POPC, 1 = tensor cores (int8), 2 = tensor cores (FP4, fastest); identical results"
   def knn2(_db, _queries_binary, _backend), do: :erlang.nif_error(:nif_not_loaded)
 
   def extract(_handle, _gray_binary, _width, _height), do: :erlang.nif_error(:nif_not_loaded)

@@ -276,7 +276,8 @@ static ERL_NIF_TERM nif_knn2_create(ErlNifEnv *env, int argc, const ERL_NIF_TERM
 }
 
 /* knn2(db, queries_binary (nq x 32 B), backend) -> {:ok, idx_binary (nq x 2 int32, global rows, -1 = missing), dist_binary (nq x 2
- * int32)}: cv::BFMatcher(NORM_HAMMING).knnMatch(k = 2) of the queries against the shard; backend 0 = POPC, 1 = tensor cores. */
+ * int32)}: cv::BFMatcher(NORM_HAMMING).knnMatch(k = 2) of the queries against the shard; backend 0 = POPC, 1 = tensor cores (int8),
+ * 2 = tensor cores (block-scaled FP4, the fastest); identical results. */
 static ERL_NIF_TERM nif_knn2(ErlNifEnv *env, int argc, const ERL_NIF_TERM argv[]) {
     nif_db *nd;
     ErlNifBinary q;

@@ -252,7 +252,7 @@ def test_nif_extract_batch_and_knn2(nif, oracle):
     dbres = L.mock_resource_keep(L.mock_tuple_elem(r, 1))
     L.mock_reset()
     idx_o, dist_o = oracle.knn2(q, db)
-    for backend in (orbx.Knn2Index.POPC, orbx.Knn2Index.TENSOR):
+    for backend in (orbx.Knn2Index.POPC, orbx.Knn2Index.TENSOR, orbx.Knn2Index.TENSOR_FP4):
         r = decode(L, call(L, "knn2", L.mock_resource_term(dbres), L.mock_binary(q.ctypes.data, q.nbytes), L.mock_int(backend)))
         L.mock_reset()
         assert r[0] == "ok", r
