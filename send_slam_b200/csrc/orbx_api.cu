@@ -82,6 +82,7 @@ struct orbx_handle {
     Fast2Tma ftma2{};               // ... and for the pair-plane FAST kernel (orbx_fast2.cu), the one the pipeline prefers
     DescTma dtma{};                 // ... and of the un-blurred / blurred planes for the descriptor kernel
     BlurTma btma{};                 // ... and of the un-blurred planes for the Gaussian pass
+    BlurTc btc{};                   // ... and, swizzled, for its tensor-core variant
     std::vector<ConeLaunch> cones;  // fused pyramid launches (empty or a failed map: the per-level resize kernels run)
     bool cones_ok = false;
     int sm_count = 148;
@@ -194,6 +195,15 @@ static void encode_fast_map(orbx_handle *h, int l) {
                     tma_make_plane_map(reinterpret_cast<CUtensorMap *>(G.map[l]), D.img, D.w, D.h, h->batch_cap, (size_t)D.pitch, D.img_fstride, 96, 118);
     G.ok = !getenv("ORBX_NO_TMA") && !getenv("ORBX_BLUR_WORDS");
     for (int k = 0; k < h->plan.nlevels; k++) G.ok = G.ok && G.level_ok[k];
+    // tensor-core Gaussian: 128 x 128 swizzled box; the blurred planes are the library's own (pitch a multiple of 32)
+    BlurTc &C = h->btc;
+    C.level_ok[l] = D.w >= 16 && D.h >= 16 && (D.blur_pitch & 31) == 0 &&
+                    tma_make_plane_map_sw128(reinterpret_cast<CUtensorMap *>(C.map[l]), D.img, D.w, D.h, h->batch_cap, (size_t)D.pitch, D.img_fstride, 128);
+    {
+        static const int blur_tc = [] { const char *e = getenv("ORBX_BLUR_TC"); return e ? atoi(e) : 0; }();
+        C.ok = blur_tc != 0 && !getenv("ORBX_NO_TMA") && C.ntiles > 0;
+    }
+    for (int k = 0; k < h->plan.nlevels; k++) C.ok = C.ok && C.level_ok[k];
 }
 
 // Box of a level = the largest ROI of its cells plus the 4-pixel-group / row-pair overhang the scoring items read.
@@ -202,6 +212,7 @@ static void build_fast_maps(orbx_handle *h) {
     std::memset(&T, 0, sizeof(T));
     std::memset(&h->dtma, 0, sizeof(h->dtma));
     std::memset(&h->btma, 0, sizeof(h->btma));
+    { const BlurTile *keep_t = h->btc.d_tiles; const int keep_n = h->btc.ntiles; std::memset(&h->btc, 0, sizeof(h->btc)); h->btc.d_tiles = keep_t; h->btc.ntiles = keep_n; }
     for (int l = 0; l < h->plan.nlevels; l++) {
         const LevelPlan &LP = h->plan.lv[l];
         int rw = 0, rh = 0;
@@ -317,6 +328,15 @@ static int ensure_plan(orbx_handle *h, int w, int ht, int batch) {
     }
     h->ntiles = (int)tiles.size();
     CU_TRY(h, dev_upload(h, &h->d_tiles, tiles));
+    {
+        std::vector<BlurTile> tc_tiles;
+        for (int l = 0; l < nl; l++)
+            for (int ty = 0; ty * kBlurTcTileH < pl.lv[l].h; ty++)
+                for (int tx = 0; tx * kBlurTcTileW < pl.lv[l].w; tx++) tc_tiles.push_back(BlurTile{(int16_t)l, (int16_t)tx, (int16_t)ty, 0});
+        BlurTile *d_tc = nullptr;
+        CU_TRY(h, dev_upload(h, &d_tc, tc_tiles));
+        h->btc.d_tiles = d_tc; h->btc.ntiles = (int)tc_tiles.size();
+    }
     h->cones.clear();
     for (const ConePlan &cp : pl.cones) {
         ConeLaunch cl;
@@ -480,7 +500,7 @@ static int run_pipeline(orbx_handle *h, int f0, int batch, int lap0, int lap1, K
     // which has the highest priority so that its few CTAs are placed first, while the Gaussian pass fills the rest of
     // the machine from the main stream.  The fork comes after FAST because two machine-filling kernels gain nothing
     // from running side by side.
-    if (!fork && !(skip & 2)) h->launches += launch_blur(h->h_levels, h->d_tiles, h->ntiles, f0, batch, stream, &h->btma);
+    if (!fork && !(skip & 2)) h->launches += h->btc.ok ? launch_blur_tc(h->h_levels, h->btc, f0, batch, stream, h->sm_count) : launch_blur(h->h_levels, h->d_tiles, h->ntiles, f0, batch, stream, &h->btma);
     STAGE_MARK(2);
     if (!(skip & 4)) {
         int nl2 = 0;
@@ -500,7 +520,7 @@ static int run_pipeline(orbx_handle *h, int f0, int batch, int lap0, int lap1, K
     STAGE_MARK(5);
     if (fork) {
         CU_TRY(h, cudaEventRecord(ev_join, side));
-        if (!(skip & 2)) h->launches += launch_blur(h->h_levels, h->d_tiles, h->ntiles, f0, batch, stream, &h->btma);
+        if (!(skip & 2)) h->launches += h->btc.ok ? launch_blur_tc(h->h_levels, h->btc, f0, batch, stream, h->sm_count) : launch_blur(h->h_levels, h->d_tiles, h->ntiles, f0, batch, stream, &h->btma);
         CU_TRY(h, cudaStreamWaitEvent(stream, ev_join, 0));
     }
     if (!(skip & 16)) h->launches += launch_describe(h->h_levels, nl, f0, batch, pl.total_out_cap, h->d_slot, h->d_items, d_kp, d_desc, cap, stream, &h->dtma, h->sm_count);

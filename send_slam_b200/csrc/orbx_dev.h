@@ -68,6 +68,16 @@ struct BlurTma {
     bool ok;
 };
 int launch_blur(const LevelDev *h_levels, const BlurTile *d_tiles, int ntiles, int f0, int batch, cudaStream_t stream, const BlurTma *tma = nullptr);
+// Tensor-core Gaussian (orbx_blur_tc.cu): 96 x 122 output tiles, swizzled tensor maps of the un-blurred planes (box 128 x 128), its own tile list
+constexpr int kBlurTcTileW = 96, kBlurTcTileH = 122;
+struct BlurTc {
+    alignas(64) unsigned char map[kMaxLevels][128];
+    bool level_ok[kMaxLevels];
+    bool ok;
+    const BlurTile *d_tiles;
+    int ntiles;
+};
+int launch_blur_tc(const LevelDev *h_levels, const BlurTc &C, int f0, int batch, cudaStream_t stream, int sm_count);
 // Tensor maps of the level planes for the TMA-staged FAST kernel (host side: orbx_api.cu builds them; 128 bytes each,
 // stored opaquely so that this header does not need <cuda.h>).
 struct FastTma {

@@ -37,6 +37,21 @@ inline bool tma_make_plane_map(CUtensorMap *map, const void *base, int width, in
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// The same plane with SWIZZLE_128B and a 128-byte-wide box: the box lands in shared memory as the canonical MN-major (or K-major) operand
+// tile of tcgen05.mma (128-byte rows, 16-byte pieces XOR-ed with the row number modulo 8).
+inline bool tma_make_plane_map_sw128(CUtensorMap *map, const void *base, int width, int rows, int frames, size_t pitch, size_t frame_stride,
+                                     int box_h) {
+    PFN_tmaEncodeTiled enc = tma_encode_fn();
+    if (!enc) return false;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (pitch & 15) || (frame_stride & 15) || box_h > 256) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)width, (cuuint64_t)rows, (cuuint64_t)frames};
+    cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)frame_stride};
+    cuuint32_t box[3] = {128u, (cuuint32_t)box_h, 1u};
+    cuuint32_t estr[3] = {1u, 1u, 1u};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t tma_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void tma_mbar_init(uint64_t *bar, uint32_t count) {
