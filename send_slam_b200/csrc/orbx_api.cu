@@ -198,9 +198,11 @@ static void encode_fast_map(orbx_handle *h, int l) {
     // tensor-core Gaussian: 128 x 128 swizzled box; the blurred planes are the library's own (pitch a multiple of 32)
     BlurTc &C = h->btc;
     C.level_ok[l] = D.w >= 16 && D.h >= 16 && (D.blur_pitch & 31) == 0 &&
-                    tma_make_plane_map_sw128(reinterpret_cast<CUtensorMap *>(C.map[l]), D.img, D.w, D.h, h->batch_cap, (size_t)D.pitch, D.img_fstride, 128);
+                    tma_make_plane_map_sw128(reinterpret_cast<CUtensorMap *>(C.map[l]), D.img, D.w, D.h, h->batch_cap, (size_t)D.pitch, D.img_fstride, 128) &&
+                    tma_make_plane_map(reinterpret_cast<CUtensorMap *>(C.omap[l]), D.blur, D.w, D.h, h->batch_cap, (size_t)D.blur_pitch, D.blur_fstride,
+                                       kBlurTcTileW, kBlurTcTileH);
     {
-        static const int blur_tc = [] { const char *e = getenv("ORBX_BLUR_TC"); return e ? atoi(e) : 0; }();
+        static const int blur_tc = [] { const char *e = getenv("ORBX_BLUR_TC"); return e ? atoi(e) : 1; }();   // default on; 0 = k_blur_tma
         C.ok = blur_tc != 0 && !getenv("ORBX_NO_TMA") && C.ntiles > 0;
     }
     for (int k = 0; k < h->plan.nlevels; k++) C.ok = C.ok && C.level_ok[k];

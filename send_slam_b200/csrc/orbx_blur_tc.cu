@@ -86,10 +86,10 @@ struct Ctl {
 
 struct BlurTcParams {
     CUtensorMap map[kMaxLevels];       // un-blurred level plane [frames][h][w], box 128 x 128 x 1, SWIZZLE_128B
-    uint8_t *blur[kMaxLevels];
-    size_t fstride[kMaxLevels];
-    int pitch[kMaxLevels], w[kMaxLevels], h[kMaxLevels];
+    CUtensorMap omap[kMaxLevels];      // blurred level plane, box 96 x 122 x 1: the finished tile leaves by one TMA store, clipped at the plane's edges
+    int w[kMaxLevels], h[kMaxLevels];
 };
+constexpr uint32_t O_BYTES = (TR * TC + 127) / 128 * 128;   // one output tile, rows of 96 bytes
 
 // Persistent CTAs; NB input boxes in flight (the box of tile i + NB - 1 is requested while tile i is multiplied: a box takes over a
 // microsecond to arrive, a tile's MMAs a tenth of that), two accumulator stages between the MMA issuer and the epilogue warps.
@@ -100,7 +100,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_blur_tc(const __grid_constant__ 
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (s32(smem_raw) & 1023u)) & 1023u);
     uint8_t *sA = smem, *sB = smem + A_BYTES;
-    Ctl &S = *reinterpret_cast<Ctl *>(smem + A_BYTES + NB * B_BYTES);
+    uint8_t *sO = smem + A_BYTES + NB * B_BYTES;
+    Ctl &S = *reinterpret_cast<Ctl *>(sO + 2 * O_BYTES);
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
     // A[m][k] = w[k - m] for m < 122, 0 <= k - m <= 6 (K-major, 128-byte rows, 16-byte pieces swizzled by the row)
@@ -208,11 +209,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_blur_tc(const __grid_constant__ 
         for (int ti = first; ti < total; ti += step, it++) {
             const int s = it % NACC, ph = (it / NACC) & 1;
             int f; const BlurTile t = tile_of(ti, f);
-            const int w = P.w[t.level], h = P.h[t.level], pitch = P.pitch[t.level], x0 = t.tx * TC;
-            const int gy = t.ty * TR + row;
-            const bool live = row < TR && gy < h;
-            uint8_t *orow = P.blur[t.level] + (size_t)(f0 + f) * P.fstride[t.level] + (size_t)gy * pitch + x0;
+            const int w = P.w[t.level], x0 = t.tx * TC;
             const int nchunk = min(3, (w - x0 + 31) >> 5);      // 32-column chunks that hold image columns
+            uint8_t *out = sO + (it & 1) * O_BYTES;
+            // the TMA store that read this output stage two tiles ago must have finished reading shared memory
+            if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");
             tma_mbar_wait(&S.acc_full[s], ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
@@ -246,13 +248,22 @@ __global__ void __launch_bounds__(THREADS, 1) k_blur_tc(const __grid_constant__ 
                     }
                     px[g] = __byte_perm(__byte_perm(a[0], a[1], 0x0062), __byte_perm(a[2], a[3], 0x0062), 0x5410);
                 }
-                if (live) {
-                    const int gx = x0 + 32 * c;       // the planes' pitch is a multiple of 32: a chunk that starts below the pitch fits
-                    if (gx < pitch) *reinterpret_cast<uint4 *>(orow + 32 * c) = make_uint4(px[0], px[1], px[2], px[3]);
-                    if (gx + 16 < pitch) *reinterpret_cast<uint4 *>(orow + 32 * c + 16) = make_uint4(px[4], px[5], px[6], px[7]);
+                if (row < TR) {
+                    uint4 *o4 = reinterpret_cast<uint4 *>(out + row * TC + 32 * c);
+                    o4[0] = make_uint4(px[0], px[1], px[2], px[3]);
+                    o4[1] = make_uint4(px[4], px[5], px[6], px[7]);
                 }
             }
+            // the tile leaves by one TMA store; rows / columns beyond the plane are clipped by the tensor map
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (warp == 2 && lane == 0) {
+                asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                             ::"l"(&P.omap[t.level]), "r"(x0), "r"(t.ty * TR), "r"(f0 + f), "r"(s32(out)) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
         }
+        if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -269,19 +280,21 @@ int launch_blur_tc(const LevelDev *h_levels, const BlurTc &C, int f0, int batch,
     static_assert(sizeof(BlurTc::map) == sizeof(BlurTcParams::map), "tensor map storage mismatch");
     BlurTcParams P;
     memcpy(P.map, C.map, sizeof(P.map));
-    for (int l = 0; l < kMaxLevels; l++) {
-        P.blur[l] = h_levels[l].blur; P.fstride[l] = h_levels[l].blur_fstride; P.pitch[l] = h_levels[l].blur_pitch;
-        P.w[l] = h_levels[l].w; P.h[l] = h_levels[l].h;
-    }
-    static const int nb = [] { const char *e = getenv("ORBX_BLUR_TC_STAGES"); const int v = e ? atoi(e) : 3; return v < 2 ? 2 : v > NBMAX ? NBMAX : v; }();
-    static const int per_sm = getenv("ORBX_BLUR_TC_CTAS") ? atoi(getenv("ORBX_BLUR_TC_CTAS")) : 1;   // 256 TMEM columns each
-    const size_t smem = A_BYTES + (size_t)nb * B_BYTES + sizeof(Ctl) + 1024;
+    memcpy(P.omap, C.omap, sizeof(P.omap));
+    for (int l = 0; l < kMaxLevels; l++) { P.w[l] = h_levels[l].w; P.h[l] = h_levels[l].h; }
+    // Measured on 64 x 640x480 (blur stage alone / four batches in flight): 2 input stages, 1 CTA per SM 56 us / 189.4 k frames/s; 2 CTAs per SM
+    // 43 us / 186.5 k; 3 stages change nothing (the epilogue warps, not the box loads, set the pace); k_blur_tma 47 us / 185.8 k.  One CTA per
+    // SM leaves room for the other frame ranges' kernels; 1080p-class frames run in fewer, longer ranges and take two.
+    static const int nb = [] { const char *e = getenv("ORBX_BLUR_TC_STAGES"); const int v = e ? atoi(e) : 2; return v < 2 ? 2 : v > NBMAX ? NBMAX : v; }();
+    static const int per_sm_env = getenv("ORBX_BLUR_TC_CTAS") ? atoi(getenv("ORBX_BLUR_TC_CTAS")) : 0;   // 256 TMEM columns each
+    const int per_sm = per_sm_env > 0 ? per_sm_env : ((long long)h_levels[0].w * h_levels[0].h >= 1500000 ? 2 : 1);
+    const size_t smem = A_BYTES + (size_t)nb * B_BYTES + 2 * O_BYTES + sizeof(Ctl) + 1024;
     static bool configured_[kMaxDevices];
     {
         std::lock_guard<std::mutex> lock(g_attr_mutex);
         bool &configured = configured_[current_device_slot()];
         if (!configured) {
-            const int big = (int)(A_BYTES + NBMAX * B_BYTES + sizeof(Ctl) + 1024);
+            const int big = (int)(A_BYTES + NBMAX * B_BYTES + 2 * O_BYTES + sizeof(Ctl) + 1024);
             cudaFuncSetAttribute(k_blur_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
             cudaFuncSetAttribute(k_blur_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
             cudaFuncSetAttribute(k_blur_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);

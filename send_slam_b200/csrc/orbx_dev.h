@@ -71,7 +71,8 @@ int launch_blur(const LevelDev *h_levels, const BlurTile *d_tiles, int ntiles, i
 // Tensor-core Gaussian (orbx_blur_tc.cu): 96 x 122 output tiles, swizzled tensor maps of the un-blurred planes (box 128 x 128), its own tile list
 constexpr int kBlurTcTileW = 96, kBlurTcTileH = 122;
 struct BlurTc {
-    alignas(64) unsigned char map[kMaxLevels][128];
+    alignas(64) unsigned char map[kMaxLevels][128];    // un-blurred planes, swizzled 128 x 128 box (input tiles)
+    alignas(64) unsigned char omap[kMaxLevels][128];   // blurred planes, 96 x 122 box (output tiles)
     bool level_ok[kMaxLevels];
     bool ok;
     const BlurTile *d_tiles;

@@ -789,3 +789,35 @@ def test_legacy_default_stream_and_repeated_calls(oracle):
         for i in range(B):
             assert n[i] == len(ref[i][0]) and np.array_equal(dd[i, :n[i]], ref[i][1]), (rep, i)
     e.close()
+
+
+def test_blur_kernel_variants_in_subprocesses(oracle):
+    """The Gaussian pass has three kernels (tensor-core k_blur_tc = default, TMA-staged k_blur_tma, word-load k_blur); the choice is read
+    from the environment once per process, so each variant runs in its own interpreter and compares every blurred level with the oracle."""
+    import subprocess, sys, textwrap
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = textwrap.dedent("""
+        import sys, numpy as np
+        sys.path.insert(0, %r)
+        from send_slam_b200 import orbx, synth
+        from oracle import oracle_lib as ol
+        bad = checked = 0
+        for (w, h) in ((640, 480), (333, 250), (1280, 720)):
+            fr = synth.textured_frame(3, w, h)
+            frames = np.stack([fr, fr[::-1].copy()])
+            e = orbx.ORBextractor(800, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=2)
+            e.extract_batch(frames)
+            for f in range(2):
+                o = ol.Oracle(800)
+                o.extract(frames[f])
+                for l in range(8):
+                    lv_o, bl_o = o.stage_level(l)
+                    if bl_o is not None:
+                        bad += int(not np.array_equal(e.debug_level(f, l, blurred=True), bl_o)); checked += 1
+            e.close()
+        print("BAD", bad, "of", checked)
+        sys.exit(1 if bad or checked < 40 else 0)
+    """) % root
+    for env in ({"ORBX_BLUR_TC": "1"}, {"ORBX_BLUR_TC": "0"}, {"ORBX_BLUR_TC": "0", "ORBX_BLUR_WORDS": "1"}):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, (env, r.stdout[-500:], r.stderr[-1500:])

@@ -1,0 +1,12 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+ORBX_BLUR_TC=1 timeout 900 python bench.py --no-cpu --no-knn > gpurun_out/g37.json 2>/dev/null
+python - <<PY
+import json
+d=json.loads(open('gpurun_out/g37.json').read().strip().splitlines()[-1])
+print('value', round(d['value']), 'single', round(d['single_lane']['value']), 'e2e', round(d['e2e']['value']), 'cfg1', round(d['config1_752x480_nf1200']['value']), 'cfg3', round(d['config3_1920x1080_nf2000']['value']), 'cfg5', round(d['config5_1280x720_nf1250']['value']))
+print([(x['shape'], x['nfeatures'], round(x['median_ms'],4)) for x in d['latency']])
+print(d['config5_1280x720_nf1250']['per_frame_stream']['ms_per_frame'], d['e2e']['blocking_call']['value'], d['e2e']['two_concurrent_callers'])
+PY
+ORBX_BLUR_TC=1 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
