@@ -1024,7 +1024,7 @@ def main():
         hbm = float(peaks["hbm_gbs"])
         ach = stage_bytes[dom] * BATCH / (acc[dom] * 1e-3) / 1e9
         total_bytes = plan["algorithmic_bytes"]
-        kname = {"pyramid": "k_pyramid_cone", "blur": "k_blur_tma", "fast": "k_fast_tma", "describe": "k_describe_tma"}[dom]
+        kname = {"pyramid": "k_pyramid_cone", "blur": "k_blur_tc", "fast": "k_fast_tma", "describe": "k_describe_tma"}[dom]
         # ncu facts of the dominant kernel come from the round's committed capture (profiles/ncu_facts_r02.json, written by
         # tools/make_profile_summaries.py from the .ncu-rep files); nothing is hard-coded: null where the capture lacks the kernel
         facts = profile_facts(kname) if dom != "pyramid" else None      # the pyramid is 7 launches; a capture holds one level

@@ -37,7 +37,9 @@ constexpr uint32_t A_BYTES = 16384, B_BYTES = 16384;
 constexpr int NACC = 2;                               // accumulator stages (128 TMEM columns each)
 constexpr int NBMAX = 4;                              // input tiles in flight (template parameter NB <= NBMAX)
 constexpr int THREADS = 192;                          // warp 0: TMA + MMA issue, warp 1: edge patches, warps 2..5: epilogue (TMEM lane quarter = warp % 4).
-                                                      // Twelve epilogue warps (one per lane quarter and 32-column chunk) were measured slower: 45 -> 52 us
+                                                      // Twelve epilogue warps (one per lane quarter and 32-column chunk) were measured slower: 45 -> 52 us;
+                                                      // requesting the next chunk's sums before working on the current one: 56 -> 55 us alone but 155
+                                                      // registers and 189 -> 186 k frames/s with four batches in flight
 
 __device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ bool elect_one() {
