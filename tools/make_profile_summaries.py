@@ -17,7 +17,7 @@ path = os.path.join(G, f"launches_{tag}.csv")
 rows = [r for r in csv.reader(open(path, errors="replace")) if len(r) > 10 and r[0].strip('"').isdigit()]
 agg = collections.OrderedDict()
 for r in rows:
-    name = re.sub(r"\(.*", "", r[4]).replace("orbx::", "").replace("(anonymous namespace)::", "")
+    name = re.sub(r"\(.*", "", r[4].replace("(anonymous namespace)::", "").replace("<unnamed>::", "")).replace("orbx::", "")
     name = re.sub(r"<.*", "", name.replace("void ", "")).strip()
     val = float(r[-1].replace(",", ""))
     unit = r[-2]
