@@ -160,6 +160,13 @@ static cudaError_t dev_upload(orbx_handle *h, T **out, const std::vector<T> &v) 
 
 static_assert(sizeof(CUtensorMap) == 128, "FastTma stores tensor maps as 128-byte blobs");
 
+// Gaussian pass: the tensor-core kernel when every plane has its swizzled map, else (or when it cannot be configured) the CUDA-core ones
+static int launch_blur_any(orbx_handle *h, int f0, int batch, cudaStream_t stream) {
+    int n = h->btc.ok ? launch_blur_tc(h->h_levels, h->btc, f0, batch, stream, h->sm_count) : 0;
+    if (!n) n = launch_blur(h->h_levels, h->d_tiles, h->ntiles, f0, batch, stream, &h->btma);
+    return n;
+}
+
 // (Re)encode the tensor map of one level plane; marks the level unusable when the plane misses the TMA alignment rules.
 static void encode_fast_map(orbx_handle *h, int l) {
     const LevelDev &D = h->h_levels[l];
@@ -502,7 +509,7 @@ static int run_pipeline(orbx_handle *h, int f0, int batch, int lap0, int lap1, K
     // which has the highest priority so that its few CTAs are placed first, while the Gaussian pass fills the rest of
     // the machine from the main stream.  The fork comes after FAST because two machine-filling kernels gain nothing
     // from running side by side.
-    if (!fork && !(skip & 2)) h->launches += h->btc.ok ? launch_blur_tc(h->h_levels, h->btc, f0, batch, stream, h->sm_count) : launch_blur(h->h_levels, h->d_tiles, h->ntiles, f0, batch, stream, &h->btma);
+    if (!fork && !(skip & 2)) h->launches += launch_blur_any(h, f0, batch, stream);
     STAGE_MARK(2);
     if (!(skip & 4)) {
         int nl2 = 0;
@@ -522,7 +529,7 @@ static int run_pipeline(orbx_handle *h, int f0, int batch, int lap0, int lap1, K
     STAGE_MARK(5);
     if (fork) {
         CU_TRY(h, cudaEventRecord(ev_join, side));
-        if (!(skip & 2)) h->launches += h->btc.ok ? launch_blur_tc(h->h_levels, h->btc, f0, batch, stream, h->sm_count) : launch_blur(h->h_levels, h->d_tiles, h->ntiles, f0, batch, stream, &h->btma);
+        if (!(skip & 2)) h->launches += launch_blur_any(h, f0, batch, stream);
         CU_TRY(h, cudaStreamWaitEvent(stream, ev_join, 0));
     }
     if (!(skip & 16)) h->launches += launch_describe(h->h_levels, nl, f0, batch, pl.total_out_cap, h->d_slot, h->d_items, d_kp, d_desc, cap, stream, &h->dtma, h->sm_count);

@@ -297,9 +297,12 @@ int launch_blur_tc(const LevelDev *h_levels, const BlurTc &C, int f0, int batch,
         bool &configured = configured_[current_device_slot()];
         if (!configured) {
             const int big = (int)(A_BYTES + NBMAX * B_BYTES + 2 * O_BYTES + sizeof(Ctl) + 1024);
-            cudaFuncSetAttribute(k_blur_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-            cudaFuncSetAttribute(k_blur_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-            cudaFuncSetAttribute(k_blur_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+            if (cudaFuncSetAttribute(k_blur_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess ||
+                cudaFuncSetAttribute(k_blur_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess ||
+                cudaFuncSetAttribute(k_blur_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess) {
+                cudaGetLastError();
+                return 0;                 // the caller takes k_blur_tma instead
+            }
             configured = true;
         }
     }
