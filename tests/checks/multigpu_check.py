@@ -28,7 +28,7 @@ index = orbx.Knn2Index(db[lo:hi], device=local, row_offset=lo)
 d_q = torch.from_numpy(q).to(dev)
 from oracle import oracle_lib as ol
 idx_o, dist_o = ol.knn2(q, db) if rank == 0 else (None, None)
-for trial, backend in enumerate((orbx.Knn2Index.TENSOR, orbx.Knn2Index.POPC, orbx.Knn2Index.TENSOR)):
+for trial, backend in enumerate((orbx.Knn2Index.TENSOR_FP4, orbx.Knn2Index.POPC, orbx.Knn2Index.TENSOR, orbx.Knn2Index.TENSOR_FP4)):
     index.set_backend(backend)
     packed = sharded.knn2_sharded(index, d_q).cpu().numpy()
     if rank == 0:
