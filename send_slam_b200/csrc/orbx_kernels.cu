@@ -516,7 +516,8 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ LevelTable
     }
 }
 
-// TMA-staged variant (the one the pipeline runs when every plane meets the TMA alignment rules and is at least 16 x 16): the halo
+// TMA-staged CUDA-core variant (what the pipeline runs with ORBX_BLUR_TC=0, or when the tensor-core kernel of orbx_blur_tc.cu cannot be
+// used; needs every plane to meet the TMA alignment rules and to be at least 16 x 16): the halo
 // tile arrives as ONE box of 96 x 118 bytes at (x0 - 16, y0 - 3) -- a TMA box starts on a 16-byte boundary, bytes outside the plane
 // arrive as 0 -- and the BORDER_REFLECT_101 rows / columns are patched in shared memory afterwards.  That takes the ~6.6 staging
 // instructions per pixel of k_blur off the SM (measured by tools/blur_tma_probe.cu on 64 x 640x480: 23.1 -> 18.8 us); the two passes
